@@ -1,0 +1,966 @@
+// ORACLE (test infrastructure only).  CPU restatement of the Pigeons.jl inner
+// PT scan — run_one_round! = n_scans x { explore!(all replicas) ; swap! } —
+// written to follow the reference's control flow statement by statement
+// (including its redundant density evaluations), with the arithmetic of
+// orc_math.hpp.  Each function cites the reference file:line it restates
+// (paths relative to /root/reference).
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference leg may load this library.  It is never on the product path.
+//
+// parity unpinned: no golden vectors exist in the reference for this path and
+// the reference cannot run here (no Julia).  What pins this file is
+// (1) the reference's tolerance-based known answers (tests/test_oracle_known_answers.py)
+// and (2) the exact-integer DEO/round-trip answer of test/test_round_trips.jl.
+//
+// Deliberate, documented deviations from Pigeons.jl:
+//   * RNG: Philox4x32-10 keyed by (seed, replica_index), one block per draw,
+//     instead of SplittableRandom + ziggurat (north star).
+//   * sums over coordinates use the canonical 32-leaf tree (orc_math.hpp)
+//     instead of Julia's pairwise/SIMD `sum` (unreproducible).
+//   * recorder statistics are accumulated per chain / per pair in scan order,
+//     not per replica followed by a replica-index tree merge
+//     (src/recorders/recorders.jl:88-120): identical counts and integer stats,
+//     float means differ from Pigeons at rounding level only.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../include/pigeons_b200.h"
+#include "orc_math.hpp"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+namespace {
+
+struct OrcError {
+  int code;
+  std::string msg;
+};
+
+// ---------------------------------------------------------------------------
+// Replica record (src/replicas/Replica.jl:5-30)
+// ---------------------------------------------------------------------------
+struct Replica {
+  std::vector<double> x;     // state
+  std::vector<uint32_t> rows;  // Ising: bit-packed rows (bit j of rows[i] = spin (i,j))
+  int ising_S = 0;           // Ising: cached sum_pair_products (examples/ising.jl:19)
+  int chain = 0;             // 1-based
+  int replica_index = 0;     // 1-based
+  Philox rng{};
+  uint64_t ctr = 0;          // draws consumed
+  int rt_state = 0;          // RoundTripRecorder.state
+  // per-scan SwapStat (src/swap/pair_swapper.jl:8-11)
+  double lr = 0.0, u = 0.0;
+  // autoMALA buffers (src/explorers/Augmentation.jl:65-71)
+  std::vector<double> momentum, precond, start_state, state_before, momentum_before, grad, g1, g2;
+  // counters local to the replica during explore (merged after the parallel loop)
+  int64_t ref_equiv_evals = 0;
+
+  double uniform() { return uniform_at(rng, ctr++); }
+  double exponential() { return exponential_at(rng, ctr++); }
+};
+
+struct MeanAcc {   // OnlineStatsBase.Mean with EqualWeight
+  int64_t n = 0;
+  double mu = 0.0;
+  void fit(double x) { n += 1; mu = mu + (1.0 / (double)n) * (x - mu); }
+};
+struct LogSumAcc {  // src/recorders/LogSum.jl:1-24
+  int64_t n = 0;
+  double value = -INF;
+  void fit(double y) { value = logaddexp_(value, y); n += 1; }
+};
+struct VarAcc {   // OnlineStatsBase.Variance with EqualWeight
+  int64_t n = 0;
+  double mu = 0.0, s2 = 0.0;
+  void fit(double x) {
+    double mu_old = mu;
+    n += 1;
+    double g = 1.0 / (double)n;
+    mu = mu_old + g * (x - mu_old);
+    s2 = s2 + g * ((x - mu) * (x - mu_old) - s2);
+  }
+  double value() const { return n > 1 ? s2 * ((double)n / (double)(n - 1)) : 1.0; }
+};
+
+struct ChainStats {
+  MeanAcc swap_acc;           // pair (c, c+1), stored at the lower chain
+  LogSumAcc ls_fwd, ls_bwd;   // keys (c,c+1) and (c+1,c)
+  MeanAcc expl_acc;           // explorer_acceptance_pr
+  int64_t n_steps = 0;        // explorer_n_steps (Sum)
+  MeanAcc am;                 // am_factors
+  MeanAcc rev;                // reversibility_rate
+};
+
+// Explore-phase events are produced inside the (possibly threaded) replica
+// loop; they only touch the stats slot of the replica's own chain, and every
+// chain is held by exactly one replica, so there is no sharing.
+
+struct Engine {
+  pgn_config cfg{};
+  std::vector<double> means, log_w;
+  pgn_explorer_params ep{};
+  std::vector<double> std_devs;
+  bool have_std = false;
+  std::vector<double> beta;            // schedule, size N
+  std::vector<Replica> replicas;       // sorted by chain between scans
+  std::vector<ChainStats> stats;       // per chain (index chain-1)
+  int64_t n_restarts = 0, n_round_trips = 0;
+  std::vector<VarAcc> online;          // per dim, target chain
+  int scan = 0;
+  int n_threads = 1;
+
+  int N() const { return cfg.n_chains; }
+  int d() const { return cfg.dim; }
+  int L() const { return (int)cfg.p[1]; }
+
+  // ------------------------------------------------------------------ densities
+  // Component log densities.  FUNNEL: test/supporting/dimensional-analysis.jl:33-47
+  // with Distributions.logpdf(Normal(0,s),x) = -(z^2+log2pi)/2 - log(s) and
+  // s = exp(y/2) => z^2 = x^2 exp(-y), log s = y/2.
+  double ref_density(const Replica& r) const {
+    const double* x = r.x.data();
+    switch (cfg.target_kind) {
+      case PGN_TARGET_FUNNEL:
+      case PGN_TARGET_GMM: {
+        const double iv = cfg.p[5], ls = cfg.p[4];
+        return tree_sum(d(), [&](int c) { return -(x[c] * x[c] * iv + LOG2PI) * 0.5 - ls; });
+      }
+      case PGN_TARGET_ISING:
+        return 0.0 * (double)r.ising_S;   // IsingLogPotential(0.0, L) (examples/ising.jl:74,77)
+      default: return QNAN;
+    }
+  }
+  double tgt_density(const Replica& r) const {
+    const double* x = r.x.data();
+    switch (cfg.target_kind) {
+      case PGN_TARGET_FUNNEL: {
+        const double y = x[0];
+        const double e = exp_(-y);
+        const double sy = cfg.p[0], lsy = cfg.p[1];
+        return tree_sum(d(), [&](int c) {
+          if (c == 0) { double zy = y / sy; return -(zy * zy + LOG2PI) * 0.5 - lsy; }
+          double t = x[c] * x[c] * e;
+          return -(t + LOG2PI) * 0.5 - 0.5 * y;
+        });
+      }
+      case PGN_TARGET_GMM: {
+        const int K = cfg.n_modes;
+        const double iv = cfg.p[2], cst = cfg.p[1];
+        double a[64];
+        double M = -INF;
+        for (int k = 0; k < K; ++k) {
+          const double* m = &means[(size_t)k * d()];
+          double q = tree_sum(d(), [&](int c) { double t = x[c] - m[c]; return t * t; });
+          a[k] = log_w[k] - 0.5 * q * iv - cst;
+          if (a[k] > M) M = a[k];
+        }
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) s = s + exp_(a[k] - M);
+        return M + log_(s);
+      }
+      case PGN_TARGET_ISING:
+        return cfg.p[0] * (double)r.ising_S;   // examples/ising.jl:74
+      default: return QNAN;
+    }
+  }
+  double ref_density_grad(const Replica& r, double* g) const {
+    const double* x = r.x.data();
+    const double iv = cfg.p[5];
+    for (int c = 0; c < d(); ++c) g[c] = -x[c] * iv;
+    return ref_density(r);
+  }
+  double tgt_density_grad(const Replica& r, double* g) const {
+    const double* x = r.x.data();
+    switch (cfg.target_kind) {
+      case PGN_TARGET_FUNNEL: {
+        const double y = x[0];
+        const double e = exp_(-y);
+        const double ivy = cfg.p[2];
+        double T = tree_sum(d(), [&](int c) {
+          if (c == 0) return 0.0;
+          return 0.5 * (x[c] * x[c] * e) - 0.5;
+        });
+        g[0] = -y * ivy + T;
+        for (int c = 1; c < d(); ++c) g[c] = -x[c] * e;
+        return tgt_density(r);
+      }
+      case PGN_TARGET_GMM: {
+        const int K = cfg.n_modes;
+        const double iv = cfg.p[2], cst = cfg.p[1];
+        double a[64];
+        double M = -INF;
+        for (int k = 0; k < K; ++k) {
+          const double* m = &means[(size_t)k * d()];
+          double q = tree_sum(d(), [&](int c) { double t = x[c] - m[c]; return t * t; });
+          a[k] = log_w[k] - 0.5 * q * iv - cst;
+          if (a[k] > M) M = a[k];
+        }
+        double w[64];
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) { w[k] = exp_(a[k] - M); s = s + w[k]; }
+        for (int c = 0; c < d(); ++c) {
+          double acc = 0.0;
+          for (int k = 0; k < K; ++k) acc = acc + w[k] * (means[(size_t)k * d() + c] - x[c]);
+          g[c] = (acc / s) * iv;
+        }
+        return M + log_(s);
+      }
+      default: return QNAN;
+    }
+  }
+
+  double toy_precision(double b) const {   // ScaledPrecisionNormalPath.jl:45-46
+    return (1.0 - b) * cfg.p[0] + b * cfg.p[1];
+  }
+  double sqr_norm(const std::vector<double>& v) const {   // src/utils/misc.jl:10
+    const double* p = v.data();
+    return tree_sum((int)v.size(), [&](int c) { return p[c] * p[c]; });
+  }
+
+  // log_potential callable of chain with parameter b.
+  //   toy MVN : ScaledPrecisionNormalPath.jl:19-20
+  //   others  : InterpolatedLogPotential.jl:10-17 + InterpolatingPath.jl:26-27
+  double log_potential(double b, Replica& r) {
+    r.ref_equiv_evals += 1;
+    if (cfg.target_kind == PGN_TARGET_TOY_MVN) return -0.5 * toy_precision(b) * sqr_norm(r.x);
+    if (b == 0.0) return ref_density(r);
+    if (b == 1.0) return tgt_density(r);
+    return (1.0 - b) * ref_density(r) + b * tgt_density(r);
+  }
+  // LogDensityProblems.logdensity of the AD wrapper (BufferedAD.jl:89-94;
+  // toy MVN: ScaledPrecisionNormalPath.jl:23)
+  double logdensity(double b, Replica& r) {
+    r.ref_equiv_evals += 1;
+    if (cfg.target_kind == PGN_TARGET_TOY_MVN) return -0.5 * toy_precision(b) * sqr_norm(r.x);
+    double l1 = ref_density(r);
+    double l2 = tgt_density(r);
+    return (1.0 - b) * l1 + b * l2;
+  }
+  // logdensity_and_gradient (BufferedAD.jl:98-111; toy: ScaledPrecisionNormalPath.jl:30-34)
+  double logdensity_and_gradient(double b, Replica& r, double* g) {
+    r.ref_equiv_evals += 1;
+    const int dd = d();
+    if (cfg.target_kind == PGN_TARGET_TOY_MVN) {
+      double prec = toy_precision(b);
+      double ld = -0.5 * prec * sqr_norm(r.x);
+      for (int c = 0; c < dd; ++c) g[c] = -prec * r.x[c];
+      return ld;
+    }
+    double logdens = 0.0;
+    double l = ref_density_grad(r, r.g1.data());
+    logdens = logdens + l * (1.0 - b);
+    for (int c = 0; c < dd; ++c) g[c] = r.g1[c] * (1.0 - b);
+    l = tgt_density_grad(r, r.g2.data());
+    logdens = logdens + l * b;
+    for (int c = 0; c < dd; ++c) g[c] = g[c] + r.g2[c] * b;
+    return logdens;
+  }
+
+  // ------------------------------------------------------------------ init / iid
+  void ising_recompute(Replica& r) const {   // examples/ising.jl:28-36 (each bond once)
+    const int l = L();
+    int s = 0;
+    for (int i = 0; i < l; ++i)
+      for (int j = 0; j < l; ++j) {
+        int me = ((r.rows[i] >> j) & 1u) ? 1 : -1;
+        s += me * ising_sum_neighbours(r, i, j);
+      }
+    r.ising_S = s / 2;
+  }
+  int ising_sum_neighbours(const Replica& r, int i, int j) const {   // examples/ising.jl:61-71
+    const int l = L();
+    auto sg = [&](int a, int b) { return ((r.rows[a] >> b) & 1u) ? 1 : -1; };
+    int up = (i == 0) ? l - 1 : i - 1, dn = (i == l - 1) ? 0 : i + 1;
+    int lf = (j == 0) ? l - 1 : j - 1, rt = (j == l - 1) ? 0 : j + 1;
+    return sg(up, j) + sg(dn, j) + sg(i, lf) + sg(i, rt);
+  }
+  void ising_flip(Replica& r, int i, int j) const {   // examples/ising.jl:39-46
+    int me = ((r.rows[i] >> j) & 1u) ? 1 : -1;
+    int before = me * ising_sum_neighbours(r, i, j);
+    r.rows[i] ^= (1u << j);
+    int after = -me * ising_sum_neighbours(r, i, j);
+    r.ising_S += after - before;
+  }
+  void ising_sync_x(Replica& r) const {
+    const int l = L();
+    for (int i = 0; i < l; ++i)
+      for (int j = 0; j < l; ++j) r.x[(size_t)i * l + j] = ((r.rows[i] >> j) & 1u) ? 1.0 : 0.0;
+  }
+
+  // initialization(target, rng, replica_index)
+  void initialization(Replica& r) {
+    const int dd = d();
+    r.x.assign(dd, 0.0);
+    switch (cfg.target_kind) {
+      case PGN_TARGET_TOY_MVN: {   // toy_mvn_target.jl:10-11
+        double sq = std::sqrt(cfg.p[1]);
+        for (int c = 0; c < dd; ++c) r.x[c] = normal_at(r.rng, r.ctr + c) / sq;
+        r.ctr += dd;
+        break;
+      }
+      case PGN_TARGET_ISING:       // examples/ising.jl:85 (all false)
+        r.rows.assign(L(), 0u);
+        ising_recompute(r);
+        break;
+      default: break;              // zeros (dimensional-analysis.jl:24)
+    }
+  }
+  // sample_iid!(reference_log_potential, replica, shared)
+  void sample_iid(double b, Replica& r) {
+    const int dd = d();
+    switch (cfg.target_kind) {
+      case PGN_TARGET_TOY_MVN: {   // toy_mvn_target.jl:15-21
+        double sq = std::sqrt(toy_precision(b));
+        for (int c = 0; c < dd; ++c) r.x[c] = normal_at(r.rng, r.ctr + c) / sq;
+        r.ctr += dd;
+        break;
+      }
+      case PGN_TARGET_FUNNEL:
+      case PGN_TARGET_GMM: {       // DistributionLogPotential.jl:26-27 (rand!(rng, MvNormal(0, s^2 I), x))
+        double sg = cfg.p[3];
+        for (int c = 0; c < dd; ++c) r.x[c] = sg * normal_at(r.rng, r.ctr + c);
+        r.ctr += dd;
+        break;
+      }
+      case PGN_TARGET_ISING: {     // examples/ising.jl:49-58 (one 32-bit word per row)
+        const int l = L();
+        uint32_t mask = (l >= 32) ? 0xffffffffu : ((1u << l) - 1u);
+        for (int i = 0; i < l; ++i) r.rows[i] = bits32_at(r.rng, r.ctr + i) & mask;
+        r.ctr += l;
+        ising_recompute(r);
+        break;
+      }
+      default: break;              // TestSwapper: nothing (pair_swapper.jl:143)
+    }
+  }
+
+  // ------------------------------------------------------------------ SliceSampler
+  // src/explorers/SliceSampler.jl:24-237
+  void slice_step(Replica& r, ChainStats& st) {
+    const double b = beta[r.chain - 1];
+    double cached_lp = -INF;
+    for (int pass = 0; pass < ep.slice_n_passes; ++pass) cached_lp = slice_sample(r, st, b, cached_lp);
+  }
+  double slice_sample(Replica& r, ChainStats& st, double b, double cached_lp) {
+    // cached_log_potential :32-41
+    if (cached_lp == -INF) {
+      double result = log_potential(b, r);
+      if (result == -INF) throw OrcError{PGN_ERR_BAD_DENSITY, "SliceSampler must be initialized in the support"};
+      cached_lp = result;
+    }
+    for (int c = 0; c < d(); ++c) {
+      cached_lp = slice_sample_coord(r, st, b, c, cached_lp);
+      if (!std::isfinite(cached_lp))
+        throw OrcError{PGN_ERR_BAD_DENSITY, "invalid log density after updating state at index " + std::to_string(c)};
+    }
+    return cached_lp;
+  }
+  double slice_sample_coord(Replica& r, ChainStats& st, double b, int c, double cached_lp) {   // :89-95
+    double z = cached_lp - r.exponential();
+    double Lq, Rq, lp_L, lp_R;
+    slice_double(r, st, b, c, z, Lq, Rq, lp_L, lp_R);
+    return slice_shrink(r, st, b, c, z, Lq, Rq, lp_L, lp_R);
+  }
+  void slice_double(Replica& r, ChainStats& st, double b, int c, double z, double& Lq, double& Rq,
+                    double& potent_L, double& potent_R) {   // :97-126
+    double& ptr = r.x[c];
+    double old_position = ptr;
+    Lq = ptr - ep.slice_w * r.uniform();   // initialize_slice_endpoints :129-133
+    Rq = Lq + ep.slice_w;
+    int K = ep.slice_p;
+    ptr = Lq; potent_L = log_potential(b, r);
+    ptr = Rq; potent_R = log_potential(b, r);
+    while (K > 0 && ((z < potent_L) || (z < potent_R))) {
+      double V = r.uniform();
+      if (V <= 0.5) {
+        Lq = Lq - (Rq - Lq);
+        ptr = Lq; potent_L = log_potential(b, r);
+      } else {
+        Rq = Rq + (Rq - Lq);
+        ptr = Rq; potent_R = log_potential(b, r);
+      }
+      K -= 1;
+    }
+    st.n_steps += ep.slice_p - K;
+    ptr = old_position;
+  }
+  static bool isapprox(double x, double y) {   // Base.isapprox, rtol = sqrt(eps) = 2^-26, atol = 0
+    const double rtol = from_bits(0x3e50000000000000ULL);
+    if (x == y) return true;
+    if (!(std::isfinite(x) && std::isfinite(y))) return false;
+    double ax = std::fabs(x), ay = std::fabs(y);
+    return std::fabs(x - y) <= rtol * (ax > ay ? ax : ay);
+  }
+  double slice_shrink(Replica& r, ChainStats& st, double b, int c, double z, double Lq, double Rq,
+                      double lp_L, double lp_R) {   // :144-186
+    double& ptr = r.x[c];
+    double old_position = ptr;
+    double Lbar = Lq, Rbar = Rq;
+    double new_lp = 0.0;
+    int n = 1;
+    while (n <= ep.slice_max_iter) {
+      double new_position = Lbar + r.uniform() * (Rbar - Lbar);   // draw_new_position :188
+      ptr = new_position;
+      new_lp = log_potential(b, r);
+      bool consider = z < new_lp;
+      ptr = old_position;
+      if (consider && slice_accept(r, st, b, c, new_position, z, Lq, Rq, lp_L, lp_R)) {
+        ptr = new_position;
+        st.n_steps += n;
+        return new_lp;
+      }
+      if (new_position < ptr) Lbar = new_position; else Rbar = new_position;
+      if (isapprox(Lbar, Rbar)) {
+        ptr = old_position;
+        st.n_steps += n;
+        return log_potential(b, r);
+      }
+      n += 1;
+    }
+    throw OrcError{PGN_ERR_SLICE_MAX_ITER, "slice_shrink: maximum number of iterations reached"};
+  }
+  bool slice_accept(Replica& r, ChainStats& st, double b, int c, double new_position, double z, double Lq,
+                    double Rq, double lp_L, double lp_R) {   // :192-237
+    double& ptr = r.x[c];
+    double old_position = ptr;
+    double Lhat = Lq, Rhat = Rq;
+    bool Rstale = false, Lstale = false;
+    bool D = false;
+    while (Rhat - Lhat > 1.1 * ep.slice_w) {
+      double M = (Lhat + Rhat) / 2.0;
+      if (((old_position < M) && (new_position >= M)) || ((old_position >= M) && (new_position < M))) D = true;
+      if (new_position < M) { Rhat = M; Rstale = true; } else { Lhat = M; Lstale = true; }
+      if (D) {
+        if (Lstale) { ptr = Lhat; lp_L = log_potential(b, r); Lstale = false; }
+        if (Rstale) { ptr = Rhat; lp_R = log_potential(b, r); Rstale = false; }
+        if ((z >= lp_L) && (z >= lp_R)) {
+          ptr = old_position;
+          st.expl_acc.fit(0.0);
+          return false;
+        }
+      }
+    }
+    ptr = old_position;
+    st.expl_acc.fit(1.0);
+    return true;
+  }
+
+  // ------------------------------------------------------------------ AutoMALA
+  // src/explorers/hamiltonian_dynamics.jl:28-29
+  double log_joint(double logp, const std::vector<double>& momentum) const { return logp - 0.5 * sqr_norm(momentum); }
+  // hamiltonian_dynamics!(…, n_steps = 1)  (hamiltonian_dynamics.jl:39-84)
+  bool leap_frog(double b, Replica& r, double step_size) {
+    const int dd = d();
+    double* grad = r.grad.data();
+    // conditioned_target_gradient :31-35
+    double logp = logdensity_and_gradient(b, r, grad);
+    for (int c = 0; c < dd; ++c) grad[c] = grad[c] / r.precond[c];
+    for (int c = 0; c < dd; ++c) r.momentum[c] = r.momentum[c] + (step_size / 2) * grad[c];
+    // full position step
+    for (int c = 0; c < dd; ++c) r.x[c] = r.x[c] + step_size * (r.momentum[c] / r.precond[c]);
+    logp = logdensity_and_gradient(b, r, grad);
+    for (int c = 0; c < dd; ++c) grad[c] = grad[c] / r.precond[c];
+    double current_log_joint = log_joint(logp, r.momentum);
+    if (!std::isfinite(current_log_joint)) return false;
+    for (int c = 0; c < dd; ++c) r.momentum[c] = r.momentum[c] + (step_size / 2) * grad[c];
+    if (!std::isfinite(sqr_norm(r.momentum))) return false;
+    return true;
+  }
+  // log_joint_difference_function :250-275 — returns h_before, caller evaluates trials
+  struct LJD { double h_before; };
+  LJD ljd_begin(double b, Replica& r) {
+    r.state_before = r.x;
+    r.momentum_before = r.momentum;
+    return LJD{log_joint(logdensity(b, r), r.momentum)};
+  }
+  double ljd_eval(double b, Replica& r, const LJD& f, double step_size) {
+    leap_frog(b, r, step_size);
+    double h_after = log_joint(logdensity(b, r), r.momentum);
+    r.x = r.state_before;
+    r.momentum = r.momentum_before;
+    return h_after - f.h_before;
+  }
+  // auto_step_size :184-214 (+ grow :216-226, shrink :228-248)
+  int auto_step_size(double b, Replica& r, ChainStats& st, double step_size, double lower_bound, double upper_bound) {
+    if (!(step_size > 0)) throw OrcError{PGN_ERR_INVALID, "autoMALA: step_size must be > 0"};
+    if (!(lower_bound < upper_bound)) throw OrcError{PGN_ERR_INVALID, "autoMALA: lower_bound < upper_bound violated"};
+    LJD f = ljd_begin(b, r);
+    double initial_difference = ljd_eval(b, r, f, step_size);
+    int n_steps = 0, exponent = 0;
+    if (!std::isfinite(initial_difference) || initial_difference < lower_bound) {
+      int n = 1;
+      double eps = step_size;
+      while (true) {
+        eps = eps / 2.0;
+        double diff = ljd_eval(b, r, f, eps);
+        if (eps == 0.0) throw OrcError{PGN_ERR_STEP_UNDERFLOW, "autoMALA: could not find a positive step size"};
+        if (diff > lower_bound) { n_steps = n; exponent = -n; break; }
+        n += 1;
+      }
+    } else if (initial_difference > upper_bound) {
+      int n = 1;
+      double eps = step_size;
+      while (true) {
+        eps = eps * 2.0;
+        double diff = ljd_eval(b, r, f, eps);
+        if (!std::isfinite(diff) || diff < upper_bound) { n_steps = n; exponent = n - 1; break; }
+        n += 1;
+      }
+    }
+    st.n_steps += 1 + n_steps;
+    st.am.fit(pow2(exponent));
+    return exponent;
+  }
+  static double pow2(int e) {   // 2.0^e, exact
+    if (e > 1023) return INF;
+    if (e < -1074) return 0.0;
+    if (e >= -1022) return pow2i(e);
+    return scale2(1.0, e);
+  }
+  // build_preconditioner! (Preconditioner.jl:57-77)
+  void build_preconditioner(Replica& r) {
+    const int dd = d();
+    if (!have_std || ep.precond_kind == PGN_PRECOND_IDENTITY) {
+      for (int c = 0; c < dd; ++c) r.precond[c] = 1.0;
+      return;
+    }
+    if (ep.precond_kind == PGN_PRECOND_DIAGONAL) {
+      for (int c = 0; c < dd; ++c) r.precond[c] = std_devs[c] == 0.0 ? 1.0 : 1.0 / std_devs[c];
+      return;
+    }
+    double u = r.uniform();
+    if (u <= ep.mix_p0) {
+      for (int c = 0; c < dd; ++c) r.precond[c] = std_devs[c] == 0.0 ? 1.0 : 1.0 / std_devs[c];
+    } else if (u <= ep.mix_p01) {
+      for (int c = 0; c < dd; ++c) r.precond[c] = 1.0;
+    } else {
+      double mix = r.uniform();
+      double rmix = 1.0 - mix;
+      for (int c = 0; c < dd; ++c) r.precond[c] = std_devs[c] == 0.0 ? 1.0 : mix + rmix / std_devs[c];
+    }
+  }
+  // auto_mala! (AutoMALA.jl:106-182)
+  void auto_mala(Replica& r, ChainStats& st, bool use_mh) {
+    const int dd = d();
+    const double b = beta[r.chain - 1];
+    build_preconditioner(r);
+    for (int i = 0; i < ep.n_refresh; ++i) {
+      r.start_state = r.x;
+      for (int c = 0; c < dd; ++c) r.momentum[c] = normal_at(r.rng, r.ctr + c);   // randn!(rng, momentum)
+      r.ctr += dd;
+      double init_joint_log = log_joint(logdensity(b, r), r.momentum);
+      if (!std::isfinite(init_joint_log))
+        throw OrcError{PGN_ERR_NOT_POSITIVE, "AutoMALA can only be called on a configuration of positive density"};
+      double a = r.uniform();
+      double bb = r.uniform();
+      double lower_bound = log_(a < bb ? a : bb);
+      double upper_bound = log_(a < bb ? bb : a);
+      int proposed_exponent = auto_step_size(b, r, st, ep.step_size, lower_bound, upper_bound);
+      double proposed_step_size = ep.step_size * pow2(proposed_exponent);
+      leap_frog(b, r, proposed_step_size);
+      if (use_mh) {
+        for (int c = 0; c < dd; ++c) r.momentum[c] = r.momentum[c] * -1.0;
+        int reversed_exponent = auto_step_size(b, r, st, ep.step_size, lower_bound, upper_bound);
+        bool reversibility_passed = reversed_exponent == proposed_exponent;
+        st.rev.fit(reversibility_passed ? 1.0 : 0.0);
+        double probability;
+        if (reversibility_passed) {
+          double final_joint_log = log_joint(logdensity(b, r), r.momentum);
+          double e = exp_(final_joint_log - init_joint_log);
+          probability = 1.0 < e ? 1.0 : e;   // min(1.0, e) (NaN propagates like Julia's min)
+          if (e != e) probability = e;
+        } else {
+          probability = 0.0;
+        }
+        st.expl_acc.fit(probability);
+        if (r.uniform() < probability) {
+          // accept
+        } else {
+          r.x = r.start_state;
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ IsingMetropolis
+  // examples/ising.jl:98-117
+  void ising_metropolis(Replica& r) {
+    const double b = beta[r.chain - 1];
+    const int l = L();
+    for (int k = 0; k < ep.ising_n_steps; ++k)
+      for (int i = 0; i < l; ++i)
+        for (int j = 0; j < l; ++j) {
+          double log_pr_before = log_potential(b, r);
+          ising_flip(r, i, j);
+          double log_pr_after = log_potential(b, r);
+          double accept_ratio = exp_(log_pr_after - log_pr_before);
+          if (accept_ratio < 1 && r.uniform() > accept_ratio) ising_flip(r, i, j);
+        }
+  }
+
+  // ------------------------------------------------------------------ explore!
+  // explore!(pt, replica, explorer)  (src/pt/pigeons.jl:101-132)
+  void explore(Replica& r) {
+    ChainStats& st = stats[r.chain - 1];
+    const bool is_reference = (r.chain == 1 && N() > 1);   // DEO.jl:13
+    if (cfg.target_kind == PGN_TARGET_TEST_SWAPPER) return;
+    if (is_reference) {
+      sample_iid(beta[0], r);
+    } else {
+      switch (ep.kind) {
+        case PGN_EXPLORER_TOY: sample_iid(beta[r.chain - 1], r); break;   // ToyExplorer.jl:7-12
+        case PGN_EXPLORER_SLICE: slice_step(r, st); break;
+        case PGN_EXPLORER_AUTOMALA: auto_mala(r, st, scan != 1); break;   // AutoMALA.jl:87,102
+        case PGN_EXPLORER_ISING_METROPOLIS: ising_metropolis(r); break;
+        default: break;
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ swap!
+  int partner_chain(int chain) const {   // OddEven.jl:23-31, DEO.jl:12
+    bool even = (scan % 2 == 0);
+    int direction = ((chain % 2 == 0) == even) ? 1 : -1;
+    int proposed = chain + direction;
+    if (proposed == 0) return 1;
+    if (proposed == N() + 1) return N();
+    return proposed;
+  }
+  // swap_stat (pair_swapper.jl:42-47) + log_unnormalized_ratio (log_potentials.jl:43-51)
+  void swap_stat(Replica& r, int partner) {
+    if (cfg.target_kind == PGN_TARGET_TEST_SWAPPER) {   // pair_swapper.jl:114
+      r.lr = 0.0;
+      r.u = r.uniform();
+      return;
+    }
+    double lp_num = log_potential(beta[partner - 1], r);
+    double lp_den = log_potential(beta[r.chain - 1], r);
+    double ans = lp_num - lp_den;
+    if (ans != ans) throw OrcError{PGN_ERR_NAN_RATIO, "Got NaN log-unnormalized ratio"};
+    r.lr = ans;
+    r.u = r.uniform();
+  }
+  void record_round_trip(Replica& r) {   // RoundTripRecorder.jl:43-54
+    bool is_ref = (r.chain == 1 && N() > 1), is_tgt = (r.chain == N());
+    if (r.rt_state == 0 && is_ref) r.rt_state = 1;
+    else if (r.rt_state == 1 && is_tgt) { r.rt_state = 2; n_restarts += 1; }
+    else if (r.rt_state == 2 && is_ref) { r.rt_state = 1; n_round_trips += 1; }
+  }
+};
+
+struct RoundLogs {
+  int32_t* index_process;
+  double* swap_lr;
+  double* swap_u;
+  uint8_t* swap_accept;
+  double* target_trace;
+};
+
+void run_round(Engine& E, int64_t n_scans, pgn_round_out* out) {
+  const int N = E.N(), d = E.d();
+  E.stats.assign(N, ChainStats{});
+  E.n_restarts = E.n_round_trips = 0;
+  E.online.assign(d, VarAcc{});
+  for (auto& r : E.replicas) { r.rt_state = 0; r.ref_equiv_evals = 0; }   // recorders are emptied every round (recorders.jl:113-118)
+  int64_t total_ref_evals = 0;
+
+  for (int64_t s = 1; s <= n_scans; ++s) {
+    E.scan = (int)s;
+    // ---- explore!(pt, explorer, multithreaded)  (pigeons.jl:82-97)
+    OrcError first_err{0, ""};
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(E.n_threads)
+#endif
+    for (int i = 0; i < N; ++i) {
+      try {
+        E.explore(E.replicas[i]);
+      } catch (OrcError& e) {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        { if (first_err.code == 0) first_err = e; }
+      }
+    }
+    if (first_err.code) throw first_err;
+    // target-chain recording (pigeons.jl:110-131)
+    {
+      Replica& rt = E.replicas[N - 1];
+      if (E.cfg.target_kind == PGN_TARGET_ISING) E.ising_sync_x(rt);
+      for (int c = 0; c < d; ++c) E.online[c].fit(rt.x[c]);
+      if (out->target_trace) std::memcpy(out->target_trace + (size_t)(s - 1) * d, rt.x.data(), sizeof(double) * d);
+    }
+    // ---- swap!  (swap.jl:6-26)
+    for (int my_chain = 1; my_chain <= N; ++my_chain) {
+      Replica& mine = E.replicas[my_chain - 1];
+      int partner = E.partner_chain(my_chain);
+      if (partner >= my_chain) {
+        Replica& other = E.replicas[partner - 1];
+        E.swap_stat(mine, partner);
+        if (partner != my_chain) E.swap_stat(other, my_chain);
+        // _swap! both halves (swap.jl:106-126): recorders first
+        Replica* both[2] = {&mine, partner != my_chain ? &other : nullptr};
+        for (Replica* r : both) {
+          if (!r) continue;
+          if (out->index_process) out->index_process[(size_t)(s - 1) * N + (r->chain - 1)] = r->replica_index;
+          if (out->swap_lr) out->swap_lr[(size_t)(s - 1) * N + (r->chain - 1)] = r->lr;
+          if (out->swap_u) out->swap_u[(size_t)(s - 1) * N + (r->chain - 1)] = r->u;
+          E.record_round_trip(*r);
+        }
+        bool do_swap = false;
+        if (partner != my_chain) {
+          double acceptance_pr;
+          if (E.cfg.target_kind == PGN_TARGET_TEST_SWAPPER) {
+            acceptance_pr = E.cfg.p[0];           // pair_swapper.jl:121-124 (no stats recorded :131)
+          } else {
+            double e = exp_(mine.lr + other.lr);  // swap_acceptance_probability :88
+            acceptance_pr = 1.0 < e ? 1.0 : e;
+            ChainStats& st = E.stats[my_chain - 1];   // record_swap_stats! :59-66
+            st.swap_acc.fit(acceptance_pr);
+            st.ls_fwd.fit(mine.lr);
+            st.ls_bwd.fit(other.lr);
+          }
+          do_swap = mine.u < acceptance_pr;       // swap_decision :81-85 (uniform of the lower chain)
+        }
+        if (out->swap_accept) {
+          out->swap_accept[(size_t)(s - 1) * N + (my_chain - 1)] = do_swap ? 1 : 0;
+          if (partner != my_chain) out->swap_accept[(size_t)(s - 1) * N + (partner - 1)] = do_swap ? 1 : 0;
+        }
+        if (do_swap) {
+          mine.chain = partner;
+          other.chain = my_chain;
+          std::swap(E.replicas[my_chain - 1], E.replicas[partner - 1]);   // resort_replicas! (swap.jl:28-39)
+        }
+      }
+    }
+  }
+  for (auto& r : E.replicas) total_ref_evals += r.ref_equiv_evals;
+
+  // ---- outputs
+  for (int c = 0; c < N; ++c) {
+    const ChainStats& st = E.stats[c];
+    if (out->swap_n) out->swap_n[c] = st.swap_acc.n;
+    if (out->swap_mean) out->swap_mean[c] = st.swap_acc.mu;
+    if (out->logsum_fwd) out->logsum_fwd[c] = st.ls_fwd.value;
+    if (out->logsum_bwd) out->logsum_bwd[c] = st.ls_bwd.value;
+    if (out->expl_acc_n) out->expl_acc_n[c] = st.expl_acc.n;
+    if (out->expl_acc_mean) out->expl_acc_mean[c] = st.expl_acc.mu;
+    if (out->expl_n_steps) out->expl_n_steps[c] = st.n_steps;
+    if (out->am_n) out->am_n[c] = st.am.n;
+    if (out->am_mean) out->am_mean[c] = st.am.mu;
+    if (out->rev_n) out->rev_n[c] = st.rev.n;
+    if (out->rev_mean) out->rev_mean[c] = st.rev.mu;
+  }
+  out->n_tempered_restarts = E.n_restarts;
+  out->n_round_trips = E.n_round_trips;
+  out->online_n = d > 0 ? E.online[0].n : n_scans;
+  for (int c = 0; c < d; ++c) {
+    if (out->online_mean) out->online_mean[c] = E.online[c].mu;
+    if (out->online_var) out->online_var[c] = E.online[c].value();
+  }
+  out->n_ref_equiv_evals = total_ref_evals;
+  out->n_density_points = 0;
+  out->kernel_ms = 0.0;
+}
+
+int fail(char** err, int code, const std::string& msg) {
+  if (err) {
+    *err = (char*)std::malloc(msg.size() + 1);
+    std::memcpy(*err, msg.c_str(), msg.size() + 1);
+  }
+  return code;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C API: same shapes as include/pigeons_b200.h with the prefix orc_, so the
+// tests can drive the oracle and the CUDA engine through one adapter.
+// ===========================================================================
+extern "C" {
+
+struct orc_handle { Engine E; };
+
+int orc_create(const pgn_config* cfg, orc_handle** out, char** err) {
+  if (!cfg || !out) return fail(err, PGN_ERR_INVALID, "null argument");
+  if (cfg->abi_version != PGN_ABI_VERSION) return fail(err, PGN_ERR_INVALID, "ABI version mismatch");
+  if (cfg->world_size != 1 || cfg->rank != 0) return fail(err, PGN_ERR_INVALID, "oracle is single-process");
+  if (cfg->n_chains < 1) return fail(err, PGN_ERR_INVALID, "n_chains must be >= 1");
+  if (cfg->target_kind == PGN_TARGET_LOGREG) return fail(err, PGN_ERR_INVALID, "LOGREG not implemented");
+  if (cfg->target_kind == PGN_TARGET_GMM && (cfg->n_modes < 1 || cfg->n_modes > 64))
+    return fail(err, PGN_ERR_INVALID, "GMM: 1 <= n_modes <= 64");
+  if (cfg->target_kind == PGN_TARGET_ISING) {
+    int L = (int)cfg->p[1];
+    if (L < 2 || L > 32 || L * L != cfg->dim) return fail(err, PGN_ERR_INVALID, "ISING: 2 <= L <= 32 and dim == L*L");
+  }
+  auto h = new orc_handle();
+  Engine& E = h->E;
+  E.cfg = *cfg;
+  if (cfg->target_kind == PGN_TARGET_GMM) {
+    E.means.assign(cfg->means, cfg->means + (size_t)cfg->n_modes * cfg->dim);
+    E.log_w.assign(cfg->log_weights, cfg->log_weights + cfg->n_modes);
+  }
+  E.cfg.means = E.cfg.log_weights = E.cfg.data_x = E.cfg.data_y = nullptr;
+  E.beta.assign(cfg->n_chains, 0.0);
+  for (int i = 0; i < cfg->n_chains; ++i) E.beta[i] = cfg->n_chains == 1 ? 1.0 : (double)i / (cfg->n_chains - 1);
+  E.ep = pgn_explorer_params{};
+  E.ep.kind = PGN_EXPLORER_NONE;
+#ifdef _OPENMP
+  E.n_threads = omp_get_max_threads();
+#endif
+  *out = h;
+  return PGN_OK;
+}
+int orc_destroy(orc_handle* h) { delete h; return PGN_OK; }
+void orc_free_string(char* s) { std::free(s); }
+int orc_set_threads(orc_handle* h, int n) { h->E.n_threads = n < 1 ? 1 : n; return PGN_OK; }
+int orc_get_threads(orc_handle* h) { return h->E.n_threads; }
+
+int orc_local_range(const orc_handle* h, int32_t* first_chain, int32_t* n_local) {
+  *first_chain = 1; *n_local = h->E.cfg.n_chains; return PGN_OK;
+}
+int orc_set_schedule(orc_handle* h, const double* beta, int32_t n, char** err) {
+  if (n != h->E.cfg.n_chains) return fail(err, PGN_ERR_INVALID, "schedule length != n_chains");
+  h->E.beta.assign(beta, beta + n);
+  return PGN_OK;
+}
+int orc_set_explorer(orc_handle* h, const pgn_explorer_params* ep, char** err) {
+  Engine& E = h->E;
+  E.ep = *ep;
+  E.have_std = ep->std_devs != nullptr;
+  if (E.have_std) E.std_devs.assign(ep->std_devs, ep->std_devs + E.cfg.dim);
+  E.ep.std_devs = nullptr;
+  (void)err;
+  return PGN_OK;
+}
+int orc_init_replicas(orc_handle* h, char** err) {
+  Engine& E = h->E;
+  const int N = E.N(), d = E.d();
+  E.replicas.assign(N, Replica{});
+  for (int i = 0; i < N; ++i) {
+    Replica& r = E.replicas[i];
+    r.chain = i + 1;
+    r.replica_index = i + 1;
+    r.rng = Philox{(uint32_t)(uint64_t)E.cfg.seed, (uint32_t)(i + 1), (uint32_t)((uint64_t)E.cfg.seed >> 32), 0u};
+    r.ctr = 0;
+    r.momentum.assign(d, 0.0); r.precond.assign(d, 1.0); r.start_state.assign(d, 0.0);
+    r.state_before.assign(d, 0.0); r.momentum_before.assign(d, 0.0);
+    r.grad.assign(d, 0.0); r.g1.assign(d, 0.0); r.g2.assign(d, 0.0);
+    E.initialization(r);
+  }
+  (void)err;
+  return PGN_OK;
+}
+int orc_get_state(orc_handle* h, pgn_replica_state* out, char** err) {
+  Engine& E = h->E;
+  const int N = E.N(), d = E.d();
+  for (int i = 0; i < N; ++i) {
+    Replica& r = E.replicas[i];
+    if (E.cfg.target_kind == PGN_TARGET_ISING) E.ising_sync_x(r);
+    if (out->x && d > 0) std::memcpy(out->x + (size_t)i * d, r.x.data(), sizeof(double) * d);
+    if (out->replica_index) out->replica_index[i] = r.replica_index;
+    if (out->rng_counter) out->rng_counter[i] = r.ctr;
+    if (out->round_trip_state) out->round_trip_state[i] = r.rt_state;
+  }
+  (void)err;
+  return PGN_OK;
+}
+int orc_set_state(orc_handle* h, const pgn_replica_state* in, char** err) {
+  Engine& E = h->E;
+  const int N = E.N(), d = E.d();
+  if ((int)E.replicas.size() != N) return fail(err, PGN_ERR_INVALID, "call init_replicas first");
+  for (int i = 0; i < N; ++i) {
+    Replica& r = E.replicas[i];
+    r.chain = i + 1;
+    if (in->x && d > 0) r.x.assign(in->x + (size_t)i * d, in->x + (size_t)(i + 1) * d);
+    if (in->replica_index) {
+      r.replica_index = in->replica_index[i];
+      r.rng.key1 = (uint32_t)r.replica_index;
+    }
+    if (in->rng_counter) r.ctr = in->rng_counter[i];
+    if (in->round_trip_state) r.rt_state = in->round_trip_state[i];
+    if (E.cfg.target_kind == PGN_TARGET_ISING && in->x) {
+      const int L = E.L();
+      r.rows.assign(L, 0u);
+      for (int a = 0; a < L; ++a)
+        for (int b = 0; b < L; ++b)
+          if (r.x[(size_t)a * L + b] != 0.0) r.rows[a] |= (1u << b);
+      E.ising_recompute(r);
+    }
+  }
+  return PGN_OK;
+}
+int orc_run_round(orc_handle* h, int64_t n_scans, pgn_round_out* out, char** err) {
+  try {
+    run_round(h->E, n_scans, out);
+  } catch (OrcError& e) {
+    return fail(err, e.code, e.msg);
+  }
+  return PGN_OK;
+}
+int orc_log_potential(orc_handle* h, const double* x, int32_t n_points, const double* beta, double* out, char** err) {
+  Engine& E = h->E;
+  const int d = E.d();
+  Replica r;
+  r.x.assign(d, 0.0);
+  for (int i = 0; i < n_points; ++i) {
+    r.x.assign(x + (size_t)i * d, x + (size_t)(i + 1) * d);
+    if (E.cfg.target_kind == PGN_TARGET_ISING) {
+      const int L = E.L();
+      r.rows.assign(L, 0u);
+      for (int a = 0; a < L; ++a)
+        for (int b = 0; b < L; ++b)
+          if (r.x[(size_t)a * L + b] != 0.0) r.rows[a] |= (1u << b);
+      E.ising_recompute(r);
+    }
+    out[i] = E.log_potential(beta[i], r);
+  }
+  (void)err;
+  return PGN_OK;
+}
+int orc_logdensity_and_gradient(orc_handle* h, const double* x, int32_t n_points, const double* beta,
+                                double* logdens, double* grad, char** err) {
+  Engine& E = h->E;
+  const int d = E.d();
+  if (E.cfg.target_kind == PGN_TARGET_ISING || E.cfg.target_kind == PGN_TARGET_TEST_SWAPPER)
+    return fail(err, PGN_ERR_INVALID, "target has no gradient");
+  Replica r;
+  r.g1.assign(d, 0.0); r.g2.assign(d, 0.0);
+  for (int i = 0; i < n_points; ++i) {
+    r.x.assign(x + (size_t)i * d, x + (size_t)(i + 1) * d);
+    logdens[i] = E.logdensity_and_gradient(beta[i], r, grad + (size_t)i * d);
+  }
+  return PGN_OK;
+}
+int orc_test_math(int32_t device, int32_t op, const double* in, double* out, int64_t n, int64_t seed,
+                  int32_t replica_index, char** err) {
+  (void)device; (void)err;
+  Philox g{(uint32_t)(uint64_t)seed, (uint32_t)replica_index, (uint32_t)((uint64_t)seed >> 32), 0u};
+  for (int64_t i = 0; i < n; ++i) {
+    switch (op) {
+      case 0: out[i] = exp_(in[i]); break;
+      case 1: out[i] = log_(in[i]); break;
+      case 2: out[i] = cospi_(in[i]); break;
+      case 3: out[i] = normal_at(g, (uint64_t)in[i]); break;
+      case 4: out[i] = uniform_at(g, (uint64_t)in[i]); break;
+      case 5: out[i] = exponential_at(g, (uint64_t)in[i]); break;
+      case 6: out[i] = logaddexp_(in[2 * i], in[2 * i + 1]); break;
+      default: out[i] = QNAN;
+    }
+  }
+  return PGN_OK;
+}
+void orc_philox(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) {
+  philox4x32_10(ctr4[0], ctr4[1], ctr4[2], ctr4[3], key2[0], key2[1], out4);
+}
+
+}  // extern "C"

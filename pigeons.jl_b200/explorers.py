@@ -1,0 +1,99 @@
+"""Explorer configuration structs (the `explorer` informal interface,
+src/explorers/explorer.jl:7-39).  These are host-side parameter records with the
+reference's field names and defaults; the kernels that execute them live in
+csrc/pgn_scan.cu.  `adapt_explorer` restates src/explorers/AutoMALA.jl:70-79.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field, replace
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+
+
+@dataclass(frozen=True)
+class ToyExplorer:
+    """src/explorers/ToyExplorer.jl:5-14: i.i.d. sampling at every chain (toy paths only)."""
+
+    def engine_params(self, dim: int) -> dict:
+        return dict(kind=_capi.EXPLORER_TOY)
+
+
+@dataclass(frozen=True)
+class SliceSampler:
+    """src/explorers/SliceSampler.jl:8-20."""
+    w: float = 10.0
+    p: int = 20
+    n_passes: int = 3
+    max_iter: int = 1024
+
+    def engine_params(self, dim: int) -> dict:
+        return dict(kind=_capi.EXPLORER_SLICE, slice_w=self.w, slice_p=self.p, slice_n_passes=self.n_passes,
+                    slice_max_iter=self.max_iter)
+
+
+@dataclass(frozen=True)
+class IdentityPreconditioner:        # Preconditioner.jl:14
+    kind: int = _capi.PRECOND_IDENTITY
+
+
+@dataclass(frozen=True)
+class DiagonalPreconditioner:        # Preconditioner.jl:22
+    kind: int = _capi.PRECOND_DIAGONAL
+
+
+@dataclass(frozen=True)
+class MixDiagonalPreconditioner:     # Preconditioner.jl:40-50 (defaults 1//3, 1//3)
+    p0: float = 1.0 / 3.0
+    p1: float = 1.0 / 3.0
+    kind: int = _capi.PRECOND_MIX_DIAGONAL
+
+    def __post_init__(self):
+        if not (0.0 <= self.p0 + self.p1 <= 1.0):
+            raise ValueError("p0+p1 < 0 or p0+p1 > 1")
+
+
+@dataclass(frozen=True)
+class AutoMALA:
+    """src/explorers/AutoMALA.jl:29-68.  `default_autodiff_backend` has no device
+    counterpart: every device target ships an analytic gradient."""
+    base_n_refresh: int = 3
+    exponent_n_refresh: float = 0.35
+    step_size: float = 1.0
+    preconditioner: object = field(default_factory=MixDiagonalPreconditioner)
+    estimated_target_std_deviations: Optional[tuple] = None
+
+    def n_refresh(self, dim: int) -> int:          # AutoMALA.jl:122
+        return self.base_n_refresh * math.ceil(dim ** self.exponent_n_refresh)
+
+    def engine_params(self, dim: int) -> dict:
+        pc = self.preconditioner
+        sd = None if self.estimated_target_std_deviations is None else np.asarray(self.estimated_target_std_deviations)
+        p0 = getattr(pc, "p0", 1.0 / 3.0)
+        p1 = getattr(pc, "p1", 1.0 / 3.0)
+        return dict(kind=_capi.EXPLORER_AUTOMALA, n_refresh=self.n_refresh(dim), step_size=self.step_size,
+                    precond_kind=pc.kind, mix_p0=p0, mix_p01=p0 + p1, std_devs=sd)
+
+    def adapt(self, round_result) -> "AutoMALA":
+        """adapt_explorer (AutoMALA.jl:70-79): new step size = old * mean over chains
+        of the mean am_factor; std devs from the target chain's online variance."""
+        am_n = np.asarray(round_result.am_n)
+        am_mean = np.asarray(round_result.am_mean)
+        recorded = am_n > 0
+        factor = float(np.mean(am_mean[recorded])) if recorded.any() else 1.0
+        sd = None
+        if self.preconditioner.kind != _capi.PRECOND_IDENTITY:     # Preconditioner.jl:53-55
+            sd = tuple(np.sqrt(np.asarray(round_result.online_var)).tolist())
+        return replace(self, step_size=self.step_size * factor, estimated_target_std_deviations=sd)
+
+
+@dataclass(frozen=True)
+class IsingMetropolis:
+    """examples/ising.jl:91-93."""
+    n_steps: int = 3
+
+    def engine_params(self, dim: int) -> dict:
+        return dict(kind=_capi.EXPLORER_ISING_METROPOLIS, ising_n_steps=self.n_steps)

@@ -1,0 +1,214 @@
+"""Host-side PT driver: `pigeons(...)`, `Inputs`, `PT`, `Shared`, `Iterators`.
+
+Mirror of the reference's host orchestration for the standalone harness
+(src/api.jl:8-19, src/pt/Inputs.jl:9-102, src/pt/PT.jl:6-50, src/pt/Shared.jl,
+src/pt/Iterators.jl:27-49, src/pt/pigeons.jl:12-28,152-162).  The only thing
+that differs from the reference's round loop is `run_one_round!`: instead of
+looping over scans on the host it makes ONE C-ABI call per round
+(`pgn_run_round`) that runs all 2^round scans on the GPU.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from .distributed import Communicator, LoadBalance, SingleProcess
+from .explorers import AutoMALA
+from .recorders import ReducedRecorders, merge_round_results
+from .tempering import (CommunicationBarriers, Schedule, communication_barriers, equally_spaced_schedule,
+                        optimal_schedule, rejections)
+
+# recorder names accepted in `record=[...]` (src/recorders/recorder.jl)
+traces = "traces"
+index_process = "index_process"
+round_trip = "round_trip"
+online = "online"
+swap_trace = "swap_trace"      # engine extension: per-scan SwapStat log
+
+
+@dataclass
+class Inputs:
+    """src/pt/Inputs.jl:9-102 (fields the scan path honours)."""
+    target: object
+    seed: int = 1
+    n_rounds: int = 10
+    n_chains: int = 10
+    explorer: object = None
+    record: Sequence[str] = ()
+    multithreaded: bool = False        # accepted for API compatibility; the device runs all replicas concurrently
+    show_report: bool = False
+    checked_round: int = 0
+    # engine plumbing (not in the reference)
+    engine_lib: Optional[_capi.EngineLib] = None
+    device: int = 0
+    comm: Optional[Communicator] = None
+
+    def __post_init__(self):
+        if self.explorer is None:
+            self.explorer = self.target.default_explorer()     # target.jl:24, explorer.jl:49-54
+        if self.comm is None:
+            self.comm = SingleProcess()
+
+
+@dataclass
+class Iterators:
+    """src/pt/Iterators.jl:8-24."""
+    round: int = 0
+    scan: int = 0
+
+
+def n_scans_in_round(it: Iterators) -> int:      # Iterators.jl:49
+    return 2 ** it.round
+
+
+@dataclass
+class NonReversiblePT:
+    """src/tempering/NonReversiblePT.jl:7-28."""
+    schedule: Schedule
+    communication_barriers: Optional[CommunicationBarriers] = None
+
+
+@dataclass
+class Shared:
+    """src/pt/Shared.jl:12-41."""
+    iterators: Iterators
+    tempering: NonReversiblePT
+    explorer: object
+
+
+@dataclass
+class PT:
+    """src/pt/PT.jl:6-50."""
+    inputs: Inputs
+    shared: Shared
+    engine: _capi.Engine
+    reduced_recorders: Optional[ReducedRecorders] = None
+    round_log: List[dict] = field(default_factory=list)
+
+    def close(self):
+        self.engine.close()
+
+
+def create_pt(inputs: Inputs) -> PT:
+    """PT(inputs) (PT.jl:46-51): Shared + create_replicas (replicas.jl:65-99)."""
+    lib = inputs.engine_lib or _capi.EngineLib()
+    comm = inputs.comm
+    cfg = inputs.target.engine_config()
+    engine = _capi.Engine(lib, n_chains=inputs.n_chains, seed=inputs.seed, rank=comm.rank,
+                          world_size=comm.world_size, device=inputs.device, **cfg)
+    lb = LoadBalance(comm.rank + 1, comm.world_size, inputs.n_chains)
+    assert engine.first_chain == lb.my_first_global_idx() and engine.n_local == lb.my_load(), \
+        "engine shard geometry disagrees with LoadBalance"
+    comm.connect_neighbours(engine)
+    tempering = NonReversiblePT(equally_spaced_schedule(inputs.n_chains))
+    shared = Shared(Iterators(), tempering, inputs.explorer)
+    engine.init_replicas()
+    return PT(inputs, shared, engine)
+
+
+def run_one_round(pt: PT) -> ReducedRecorders:
+    """run_one_round! (pigeons.jl:46-55) — one engine call for the whole round,
+    then reduce_recorders! across shards (recorders.jl:88-120)."""
+    it = pt.shared.iterators
+    eng = pt.engine
+    dim = pt.inputs.target.dim
+    eng.set_schedule(pt.shared.tempering.schedule.grids)
+    if pt.shared.explorer is None:
+        eng.set_explorer(kind=_capi.EXPLORER_NONE)
+    else:
+        eng.set_explorer(**pt.shared.explorer.engine_params(dim))
+    rec = set(pt.inputs.record)
+    res = eng.run_round(n_scans_in_round(it),
+                        log_index_process=index_process in rec,
+                        log_swaps=swap_trace in rec,
+                        log_target_trace=traces in rec)
+    merged = merge_round_results(pt.inputs.comm, res, pt.inputs.n_chains, dim)
+    return merged
+
+
+def adapt(pt: PT, rr: ReducedRecorders) -> PT:
+    """adapt (pigeons.jl:152-162): adapt_tempering (NonReversiblePT.jl:52-66) then adapt_explorer."""
+    temp = pt.shared.tempering
+    n = temp.schedule.n_chains
+    if n > 1 and rr.has_swap_stats:
+        rej = rejections(rr.swap_n, rr.swap_mean, n)
+        new_temp = NonReversiblePT(optimal_schedule(rej, temp.schedule),
+                                   communication_barriers(rej, temp.schedule.grids))
+    else:
+        new_temp = temp
+    explorer = pt.shared.explorer
+    if isinstance(explorer, AutoMALA):
+        explorer = explorer.adapt(rr)
+    pt.shared = Shared(pt.shared.iterators, new_temp, explorer)
+    pt.reduced_recorders = rr
+    return pt
+
+
+def pigeons_pt(pt: PT) -> PT:
+    """pigeons(pt::PT) (pigeons.jl:12-28)."""
+    it = pt.shared.iterators
+    while it.round + 1 <= pt.inputs.n_rounds:       # next_round! (Iterators.jl:27-35)
+        it.round += 1
+        rr = run_one_round(pt)
+        pt = adapt(pt, rr)
+        pt.round_log.append(dict(round=it.round, n_scans=n_scans_in_round(it), kernel_ms=rr.kernel_ms,
+                                 wall_s=rr.wall_s, global_barrier=global_barrier(pt) if pt.inputs.n_chains > 1 and rr.has_swap_stats else float("nan"),
+                                 stepping_stone=stepping_stone(pt) if rr.has_swap_stats else float("nan"),
+                                 n_round_trips=rr.n_round_trips))
+        if pt.inputs.show_report:
+            r = pt.round_log[-1]
+            print(f"round {r['round']:3d}  scans {r['n_scans']:8d}  Λ {r['global_barrier']:.4g}  "
+                  f"log(Z1/Z0) {r['stepping_stone']:.6g}  kernel {r['kernel_ms']:.3f} ms")
+    return pt
+
+
+def pigeons(**kwargs) -> PT:
+    """pigeons(; target, n_chains, explorer, ...) (src/api.jl:16-19)."""
+    return pigeons_pt(create_pt(Inputs(**kwargs)))
+
+
+# ---- post-processing ---------------------------------------------------------
+def stepping_stone_pair(pt: PT):
+    """src/evidence/stepping_stone.jl:28-43."""
+    rr = pt.reduced_recorders
+    e1 = 0.0
+    e2 = 0.0
+    for i in range(pt.inputs.n_chains - 1):
+        if rr.swap_n[i] > 0:
+            e1 += rr.logsum_fwd[i] - math.log(rr.swap_n[i])
+            e2 += rr.logsum_bwd[i] - math.log(rr.swap_n[i])
+    return (e1, -e2)
+
+
+def stepping_stone(pt: PT) -> float:
+    """src/evidence/stepping_stone.jl:9-18."""
+    p = stepping_stone_pair(pt)
+    if not math.isfinite(p[0]):
+        return p[1]
+    if not math.isfinite(p[1]):
+        return p[0]
+    return (p[0] + p[1]) / 2.0
+
+
+def global_barrier(pt: PT) -> float:        # NonReversiblePT.jl:74
+    return pt.shared.tempering.communication_barriers.globalbarrier
+
+
+def n_round_trips(pt: PT) -> int:           # RoundTripRecorder.jl:23
+    return pt.reduced_recorders.n_round_trips
+
+
+def n_tempered_restarts(pt: PT) -> int:     # RoundTripRecorder.jl:21
+    return pt.reduced_recorders.n_tempered_restarts
+
+
+def sample_array(pt: PT) -> np.ndarray:
+    """process_sample.jl:19-32 restricted to the target chain: [n_scans, d] of the last round."""
+    tr = pt.reduced_recorders.target_trace
+    if tr is None:
+        raise ValueError("record=[traces] was not requested")
+    return tr

@@ -1,0 +1,159 @@
+"""Device target families and the `target` informal interface.
+
+Mirrors src/targets/target.jl:4-76 (`initialization`, `default_explorer`,
+`default_reference`, `sample_iid!`, `create_path`) for the closed family of
+targets the engine implements on the device.  Arbitrary host callables cannot
+run inside the scan kernel; an unsupported target raises (no CPU fallback).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from .explorers import IsingMetropolis, SliceSampler, ToyExplorer
+
+
+class Target:
+    """Base class: anything `pigeons(target=...)` accepts."""
+    dim: int
+
+    def default_explorer(self):          # target.jl:24
+        return SliceSampler()
+
+    def engine_config(self) -> dict:     # -> kwargs of _capi.Engine
+        raise NotImplementedError
+
+
+@dataclass
+class ScaledPrecisionNormalPath(Target):
+    """src/paths/ScaledPrecisionNormalPath.jl:5-78: zero-mean normals whose
+    *precision* is interpolated, prec(b) = (1-b)*precision0 + b*precision1."""
+    precision0: float
+    precision1: float
+    dim: int
+
+    def default_explorer(self):          # toy_mvn_target.jl:13
+        return ToyExplorer()
+
+    def engine_config(self):
+        return dict(target_kind=_capi.TARGET_TOY_MVN, dim=self.dim, p=(self.precision0, self.precision1))
+
+    # known answers used by the reference's own tests
+    def analytic_cumulativebarrier(self):     # ScaledPrecisionNormalPath.jl:56-64
+        from scipy.special import beta as beta_fn
+        b = beta_fn(self.dim / 2.0, self.dim / 2.0)
+
+        def cumulativebarrier(beta):
+            sigma0 = 1.0 / math.sqrt(self.precision0)
+            sigmab = 1.0 / math.sqrt((1.0 - beta) * self.precision0 + beta * self.precision1)
+            return 2.0 ** (2.0 - self.dim) / b * math.log(sigma0 / sigmab)
+        return cumulativebarrier
+
+    def analytic_lognormalization(self):      # ScaledPrecisionNormalPath.jl:66-71
+        return 0.5 * self.dim * (math.log(self.precision0) - math.log(self.precision1))
+
+
+def toy_mvn_target(dim: int) -> ScaledPrecisionNormalPath:
+    """src/targets/toy_mvn_target.jl:8 and ScaledPrecisionNormalPath.jl:43-44."""
+    return ScaledPrecisionNormalPath(1.0, 10.0, int(dim))
+
+
+def _normal_ref_params(sigma_ref: float):
+    return (float(sigma_ref), math.log(sigma_ref), 1.0 / (sigma_ref * sigma_ref))
+
+
+@dataclass
+class Funnel(Target):
+    """Neal's funnel as in test/supporting/dimensional-analysis.jl:33-47:
+    y ~ N(0, scale), z_i ~ N(0, exp(y/2)), i = 2..dim.  The reference repo has no
+    PT reference for it; we use N(0, reference_sigma^2 I)."""
+    dim: int
+    scale: float = 3.0
+    reference_sigma: float = 3.0
+
+    def default_explorer(self):
+        from .explorers import AutoMALA
+        return AutoMALA()
+
+    def engine_config(self):
+        s = float(self.scale)
+        p = (s, math.log(s), 1.0 / (s * s)) + _normal_ref_params(self.reference_sigma)
+        return dict(target_kind=_capi.TARGET_FUNNEL, dim=self.dim, p=p)
+
+
+@dataclass
+class GaussianMixture(Target):
+    """DistributionLogPotential(MixtureModel([MvNormal(m_k, sigma^2 I)...], w))
+    (src/targets/DistributionLogPotential.jl:5-41; pattern of
+    test/test_auto_mala.jl:126-132) with reference MvNormal(0, reference_sigma^2 I)."""
+    means: np.ndarray                  # [K, d]
+    weights: Optional[Sequence[float]] = None
+    sigma: float = 1.0
+    reference_sigma: float = 1.0
+    dim: int = field(init=False)
+
+    def __post_init__(self):
+        self.means = np.ascontiguousarray(self.means, dtype=np.float64)
+        assert self.means.ndim == 2
+        self.dim = int(self.means.shape[1])
+        k = self.means.shape[0]
+        w = np.full(k, 1.0 / k) if self.weights is None else np.asarray(self.weights, dtype=np.float64)
+        assert w.size == k and abs(w.sum() - 1.0) < 1e-12
+        self.weights = w
+
+    def default_explorer(self):
+        from .explorers import AutoMALA
+        return AutoMALA()
+
+    def engine_config(self):
+        d, s = self.dim, float(self.sigma)
+        cst = d * math.log(s) + 0.5 * d * math.log(2.0 * math.pi)
+        p = (s, cst, 1.0 / (s * s)) + _normal_ref_params(self.reference_sigma)
+        return dict(target_kind=_capi.TARGET_GMM, dim=d, p=p, means=self.means,
+                    log_weights=np.log(self.weights), n_modes=int(self.means.shape[0]))
+
+
+def eight_mode_mixture(dim: int = 128, mu: float = 8.0) -> GaussianMixture:
+    """BASELINE config 3: 8 modes at (+-mu, +-mu, +-mu, 0, ..., 0), identity
+    covariances, equal weights, reference N(0, mu^2 I)."""
+    means = np.zeros((8, dim))
+    for k in range(8):
+        for j in range(3):
+            means[k, j] = mu if (k >> j) & 1 else -mu
+    return GaussianMixture(means=means, sigma=1.0, reference_sigma=mu)
+
+
+@dataclass
+class IsingLogPotential(Target):
+    """examples/ising.jl:6-117: l(state) = beta * sum_<ij> s_i s_j on an L x L
+    torus; reference = same with beta = 0 (i.i.d. Bernoulli(1/2) spins)."""
+    beta: float = 1.0
+    base_length: int = 5
+
+    @property
+    def dim(self):
+        return self.base_length * self.base_length
+
+    def default_explorer(self):          # examples/ising.jl:95
+        return IsingMetropolis()
+
+    def engine_config(self):
+        return dict(target_kind=_capi.TARGET_ISING, dim=self.dim, p=(self.beta, self.base_length))
+
+
+@dataclass
+class TestSwapper(Target):
+    """src/swap/pair_swapper.jl:100-149: every swap has the same acceptance probability."""
+    constant_swap_accept_pr: float
+    dim: int = 0
+    __test__ = False   # not a pytest class
+
+    def default_explorer(self):
+        return None
+
+    def engine_config(self):
+        return dict(target_kind=_capi.TARGET_TEST_SWAPPER, dim=0, p=(self.constant_swap_accept_pr,))
