@@ -696,7 +696,10 @@ void run_round(Engine& E, int64_t n_scans, pgn_round_out* out) {
     {
       Replica& rt = E.replicas[N - 1];
       if (E.cfg.target_kind == PGN_TARGET_ISING) E.ising_sync_x(rt);
-      for (int c = 0; c < d; ++c) E.online[c].fit(rt.x[c]);
+      // online statistics are kept for vector states only (IsingState is not a
+      // continuous-variable state; OnlineStateRecorder.jl:87-110 does not apply)
+      if (E.cfg.target_kind != PGN_TARGET_ISING)
+        for (int c = 0; c < d; ++c) E.online[c].fit(rt.x[c]);
       if (out->target_trace) std::memcpy(out->target_trace + (size_t)(s - 1) * d, rt.x.data(), sizeof(double) * d);
     }
     // ---- swap!  (swap.jl:6-26)
@@ -762,8 +765,9 @@ void run_round(Engine& E, int64_t n_scans, pgn_round_out* out) {
   }
   out->n_tempered_restarts = E.n_restarts;
   out->n_round_trips = E.n_round_trips;
-  out->online_n = d > 0 ? E.online[0].n : n_scans;
-  for (int c = 0; c < d; ++c) {
+  const bool vec_state = E.cfg.target_kind != PGN_TARGET_ISING && d > 0;
+  out->online_n = vec_state ? E.online[0].n : n_scans;
+  for (int c = 0; c < d && vec_state; ++c) {
     if (out->online_mean) out->online_mean[c] = E.online[c].mu;
     if (out->online_var) out->online_var[c] = E.online[c].value();
   }

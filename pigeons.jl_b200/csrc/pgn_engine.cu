@@ -1,0 +1,623 @@
+// pgn_engine.cu — host side of libpigeons_b200.so: device memory, kernel
+// dispatch, and the C ABI declared in include/pigeons_b200.h.
+//
+// One handle = one shard of the chain ladder on one GPU.  `pgn_run_round`
+// is the single call per round that replaces the reference's host scan loop
+// (src/pt/pigeons.jl:46-55).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pgn_kernels.cuh"
+
+using namespace pgn;
+
+namespace {
+
+struct CudaError {
+  int code;
+  std::string msg;
+};
+
+#define CUDA_CHECK(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      throw CudaError{PGN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)};          \
+  } while (0)
+
+int fail(char** err, int code, const std::string& msg) {
+  if (err) {
+    *err = (char*)std::malloc(msg.size() + 1);
+    std::memcpy(*err, msg.c_str(), msg.size() + 1);
+  }
+  return code;
+}
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count, bool zero = true) {
+    release();
+    n = count;
+    if (count == 0) count = 1;
+    CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    if (zero) CUDA_CHECK(cudaMemset(p, 0, count * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  void upload(const T* h, size_t count) { CUDA_CHECK(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice)); }
+  void download(T* h, size_t count) const { CUDA_CHECK(cudaMemcpy(h, p, count * sizeof(T), cudaMemcpyDeviceToHost)); }
+  ~DevBuf() { release(); }
+};
+
+// LoadBalance (src/mpi_utils/LoadBalance.jl:70-73,119-128), 0-based rank
+void shard_range(int n_chains, int world, int rank, int& first_chain, int& n_local) {
+  const int basic = n_chains / world, extras = n_chains % world;
+  n_local = basic + (rank < extras ? 1 : 0);
+  const int with_extra = std::min(rank, extras);
+  first_chain = 1 + (rank - with_extra) * basic + with_extra * (basic + 1);
+}
+
+}  // namespace
+
+struct pgn_handle {
+  pgn_config cfg{};
+  pgn_explorer_params ep{};
+  bool have_std = false;
+  int first_chain = 1, n_local = 0;
+  int cpl = 1, d_pad = 32, pay_doubles = 32;
+  size_t slot_bytes = 0, mail_bytes = 0;
+  unsigned int epoch = 0;
+  int n_sms = 0;
+  DevBuf<double> beta, x, means, log_w, std_devs, online_mean, online_s2;
+  DevBuf<int> replica_index, rt_state, error_flag;
+  DevBuf<unsigned long long> rng_ctr;
+  DevBuf<long long> online_n;
+  DevBuf<ChainStatsDev> stats;
+  DevBuf<char> mail;
+  char* mail_left = nullptr;
+  char* mail_right = nullptr;
+  bool left_is_ipc = false, right_is_ipc = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool initialised = false;
+  unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+};
+
+namespace {
+
+void fill_params(pgn_handle* h, Params& P) {
+  std::memset(&P, 0, sizeof(P));
+  P.target_kind = h->cfg.target_kind;
+  P.d = h->cfg.dim; P.d_pad = h->d_pad; P.n_chains = h->cfg.n_chains;
+  P.first_chain = h->first_chain; P.n_local = h->n_local;
+  P.seed_lo = (unsigned int)(unsigned long long)h->cfg.seed;
+  P.seed_hi = (unsigned int)((unsigned long long)h->cfg.seed >> 32);
+  P.epoch = h->epoch;
+  for (int i = 0; i < 8; ++i) P.p[i] = h->cfg.p[i];
+  P.n_modes = h->cfg.n_modes;
+  P.means = h->means.p; P.log_w = h->log_w.p; P.beta = h->beta.p;
+  P.slice_w = h->ep.slice_w; P.slice_p = h->ep.slice_p; P.slice_n_passes = h->ep.slice_n_passes;
+  P.slice_max_iter = h->ep.slice_max_iter;
+  P.n_refresh = h->ep.n_refresh; P.step_size = h->ep.step_size; P.precond_kind = h->ep.precond_kind;
+  P.mix_p0 = h->ep.mix_p0; P.mix_p01 = h->ep.mix_p01;
+  P.std_devs = h->have_std ? h->std_devs.p : nullptr;
+  P.ising_n_steps = h->ep.ising_n_steps;
+  P.x = h->x.p; P.replica_index = h->replica_index.p; P.rng_ctr = h->rng_ctr.p; P.rt_state = h->rt_state.p;
+  P.mail = h->mail.p; P.mail_left = h->mail_left; P.mail_right = h->mail_right;
+  P.slot_bytes = h->slot_bytes;
+  P.stats = h->stats.p;
+  P.online_mean = h->online_mean.p; P.online_s2 = h->online_s2.p; P.online_n = h->online_n.p;
+  P.error_flag = h->error_flag.p;
+  P.timeout_ns = h->timeout_ns;
+}
+
+template <class Chain>
+void* scan_kernel_ptr() { return (void*)scan_kernel<Chain>; }
+
+template <int TK, int CPL>
+void* vec_kernel_for(int ex) {
+  switch (ex) {
+    case PGN_EXPLORER_TOY: return TK == PGN_TARGET_TOY_MVN ? scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_TOY>>() : nullptr;
+    case PGN_EXPLORER_SLICE: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_SLICE>>();
+    case PGN_EXPLORER_AUTOMALA: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_AUTOMALA>>();
+    default: return nullptr;
+  }
+}
+template <int TK>
+void* vec_kernel_cpl(int cpl, int ex) {
+  switch (cpl) {
+    case 1: return vec_kernel_for<TK, 1>(ex);
+    case 2: return vec_kernel_for<TK, 2>(ex);
+    case 4: return vec_kernel_for<TK, 4>(ex);
+    default: return nullptr;
+  }
+}
+void* select_scan_kernel(const pgn_handle* h) {
+  const int ex = h->ep.kind;
+  switch (h->cfg.target_kind) {
+    case PGN_TARGET_TOY_MVN: return vec_kernel_cpl<PGN_TARGET_TOY_MVN>(h->cpl, ex);
+    case PGN_TARGET_FUNNEL: return vec_kernel_cpl<PGN_TARGET_FUNNEL>(h->cpl, ex);
+    case PGN_TARGET_GMM: return vec_kernel_cpl<PGN_TARGET_GMM>(h->cpl, ex);
+    case PGN_TARGET_ISING: return ex == PGN_EXPLORER_ISING_METROPOLIS ? scan_kernel_ptr<IsingChain>() : nullptr;
+    case PGN_TARGET_TEST_SWAPPER: return ex == PGN_EXPLORER_NONE ? scan_kernel_ptr<TestSwapperChain>() : nullptr;
+    default: return nullptr;
+  }
+}
+size_t scan_smem_bytes(const pgn_handle* h) {
+  if (h->cfg.target_kind == PGN_TARGET_GMM) return ((size_t)h->cfg.n_modes * h->d_pad + KMAX_MODES) * sizeof(double);
+  return 0;
+}
+
+template <int TK>
+void launch_eval_points(pgn_handle* h, const Params& P, const double* xs, const double* betas, int n, double* lp,
+                        double* ld, double* grad) {
+  const int wpb = 4;
+  const int grid = (n + wpb - 1) / wpb;
+  const size_t smem = scan_smem_bytes(h);
+  switch (h->cpl) {
+    case 1: eval_points_kernel<TK, 1><<<grid, wpb * 32, smem, h->stream>>>(P, xs, betas, n, lp, ld, grad); break;
+    case 2: eval_points_kernel<TK, 2><<<grid, wpb * 32, smem, h->stream>>>(P, xs, betas, n, lp, ld, grad); break;
+    case 4: eval_points_kernel<TK, 4><<<grid, wpb * 32, smem, h->stream>>>(P, xs, betas, n, lp, ld, grad); break;
+    default: throw CudaError{PGN_ERR_INVALID, "unsupported dimension"};
+  }
+}
+
+void use_device(const pgn_handle* h) { CUDA_CHECK(cudaSetDevice(h->cfg.device)); }
+
+}  // namespace
+
+extern "C" {
+
+int pgn_abi_version(void) { return PGN_ABI_VERSION; }
+
+void pgn_free_string(char* s) { std::free(s); }
+
+int pgn_device_info(int device, pgn_device_info_t* out, char** err) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device >= count)
+    return fail(err, PGN_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(err, PGN_ERR_CUDA, "cudaGetDeviceProperties failed");
+  std::memset(out, 0, sizeof(*out));
+  out->sm_major = prop.major; out->sm_minor = prop.minor; out->n_sms = prop.multiProcessorCount;
+  out->global_mem_bytes = (int64_t)prop.totalGlobalMem;
+  out->max_resident_chains = prop.multiProcessorCount * (prop.maxThreadsPerMultiProcessor / 32);
+  std::strncpy(out->name, prop.name, sizeof(out->name) - 1);
+  return PGN_OK;
+}
+
+int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
+  if (!cfg || !out) return fail(err, PGN_ERR_INVALID, "null argument");
+  if (cfg->abi_version != PGN_ABI_VERSION) return fail(err, PGN_ERR_INVALID, "ABI version mismatch");
+  if (cfg->n_chains < 1) return fail(err, PGN_ERR_INVALID, "n_chains must be >= 1");
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size || cfg->world_size > cfg->n_chains)
+    return fail(err, PGN_ERR_INVALID, "need 0 <= rank < world_size <= n_chains");
+  switch (cfg->target_kind) {
+    case PGN_TARGET_TOY_MVN: case PGN_TARGET_FUNNEL: case PGN_TARGET_GMM:
+      if (cfg->dim < 1) return fail(err, PGN_ERR_INVALID, "dim must be >= 1");
+      if (cfg->dim > 128) return fail(err, PGN_ERR_INVALID, "register-resident chains support dim <= 128 in this build");
+      break;
+    case PGN_TARGET_ISING: {
+      const int L = (int)cfg->p[1];
+      if (L < 2 || L > 32 || L * L != cfg->dim) return fail(err, PGN_ERR_INVALID, "ISING: 2 <= L <= 32 and dim == L*L");
+      break;
+    }
+    case PGN_TARGET_TEST_SWAPPER: break;
+    case PGN_TARGET_LOGREG: return fail(err, PGN_ERR_INVALID, "LOGREG is not implemented in this build");
+    default: return fail(err, PGN_ERR_INVALID, "unknown target_kind (device targets are a closed family)");
+  }
+  if (cfg->target_kind == PGN_TARGET_GMM) {
+    if (cfg->n_modes < 1 || cfg->n_modes > KMAX_MODES) return fail(err, PGN_ERR_INVALID, "GMM: 1 <= n_modes <= 8");
+    if (!cfg->means || !cfg->log_weights) return fail(err, PGN_ERR_INVALID, "GMM: means / log_weights missing");
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(err, PGN_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= count) return fail(err, PGN_ERR_NO_DEVICE, "device ordinal out of range");
+
+  pgn_handle* h = new pgn_handle();
+  try {
+    h->cfg = *cfg;
+    h->cfg.means = h->cfg.log_weights = h->cfg.data_x = h->cfg.data_y = nullptr;
+    use_device(h);
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (!prop.cooperativeLaunch) throw CudaError{PGN_ERR_NO_DEVICE, "device lacks cooperative launch"};
+    h->n_sms = prop.multiProcessorCount;
+    shard_range(cfg->n_chains, cfg->world_size, cfg->rank, h->first_chain, h->n_local);
+    const int d = cfg->dim;
+    if (cfg->target_kind == PGN_TARGET_ISING) { h->cpl = 1; h->d_pad = 64; h->pay_doubles = 32; }
+    else if (cfg->target_kind == PGN_TARGET_TEST_SWAPPER) { h->cpl = 1; h->d_pad = 1; h->pay_doubles = 0; }
+    else {
+      h->cpl = d <= 32 ? 1 : (d <= 64 ? 2 : 4);
+      h->d_pad = h->cpl * 32;
+      h->pay_doubles = h->d_pad;
+    }
+    h->slot_bytes = (size_t)MAIL_HDR_BYTES + (size_t)h->pay_doubles * sizeof(double);
+    h->slot_bytes = (h->slot_bytes + 127) / 128 * 128;
+    h->mail_bytes = (size_t)(h->n_local + 2) * MAIL_RINGS * h->slot_bytes;
+    const int nl = h->n_local;
+    h->beta.alloc(cfg->n_chains);
+    h->x.alloc((size_t)nl * h->d_pad);
+    h->replica_index.alloc(nl); h->rt_state.alloc(nl); h->rng_ctr.alloc(nl);
+    h->stats.alloc(nl);
+    h->error_flag.alloc(1);
+    h->online_mean.alloc(h->d_pad); h->online_s2.alloc(h->d_pad); h->online_n.alloc(1);
+    h->mail.alloc(h->mail_bytes);
+    h->std_devs.alloc(std::max(d, 1));
+    if (cfg->target_kind == PGN_TARGET_GMM) {
+      std::vector<double> padded((size_t)cfg->n_modes * h->d_pad, 0.0);
+      for (int k = 0; k < cfg->n_modes; ++k)
+        for (int c = 0; c < d; ++c) padded[(size_t)k * h->d_pad + c] = cfg->means[(size_t)k * d + c];
+      h->means.alloc(padded.size());
+      h->means.upload(padded.data(), padded.size());
+      h->log_w.alloc(cfg->n_modes);
+      h->log_w.upload(cfg->log_weights, cfg->n_modes);
+    }
+    // default schedule: equally spaced (src/schedules/Schedule.jl:36-44)
+    std::vector<double> b(cfg->n_chains);
+    for (int i = 0; i < cfg->n_chains; ++i) b[i] = cfg->n_chains == 1 ? 1.0 : (double)i / (cfg->n_chains - 1);
+    h->beta.upload(b.data(), b.size());
+    h->ep = pgn_explorer_params{};
+    h->ep.kind = PGN_EXPLORER_NONE;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreate(&h->ev0));
+    CUDA_CHECK(cudaEventCreate(&h->ev1));
+  } catch (CudaError& e) {
+    delete h;
+    return fail(err, e.code, e.msg);
+  }
+  *out = h;
+  return PGN_OK;
+}
+
+int pgn_destroy(pgn_handle* h) {
+  if (!h) return PGN_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->left_is_ipc && h->mail_left) cudaIpcCloseMemHandle(h->mail_left);
+  if (h->right_is_ipc && h->mail_right) cudaIpcCloseMemHandle(h->mail_right);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return PGN_OK;
+}
+
+int pgn_local_range(const pgn_handle* h, int32_t* first_chain, int32_t* n_local) {
+  *first_chain = h->first_chain;
+  *n_local = h->n_local;
+  return PGN_OK;
+}
+
+int pgn_set_schedule(pgn_handle* h, const double* beta, int32_t n, char** err) {
+  if (n != h->cfg.n_chains) return fail(err, PGN_ERR_INVALID, "schedule length != n_chains");
+  try {
+    use_device(h);
+    h->beta.upload(beta, n);
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_set_explorer(pgn_handle* h, const pgn_explorer_params* ep, char** err) {
+  try {
+    use_device(h);
+    h->ep = *ep;
+    h->have_std = ep->std_devs != nullptr;
+    if (h->have_std) h->std_devs.upload(ep->std_devs, h->cfg.dim);
+    h->ep.std_devs = nullptr;
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_init_replicas(pgn_handle* h, char** err) {
+  try {
+    use_device(h);
+    const int nl = h->n_local;
+    std::vector<int> ri(nl), rt(nl, 0);
+    std::vector<unsigned long long> ctr(nl, 0ull);
+    for (int i = 0; i < nl; ++i) ri[i] = h->first_chain + i;
+    h->replica_index.upload(ri.data(), nl);
+    h->rt_state.upload(rt.data(), nl);
+    h->rng_ctr.upload(ctr.data(), nl);
+    CUDA_CHECK(cudaMemset(h->x.p, 0, std::max<size_t>(1, (size_t)nl * h->d_pad) * sizeof(double)));
+    if (h->cfg.target_kind == PGN_TARGET_TOY_MVN) {
+      Params P;
+      fill_params(h, P);
+      const int wpb = 4;
+      init_toy_kernel<<<(nl + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>(P);
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
+    h->initialised = true;
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_get_state(pgn_handle* h, pgn_replica_state* out, char** err) {
+  try {
+    use_device(h);
+    const int nl = h->n_local, d = h->cfg.dim;
+    if (out->x && d > 0) {
+      std::vector<double> raw((size_t)nl * h->d_pad);
+      h->x.download(raw.data(), raw.size());
+      if (h->cfg.target_kind == PGN_TARGET_ISING) {
+        const int L = (int)h->cfg.p[1];
+        for (int i = 0; i < nl; ++i) {
+          const unsigned int* rows = reinterpret_cast<const unsigned int*>(&raw[(size_t)i * h->d_pad]);
+          for (int a = 0; a < L; ++a)
+            for (int b = 0; b < L; ++b) out->x[(size_t)i * d + a * L + b] = ((rows[a] >> b) & 1u) ? 1.0 : 0.0;
+        }
+      } else {
+        for (int i = 0; i < nl; ++i) std::memcpy(out->x + (size_t)i * d, &raw[(size_t)i * h->d_pad], sizeof(double) * d);
+      }
+    }
+    if (out->replica_index) h->replica_index.download(out->replica_index, nl);
+    if (out->rng_counter) h->rng_ctr.download(reinterpret_cast<unsigned long long*>(out->rng_counter), nl);
+    if (out->round_trip_state) h->rt_state.download(out->round_trip_state, nl);
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_set_state(pgn_handle* h, const pgn_replica_state* in, char** err) {
+  if (!h->initialised) return fail(err, PGN_ERR_INVALID, "call pgn_init_replicas first");
+  try {
+    use_device(h);
+    const int nl = h->n_local, d = h->cfg.dim;
+    if (in->x && d > 0) {
+      std::vector<double> raw((size_t)nl * h->d_pad, 0.0);
+      if (h->cfg.target_kind == PGN_TARGET_ISING) {
+        const int L = (int)h->cfg.p[1];
+        for (int i = 0; i < nl; ++i) {
+          unsigned int* rows = reinterpret_cast<unsigned int*>(&raw[(size_t)i * h->d_pad]);
+          for (int a = 0; a < L; ++a)
+            for (int b = 0; b < L; ++b)
+              if (in->x[(size_t)i * d + a * L + b] != 0.0) rows[a] |= (1u << b);
+        }
+      } else {
+        for (int i = 0; i < nl; ++i) std::memcpy(&raw[(size_t)i * h->d_pad], in->x + (size_t)i * d, sizeof(double) * d);
+      }
+      h->x.upload(raw.data(), raw.size());
+    }
+    if (in->replica_index) h->replica_index.upload(in->replica_index, nl);
+    if (in->rng_counter) h->rng_ctr.upload(reinterpret_cast<const unsigned long long*>(in->rng_counter), nl);
+    if (in->round_trip_state) h->rt_state.upload(in->round_trip_state, nl);
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err) {
+  if (!h || !out) return fail(err, PGN_ERR_INVALID, "null argument");
+  if (!h->initialised) return fail(err, PGN_ERR_INVALID, "call pgn_init_replicas first");
+  if (n_scans < 0 || n_scans >= (1LL << 32)) return fail(err, PGN_ERR_INVALID, "n_scans out of range");
+  if (h->cfg.world_size > 1) {
+    if (h->cfg.rank > 0 && !h->mail_left) return fail(err, PGN_ERR_INVALID, "left neighbour mailbox not attached");
+    if (h->cfg.rank < h->cfg.world_size - 1 && !h->mail_right)
+      return fail(err, PGN_ERR_INVALID, "right neighbour mailbox not attached");
+  }
+  try {
+    use_device(h);
+    void* kernel = select_scan_kernel(h);
+    if (!kernel) throw CudaError{PGN_ERR_INVALID, "explorer not supported for this target on the device"};
+    const int nl = h->n_local, d = h->cfg.dim;
+    h->epoch += 1;
+    Params P;
+    fill_params(h, P);
+    P.n_scans = n_scans;
+    // optional event logs
+    DevBuf<int> d_index;
+    DevBuf<double> d_lr, d_u, d_trace;
+    DevBuf<unsigned char> d_acc;
+    const size_t nlog = (size_t)n_scans * nl;
+    if (out->index_process) { d_index.alloc(nlog, false); P.index_process = d_index.p; }
+    if (out->swap_lr) { d_lr.alloc(nlog, false); P.swap_lr = d_lr.p; }
+    if (out->swap_u) { d_u.alloc(nlog, false); P.swap_u = d_u.p; }
+    if (out->swap_accept) { d_acc.alloc(nlog, false); P.swap_accept = d_acc.p; }
+    const bool owns_target = (h->first_chain + nl - 1 == h->cfg.n_chains);
+    if (out->target_trace && owns_target) { d_trace.alloc((size_t)n_scans * std::max(d, 1), false); P.target_trace = d_trace.p; }
+    CUDA_CHECK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int), h->stream));
+
+    // launch geometry: one warp per chain, all warps co-resident
+    const size_t smem = scan_smem_bytes(h);
+    int wpb = 0, grid = 0;
+    for (int w = 1; w <= 8; w *= 2) {
+      int per_sm = 0;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, smem));
+      const int g = (nl + w - 1) / w;
+      if ((long long)per_sm * h->n_sms >= g) { wpb = w; grid = g; break; }
+    }
+    if (wpb == 0)
+      throw CudaError{PGN_ERR_INVALID, "too many chains for one GPU: all chains of a shard must be co-resident"};
+    void* args[] = {(void*)&P};
+    CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+    if (n_scans > 0)
+      CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(wpb * 32), args, smem, h->stream));
+    CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    int flag = 0;
+    h->error_flag.download(&flag, 1);
+
+    // statistics
+    std::vector<ChainStatsDev> st(nl);
+    if (n_scans > 0) h->stats.download(st.data(), nl);
+    else std::memset(st.data(), 0, sizeof(ChainStatsDev) * nl);
+    long long restarts = 0, trips = 0, pts = 0, evals = 0;
+    for (int i = 0; i < nl; ++i) {
+      const ChainStatsDev& s = st[i];
+      if (out->swap_n) out->swap_n[i] = s.swap_n;
+      if (out->swap_mean) out->swap_mean[i] = s.swap_mean;
+      if (out->logsum_fwd) out->logsum_fwd[i] = n_scans > 0 ? s.ls_fwd : -INFINITY;
+      if (out->logsum_bwd) out->logsum_bwd[i] = n_scans > 0 ? s.ls_bwd : -INFINITY;
+      if (out->expl_acc_n) out->expl_acc_n[i] = s.expl_acc_n;
+      if (out->expl_acc_mean) out->expl_acc_mean[i] = s.expl_acc_mean;
+      if (out->expl_n_steps) out->expl_n_steps[i] = s.n_steps;
+      if (out->am_n) out->am_n[i] = s.am_n;
+      if (out->am_mean) out->am_mean[i] = s.am_mean;
+      if (out->rev_n) out->rev_n[i] = s.rev_n;
+      if (out->rev_mean) out->rev_mean[i] = s.rev_mean;
+      restarts += s.n_restarts; trips += s.n_round_trips; pts += s.n_points; evals += s.n_ref_evals;
+    }
+    out->n_tempered_restarts = restarts;
+    out->n_round_trips = trips;
+    out->n_density_points = pts;
+    out->n_ref_equiv_evals = evals;
+    out->kernel_ms = (double)ms;
+    out->online_n = 0;
+    if (owns_target && n_scans > 0) {
+      long long on = 0;
+      h->online_n.download(&on, 1);
+      const bool vec = h->cfg.target_kind != PGN_TARGET_ISING && h->cfg.target_kind != PGN_TARGET_TEST_SWAPPER;
+      out->online_n = vec ? on : n_scans;
+      if (vec && d > 0) {
+        std::vector<double> mu(h->d_pad), s2(h->d_pad);
+        h->online_mean.download(mu.data(), h->d_pad);
+        h->online_s2.download(s2.data(), h->d_pad);
+        for (int c = 0; c < d; ++c) {
+          if (out->online_mean) out->online_mean[c] = mu[c];
+          if (out->online_var) out->online_var[c] = on > 1 ? s2[c] * ((double)on / (double)(on - 1)) : 1.0;
+        }
+      }
+    }
+    if (out->index_process) d_index.download(out->index_process, nlog);
+    if (out->swap_lr) d_lr.download(out->swap_lr, nlog);
+    if (out->swap_u) d_u.download(out->swap_u, nlog);
+    if (out->swap_accept) d_acc.download(out->swap_accept, nlog);
+    if (out->target_trace && owns_target && d > 0) d_trace.download(out->target_trace, (size_t)n_scans * d);
+    if (flag != 0) {
+      static const char* names[] = {"", "invalid explorer state (autoMALA bounds / step size)", "", "",
+                                    "Got NaN log-unnormalized ratio", "non-finite log density in SliceSampler",
+                                    "slice_shrink: maximum number of iterations reached",
+                                    "autoMALA: could not find a positive step size",
+                                    "AutoMALA can only be called on a configuration of positive density",
+                                    "neighbour hand-shake timed out"};
+      return fail(err, flag, flag >= 1 && flag <= 9 ? names[flag] : "device error");
+    }
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_log_potential(pgn_handle* h, const double* x, int32_t n_points, const double* beta, double* out, char** err) {
+  try {
+    use_device(h);
+    const int d = h->cfg.dim;
+    if (h->cfg.target_kind == PGN_TARGET_TEST_SWAPPER) return fail(err, PGN_ERR_INVALID, "TestSwapper has no log_potential");
+    DevBuf<double> dx, db, dout;
+    dx.alloc((size_t)n_points * d, false); db.alloc(n_points, false); dout.alloc(n_points, false);
+    dx.upload(x, (size_t)n_points * d); db.upload(beta, n_points);
+    Params P;
+    fill_params(h, P);
+    switch (h->cfg.target_kind) {
+      case PGN_TARGET_TOY_MVN: launch_eval_points<PGN_TARGET_TOY_MVN>(h, P, dx.p, db.p, n_points, dout.p, nullptr, nullptr); break;
+      case PGN_TARGET_FUNNEL: launch_eval_points<PGN_TARGET_FUNNEL>(h, P, dx.p, db.p, n_points, dout.p, nullptr, nullptr); break;
+      case PGN_TARGET_GMM: launch_eval_points<PGN_TARGET_GMM>(h, P, dx.p, db.p, n_points, dout.p, nullptr, nullptr); break;
+      case PGN_TARGET_ISING: ising_lp_kernel<<<(n_points + 3) / 4, 128, 0, h->stream>>>(P, dx.p, db.p, n_points, dout.p); break;
+      default: return fail(err, PGN_ERR_INVALID, "unsupported target");
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    dout.download(out, n_points);
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_logdensity_and_gradient(pgn_handle* h, const double* x, int32_t n_points, const double* beta, double* logdens,
+                                double* grad, char** err) {
+  try {
+    use_device(h);
+    const int d = h->cfg.dim;
+    const int tk = h->cfg.target_kind;
+    if (tk != PGN_TARGET_TOY_MVN && tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM)
+      return fail(err, PGN_ERR_INVALID, "target has no gradient");
+    DevBuf<double> dx, db, dld, dg;
+    dx.alloc((size_t)n_points * d, false); db.alloc(n_points, false); dld.alloc(n_points, false);
+    dg.alloc((size_t)n_points * d, false);
+    dx.upload(x, (size_t)n_points * d); db.upload(beta, n_points);
+    Params P;
+    fill_params(h, P);
+    switch (tk) {
+      case PGN_TARGET_TOY_MVN: launch_eval_points<PGN_TARGET_TOY_MVN>(h, P, dx.p, db.p, n_points, nullptr, dld.p, dg.p); break;
+      case PGN_TARGET_FUNNEL: launch_eval_points<PGN_TARGET_FUNNEL>(h, P, dx.p, db.p, n_points, nullptr, dld.p, dg.p); break;
+      default: launch_eval_points<PGN_TARGET_GMM>(h, P, dx.p, db.p, n_points, nullptr, dld.p, dg.p); break;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    dld.download(logdens, n_points);
+    dg.download(grad, (size_t)n_points * d);
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_ipc_export(pgn_handle* h, void* handle64, char** err) {
+  try {
+    use_device(h);
+    cudaIpcMemHandle_t mh;
+    CUDA_CHECK(cudaIpcGetMemHandle(&mh, h->mail.p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle64, &mh, 64);
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_ipc_attach(pgn_handle* h, int32_t side, const void* handle64, char** err) {
+  try {
+    use_device(h);
+    cudaIpcMemHandle_t mh;
+    std::memcpy(&mh, handle64, 64);
+    void* p = nullptr;
+    CUDA_CHECK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+    if (side == 0) { h->mail_left = (char*)p; h->left_is_ipc = true; }
+    else { h->mail_right = (char*)p; h->right_is_ipc = true; }
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_peer_attach(pgn_handle* h, int32_t side, pgn_handle* neighbour, char** err) {
+  try {
+    use_device(h);
+    if (neighbour->cfg.device != h->cfg.device) {
+      int can = 0;
+      CUDA_CHECK(cudaDeviceCanAccessPeer(&can, h->cfg.device, neighbour->cfg.device));
+      if (!can) throw CudaError{PGN_ERR_CUDA, "devices cannot access each other's memory"};
+      cudaError_t e = cudaDeviceEnablePeerAccess(neighbour->cfg.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(e);
+      cudaGetLastError();
+    }
+    if (side == 0) h->mail_left = neighbour->mail.p; else h->mail_right = neighbour->mail.p;
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_test_math(int32_t device, int32_t op, const double* in, double* out, int64_t n, int64_t seed,
+                  int32_t replica_index, char** err) {
+  try {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+      return fail(err, PGN_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");
+    CUDA_CHECK(cudaSetDevice(device));
+    const size_t nin = op == 6 ? 2 * (size_t)n : (size_t)n;
+    DevBuf<double> din, dout;
+    din.alloc(nin, false); dout.alloc(n, false);
+    din.upload(in, nin);
+    test_math_kernel<<<(unsigned)((n + 127) / 128), 128>>>(op, din.p, dout.p, n, (unsigned int)(unsigned long long)seed,
+                                                            (unsigned int)((unsigned long long)seed >> 32),
+                                                            (unsigned int)replica_index);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaDeviceSynchronize());
+    dout.download(out, n);
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+}  // extern "C"

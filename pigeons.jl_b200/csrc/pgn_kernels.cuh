@@ -1,0 +1,1007 @@
+// pgn_kernels.cuh — the persistent PT scan kernel (explore! + DEO swap!) for sm_100a.
+//
+// One warp owns one CHAIN (one annealing parameter beta_c) for a whole round.
+// The replica sitting at that chain — its state, RNG stream, replica index and
+// round-trip state — lives in the warp's registers; HBM is touched once when
+// the round starts and once when it ends.  A scan is
+//
+//   explore : sample_iid! at chain 1, else SliceSampler / autoMALA / IsingMetropolis
+//             (src/pt/pigeons.jl:101-132), every lane owning the coordinates
+//             c = lane, lane+32, ... and sums running through the canonical
+//             warp butterfly;
+//   swap    : the chain posts its SwapStat (log_ratio, uniform) + replica
+//             payload into its mailbox slot, waits for its DEO partner's post
+//             (src/swap/OddEven.jl:23-31), both sides take the identical
+//             accept decision (src/swap/pair_swapper.jl:81-88) and on accept
+//             adopt each other's replica.
+//
+// There is NO grid-wide barrier: DEO couples a chain only to its two
+// neighbours, so warps synchronise pairwise through release/acquire flags in
+// L2 (or, across GPUs, in the neighbour's peer-mapped mailbox over NVLink).
+// All warps are co-resident (cooperative launch), so the spin-waits cannot
+// deadlock; a spin limit turns any lost hand-shake into PGN_ERR_TIMEOUT.
+#pragma once
+#include <cstdint>
+
+#include "../../include/pigeons_b200.h"
+#include "pgn_numerics.cuh"
+
+namespace pgn {
+
+constexpr int KMAX_MODES = 8;      // GMM components held in registers
+constexpr int MAIL_RINGS = 8;      // 2 round banks x 4 scans (see DESIGN.md "mailbox ring")
+constexpr int MAIL_HDR_BYTES = 64; // [flag u64 | pad | MailHdr 32B]
+
+struct MeanAcc {   // OnlineStatsBase.Mean (EqualWeight)
+  long long n;
+  double mu;
+  __device__ __forceinline__ void fit(double x) { n += 1; mu = mu + (1.0 / (double)n) * (x - mu); }
+};
+struct LogSumAcc {  // src/recorders/LogSum.jl:1-24
+  long long n;
+  double value;
+  __device__ __forceinline__ void fit(double y) { value = logaddexp_(value, y); n += 1; }
+};
+
+struct ChainStatsDev {   // one per local chain, written when the round ends
+  long long swap_n; double swap_mean; double ls_fwd; double ls_bwd;
+  long long expl_acc_n; double expl_acc_mean; long long n_steps;
+  long long am_n; double am_mean; long long rev_n; double rev_mean;
+  long long n_restarts, n_round_trips;
+  long long n_points, n_ref_evals;
+};
+
+struct MailHdr {   // 32 bytes
+  double lr, u;
+  unsigned long long ctr;
+  int replica_index, rt_state;
+};
+
+struct Params {
+  // geometry
+  int target_kind, d, d_pad, n_chains, first_chain, n_local;
+  long long n_scans;
+  unsigned int seed_lo, seed_hi;
+  unsigned int epoch;
+  double p[8];
+  int n_modes;
+  const double* means;      // [K][d_pad]
+  const double* log_w;      // [K]
+  const double* beta;       // [N]
+  // explorer
+  double slice_w; int slice_p, slice_n_passes, slice_max_iter;
+  int n_refresh; double step_size; int precond_kind; double mix_p0, mix_p01;
+  const double* std_devs;   // [d] or null
+  int ising_n_steps;
+  // replica state in HBM, chain order
+  double* x;                // [n_local][d_pad]
+  int* replica_index;
+  unsigned long long* rng_ctr;
+  int* rt_state;
+  // mailboxes: slot-major, slot 0/1 = left/right ghost, 2.. = local chains
+  char* mail; char* mail_left; char* mail_right;
+  unsigned long long slot_bytes;
+  // outputs
+  ChainStatsDev* stats;
+  double* online_mean; double* online_s2; long long* online_n;
+  int* index_process; double* swap_lr; double* swap_u; unsigned char* swap_accept; double* target_trace;
+  int* error_flag;
+  unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// ===========================================================================
+// Vector-state chains: TOY_MVN / FUNNEL / GMM with ToyExplorer, SliceSampler, autoMALA
+// ===========================================================================
+template <int TK, int CPL, int EX>
+struct VecChain {
+  static constexpr bool kTestSwapper = false;
+  const Params* P;
+  const double* sm_means;
+  int lane, d;
+  double beta;
+  double x[CPL];
+  double e0, e1;        // densities at x: (S, -) for toy MVN, (l_ref, l_tgt) otherwise
+  Rng rng;
+  MeanAcc expl_acc, am, rev;
+  long long n_steps, n_points, n_ref;
+  int err;
+  // target-chain online statistics (OnlineStatsBase.Variance per coordinate)
+  double on_mu[CPL], on_s2[CPL];
+  long long on_n;
+
+  static __device__ void stage_shared(const Params& P, double* smem) {
+    if (TK == PGN_TARGET_GMM) {
+      const int n = P.n_modes * P.d_pad;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = P.means[i];
+      for (int i = threadIdx.x; i < KMAX_MODES; i += blockDim.x) smem[n + i] = i < P.n_modes ? P.log_w[i] : 0.0;
+    }
+  }
+
+  __device__ __forceinline__ bool valid(int k) const { return k * 32 + lane < d; }
+
+  __device__ void init(const Params& Pr, const double* smem, int wl, int lane_, int replica_index) {
+    P = &Pr; sm_means = smem; lane = lane_; d = Pr.d;
+    beta = Pr.beta[Pr.first_chain + wl - 1];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      x[k] = valid(k) ? Pr.x[(size_t)wl * Pr.d_pad + k * 32 + lane] : 0.0;
+      on_mu[k] = 0.0; on_s2[k] = 0.0;
+    }
+    on_n = 0;
+    rng.key0 = Pr.seed_lo; rng.key1 = (unsigned int)replica_index; rng.c2 = Pr.seed_hi; rng.c3 = 0u;
+    rng.ctr = Pr.rng_ctr[wl];
+    expl_acc = MeanAcc{0, 0.0}; am = MeanAcc{0, 0.0}; rev = MeanAcc{0, 0.0};
+    n_steps = n_points = n_ref = 0;
+    err = 0; e0 = e1 = 0.0;
+  }
+  __device__ void store(int wl) {
+#pragma unroll
+    for (int k = 0; k < CPL; ++k)
+      if (valid(k)) P->x[(size_t)wl * P->d_pad + k * 32 + lane] = x[k];
+  }
+  __device__ void post(double* pay) const {
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) pay[k * 32 + lane] = x[k];
+  }
+  __device__ void adopt(const double* pay) {
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) x[k] = __ldcg(pay + k * 32 + lane);
+  }
+  __device__ void write_trace(double* row) const {
+#pragma unroll
+    for (int k = 0; k < CPL; ++k)
+      if (valid(k)) row[k * 32 + lane] = x[k];
+  }
+  __device__ void online_fit() {
+    on_n += 1;
+    const double g = 1.0 / (double)on_n;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      double mu_old = on_mu[k];
+      double mu = mu_old + g * (x[k] - mu_old);
+      on_s2[k] = on_s2[k] + g * ((x[k] - mu) * (x[k] - mu_old) - on_s2[k]);
+      on_mu[k] = mu;
+    }
+  }
+  __device__ void store_online() const {
+#pragma unroll
+    for (int k = 0; k < CPL; ++k)
+      if (valid(k)) { P->online_mean[k * 32 + lane] = on_mu[k]; P->online_s2[k * 32 + lane] = on_s2[k]; }
+    if (lane == 0) *P->online_n = on_n;
+  }
+
+  // ---- densities -----------------------------------------------------------
+  __device__ __forceinline__ double toy_precision(double b) const { return (1.0 - b) * P->p[0] + b * P->p[1]; }
+
+  // log_potential callable (InterpolatedLogPotential.jl:10-17 / ScaledPrecisionNormalPath.jl:19-20)
+  __device__ __forceinline__ double lp_call(double b, double a0, double a1) const {
+    if (TK == PGN_TARGET_TOY_MVN) return -0.5 * toy_precision(b) * a0;
+    if (b == 0.0) return a0;
+    if (b == 1.0) return a1;
+    return (1.0 - b) * a0 + b * a1;
+  }
+  // LogDensityProblems.logdensity of the AD wrapper (BufferedAD.jl:89-94)
+  __device__ __forceinline__ double lp_ad(double b, double a0, double a1) const {
+    if (TK == PGN_TARGET_TOY_MVN) return -0.5 * toy_precision(b) * a0;
+    return (1.0 - b) * a0 + b * a1;
+  }
+
+  // component densities at xx
+  __device__ void eval(const double (&xx)[CPL], double& a0, double& a1) {
+    n_points += 1;
+    if (TK == PGN_TARGET_TOY_MVN) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) if (valid(k)) acc = acc + xx[k] * xx[k];
+      a0 = warp_sum(acc); a1 = 0.0;
+    } else if (TK == PGN_TARGET_FUNNEL) {
+      const double y = __shfl_sync(PGN_FULL_MASK, xx[0], 0);
+      const double e = exp_(-y);
+      const double sy = P->p[0], lsy = P->p[1], ivr = P->p[5], lsr = P->p[4];
+      double v[2] = {0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) if (valid(k)) {
+        const double xv = xx[k];
+        v[0] = v[0] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
+        if (k == 0 && lane == 0) { double zy = y / sy; v[1] = v[1] + (-(zy * zy + PGN_LOG2PI) * 0.5 - lsy); }
+        else { double t = xv * xv * e; v[1] = v[1] + (-(t + PGN_LOG2PI) * 0.5 - 0.5 * y); }
+      }
+      warp_sum_n<2>(v);
+      a0 = v[0]; a1 = v[1];
+    } else {   // GMM
+      const double ivr = P->p[5], lsr = P->p[4], ivm = P->p[2], cst = P->p[1];
+      const int K = P->n_modes;
+      double v[KMAX_MODES + 1];
+#pragma unroll
+      for (int m = 0; m <= KMAX_MODES; ++m) v[m] = 0.0;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) if (valid(k)) {
+        const double xv = xx[k];
+        v[KMAX_MODES] = v[KMAX_MODES] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
+#pragma unroll
+        for (int m = 0; m < KMAX_MODES; ++m) if (m < K) {
+          double t = xv - sm_means[m * P->d_pad + k * 32 + lane];
+          v[m] = v[m] + t * t;
+        }
+      }
+      warp_sum_n<KMAX_MODES + 1>(v);
+      a0 = v[KMAX_MODES];
+      const double* lw = sm_means + (size_t)K * P->d_pad;
+      double a[KMAX_MODES];
+      double M = -PGN_INF;
+#pragma unroll
+      for (int m = 0; m < KMAX_MODES; ++m) if (m < K) {
+        a[m] = lw[m] - 0.5 * v[m] * ivm - cst;
+        if (a[m] > M) M = a[m];
+      }
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < KMAX_MODES; ++m) if (m < K) s = s + exp_(a[m] - M);
+      a1 = M + log_(s);
+    }
+  }
+
+  // densities + beta-combined raw gradient (BufferedAD.jl:98-111); `extra` is a
+  // lane partial that rides along in the same butterfly (in: partial, out: sum)
+  __device__ void eval_grad(const double (&xx)[CPL], double b, double& a0, double& a1, double (&g)[CPL], double& extra) {
+    n_points += 1;
+    if (TK == PGN_TARGET_TOY_MVN) {
+      double v[2] = {0.0, extra};
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) if (valid(k)) v[0] = v[0] + xx[k] * xx[k];
+      warp_sum_n<2>(v);
+      a0 = v[0]; a1 = 0.0; extra = v[1];
+      const double prec = toy_precision(b);
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) g[k] = valid(k) ? -prec * xx[k] : 0.0;
+    } else if (TK == PGN_TARGET_FUNNEL) {
+      const double y = __shfl_sync(PGN_FULL_MASK, xx[0], 0);
+      const double e = exp_(-y);
+      const double sy = P->p[0], lsy = P->p[1], ivy = P->p[2], ivr = P->p[5], lsr = P->p[4];
+      double v[4] = {0.0, 0.0, 0.0, extra};
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) if (valid(k)) {
+        const double xv = xx[k];
+        v[0] = v[0] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
+        if (k == 0 && lane == 0) {
+          double zy = y / sy;
+          v[1] = v[1] + (-(zy * zy + PGN_LOG2PI) * 0.5 - lsy);
+          v[2] = v[2] + 0.0;
+        } else {
+          double t = xv * xv * e;
+          v[1] = v[1] + (-(t + PGN_LOG2PI) * 0.5 - 0.5 * y);
+          v[2] = v[2] + (0.5 * (xv * xv * e) - 0.5);
+        }
+      }
+      warp_sum_n<4>(v);
+      a0 = v[0]; a1 = v[1]; extra = v[3];
+      const double T = v[2];
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        if (!valid(k)) { g[k] = 0.0; continue; }
+        const double xv = xx[k];
+        double gr = -xv * ivr;
+        double gt = (k == 0 && lane == 0) ? (-y * ivy + T) : (-xv * e);
+        double acc = gr * (1.0 - b);
+        g[k] = acc + gt * b;
+      }
+    } else {   // GMM
+      const double ivr = P->p[5], lsr = P->p[4], ivm = P->p[2], cst = P->p[1];
+      const int K = P->n_modes;
+      double v[KMAX_MODES + 2];
+#pragma unroll
+      for (int m = 0; m < KMAX_MODES + 2; ++m) v[m] = 0.0;
+      v[KMAX_MODES + 1] = extra;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) if (valid(k)) {
+        const double xv = xx[k];
+        v[KMAX_MODES] = v[KMAX_MODES] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
+#pragma unroll
+        for (int m = 0; m < KMAX_MODES; ++m) if (m < K) {
+          double t = xv - sm_means[m * P->d_pad + k * 32 + lane];
+          v[m] = v[m] + t * t;
+        }
+      }
+      warp_sum_n<KMAX_MODES + 2>(v);
+      a0 = v[KMAX_MODES]; extra = v[KMAX_MODES + 1];
+      const double* lw = sm_means + (size_t)K * P->d_pad;
+      double w[KMAX_MODES];
+      double M = -PGN_INF;
+#pragma unroll
+      for (int m = 0; m < KMAX_MODES; ++m) if (m < K) {
+        w[m] = lw[m] - 0.5 * v[m] * ivm - cst;
+        if (w[m] > M) M = w[m];
+      }
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < KMAX_MODES; ++m) if (m < K) { w[m] = exp_(w[m] - M); s = s + w[m]; }
+      a1 = M + log_(s);
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        if (!valid(k)) { g[k] = 0.0; continue; }
+        const double xv = xx[k];
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < KMAX_MODES; ++m) if (m < K) acc = acc + w[m] * (sm_means[m * P->d_pad + k * 32 + lane] - xv);
+        double gt = (acc / s) * ivm;
+        double gr = -xv * ivr;
+        double t = gr * (1.0 - b);
+        g[k] = t + gt * b;
+      }
+    }
+  }
+
+  // ---- sample_iid! / ToyExplorer ---------------------------------------------
+  __device__ void sample_iid(double b) {
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      if (!valid(k)) continue;
+      double z = normal_at(rng, rng.ctr + (unsigned long long)(k * 32 + lane));
+      if (TK == PGN_TARGET_TOY_MVN) x[k] = z / sqrt(toy_precision(b));   // toy_mvn_target.jl:18-21
+      else x[k] = P->p[3] * z;                                           // rand!(rng, MvNormal(0, s^2 I), x)
+    }
+    rng.ctr += (unsigned long long)d;
+  }
+
+  // ---- SliceSampler (src/explorers/SliceSampler.jl:24-237) --------------------
+  template <int KO>
+  __device__ __forceinline__ double lp_at(int lo, double v) {
+    double xx[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) xx[k] = (k == KO && lane == lo) ? v : x[k];
+    double a0, a1;
+    eval(xx, a0, a1);
+    n_ref += 1;
+    return lp_call(beta, a0, a1);
+  }
+  static __device__ __forceinline__ bool isapprox(double a, double b) {
+    const double rtol = bits_to_double(0x3e50000000000000ULL);   // sqrt(eps(Float64)) = 2^-26
+    if (a == b) return true;
+    if (!(is_finite(a) && is_finite(b))) return false;
+    double aa = fabs(a), ab = fabs(b);
+    return fabs(a - b) <= rtol * (aa > ab ? aa : ab);
+  }
+  template <int KO>
+  __device__ bool slice_accept(int lo, double old_position, double new_position, double z, double L, double R,
+                               double lp_L, double lp_R) {   // :192-237
+    const double w = P->slice_w;
+    double Lhat = L, Rhat = R;
+    bool Rstale = false, Lstale = false, D = false;
+    while (Rhat - Lhat > 1.1 * w) {
+      double M = (Lhat + Rhat) / 2.0;
+      if (((old_position < M) && (new_position >= M)) || ((old_position >= M) && (new_position < M))) D = true;
+      if (new_position < M) { Rhat = M; Rstale = true; } else { Lhat = M; Lstale = true; }
+      if (D) {
+        if (Lstale) { lp_L = lp_at<KO>(lo, Lhat); Lstale = false; }
+        if (Rstale) { lp_R = lp_at<KO>(lo, Rhat); Rstale = false; }
+        if ((z >= lp_L) && (z >= lp_R)) { expl_acc.fit(0.0); return false; }
+      }
+    }
+    expl_acc.fit(1.0);
+    return true;
+  }
+  template <int KO>
+  __device__ double slice_coord(int lo, double cached_lp) {   // :89-186
+    const double w = P->slice_w;
+    const double cur = __shfl_sync(PGN_FULL_MASK, x[KO], lo);
+    const double z = cached_lp - next_exponential(rng);
+    // slice_double :97-126
+    double L = cur - w * next_uniform(rng);
+    double R = L + w;
+    int K = P->slice_p;
+    double lp_L = lp_at<KO>(lo, L);
+    double lp_R = lp_at<KO>(lo, R);
+    while (K > 0 && ((z < lp_L) || (z < lp_R))) {
+      double V = next_uniform(rng);
+      if (V <= 0.5) { L = L - (R - L); lp_L = lp_at<KO>(lo, L); }
+      else { R = R + (R - L); lp_R = lp_at<KO>(lo, R); }
+      K -= 1;
+    }
+    n_steps += P->slice_p - K;
+    // slice_shrink! :144-186
+    double Lbar = L, Rbar = R;
+    int n = 1;
+    while (n <= P->slice_max_iter) {
+      double new_position = Lbar + next_uniform(rng) * (Rbar - Lbar);
+      double new_lp = lp_at<KO>(lo, new_position);
+      bool consider = z < new_lp;
+      if (consider && slice_accept<KO>(lo, cur, new_position, z, L, R, lp_L, lp_R)) {
+        if (lane == lo) x[KO] = new_position;
+        n_steps += n;
+        return new_lp;
+      }
+      if (new_position < cur) Lbar = new_position; else Rbar = new_position;
+      if (isapprox(Lbar, Rbar)) {
+        n_steps += n;
+        return lp_at<KO>(lo, cur);
+      }
+      n += 1;
+    }
+    err = PGN_ERR_SLICE_MAX_ITER;
+    return 0.0;
+  }
+  template <int KO>
+  __device__ double slice_block(double cached_lp) {
+    if (KO * 32 >= d) return cached_lp;
+    const int hi = (d - KO * 32) < 32 ? (d - KO * 32) : 32;
+    for (int lo = 0; lo < hi; ++lo) {
+      cached_lp = slice_coord<KO>(lo, cached_lp);
+      if (err) return cached_lp;
+      if (!is_finite(cached_lp)) { err = PGN_ERR_BAD_DENSITY; return cached_lp; }   // :52-59
+    }
+    return cached_lp;
+  }
+  __device__ void slice_step() {   // :24-30
+    double cached_lp = -PGN_INF;
+    for (int pass = 0; pass < P->slice_n_passes; ++pass) {
+      if (cached_lp == -PGN_INF) {   // cached_log_potential :32-41
+        double a0, a1;
+        eval(x, a0, a1);
+        n_ref += 1;
+        double result = lp_call(beta, a0, a1);
+        if (result == -PGN_INF) { err = PGN_ERR_BAD_DENSITY; return; }
+        cached_lp = result;
+      }
+      cached_lp = slice_block<0>(cached_lp); if (err) return;
+      if (CPL > 1) { cached_lp = slice_block<(CPL > 1 ? 1 : 0)>(cached_lp); if (err) return; }
+      if (CPL > 2) { cached_lp = slice_block<(CPL > 2 ? 2 : 0)>(cached_lp); if (err) return; }
+      if (CPL > 3) { cached_lp = slice_block<(CPL > 3 ? 3 : 0)>(cached_lp); if (err) return; }
+    }
+    eval(x, e0, e1);   // densities at the final state, consumed by the swap
+  }
+
+  // ---- autoMALA (src/explorers/AutoMALA.jl:84-275, hamiltonian_dynamics.jl:28-84) ----
+  struct Trial {
+    double x1[CPL], p1[CPL], g1c[CPL];
+    double a0, a1, lp1, h_after, eps;
+  };
+  // one leap_frog! + log_joint from (xs, ps) with conditioned gradient gs at xs;
+  // returns h_after - h_before (log_joint_difference_function :250-275)
+  __device__ double run_trial(const double (&xs)[CPL], const double (&ps)[CPL], const double (&gs)[CPL],
+                              const double (&pre)[CPL], double eps, double h_before, Trial& T) {
+    double ph[CPL];
+    double pp = 0.0;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      ph[k] = ps[k] + (eps / 2) * gs[k];
+      T.x1[k] = xs[k] + eps * (ph[k] / pre[k]);
+      if (valid(k)) pp = pp + ph[k] * ph[k];
+    }
+    double graw[CPL];
+    eval_grad(T.x1, beta, T.a0, T.a1, graw, pp);
+    T.lp1 = lp_ad(beta, T.a0, T.a1);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) T.g1c[k] = graw[k] / pre[k];
+    const double cur = T.lp1 - 0.5 * pp;
+    double s2;
+    if (!is_finite(cur)) {   // hamiltonian_dynamics.jl:56-59: early return, no last half-step
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) T.p1[k] = ph[k];
+      s2 = pp;
+    } else {
+      double q = 0.0;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        T.p1[k] = ph[k] + (eps / 2) * T.g1c[k];
+        if (valid(k)) q = q + T.p1[k] * T.p1[k];
+      }
+      s2 = warp_sum(q);
+    }
+    T.h_after = T.lp1 - 0.5 * s2;
+    T.eps = eps;
+    return T.h_after - h_before;
+  }
+  // auto_step_size :184-248; returns the exponent, n_steps via reference
+  __device__ int search(const double (&xs)[CPL], const double (&ps)[CPL], const double (&gs)[CPL],
+                        const double (&pre)[CPL], double h_before, double lower, double upper, Trial& T,
+                        int& n_steps_out) {
+    n_steps_out = 0;
+    if (!(P->step_size > 0) || !(lower < upper)) { err = PGN_ERR_INVALID; return 0; }
+    double eps = P->step_size;
+    const double diff0 = run_trial(xs, ps, gs, pre, eps, h_before, T);
+    int exponent = 0;
+    if (!is_finite(diff0) || diff0 < lower) {          // shrink_step_size :228-248
+      int n = 1;
+      while (true) {
+        eps = eps / 2.0;
+        double diff = run_trial(xs, ps, gs, pre, eps, h_before, T);
+        if (eps == 0.0) { err = PGN_ERR_STEP_UNDERFLOW; return 0; }
+        if (diff > lower) { n_steps_out = n; exponent = -n; break; }
+        n += 1;
+      }
+    } else if (diff0 > upper) {                        // grow_step_size :216-226
+      int n = 1;
+      while (true) {
+        eps = eps * 2.0;
+        double diff = run_trial(xs, ps, gs, pre, eps, h_before, T);
+        if (!is_finite(diff) || diff < upper) { n_steps_out = n; exponent = n - 1; break; }
+        n += 1;
+      }
+    }
+    return exponent;
+  }
+  __device__ void build_preconditioner(double (&pre)[CPL]) {   // Preconditioner.jl:57-77
+    const bool have = P->std_devs != nullptr;
+    if (!have || P->precond_kind == PGN_PRECOND_IDENTITY) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) pre[k] = 1.0;
+      return;
+    }
+    double sd[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) sd[k] = valid(k) ? P->std_devs[k * 32 + lane] : 0.0;
+    if (P->precond_kind == PGN_PRECOND_DIAGONAL) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : 1.0 / sd[k];
+      return;
+    }
+    const double u = next_uniform(rng);
+    if (u <= P->mix_p0) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : 1.0 / sd[k];
+    } else if (u <= P->mix_p01) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) pre[k] = 1.0;
+    } else {
+      const double mix = next_uniform(rng);
+      const double rmix = 1.0 - mix;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : mix + rmix / sd[k];
+    }
+  }
+  __device__ void automala(bool use_mh) {   // auto_mala! :106-182
+    double pre[CPL];
+    build_preconditioner(pre);
+    double g0[CPL];
+    {
+      double dummy = 0.0;
+      double graw[CPL];
+      eval_grad(x, beta, e0, e1, graw, dummy);
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) g0[k] = graw[k] / pre[k];
+    }
+    double lp0 = lp_ad(beta, e0, e1);
+    Trial T, R;
+    for (int i = 0; i < P->n_refresh; ++i) {
+      double p[CPL];
+      double pp = 0.0;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        p[k] = valid(k) ? normal_at(rng, rng.ctr + (unsigned long long)(k * 32 + lane)) : 0.0;   // randn!(rng, momentum)
+        if (valid(k)) pp = pp + p[k] * p[k];
+      }
+      rng.ctr += (unsigned long long)d;
+      const double init_joint = lp0 - 0.5 * warp_sum(pp);
+      if (!is_finite(init_joint)) { err = PGN_ERR_NOT_POSITIVE; return; }
+      const double a = next_uniform(rng);
+      const double b = next_uniform(rng);
+      const double lower = log_(a < b ? a : b);
+      const double upper = log_(a < b ? b : a);
+      int nf = 0;
+      const int ef = search(x, p, g0, pre, init_joint, lower, upper, T, nf);
+      if (err) return;
+      n_steps += 1 + nf;
+      am.fit(pow2(ef));
+      const double eps_final = P->step_size * pow2(ef);
+      if (T.eps != eps_final) run_trial(x, p, g0, pre, eps_final, init_joint, T);   // leap_frog! at the chosen step :147-151
+      n_ref += 1 + 1 + 3 * (1 + nf) + 2;
+      bool accept = true;
+      if (use_mh) {
+        double pm[CPL];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) pm[k] = T.p1[k] * -1.0;
+        const double h_rev = T.h_after;   // log_joint at (x1, -p1): same partial sums as h_after
+        int nr = 0;
+        const int er = search(T.x1, pm, T.g1c, pre, h_rev, lower, upper, R, nr);
+        if (err) return;
+        n_steps += 1 + nr;
+        am.fit(pow2(er));
+        const bool passed = (er == ef);
+        rev.fit(passed ? 1.0 : 0.0);
+        double prob = 0.0;
+        if (passed) { double e = exp_(h_rev - init_joint); prob = 1.0 < e ? 1.0 : e; }
+        expl_acc.fit(prob);
+        n_ref += 1 + 3 * (1 + nr) + (passed ? 1 : 0);
+        accept = next_uniform(rng) < prob;
+      }
+      if (accept) {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) { x[k] = T.x1[k]; g0[k] = T.g1c[k]; }
+        e0 = T.a0; e1 = T.a1; lp0 = T.lp1;
+      }
+    }
+  }
+
+  // ---- explore!(pt, replica, explorer) (src/pt/pigeons.jl:101-132) --------------
+  __device__ void explore(long long scan, bool is_reference) {
+    if (is_reference) { sample_iid(beta); eval(x, e0, e1); return; }
+    if (EX == PGN_EXPLORER_TOY) { sample_iid(beta); eval(x, e0, e1); }
+    else if (EX == PGN_EXPLORER_SLICE) slice_step();
+    else automala(scan != 1);   // AutoMALA.jl:87,102
+  }
+  // log_unnormalized_ratio (src/log_potentials/log_potentials.jl:43-51)
+  __device__ double log_ratio(double beta_partner) const {
+    return lp_call(beta_partner, e0, e1) - lp_call(beta, e0, e1);
+  }
+};
+
+// ===========================================================================
+// Ising chain (examples/ising.jl): lane i holds row i of the bit-packed lattice
+// ===========================================================================
+struct IsingChain {
+  static constexpr bool kTestSwapper = false;
+  const Params* P;
+  int lane, L;
+  double beta;
+  unsigned int row;
+  int S;               // sum_pair_products (examples/ising.jl:19)
+  Rng rng;
+  MeanAcc expl_acc, am, rev;
+  long long n_steps, n_points, n_ref;
+  int err;
+
+  static __device__ void stage_shared(const Params&, double*) {}
+
+  __device__ __forceinline__ int sgn(unsigned int r, int j) const { return ((r >> j) & 1u) ? 1 : -1; }
+  __device__ void recompute_S() {   // examples/ising.jl:28-36
+    const unsigned int up = __shfl_sync(PGN_FULL_MASK, row, (lane + L - 1) % L);
+    const unsigned int dn = __shfl_sync(PGN_FULL_MASK, row, (lane + 1) % L);
+    int s = 0;
+    if (lane < L)
+      for (int j = 0; j < L; ++j) {
+        int jl = j == 0 ? L - 1 : j - 1, jr = j == L - 1 ? 0 : j + 1;
+        s += sgn(row, j) * (sgn(up, j) + sgn(dn, j) + sgn(row, jl) + sgn(row, jr));
+      }
+    S = __reduce_add_sync(PGN_FULL_MASK, s) / 2;
+  }
+  __device__ void init(const Params& Pr, const double*, int wl, int lane_, int replica_index) {
+    P = &Pr; lane = lane_; L = (int)Pr.p[1];
+    beta = Pr.beta[Pr.first_chain + wl - 1];
+    const unsigned int* rows = reinterpret_cast<const unsigned int*>(Pr.x + (size_t)wl * Pr.d_pad);
+    row = lane < L ? rows[lane] : 0u;
+    recompute_S();
+    rng.key0 = Pr.seed_lo; rng.key1 = (unsigned int)replica_index; rng.c2 = Pr.seed_hi; rng.c3 = 0u;
+    rng.ctr = Pr.rng_ctr[wl];
+    expl_acc = MeanAcc{0, 0.0}; am = MeanAcc{0, 0.0}; rev = MeanAcc{0, 0.0};
+    n_steps = n_points = n_ref = 0; err = 0;
+  }
+  __device__ void store(int wl) {
+    unsigned int* rows = reinterpret_cast<unsigned int*>(P->x + (size_t)wl * P->d_pad);
+    if (lane < L) rows[lane] = row;
+  }
+  __device__ void post(double* pay) const { reinterpret_cast<unsigned int*>(pay)[lane] = row; }
+  __device__ void adopt(const double* pay) {
+    row = __ldcg(reinterpret_cast<const unsigned int*>(pay) + lane);
+    recompute_S();
+  }
+  __device__ void write_trace(double* out) const {
+    if (lane < L)
+      for (int j = 0; j < L; ++j) out[lane * L + j] = ((row >> j) & 1u) ? 1.0 : 0.0;
+  }
+  __device__ void online_fit() {}
+  __device__ void store_online() const {}
+
+  // InterpolatedLogPotential over two IsingLogPotential's (examples/ising.jl:74,77)
+  __device__ __forceinline__ double lp(double b, int s) const {
+    const double ref = 0.0 * (double)s;
+    const double tgt = P->p[0] * (double)s;
+    if (b == 0.0) return ref;
+    if (b == 1.0) return tgt;
+    return (1.0 - b) * ref + b * tgt;
+  }
+  __device__ void sample_iid() {   // examples/ising.jl:49-58
+    const unsigned int mask = L >= 32 ? 0xffffffffu : ((1u << L) - 1u);
+    row = lane < L ? (bits32_at(rng, rng.ctr + (unsigned long long)lane) & mask) : 0u;
+    rng.ctr += (unsigned long long)L;
+    recompute_S();
+  }
+  __device__ void metropolis() {   // examples/ising.jl:98-117
+    for (int k = 0; k < P->ising_n_steps; ++k)
+      for (int i = 0; i < L; ++i) {
+        const unsigned int up = __shfl_sync(PGN_FULL_MASK, row, (i + L - 1) % L);
+        const unsigned int dn = __shfl_sync(PGN_FULL_MASK, row, (i + 1) % L);
+        unsigned int cur = __shfl_sync(PGN_FULL_MASK, row, i);
+        for (int j = 0; j < L; ++j) {
+          const int jl = j == 0 ? L - 1 : j - 1, jr = j == L - 1 ? 0 : j + 1;
+          const int me = sgn(cur, j);
+          const int nb = sgn(up, j) + sgn(dn, j) + sgn(cur, jl) + sgn(cur, jr);
+          const int S_new = S + (-me * nb - me * nb);
+          const double log_pr_before = lp(beta, S);
+          const double log_pr_after = lp(beta, S_new);
+          const double accept_ratio = exp_(log_pr_after - log_pr_before);
+          bool reject = false;
+          if (accept_ratio < 1) reject = next_uniform(rng) > accept_ratio;
+          if (!reject) { cur ^= (1u << j); S = S_new; }
+        }
+        if (lane == i) row = cur;
+      }
+    n_ref += 2LL * P->ising_n_steps * L * L;
+    n_points += (long long)P->ising_n_steps * L * L;
+  }
+  __device__ void explore(long long, bool is_reference) {
+    if (is_reference) sample_iid(); else metropolis();
+  }
+  __device__ double log_ratio(double beta_partner) const { return lp(beta_partner, S) - lp(beta, S); }
+};
+
+// ===========================================================================
+// TestSwapper (src/swap/pair_swapper.jl:100-149): no state, constant acceptance
+// ===========================================================================
+struct TestSwapperChain {
+  static constexpr bool kTestSwapper = true;
+  const Params* P;
+  Rng rng;
+  MeanAcc expl_acc, am, rev;
+  long long n_steps, n_points, n_ref;
+  int err;
+  static __device__ void stage_shared(const Params&, double*) {}
+  __device__ void init(const Params& Pr, const double*, int wl, int, int replica_index) {
+    P = &Pr;
+    rng.key0 = Pr.seed_lo; rng.key1 = (unsigned int)replica_index; rng.c2 = Pr.seed_hi; rng.c3 = 0u;
+    rng.ctr = Pr.rng_ctr[wl];
+    expl_acc = MeanAcc{0, 0.0}; am = MeanAcc{0, 0.0}; rev = MeanAcc{0, 0.0};
+    n_steps = n_points = n_ref = 0; err = 0;
+  }
+  __device__ void store(int) {}
+  __device__ void post(double*) const {}
+  __device__ void adopt(const double*) {}
+  __device__ void write_trace(double*) const {}
+  __device__ void online_fit() {}
+  __device__ void store_online() const {}
+  __device__ void explore(long long, bool) {}
+  __device__ double log_ratio(double) const { return 0.0; }
+};
+
+// ===========================================================================
+// The scan kernel
+// ===========================================================================
+template <class Chain>
+__global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Params P) {
+  extern __shared__ double smem[];
+  Chain::stage_shared(P, smem);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wl >= P.n_local) return;
+  const int N = P.n_chains;
+  const int chain = P.first_chain + wl;   // 1-based global chain index
+  const int last_local = P.first_chain + P.n_local - 1;
+  int replica_index = P.replica_index[wl];
+  int rt_state = 0;   // recorders are emptied at every round (recorders.jl:113-118)
+  Chain ch;
+  ch.init(P, smem, wl, lane, replica_index);
+  MeanAcc swap_acc{0, 0.0};
+  LogSumAcc ls_fwd{0, -PGN_INF}, ls_bwd{0, -PGN_INF};
+  long long n_restarts = 0, n_trips = 0;
+  const bool is_ref = (chain == 1 && N > 1);   // DEO.jl:13
+  const bool is_tgt = (chain == N);            // DEO.jl:14
+  int err = 0;
+
+  for (long long scan = 1; scan <= P.n_scans; ++scan) {
+    // ---------------- explore ----------------
+    ch.explore(scan, is_ref);
+    if (ch.err) { err = ch.err; break; }
+    if (is_tgt) {   // pigeons.jl:110-131
+      ch.online_fit();
+      if (P.target_trace) ch.write_trace(P.target_trace + (size_t)(scan - 1) * P.d);
+    }
+    // ---------------- swap ----------------
+    const bool even = (scan & 1LL) == 0;                                   // DEO.jl:12
+    int partner = chain + ((((chain & 1) == 0) == even) ? 1 : -1);         // OddEven.jl:23-31
+    if (partner == 0) partner = 1;
+    if (partner == N + 1) partner = N;
+    double lr = 0.0;
+    if (!Chain::kTestSwapper) {
+      lr = ch.log_ratio(P.beta[partner - 1]);                              // swap_stat, pair_swapper.jl:42-47
+      ch.n_ref += 2;
+      if (lr != lr) { err = PGN_ERR_NAN_RATIO; break; }
+    }
+    const double u = next_uniform(ch.rng);
+    const size_t log_at = (size_t)(scan - 1) * P.n_local + wl;
+    if (lane == 0) {   // recorded before the swap (swap.jl:110-111)
+      if (P.index_process) P.index_process[log_at] = replica_index;
+      if (P.swap_lr) P.swap_lr[log_at] = lr;
+      if (P.swap_u) P.swap_u[log_at] = u;
+    }
+    if (rt_state == 0 && is_ref) rt_state = 1;                             // RoundTripRecorder.jl:43-54
+    else if (rt_state == 1 && is_tgt) { rt_state = 2; n_restarts += 1; }
+    else if (rt_state == 2 && is_ref) { rt_state = 1; n_trips += 1; }
+
+    bool accepted = false;
+    if (partner != chain) {
+      const int ring = (int)((P.epoch & 1u) * 4u + (unsigned int)(scan & 3LL));
+      const unsigned long long tag = ((unsigned long long)P.epoch << 32) | (unsigned long long)scan;
+      const bool remote = partner < P.first_chain || partner > last_local;
+      // ---- post my SwapStat + replica where my partner will look for it
+      char* dst;
+      const char* src;
+      if (!remote) {
+        dst = P.mail + ((size_t)(2 + wl) * MAIL_RINGS + ring) * P.slot_bytes;
+        src = P.mail + ((size_t)(2 + (partner - P.first_chain)) * MAIL_RINGS + ring) * P.slot_bytes;
+      } else if (partner > chain) {   // partner lives on the right neighbour: I am its LEFT ghost
+        dst = P.mail_right + ((size_t)0 * MAIL_RINGS + ring) * P.slot_bytes;
+        src = P.mail + ((size_t)1 * MAIL_RINGS + ring) * P.slot_bytes;
+      } else {
+        dst = P.mail_left + ((size_t)1 * MAIL_RINGS + ring) * P.slot_bytes;
+        src = P.mail + ((size_t)0 * MAIL_RINGS + ring) * P.slot_bytes;
+      }
+      if (lane == 0) {
+        MailHdr* h = reinterpret_cast<MailHdr*>(dst + 32);
+        h->lr = lr; h->u = u; h->ctr = ch.rng.ctr; h->replica_index = replica_index; h->rt_state = rt_state;
+      }
+      ch.post(reinterpret_cast<double*>(dst + MAIL_HDR_BYTES));
+      __syncwarp();
+      if (lane == 0) {
+        if (remote) st_release_sys(reinterpret_cast<unsigned long long*>(dst), tag);
+        else st_release_gpu(reinterpret_cast<unsigned long long*>(dst), tag);
+      }
+      // ---- wait for the partner's post
+      int status = 0;
+      if (lane == 0) {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(src);
+        unsigned long long t0 = 0;
+        unsigned int it = 0;
+        while (ld_relaxed_sys(flag) != tag) {
+          ++it;
+          if ((it & 255u) == 0u) {
+            if (*reinterpret_cast<volatile int*>(P.error_flag) != 0) { status = 1; break; }
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > P.timeout_ns) { status = 2; break; }
+            if (it > 65536u) __nanosleep(200);
+          }
+        }
+        if (remote) fence_acq_rel_sys(); else fence_acq_rel_gpu();
+      }
+      status = __shfl_sync(PGN_FULL_MASK, status, 0);
+      if (status != 0) { err = status == 2 ? PGN_ERR_TIMEOUT : -1; break; }
+      const MailHdr* hp = reinterpret_cast<const MailHdr*>(src + 32);
+      const double lr_p = __ldcg(&hp->lr);
+      const double u_p = __ldcg(&hp->u);
+      // ---- decision (identical on both sides; swap_decision pair_swapper.jl:81-88)
+      const bool lower = chain < partner;
+      double acceptance_pr;
+      if (Chain::kTestSwapper) {
+        acceptance_pr = P.p[0];
+      } else {
+        const double e = lower ? exp_(lr + lr_p) : exp_(lr_p + lr);
+        acceptance_pr = 1.0 < e ? 1.0 : e;
+        if (lower) {   // record_swap_stats! :59-66, by the replica holding the lower chain
+          swap_acc.fit(acceptance_pr);
+          ls_fwd.fit(lr);
+          ls_bwd.fit(lr_p);
+        }
+      }
+      accepted = (lower ? u : u_p) < acceptance_pr;
+      if (accepted) {   // adopt the partner's replica (states move, chains stay)
+        replica_index = __ldcg(&hp->replica_index);
+        rt_state = __ldcg(&hp->rt_state);
+        ch.rng.ctr = __ldcg(&hp->ctr);
+        ch.rng.key1 = (unsigned int)replica_index;
+        ch.adopt(reinterpret_cast<const double*>(src + MAIL_HDR_BYTES));
+      }
+    }
+    if (lane == 0 && P.swap_accept) P.swap_accept[log_at] = accepted ? 1 : 0;
+  }
+
+  if (err > 0 && lane == 0) atomicCAS(P.error_flag, 0, err);
+  // ---------------- epilogue: replica back to HBM, statistics out ----------------
+  ch.store(wl);
+  if (is_tgt) ch.store_online();
+  if (lane == 0) {
+    P.replica_index[wl] = replica_index;
+    P.rng_ctr[wl] = ch.rng.ctr;
+    P.rt_state[wl] = rt_state;
+    ChainStatsDev s;
+    s.swap_n = swap_acc.n; s.swap_mean = swap_acc.mu; s.ls_fwd = ls_fwd.value; s.ls_bwd = ls_bwd.value;
+    s.expl_acc_n = ch.expl_acc.n; s.expl_acc_mean = ch.expl_acc.mu; s.n_steps = ch.n_steps;
+    s.am_n = ch.am.n; s.am_mean = ch.am.mu; s.rev_n = ch.rev.n; s.rev_mean = ch.rev.mu;
+    s.n_restarts = n_restarts; s.n_round_trips = n_trips;
+    s.n_points = ch.n_points; s.n_ref_evals = ch.n_ref;
+    P.stats[wl] = s;
+  }
+}
+
+// ===========================================================================
+// Small helper kernels
+// ===========================================================================
+// initialization(target, rng, replica_index) for toy MVN (toy_mvn_target.jl:10-11):
+// x = randn(rng, dim) / sqrt(precision1); one warp per replica.
+__global__ void init_toy_kernel(const __grid_constant__ Params P) {
+  const int lane = threadIdx.x & 31;
+  const int wl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wl >= P.n_local) return;
+  Rng rng{P.seed_lo, (unsigned int)(P.first_chain + wl), P.seed_hi, 0u, 0ull};
+  const double sq = sqrt(P.p[1]);
+  for (int c = lane; c < P.d; c += 32) P.x[(size_t)wl * P.d_pad + c] = normal_at(rng, (unsigned long long)c) / sq;
+  if (lane == 0) P.rng_ctr[wl] = (unsigned long long)P.d;
+}
+
+// parity entry points: one warp per point
+template <int TK, int CPL>
+__global__ void eval_points_kernel(const __grid_constant__ Params P, const double* xs, const double* betas, int n_points, double* lp_out,
+                                   double* ld_out, double* grad_out) {
+  extern __shared__ double smem[];
+  typedef VecChain<TK, CPL, PGN_EXPLORER_SLICE> Chain;
+  Chain::stage_shared(P, smem);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n_points) return;
+  Chain ch;
+  ch.P = &P; ch.sm_means = smem; ch.lane = lane; ch.d = P.d; ch.beta = betas[w];
+  ch.n_points = 0; ch.n_ref = 0; ch.err = 0;
+  double xx[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) xx[k] = (k * 32 + lane < P.d) ? xs[(size_t)w * P.d + k * 32 + lane] : 0.0;
+  if (lp_out) {
+    double a0, a1;
+    ch.eval(xx, a0, a1);
+    if (lane == 0) lp_out[w] = ch.lp_call(ch.beta, a0, a1);
+  }
+  if (ld_out) {
+    double a0, a1, g[CPL], extra = 0.0;
+    ch.eval_grad(xx, ch.beta, a0, a1, g, extra);
+    // logdens = 0.0 + l_ref (1-b) + l_tgt b (BufferedAD.jl:99-108); toy: ScaledPrecisionNormalPath.jl:30-34
+    if (lane == 0) ld_out[w] = (TK == PGN_TARGET_TOY_MVN) ? ch.lp_ad(ch.beta, a0, a1)
+                                                          : ((0.0 + a0 * (1.0 - ch.beta)) + a1 * ch.beta);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k)
+      if (k * 32 + lane < P.d) grad_out[(size_t)w * P.d + k * 32 + lane] = g[k];
+  }
+}
+
+__global__ void ising_lp_kernel(const __grid_constant__ Params P, const double* xs, const double* betas, int n_points, double* lp_out) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n_points) return;
+  IsingChain ch;
+  ch.P = &P; ch.lane = lane; ch.L = (int)P.p[1];
+  unsigned int r = 0u;
+  if (lane < ch.L)
+    for (int j = 0; j < ch.L; ++j)
+      if (xs[(size_t)w * P.d + lane * ch.L + j] != 0.0) r |= (1u << j);
+  ch.row = r;
+  ch.recompute_S();
+  if (lane == 0) lp_out[w] = ch.lp(betas[w], ch.S);
+}
+
+__global__ void test_math_kernel(int op, const double* in, double* out, long long n, unsigned int seed_lo,
+                                 unsigned int seed_hi, unsigned int replica_index) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Rng g{seed_lo, replica_index, seed_hi, 0u, 0ull};
+  double r;
+  switch (op) {
+    case 0: r = exp_(in[i]); break;
+    case 1: r = log_(in[i]); break;
+    case 2: r = cospi_(in[i]); break;
+    case 3: r = normal_at(g, (unsigned long long)in[i]); break;
+    case 4: r = uniform_at(g, (unsigned long long)in[i]); break;
+    case 5: r = exponential_at(g, (unsigned long long)in[i]); break;
+    case 6: r = logaddexp_(in[2 * i], in[2 * i + 1]); break;
+    default: r = PGN_NAN;
+  }
+  out[i] = r;
+}
+
+}  // namespace pgn

@@ -1,0 +1,156 @@
+"""GPU parity tests proper: the CUDA engine, called through the C ABI, against the
+CPU oracle on the same seeded inputs.  Bit-exact for the swap index permutation,
+the uniforms, the accept decisions and every integer statistic; log-densities /
+log-ratios are compared bit-exactly too (the two sides implement one arithmetic
+spec), which is stricter than the 1e-10 relative tolerance north_star asks for —
+the tolerance assertion is kept next to the exact one so a future relaxation of
+the device arithmetic (e.g. FMA contraction) has a stated bar."""
+import numpy as np
+import pytest
+
+import pigeons_jl_b200 as pg
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10   # north_star: fp64 log-densities within 1e-10 relative
+
+
+def run_pt(lib, **kw):
+    kw.setdefault("record", [pg.index_process, pg.swap_trace, pg.traces])
+    pt = pg.pigeons(engine_lib=lib, **kw)
+    rr = pt.reduced_recorders
+    state = pt.engine.get_state()
+    out = dict(rr=rr, schedule=pt.shared.tempering.schedule.grids.copy(), logz=pg.stepping_stone(pt), state=state,
+               explorer=pt.shared.explorer, log=pt.round_log)
+    pt.close()
+    return out
+
+
+def assert_same(g, c, label=""):
+    rg, rc = g["rr"], c["rr"]
+    assert np.array_equal(rg.index_process, rc.index_process), f"{label}: swap index permutation differs"
+    assert np.array_equal(rg.swap_accept, rc.swap_accept), f"{label}: accept decisions differ"
+    assert np.array_equal(rg.swap_u, rc.swap_u), f"{label}: uniforms differ"
+    np.testing.assert_allclose(rg.swap_lr, rc.swap_lr, rtol=RTOL, atol=0, err_msg=f"{label}: log ratios")
+    assert np.array_equal(rg.swap_lr, rc.swap_lr), f"{label}: log ratios not bit-identical"
+    for k in ("swap_n", "expl_acc_n", "expl_n_steps", "am_n", "rev_n"):
+        assert np.array_equal(getattr(rg, k), getattr(rc, k)), f"{label}: {k}"
+    for k in ("swap_mean", "logsum_fwd", "logsum_bwd", "expl_acc_mean", "am_mean", "rev_mean", "online_mean", "online_var"):
+        np.testing.assert_allclose(getattr(rg, k), getattr(rc, k), rtol=RTOL, atol=0, err_msg=f"{label}: {k}")
+        assert np.array_equal(getattr(rg, k), getattr(rc, k)), f"{label}: {k} not bit-identical"
+    assert rg.n_round_trips == rc.n_round_trips and rg.n_tempered_restarts == rc.n_tempered_restarts
+    assert rg.n_ref_equiv_evals == rc.n_ref_equiv_evals, f"{label}: reference-equivalent eval count"
+    if rg.target_trace is not None and rg.target_trace.size:
+        assert np.array_equal(rg.target_trace, rc.target_trace), f"{label}: target-chain samples differ"
+    assert np.array_equal(g["schedule"], c["schedule"]), f"{label}: adapted schedule differs"
+    assert g["logz"] == c["logz"] or (np.isnan(g["logz"]) and np.isnan(c["logz"])), f"{label}: stepping stone differs"
+    for k in ("x", "replica_index", "rng_counter", "round_trip_state"):
+        assert np.array_equal(g["state"][k], c["state"][k]), f"{label}: final replica {k}"
+
+
+CASES = {
+    "c1_toy_slice": dict(target=pg.toy_mvn_target(2), explorer=pg.SliceSampler(), n_chains=10, n_rounds=10, seed=1),
+    "toy_default_explorer": dict(target=pg.toy_mvn_target(3), n_chains=7, n_rounds=8, seed=3),
+    "toy10_automala": dict(target=pg.toy_mvn_target(10), explorer=pg.AutoMALA(), n_chains=6, n_rounds=8, seed=2),
+    "toy40_slice_2cpl": dict(target=pg.toy_mvn_target(40), explorer=pg.SliceSampler(), n_chains=5, n_rounds=5, seed=5),
+    "toy100_automala_4cpl": dict(target=pg.toy_mvn_target(100), explorer=pg.AutoMALA(), n_chains=5, n_rounds=6, seed=6),
+    "funnel32_automala": dict(target=pg.Funnel(32), explorer=pg.AutoMALA(), n_chains=24, n_rounds=7, seed=1),
+    "funnel8_slice": dict(target=pg.Funnel(8), explorer=pg.SliceSampler(), n_chains=9, n_rounds=6, seed=4),
+    "funnel_identity_precond": dict(target=pg.Funnel(16), explorer=pg.AutoMALA(preconditioner=pg.IdentityPreconditioner()),
+                                    n_chains=8, n_rounds=6, seed=9),
+    "funnel_diag_precond": dict(target=pg.Funnel(16), explorer=pg.AutoMALA(preconditioner=pg.DiagonalPreconditioner()),
+                                n_chains=8, n_rounds=6, seed=10),
+    "gmm128_automala": dict(target=pg.eight_mode_mixture(128, 8.0), explorer=pg.AutoMALA(), n_chains=12, n_rounds=5, seed=1),
+    "gmm6_slice": dict(target=pg.eight_mode_mixture(6, 3.0), explorer=pg.SliceSampler(), n_chains=8, n_rounds=5, seed=2),
+    "gmm2_two_modes": dict(target=pg.GaussianMixture(means=[[-8.0, -8.0], [8.0, 8.0]], reference_sigma=8.0),
+                           explorer=pg.AutoMALA(), n_chains=5, n_rounds=7, seed=3),
+    "ising5": dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=7, seed=1),
+    "ising32": dict(target=pg.IsingLogPotential(0.44, 32), n_chains=6, n_rounds=3, seed=2),
+    "test_swapper": dict(target=pg.TestSwapper(0.6), n_chains=9, n_rounds=8, seed=7, record=[pg.index_process, pg.swap_trace]),
+    "single_chain": dict(target=pg.toy_mvn_target(4), explorer=pg.SliceSampler(), n_chains=1, n_rounds=5, seed=1),
+    "two_chains": dict(target=pg.toy_mvn_target(2), explorer=pg.AutoMALA(), n_chains=2, n_rounds=6, seed=8),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_multi_round_parity(name, gpu_lib, oracle_lib):
+    kw = CASES[name]
+    assert_same(run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw), name)
+
+
+def test_round_trips_known_answer(gpu_lib):
+    """test/test_round_trips.jl:1-14 on the device: exactly 13 round trips."""
+    pt = pg.pigeons(target=pg.TestSwapper(1.0), record=[pg.round_trip], n_chains=4, n_rounds=5, engine_lib=gpu_lib)
+    assert pg.n_round_trips(pt) == 13
+    pt.close()
+
+
+def _points(rng, n, d, scale=2.0):
+    return rng.normal(0.0, scale, size=(n, d))
+
+
+@pytest.mark.parametrize("target", [pg.toy_mvn_target(2), pg.toy_mvn_target(77), pg.Funnel(32), pg.Funnel(5),
+                                    pg.eight_mode_mixture(128, 8.0), pg.eight_mode_mixture(40, 2.0)])
+def test_log_potential_and_gradient_entry_points(target, gpu_lib, oracle_lib):
+    """pgn_log_potential / pgn_logdensity_and_gradient against the oracle, incl. beta in {0, 1}."""
+    rng = np.random.default_rng(0)
+    cfg = target.engine_config()
+    eg = pg.Engine(gpu_lib, n_chains=4, seed=1, **cfg)
+    eo = pg.Engine(oracle_lib, n_chains=4, seed=1, **cfg)
+    x = _points(rng, 64, target.dim)
+    beta = rng.uniform(0, 1, 64)
+    beta[:8] = 0.0
+    beta[8:16] = 1.0
+    lg, lo = eg.log_potential(x, beta), eo.log_potential(x, beta)
+    np.testing.assert_allclose(lg, lo, rtol=RTOL, atol=0)
+    assert np.array_equal(lg, lo)
+    (ldg, gg), (ldo, go) = eg.logdensity_and_gradient(x, beta), eo.logdensity_and_gradient(x, beta)
+    np.testing.assert_allclose(ldg, ldo, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(gg, go, rtol=RTOL, atol=1e-300)
+    assert np.array_equal(ldg, ldo) and np.array_equal(gg, go)
+    # analytic gradient vs central finite differences of the device density itself
+    h = 1e-6
+    for j in (0, target.dim - 1):
+        xp, xm = x.copy(), x.copy()
+        xp[:, j] += h
+        xm[:, j] -= h
+        fd = (eg.logdensity_and_gradient(xp, beta)[0] - eg.logdensity_and_gradient(xm, beta)[0]) / (2 * h)
+        np.testing.assert_allclose(gg[:, j], fd, rtol=2e-5, atol=2e-5)
+    eg.close(); eo.close()
+
+
+def test_device_numerics_bit_identical(gpu_lib, oracle_lib):
+    """The device elementary functions and the Philox draws equal the oracle's, bit for bit."""
+    rng = np.random.default_rng(1)
+    xs = {
+        0: np.concatenate([rng.uniform(-745, 709, 20000), rng.normal(0, 1, 20000), [0.0, -0.0, np.inf, -np.inf, np.nan, 710.0, -746.0]]),
+        1: np.concatenate([np.exp(rng.uniform(-700, 700, 20000)), rng.uniform(0, 2, 20000), [0.0, 1.0, np.inf, -1.0, np.nan, 5e-324]]),
+        2: rng.uniform(0, 2, 40000),
+        3: np.arange(0, 40000, dtype=np.float64),
+        4: np.arange(0, 40000, dtype=np.float64),
+        5: np.arange(0, 40000, dtype=np.float64),
+        6: rng.normal(0, 30, 40000),
+    }
+    for op, v in xs.items():
+        a = gpu_lib.test_math(op, v, seed=12345678901, replica_index=17)
+        b = oracle_lib.test_math(op, v, seed=12345678901, replica_index=17)
+        assert np.array_equal(a, b, equal_nan=True), f"op {op}: device and oracle differ"
+
+
+def test_errors_are_reported_not_swallowed(gpu_lib):
+    """NaN log ratio -> rc != 0 with a message (src/log_potentials/log_potentials.jl:47-49)."""
+    t = pg.Funnel(4)
+    e = pg.Engine(gpu_lib, n_chains=3, seed=1, **t.engine_config())
+    e.init_replicas()
+    e.set_explorer(**pg.SliceSampler().engine_params(4))
+    x = np.zeros((3, 4))
+    x[1, 0] = np.inf     # y = +inf: ref = -inf, target = nan
+    e.set_state(x=x)
+    with pytest.raises(pg.EngineError):
+        e.run_round(2)
+    e.close()
+
+
+def test_unsupported_configuration_raises(gpu_lib):
+    with pytest.raises(pg.EngineError):
+        pg.Engine(gpu_lib, n_chains=4, seed=1, **pg.toy_mvn_target(1000).engine_config())
