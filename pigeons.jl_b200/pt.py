@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, field
-from typing import List, Optional, Sequence
+from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 
@@ -44,6 +44,7 @@ class Inputs:
     checked_round: int = 0
     # engine plumbing (not in the reference)
     engine_lib: Optional[_capi.EngineLib] = None
+    engine_factory: Optional[Callable] = None     # (n_chains, seed, rank, world_size, device, **target_cfg) -> Engine-like
     device: int = 0
     comm: Optional[Communicator] = None
 
@@ -95,11 +96,14 @@ class PT:
 
 def create_pt(inputs: Inputs) -> PT:
     """PT(inputs) (PT.jl:46-51): Shared + create_replicas (replicas.jl:65-99)."""
-    lib = inputs.engine_lib or _capi.EngineLib()
     comm = inputs.comm
     cfg = inputs.target.engine_config()
-    engine = _capi.Engine(lib, n_chains=inputs.n_chains, seed=inputs.seed, rank=comm.rank,
-                          world_size=comm.world_size, device=inputs.device, **cfg)
+    kw = dict(n_chains=inputs.n_chains, seed=inputs.seed, rank=comm.rank, world_size=comm.world_size,
+              device=inputs.device, **cfg)
+    if inputs.engine_factory is not None:
+        engine = inputs.engine_factory(**kw)
+    else:
+        engine = _capi.Engine(inputs.engine_lib or _capi.EngineLib(), **kw)
     lb = LoadBalance(comm.rank + 1, comm.world_size, inputs.n_chains)
     assert engine.first_chain == lb.my_first_global_idx() and engine.n_local == lb.my_load(), \
         "engine shard geometry disagrees with LoadBalance"

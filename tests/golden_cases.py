@@ -1,0 +1,44 @@
+"""Shared by tests/golden/make_golden.py and tests/test_golden.py."""
+import hashlib
+
+import numpy as np
+
+import pigeons_jl_b200 as pg
+
+GOLDEN_CASES = {
+    # BASELINE config 1: toy_mvn_target(2), 10 chains, SliceSampler, 10 rounds (2046 scans)
+    "c1_toy_mvn2_slice_n10_r10": lambda: dict(target=pg.toy_mvn_target(2), explorer=pg.SliceSampler(), n_chains=10,
+                                              n_rounds=10, seed=1),
+    # BASELINE config 2 shape, reduced chain count
+    "c2_funnel32_automala_n32_r7": lambda: dict(target=pg.Funnel(32), explorer=pg.AutoMALA(), n_chains=32, n_rounds=7, seed=1),
+    # BASELINE config 3 shape, reduced chain count
+    "c3_gmm128_automala_n16_r5": lambda: dict(target=pg.eight_mode_mixture(128, 8.0), explorer=pg.AutoMALA(), n_chains=16,
+                                              n_rounds=5, seed=1),
+    # BASELINE config 4 shape, reduced chain count
+    "c4_ising32_n8_r4": lambda: dict(target=pg.IsingLogPotential(0.4406867935097715, 32), n_chains=8, n_rounds=4, seed=1),
+    "ising5_n10_r8": lambda: dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=8, seed=1),
+}
+
+
+def _hex(a):
+    return [float(v).hex() for v in np.asarray(a, dtype=np.float64).ravel()]
+
+
+def summarise(pt):
+    rr = pt.reduced_recorders
+    return {
+        "n_scans_last_round": int(rr.n_scans),
+        "index_process_sha256": hashlib.sha256(np.ascontiguousarray(rr.index_process, dtype=np.int32).tobytes()).hexdigest(),
+        "index_process_head": rr.index_process[:16].tolist(),
+        "swap_accept_sha256": hashlib.sha256(np.ascontiguousarray(rr.swap_accept, dtype=np.uint8).tobytes()).hexdigest(),
+        "swap_u_head": _hex(rr.swap_u[:4]),
+        "swap_lr_head": _hex(rr.swap_lr[:4]),
+        "swap_lr_sha256": hashlib.sha256(np.ascontiguousarray(rr.swap_lr, dtype=np.float64).tobytes()).hexdigest(),
+        "swap_mean": _hex(rr.swap_mean),
+        "logsum_fwd": _hex(rr.logsum_fwd),
+        "schedule": _hex(pt.shared.tempering.schedule.grids),
+        "stepping_stone": float(pg.stepping_stone(pt)).hex(),
+        "n_round_trips": int(rr.n_round_trips),
+        "n_ref_equiv_evals": int(rr.n_ref_equiv_evals),
+        "expl_n_steps": [int(v) for v in rr.expl_n_steps],
+    }

@@ -1,0 +1,116 @@
+"""Host-side logic that needs neither GPU nor oracle: LoadBalance, the
+Fritsch-Carlson schedule update, explorer parameter derivation, C-ABI symbols."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pigeons_jl_b200 as pg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_load_balance_partition():
+    """test/test_mpi_utils.jl:6-23: the slices partition 1..n for all (p, n) <= (20, 30)."""
+    for p in range(1, 21):
+        for n in range(p, 31):
+            seen = []
+            for i in range(1, p + 1):
+                lb = pg.LoadBalance(i, p, n)
+                idx = list(lb.my_global_indices())
+                assert len(idx) == lb.my_load()
+                for g in idx:
+                    assert lb.find_process(g) == i
+                seen += idx
+            assert seen == list(range(1, n + 1))
+
+
+def test_monotone_cubic_interpolates_and_is_monotone():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([[0.0], np.cumsum(rng.uniform(0.01, 1, 12))])
+    y = np.concatenate([[0.0], np.cumsum(rng.uniform(0.0, 1, 12))])
+    f = pg.MonotoneCubic(x, y)
+    np.testing.assert_allclose(f(x), y, rtol=0, atol=1e-12)
+    t = np.linspace(x[0], x[-1], 4001)
+    assert np.all(np.diff(f(t)) >= -1e-12)
+    h = 1e-6
+    np.testing.assert_allclose(f.gradient(t[1:-1]), (f(t[1:-1] + h) - f(t[1:-1] - h)) / (2 * h), rtol=1e-4, atol=1e-5)
+
+
+def test_optimal_schedule_equalises_rejection():
+    """adaptation.jl:74-93: with a uniform intensity the schedule is unchanged; with a
+    skewed one the new grid points move toward the high-rejection region."""
+    old = pg.equally_spaced_schedule(6)
+    same = pg.optimal_schedule(np.full(5, 0.3), old)
+    np.testing.assert_allclose(same.grids, old.grids, atol=1e-12)
+    skew = pg.optimal_schedule(np.array([0.9, 0.1, 0.1, 0.1, 0.1]), old)
+    assert skew.grids[0] == 0.0 and skew.grids[-1] == 1.0 and np.all(np.diff(skew.grids) > 0)
+    assert skew.grids[1] < old.grids[1]
+    # zero intensities are nudged (adaptation.jl:81-84)
+    z = pg.optimal_schedule(np.array([0.0, 0.0, 0.5, 0.0, 0.0]), old)
+    assert np.all(np.diff(z.grids) > 0)
+
+
+def test_rejections_default_one_half():
+    r = pg.rejections(np.array([4, 0, 2, 0]), np.array([0.25, 0.0, 1.0, 0.0]), 4)
+    np.testing.assert_allclose(r, [0.75, 0.5, 0.0])
+
+
+def test_automala_n_refresh():
+    """AutoMALA.jl:122: base_n_refresh * ceil(Int, d^0.35)."""
+    a = pg.AutoMALA()
+    assert [a.n_refresh(d) for d in (1, 2, 10, 32, 128, 1000, 4096)] == [3, 6, 9, 12, 18, 36, 57]
+
+
+def test_default_explorers():
+    assert isinstance(pg.toy_mvn_target(2).default_explorer(), pg.ToyExplorer)       # toy_mvn_target.jl:13
+    assert isinstance(pg.IsingLogPotential().default_explorer(), pg.IsingMetropolis)  # examples/ising.jl:95
+    s = pg.SliceSampler()
+    assert (s.w, s.p, s.n_passes, s.max_iter) == (10.0, 20, 3, 1024)                  # SliceSampler.jl:8-20
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "pigeons_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(pgn_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_header_and_binding_agree():
+    from pigeons_jl_b200 import _capi
+    assert declared_symbols() == sorted(_capi.DECLARED_SYMBOLS)
+
+
+def test_capi_library_loads_and_exports_every_symbol():
+    """The C-ABI shared library loads on a machine without a GPU and exports every
+    symbol include/pigeons_b200.h declares (no compute calls here)."""
+    path = pg.default_library_path()
+    if not os.path.exists(path):
+        import __graft_entry__ as g
+        g.build()
+    lib = C.CDLL(path)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    lib.pgn_abi_version.restype = C.c_int
+    assert lib.pgn_abi_version() == 1
+
+
+def test_product_fails_loudly_without_gpu():
+    """No CPU fallback: without a CUDA device pgn_create returns PGN_ERR_NO_DEVICE."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = pg.EngineLib()
+    with pytest.raises(pg.EngineError) as ei:
+        pg.Engine(lib, n_chains=4, seed=1, **pg.toy_mvn_target(2).engine_config())
+    assert ei.value.code == 2
+
+
+def test_package_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "pigeons.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "liborc" not in text and "oracle_adapter" not in text and "orc_engine" not in text, f
