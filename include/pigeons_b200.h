@@ -64,6 +64,7 @@ extern "C" {
 #define PGN_EXPLORER_SLICE 2            /* src/explorers/SliceSampler.jl:8-237                     */
 #define PGN_EXPLORER_AUTOMALA 3         /* src/explorers/AutoMALA.jl:29-294                        */
 #define PGN_EXPLORER_ISING_METROPOLIS 4 /* examples/ising.jl:91-117                                */
+#define PGN_EXPLORER_MALA 5             /* src/explorers/MALA.jl:19-104 (fixed step size)          */
 
 /* ---- preconditioners (src/explorers/Preconditioner.jl:7-77) --------------- */
 #define PGN_PRECOND_IDENTITY 0

@@ -592,6 +592,32 @@ struct Engine {
     }
   }
 
+  // mala! (src/explorers/MALA.jl:74-97)
+  void mala(Replica& r, ChainStats& st) {
+    const int dd = d();
+    const double b = beta[r.chain - 1];
+    build_preconditioner(r);
+    for (int i = 0; i < ep.n_refresh; ++i) {
+      r.start_state = r.x;
+      for (int c = 0; c < dd; ++c) r.momentum[c] = normal_at(r.rng, r.ctr + c);
+      r.ctr += dd;
+      double init_joint_log = log_joint(logdensity(b, r), r.momentum);
+      if (!std::isfinite(init_joint_log))
+        throw OrcError{PGN_ERR_NOT_POSITIVE, "MALA can only be called on a configuration of positive density"};
+      leap_frog(b, r, ep.step_size);
+      for (int c = 0; c < dd; ++c) r.momentum[c] = r.momentum[c] * -1.0;
+      double final_joint_log = log_joint(logdensity(b, r), r.momentum);
+      double e = exp_(final_joint_log - init_joint_log);
+      double probability = 1.0 < e ? 1.0 : e;
+      st.expl_acc.fit(probability);
+      if (r.uniform() < probability) {
+      } else {
+        r.x = r.start_state;
+      }
+      st.n_steps += 1;
+    }
+  }
+
   // ------------------------------------------------------------------ IsingMetropolis
   // examples/ising.jl:98-117
   void ising_metropolis(Replica& r) {
@@ -621,6 +647,7 @@ struct Engine {
         case PGN_EXPLORER_TOY: sample_iid(beta[r.chain - 1], r); break;   // ToyExplorer.jl:7-12
         case PGN_EXPLORER_SLICE: slice_step(r, st); break;
         case PGN_EXPLORER_AUTOMALA: auto_mala(r, st, scan != 1); break;   // AutoMALA.jl:87,102
+        case PGN_EXPLORER_MALA: mala(r, st); break;
         case PGN_EXPLORER_ISING_METROPOLIS: ising_metropolis(r); break;
         default: break;
       }

@@ -30,7 +30,7 @@ ERR_NAMES = {
 }
 
 TARGET_TOY_MVN, TARGET_FUNNEL, TARGET_GMM, TARGET_ISING, TARGET_LOGREG, TARGET_TEST_SWAPPER = 1, 2, 3, 4, 5, 6
-EXPLORER_NONE, EXPLORER_TOY, EXPLORER_SLICE, EXPLORER_AUTOMALA, EXPLORER_ISING_METROPOLIS = 0, 1, 2, 3, 4
+EXPLORER_NONE, EXPLORER_TOY, EXPLORER_SLICE, EXPLORER_AUTOMALA, EXPLORER_ISING_METROPOLIS, EXPLORER_MALA = 0, 1, 2, 3, 4, 5
 PRECOND_IDENTITY, PRECOND_DIAGONAL, PRECOND_MIX_DIAGONAL = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)

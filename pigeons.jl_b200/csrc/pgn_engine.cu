@@ -131,6 +131,7 @@ void* vec_kernel_for(int ex) {
     case PGN_EXPLORER_TOY: return TK == PGN_TARGET_TOY_MVN ? scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_TOY>>() : nullptr;
     case PGN_EXPLORER_SLICE: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_SLICE>>();
     case PGN_EXPLORER_AUTOMALA: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_AUTOMALA>>();
+    case PGN_EXPLORER_MALA: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_MALA>>();
     default: return nullptr;
   }
 }

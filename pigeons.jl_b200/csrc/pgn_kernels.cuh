@@ -475,22 +475,25 @@ struct VecChain {
     double a0, a1, lp1, h_after, eps;
   };
   // one leap_frog! + log_joint from (xs, ps) with conditioned gradient gs at xs;
-  // returns h_after - h_before (log_joint_difference_function :250-275)
-  __device__ double run_trial(const double (&xs)[CPL], const double (&ps)[CPL], const double (&gs)[CPL],
-                              const double (&pre)[CPL], double eps, double h_before, Trial& T) {
+  // returns h_after - h_before (log_joint_difference_function :250-275).
+  // pre_one: the preconditioner is exactly the identity, x / 1.0 == x bit for bit.
+  __device__ __forceinline__ double run_trial(const double (&xs)[CPL], const double (&ps)[CPL],
+                                              const double (&gs)[CPL], const double (&pre)[CPL], bool pre_one,
+                                              double eps, double h_before, Trial& T) {
     double ph[CPL];
     double pp = 0.0;
+    const double half_eps = eps / 2;
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
-      ph[k] = ps[k] + (eps / 2) * gs[k];
-      T.x1[k] = xs[k] + eps * (ph[k] / pre[k]);
-      if (valid(k)) pp = pp + ph[k] * ph[k];
+      ph[k] = ps[k] + half_eps * gs[k];
+      T.x1[k] = xs[k] + eps * (pre_one ? ph[k] : ph[k] / pre[k]);
+      pp = valid(k) ? pp + ph[k] * ph[k] : pp;
     }
     double graw[CPL];
     eval_grad(T.x1, beta, T.a0, T.a1, graw, pp);
     T.lp1 = lp_ad(beta, T.a0, T.a1);
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) T.g1c[k] = graw[k] / pre[k];
+    for (int k = 0; k < CPL; ++k) T.g1c[k] = pre_one ? graw[k] : graw[k] / pre[k];
     const double cur = T.lp1 - 0.5 * pp;
     double s2;
     if (!is_finite(cur)) {   // hamiltonian_dynamics.jl:56-59: early return, no last half-step
@@ -501,8 +504,8 @@ struct VecChain {
       double q = 0.0;
 #pragma unroll
       for (int k = 0; k < CPL; ++k) {
-        T.p1[k] = ph[k] + (eps / 2) * T.g1c[k];
-        if (valid(k)) q = q + T.p1[k] * T.p1[k];
+        T.p1[k] = ph[k] + half_eps * T.g1c[k];
+        q = valid(k) ? q + T.p1[k] * T.p1[k] : q;
       }
       s2 = warp_sum(q);
     }
@@ -510,41 +513,12 @@ struct VecChain {
     T.eps = eps;
     return T.h_after - h_before;
   }
-  // auto_step_size :184-248; returns the exponent, n_steps via reference
-  __device__ int search(const double (&xs)[CPL], const double (&ps)[CPL], const double (&gs)[CPL],
-                        const double (&pre)[CPL], double h_before, double lower, double upper, Trial& T,
-                        int& n_steps_out) {
-    n_steps_out = 0;
-    if (!(P->step_size > 0) || !(lower < upper)) { err = PGN_ERR_INVALID; return 0; }
-    double eps = P->step_size;
-    const double diff0 = run_trial(xs, ps, gs, pre, eps, h_before, T);
-    int exponent = 0;
-    if (!is_finite(diff0) || diff0 < lower) {          // shrink_step_size :228-248
-      int n = 1;
-      while (true) {
-        eps = eps / 2.0;
-        double diff = run_trial(xs, ps, gs, pre, eps, h_before, T);
-        if (eps == 0.0) { err = PGN_ERR_STEP_UNDERFLOW; return 0; }
-        if (diff > lower) { n_steps_out = n; exponent = -n; break; }
-        n += 1;
-      }
-    } else if (diff0 > upper) {                        // grow_step_size :216-226
-      int n = 1;
-      while (true) {
-        eps = eps * 2.0;
-        double diff = run_trial(xs, ps, gs, pre, eps, h_before, T);
-        if (!is_finite(diff) || diff < upper) { n_steps_out = n; exponent = n - 1; break; }
-        n += 1;
-      }
-    }
-    return exponent;
-  }
-  __device__ void build_preconditioner(double (&pre)[CPL]) {   // Preconditioner.jl:57-77
+  __device__ bool build_preconditioner(double (&pre)[CPL]) {   // Preconditioner.jl:57-77; returns "is identity"
     const bool have = P->std_devs != nullptr;
     if (!have || P->precond_kind == PGN_PRECOND_IDENTITY) {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pre[k] = 1.0;
-      return;
+      return true;
     }
     double sd[CPL];
 #pragma unroll
@@ -552,82 +526,170 @@ struct VecChain {
     if (P->precond_kind == PGN_PRECOND_DIAGONAL) {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : 1.0 / sd[k];
-      return;
+      return false;
     }
     const double u = next_uniform(rng);
     if (u <= P->mix_p0) {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : 1.0 / sd[k];
+      return false;
     } else if (u <= P->mix_p01) {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pre[k] = 1.0;
+      return true;
     } else {
       const double mix = next_uniform(rng);
       const double rmix = 1.0 - mix;
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : mix + rmix / sd[k];
+      return false;
     }
   }
-  __device__ void automala(bool use_mh) {   // auto_mala! :106-182
+  // auto_mala! :106-182.  The forward and the reversed step-size searches
+  // (auto_step_size :184-248) share ONE inlined copy of run_trial: `dir` selects the
+  // start point, `mode` walks initial -> shrink | grow -> (re-evaluate at the chosen
+  // step) exactly as shrink_step_size / grow_step_size do.
+  __device__ void automala(bool use_mh) {
     double pre[CPL];
-    build_preconditioner(pre);
+    const bool pre_one = build_preconditioner(pre);
     double g0[CPL];
     {
       double dummy = 0.0;
       double graw[CPL];
       eval_grad(x, beta, e0, e1, graw, dummy);
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) g0[k] = graw[k] / pre[k];
+      for (int k = 0; k < CPL; ++k) g0[k] = pre_one ? graw[k] : graw[k] / pre[k];
     }
     double lp0 = lp_ad(beta, e0, e1);
-    Trial T, R;
+    if (!(P->step_size > 0)) { err = PGN_ERR_INVALID; return; }
+    Trial T;
     for (int i = 0; i < P->n_refresh; ++i) {
       double p[CPL];
       double pp = 0.0;
 #pragma unroll
       for (int k = 0; k < CPL; ++k) {
         p[k] = valid(k) ? normal_at(rng, rng.ctr + (unsigned long long)(k * 32 + lane)) : 0.0;   // randn!(rng, momentum)
-        if (valid(k)) pp = pp + p[k] * p[k];
+        pp = valid(k) ? pp + p[k] * p[k] : pp;
+      }
+      rng.ctr += (unsigned long long)d;
+      // a, b (:132-133) and the MH uniform (:173) are the next three ticks of this replica's
+      // stream; lanes 0..2 draw them (and the logs of a, b) in one SIMT pass
+      double mine = uniform_at(rng, rng.ctr + (unsigned long long)(lane < 3 ? lane : 0));
+      double lmine = log_(mine);
+      rng.ctr += use_mh ? 3ull : 2ull;
+      const double a = __shfl_sync(PGN_FULL_MASK, mine, 0), b = __shfl_sync(PGN_FULL_MASK, mine, 1);
+      const double la = __shfl_sync(PGN_FULL_MASK, lmine, 0), lb = __shfl_sync(PGN_FULL_MASK, lmine, 1);
+      const double u_mh = __shfl_sync(PGN_FULL_MASK, mine, 2);
+      const double lower = a < b ? la : lb;     // log(min(a, b))
+      const double upper = a < b ? lb : la;     // log(max(a, b))
+      const double init_joint = lp0 - 0.5 * warp_sum(pp);
+      if (!is_finite(init_joint)) { err = PGN_ERR_NOT_POSITIVE; return; }
+      if (!(lower < upper)) { err = PGN_ERR_INVALID; return; }
+
+      double sx[CPL], sp[CPL], sg[CPL];     // start point of the current search
+      double fx[CPL], fg[CPL];              // forward proposal (kept across the reversed search)
+      double f_a0 = 0.0, f_a1 = 0.0, f_lp = 0.0, h_rev = 0.0;
+      int expo[2] = {0, 0};
+      double h_before = init_joint;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) { sx[k] = x[k]; sp[k] = p[k]; sg[k] = g0[k]; fx[k] = 0.0; fg[k] = 0.0; }
+      const int n_dir = use_mh ? 2 : 1;
+      for (int dir = 0; dir < n_dir; ++dir) {
+        int mode = 0, n = 0, exponent = 0, nst = 0;
+        double eps = P->step_size;
+        while (true) {
+          const double diff = run_trial(sx, sp, sg, pre, pre_one, eps, h_before, T);
+          bool decided = false;
+          if (mode == 0) {
+            if (!is_finite(diff) || diff < lower) { mode = 1; n = 1; eps = eps / 2.0; }
+            else if (diff > upper) { mode = 2; n = 1; eps = eps * 2.0; }
+            else decided = true;
+          } else if (mode == 1) {                         // shrink_step_size :228-248
+            if (eps == 0.0) { err = PGN_ERR_STEP_UNDERFLOW; return; }
+            if (diff > lower) { nst = n; exponent = -n; decided = true; }
+            else { n += 1; eps = eps / 2.0; }
+          } else if (mode == 2) {                         // grow_step_size :216-226
+            if (!is_finite(diff) || diff < upper) { nst = n; exponent = n - 1; decided = true; }
+            else { n += 1; eps = eps * 2.0; }
+          } else {
+            break;                                        // mode 3: re-evaluated at the chosen step
+          }
+          if (decided) {
+            const double eps_final = P->step_size * pow2(exponent);   // leap_frog! at the chosen step :144-151
+            if (T.eps == eps_final) break;
+            mode = 3; eps = eps_final;
+          }
+        }
+        n_steps += 1 + nst;
+        am.fit(pow2(exponent));
+        expo[dir] = exponent;
+        if (dir == 0) {
+          n_ref += 1 + 1 + 3 * (1 + nst) + 2;
+          h_rev = T.h_after;      // log_joint at (x1, -p1): same partial sums as h_after
+          h_before = h_rev;
+          f_a0 = T.a0; f_a1 = T.a1; f_lp = T.lp1;
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) {
+            fx[k] = T.x1[k]; fg[k] = T.g1c[k];
+            sx[k] = T.x1[k]; sp[k] = T.p1[k] * -1.0; sg[k] = T.g1c[k];   // momentum .*= -1.0 :155
+          }
+        } else {
+          n_ref += 1 + 3 * (1 + nst);
+        }
+      }
+      bool accept = true;
+      if (use_mh) {
+        const bool passed = (expo[1] == expo[0]);
+        rev.fit(passed ? 1.0 : 0.0);
+        double prob = 0.0;
+        if (passed) { double e = exp_(h_rev - init_joint); prob = 1.0 < e ? 1.0 : e; n_ref += 1; }
+        expl_acc.fit(prob);
+        accept = u_mh < prob;
+      }
+      if (accept) {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) { x[k] = fx[k]; g0[k] = fg[k]; }
+        e0 = f_a0; e1 = f_a1; lp0 = f_lp;
+      }
+    }
+  }
+
+  // mala! (src/explorers/MALA.jl:74-97): one leapfrog at the fixed step size + MH, n_refresh times
+  __device__ void mala() {
+    double pre[CPL];
+    const bool pre_one = build_preconditioner(pre);
+    double g0[CPL];
+    {
+      double dummy = 0.0;
+      double graw[CPL];
+      eval_grad(x, beta, e0, e1, graw, dummy);
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) g0[k] = pre_one ? graw[k] : graw[k] / pre[k];
+    }
+    double lp0 = lp_ad(beta, e0, e1);
+    Trial T;
+    for (int i = 0; i < P->n_refresh; ++i) {
+      double p[CPL];
+      double pp = 0.0;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        p[k] = valid(k) ? normal_at(rng, rng.ctr + (unsigned long long)(k * 32 + lane)) : 0.0;
+        pp = valid(k) ? pp + p[k] * p[k] : pp;
       }
       rng.ctr += (unsigned long long)d;
       const double init_joint = lp0 - 0.5 * warp_sum(pp);
       if (!is_finite(init_joint)) { err = PGN_ERR_NOT_POSITIVE; return; }
-      const double a = next_uniform(rng);
-      const double b = next_uniform(rng);
-      const double lower = log_(a < b ? a : b);
-      const double upper = log_(a < b ? b : a);
-      int nf = 0;
-      const int ef = search(x, p, g0, pre, init_joint, lower, upper, T, nf);
-      if (err) return;
-      n_steps += 1 + nf;
-      am.fit(pow2(ef));
-      const double eps_final = P->step_size * pow2(ef);
-      if (T.eps != eps_final) run_trial(x, p, g0, pre, eps_final, init_joint, T);   // leap_frog! at the chosen step :147-151
-      n_ref += 1 + 1 + 3 * (1 + nf) + 2;
-      bool accept = true;
-      if (use_mh) {
-        double pm[CPL];
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) pm[k] = T.p1[k] * -1.0;
-        const double h_rev = T.h_after;   // log_joint at (x1, -p1): same partial sums as h_after
-        int nr = 0;
-        const int er = search(T.x1, pm, T.g1c, pre, h_rev, lower, upper, R, nr);
-        if (err) return;
-        n_steps += 1 + nr;
-        am.fit(pow2(er));
-        const bool passed = (er == ef);
-        rev.fit(passed ? 1.0 : 0.0);
-        double prob = 0.0;
-        if (passed) { double e = exp_(h_rev - init_joint); prob = 1.0 < e ? 1.0 : e; }
-        expl_acc.fit(prob);
-        n_ref += 1 + 3 * (1 + nr) + (passed ? 1 : 0);
-        accept = next_uniform(rng) < prob;
-      }
-      if (accept) {
+      run_trial(x, p, g0, pre, pre_one, P->step_size, init_joint, T);
+      const double e = exp_(T.h_after - init_joint);   // final_joint_log at (x1, -p1) has the same partial sums
+      const double prob = 1.0 < e ? 1.0 : e;
+      expl_acc.fit(prob);
+      n_ref += 4;
+      if (next_uniform(rng) < prob) {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) { x[k] = T.x1[k]; g0[k] = T.g1c[k]; }
         e0 = T.a0; e1 = T.a1; lp0 = T.lp1;
       }
+      n_steps += 1;
     }
   }
 
@@ -636,6 +698,7 @@ struct VecChain {
     if (is_reference) { sample_iid(beta); eval(x, e0, e1); return; }
     if (EX == PGN_EXPLORER_TOY) { sample_iid(beta); eval(x, e0, e1); }
     else if (EX == PGN_EXPLORER_SLICE) slice_step();
+    else if (EX == PGN_EXPLORER_MALA) mala();
     else automala(scan != 1);   // AutoMALA.jl:87,102
   }
   // log_unnormalized_ratio (src/log_potentials/log_potentials.jl:43-51)
@@ -708,6 +771,12 @@ struct IsingChain {
     if (b == 1.0) return tgt;
     return (1.0 - b) * ref + b * tgt;
   }
+  __device__ __forceinline__ double lp_fast(int s) const {
+    const double tgt = P->p[0] * (double)s;
+    if (beta == 0.0) return 0.0 * (double)s;
+    if (beta == 1.0) return tgt;
+    return beta * tgt;
+  }
   __device__ void sample_iid() {   // examples/ising.jl:49-58
     const unsigned int mask = L >= 32 ? 0xffffffffu : ((1u << L) - 1u);
     row = lane < L ? (bits32_at(rng, rng.ctr + (unsigned long long)lane) & mask) : 0u;
@@ -725,11 +794,16 @@ struct IsingChain {
           const int me = sgn(cur, j);
           const int nb = sgn(up, j) + sgn(dn, j) + sgn(cur, jl) + sgn(cur, jr);
           const int S_new = S + (-me * nb - me * nb);
-          const double log_pr_before = lp(beta, S);
-          const double log_pr_after = lp(beta, S_new);
-          const double accept_ratio = exp_(log_pr_after - log_pr_before);
+          // lp_fast == lp bit for bit up to the sign of zero (adding the reference term
+          // (1-b)*(0.0*S) = +-0 to b*(beta_model*S) changes nothing); and exp_(delta) >= 1
+          // whenever delta >= 0, so that branch accepts without exp and without a draw,
+          // exactly like `accept_ratio < 1 && rand > accept_ratio` (examples/ising.jl:109-110).
+          const double delta = lp_fast(S_new) - lp_fast(S);
           bool reject = false;
-          if (accept_ratio < 1) reject = next_uniform(rng) > accept_ratio;
+          if (delta < 0.0 || delta != delta) {
+            const double accept_ratio = exp_(delta);
+            if (accept_ratio < 1) reject = next_uniform(rng) > accept_ratio;
+          }
           if (!reject) { cur ^= (1u << j); S = S_new; }
         }
         if (lane == i) row = cur;

@@ -55,10 +55,9 @@ __device__ __forceinline__ double pow2(int e) {
 }
 
 // exp(x): Cody-Waite reduction, degree-13 Taylor polynomial, Horner with fma.
+// Special cases are patched in with selects after the main path (no branches on
+// the critical path); the main path is harmless on NaN/inf inputs.
 __device__ __forceinline__ double exp_(double x) {
-  if (x != x) return x;
-  if (x > PGN_EXP_OVERFLOW) return PGN_INF;
-  if (x < PGN_EXP_UNDERFLOW) return 0.0;
   double kf = rint(x * PGN_INV_LN2);
   double r = fma(-kf, PGN_LN2_HI, x);
   r = fma(-kf, PGN_LN2_LO, r);
@@ -76,22 +75,24 @@ __device__ __forceinline__ double exp_(double x) {
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  return scale2(p, (int)kf);
+  int k = (int)kf;
+  k = k > 1100 ? 1100 : (k < -1100 ? -1100 : k);
+  double res = scale2(p, k);
+  res = x > PGN_EXP_OVERFLOW ? PGN_INF : res;
+  res = x < PGN_EXP_UNDERFLOW ? 0.0 : res;
+  res = x != x ? x : res;
+  return res;
 }
 
 // log(x): x = 2^k (1+f), s = f/(2+f), log(1+f) = f - hfsq + s (hfsq + R(s^2)).
+// Branch-free main path; special cases selected at the end.
 __device__ __forceinline__ double log_(double x) {
-  if (x != x) return x;
-  if (x < 0.0) return PGN_NAN;
-  if (x == 0.0) return -PGN_INF;
-  if (x == PGN_INF) return PGN_INF;
-  int k = 0;
+  const double x_in = x;
   unsigned long long ix = double_to_bits(x);
-  if (ix < 0x0010000000000000ULL) {
-    x = x * bits_to_double(0x4350000000000000ULL);
-    k -= 54;
-    ix = double_to_bits(x);
-  }
+  const bool sub = ix < 0x0010000000000000ULL;   // positive subnormal (or +0)
+  const double xs = x * bits_to_double(0x4350000000000000ULL);
+  ix = sub ? double_to_bits(xs) : ix;
+  int k = sub ? -54 : 0;
   unsigned int hx = (unsigned int)(ix >> 32);
   k += (int)(hx >> 20) - 1023;
   hx &= 0x000fffffu;
@@ -115,7 +116,12 @@ __device__ __forceinline__ double log_(double x) {
   double t2 = z * fma(w, fma(w, fma(w, LG7, LG5), LG3), LG1);
   double R = t2 + t1;
   double dk = (double)k;
-  return s * (hfsq + R) + dk * PGN_LN2_LO - hfsq + f + dk * PGN_LN2_HI;
+  double res = s * (hfsq + R) + dk * PGN_LN2_LO - hfsq + f + dk * PGN_LN2_HI;
+  res = x_in == PGN_INF ? PGN_INF : res;
+  res = x_in == 0.0 ? -PGN_INF : res;
+  res = x_in < 0.0 ? PGN_NAN : res;
+  res = x_in != x_in ? x_in : res;
+  return res;
 }
 
 __device__ __forceinline__ double sin_kernel(double y) {
@@ -225,16 +231,49 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(PGN_FULL_MASK, v, off);
   return v;
 }
+// Sum NV values over the warp.  Same binary tree per value as warp_sum (pairs
+// (l, l^16), then (l, l^8), ...), but evaluated as a reduce-scatter: at each of
+// the first log2(NV) levels a lane keeps half of its values and ships the other
+// half, so the shuffle count is NV/2 + NV/4 + ... instead of 5*NV; the totals are
+// then broadcast.  fp addition is commutative, so every total is bit-identical to
+// the plain butterfly's.
+template <int NV, int OFF>
+struct ReduceScatter {
+  static __device__ __forceinline__ void run(double* v, int lane) {
+    if constexpr (OFF >= 1) {
+      if constexpr (NV > 1) {
+        constexpr int H = NV / 2;
+        const bool hi = (lane & OFF) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          const double keep = hi ? v[H + i] : v[i];
+          const double send = hi ? v[i] : v[H + i];
+          v[i] = keep + __shfl_xor_sync(PGN_FULL_MASK, send, OFF);
+        }
+        ReduceScatter<H, OFF / 2>::run(v, lane);
+      } else {
+        v[0] = v[0] + __shfl_xor_sync(PGN_FULL_MASK, v[0], OFF);
+        ReduceScatter<1, OFF / 2>::run(v, lane);
+      }
+    }
+  }
+};
+template <int NV> struct Log2 { static constexpr int value = 1 + Log2<NV / 2>::value; };
+template <> struct Log2<1> { static constexpr int value = 0; };
+
+// NP = NV rounded up to a power of two (2, 4, 8 or 16)
 template <int NV>
 __device__ __forceinline__ void warp_sum_n(double (&v)[NV]) {
+  constexpr int NP = NV <= 2 ? 2 : (NV <= 4 ? 4 : (NV <= 8 ? 8 : 16));
+  static_assert(NV <= 16, "warp_sum_n supports at most 16 values");
+  const int lane = threadIdx.x & 31;
+  double w[NP];
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    double o[NV];
+  for (int i = 0; i < NP; ++i) w[i] = i < NV ? v[i] : 0.0;
+  ReduceScatter<NP, 16>::run(w, lane);
+  constexpr int SH = 5 - Log2<NP>::value;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) o[i] = __shfl_xor_sync(PGN_FULL_MASK, v[i], off);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = v[i] + o[i];
-  }
+  for (int i = 0; i < NV; ++i) v[i] = __shfl_sync(PGN_FULL_MASK, w[0], i << SH);
 }
 
 }  // namespace pgn

@@ -91,6 +91,34 @@ class AutoMALA:
 
 
 @dataclass(frozen=True)
+class MALA:
+    """src/explorers/MALA.jl:19-55: fixed step size, preconditioner adapted every round."""
+    base_n_refresh: int = 3
+    exponent_n_refresh: float = 0.35
+    step_size: float = 1.0
+    preconditioner: object = field(default_factory=MixDiagonalPreconditioner)
+    estimated_target_std_deviations: Optional[tuple] = None
+
+    def n_refresh(self, dim: int) -> int:          # MALA.jl:80
+        return self.base_n_refresh * math.ceil(dim ** self.exponent_n_refresh)
+
+    def engine_params(self, dim: int) -> dict:
+        pc = self.preconditioner
+        sd = None if self.estimated_target_std_deviations is None else np.asarray(self.estimated_target_std_deviations)
+        p0 = getattr(pc, "p0", 1.0 / 3.0)
+        p1 = getattr(pc, "p1", 1.0 / 3.0)
+        return dict(kind=_capi.EXPLORER_MALA, n_refresh=self.n_refresh(dim), step_size=self.step_size,
+                    precond_kind=pc.kind, mix_p0=p0, mix_p01=p0 + p1, std_devs=sd)
+
+    def adapt(self, round_result) -> "MALA":
+        """adapt_explorer (MALA.jl:57-63): only the preconditioner's std devs change."""
+        sd = None
+        if self.preconditioner.kind != _capi.PRECOND_IDENTITY:
+            sd = tuple(np.sqrt(np.asarray(round_result.online_var)).tolist())
+        return replace(self, estimated_target_std_deviations=sd)
+
+
+@dataclass(frozen=True)
 class IsingMetropolis:
     """examples/ising.jl:91-93."""
     n_steps: int = 3

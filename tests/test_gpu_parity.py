@@ -64,6 +64,9 @@ CASES = {
     "gmm6_slice": dict(target=pg.eight_mode_mixture(6, 3.0), explorer=pg.SliceSampler(), n_chains=8, n_rounds=5, seed=2),
     "gmm2_two_modes": dict(target=pg.GaussianMixture(means=[[-8.0, -8.0], [8.0, 8.0]], reference_sigma=8.0),
                            explorer=pg.AutoMALA(), n_chains=5, n_rounds=7, seed=3),
+    "toy10_mala": dict(target=pg.toy_mvn_target(10), explorer=pg.MALA(step_size=0.3), n_chains=6, n_rounds=7, seed=11),
+    "funnel16_mala": dict(target=pg.Funnel(16), explorer=pg.MALA(step_size=0.2), n_chains=8, n_rounds=6, seed=12),
+    "gmm70_mala_4cpl": dict(target=pg.eight_mode_mixture(70, 4.0), explorer=pg.MALA(step_size=0.5), n_chains=6, n_rounds=5, seed=13),
     "ising5": dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=7, seed=1),
     "ising32": dict(target=pg.IsingLogPotential(0.44, 32), n_chains=6, n_rounds=3, seed=2),
     "test_swapper": dict(target=pg.TestSwapper(0.6), n_chains=9, n_rounds=8, seed=7, record=[pg.index_process, pg.swap_trace]),
