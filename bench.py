@@ -47,6 +47,10 @@ CONFIGS = {
                kernel="pgn::scan_kernel<IsingChain>",
                workload="C4: Ising 32x32 torus (examples/ising.jl), beta = log(1+sqrt 2)/2 (critical), "
                         "IsingMetropolis(n_steps=3), 512 chains per GPU (4096 on 8 GPUs)"),
+    "c5": dict(chains_per_gpu=256, dim=4096, explorer="AutoMALA", state_bytes=4096 * 8, n_data=65536,
+               kernel="pgn::dgemm_km_kernel<0/1> (two FP64 GEMMs per batched evaluation) + logreg_controller_kernel",
+               workload="C5: synthetic logistic regression d=4096, N_data=65536 (X ~ N(0,1)/sqrt d), prior N(0,I), "
+                        "AutoMALA defaults, 256 chains per GPU"),
 }
 CFG = CONFIGS["c2"]
 CHAINS_PER_GPU = CFG["chains_per_gpu"]
@@ -67,6 +71,8 @@ def make_target_and_explorer(pg, name):
         return pg.Funnel(32), pg.AutoMALA()
     if name == "c3":
         return pg.eight_mode_mixture(128, 8.0), pg.AutoMALA()
+    if name == "c5":
+        return pg.synthetic_logistic_regression(CFG["n_data"], CFG["dim"]), pg.AutoMALA()
     return pg.IsingLogPotential(0.4406867935097715, 32), pg.IsingMetropolis()
 
 
@@ -137,12 +143,14 @@ class ClockSampler:
 
 
 CFG_NAME = "c2"
+BURN_ROUNDS_OVERRIDE = None
 
 
 def build_problem(pg, lib, n_chains, comm, device, seed=1):
     """C2 workload: create the PT object and run the untimed adaptive burn-in."""
     target, explorer = make_target_and_explorer(pg, CFG_NAME)
-    inputs = pg.Inputs(target=target, explorer=explorer, n_chains=n_chains, n_rounds=BURN_IN_ROUNDS,
+    inputs = pg.Inputs(target=target, explorer=explorer, n_chains=n_chains,
+                       n_rounds=BURN_ROUNDS_OVERRIDE if BURN_ROUNDS_OVERRIDE is not None else BURN_IN_ROUNDS,
                        seed=seed, engine_lib=lib, device=device, comm=comm)
     pt = pg.create_pt(inputs)
     pt = pg.pigeons_pt(pt)
@@ -202,15 +210,22 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--scans", type=int, default=1024, help="PT scans per step (one run_round call)")
+    ap.add_argument("--scans", type=int, default=None, help="PT scans per step (one run_round call); default 1024 (c5: 1)")
+    ap.add_argument("--burn-rounds", type=int, default=None, help="adaptive burn-in rounds before timing (default 8; c5: 2)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config (default c2)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU baseline (0 = pick the fastest of a sweep)")
     args = ap.parse_args()
-    global CFG_NAME
+    global CFG_NAME, BURN_ROUNDS_OVERRIDE
     CFG_NAME = args.config
     select_config(args.config)
+    if args.burn_rounds is not None:
+        BURN_ROUNDS_OVERRIDE = args.burn_rounds
+    elif args.config == "c5":
+        BURN_ROUNDS_OVERRIDE = 2          # a C5 scan is seconds of FP64 GEMMs
+    if args.scans is None:
+        args.scans = 1 if args.config == "c5" else 1024
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,7 +235,7 @@ def main():
     n_chains = CHAINS_PER_GPU * max(args.gpus, 1)
     config = {"workload": CFG["workload"],
               "n_chains": n_chains, "dim": DIM, "explorer": CFG["explorer"], "scans_per_step": args.scans,
-              "burn_in_rounds": BURN_IN_ROUNDS, "parallelism": f"chains/{args.gpus}",
+              "burn_in_rounds": BURN_ROUNDS_OVERRIDE if BURN_ROUNDS_OVERRIDE is not None else BURN_IN_ROUNDS, "parallelism": f"chains/{args.gpus}",
               "scan_unit": f"one PT scan of {CHAINS_PER_GPU} chains; with N GPUs the ladder has {CHAINS_PER_GPU}*N chains "
                            "and value = N * ladder scans/s",
               "l2": "flushed between timed steps (256 MiB write); the working set is register-resident"}
@@ -275,6 +290,7 @@ def main():
         sampler.start()
     sync_all()
     kernel_ms, wall_s = 0.0, 0.0
+    gemm_ms, batch_steps = 0.0, 0
     pts = evals = 0
     t_region0 = time.perf_counter()
     for _ in range(args.steps):
@@ -284,6 +300,8 @@ def main():
         r = one_step(pt, pg, args.scans)     # synchronous: returns after the stream sync + D2H of the statistics
         wall_s += time.perf_counter() - t0
         kernel_ms += r.kernel_ms
+        gemm_ms += r.gemm_ms
+        batch_steps += r.batch_steps
         pts += r.n_density_points
         evals += r.n_ref_equiv_evals
     sync_all()
@@ -334,7 +352,17 @@ def main():
         "clocks": clocks,
         "timed_region_s": t_region,
     }
-    if not args.no_cpu_baseline and args.gpus == 1:
+    if CFG_NAME == "c5" and batch_steps > 0:
+        flops_per_batch = 2 * 2.0 * CFG["n_data"] * CFG["dim"] * CHAINS_PER_GPU      # two GEMMs, 2 flops per fma
+        fp64_peak = lib.measure_fp64_peak(local_rank)
+        line["fp64_roofline"] = {
+            "bound": "fp64 fma (tcgen05 has no FP64 path; SIMT DFMA GEMM with a fixed summation order)",
+            "achieved_tflops": flops_per_batch * batch_steps / (gemm_ms * 1e-3) / 1e12,
+            "peak_tflops": fp64_peak, "peak_source": "measured in-run: register-resident DFMA loop on all SMs",
+            "frac": flops_per_batch * batch_steps / (gemm_ms * 1e-3) / 1e12 / fp64_peak,
+            "gemm_share_of_kernel_time": gemm_ms / kernel_ms, "batched_evaluations": batch_steps,
+            "flops_per_batched_evaluation": flops_per_batch}
+    if not args.no_cpu_baseline and args.gpus == 1 and CFG_NAME != "c5":
         cpt, clib, n_threads, scans = cpu_reference_run(pg, args.scans, CHAINS_PER_GPU, threads=args.cpu_threads, budget_s=12.0,
                                                           clone_from=pt)
         r = one_step(cpt, pg, scans)

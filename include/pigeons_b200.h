@@ -161,6 +161,8 @@ typedef struct pgn_round_out {
   int64_t n_density_points;   /* distinct (state) points at which the device evaluated ref+target densities */
   int64_t n_ref_equiv_evals;  /* log_potential / logdensity[_and_gradient] calls the reference code path would have made */
   double kernel_ms;           /* CUDA-event duration of the scan kernel(s) of this round */
+  double gemm_ms;             /* LOGREG: device time inside the two FP64 GEMMs of this round (0 otherwise) */
+  int64_t batch_steps;        /* LOGREG: number of batched density/gradient evaluations (0 otherwise) */
 } pgn_round_out;
 
 /* Replica state for checkpoint / inspection, in chain order:
@@ -221,6 +223,10 @@ int pgn_ipc_export(pgn_handle* h, void* handle64, char** err);
 int pgn_ipc_attach(pgn_handle* h, int32_t side /*0=left,1=right*/, const void* handle64, char** err);
 /* same-process multi-GPU (tests): attach another handle's mailbox directly */
 int pgn_peer_attach(pgn_handle* h, int32_t side, pgn_handle* neighbour, char** err);
+
+/* Measured FP64 FMA throughput of the device (register-resident DFMA loop, all SMs):
+ * the roofline denominator for the GEMM-shaped LOGREG path. */
+int pgn_measure_fp64_peak(int32_t device, double* tflops, char** err);
 
 /* Numerics self-test hook: evaluates the device elementary functions / RNG
  * (op: 0 exp, 1 log, 2 cospi, 3 normal_at(ctr), 4 uniform_at(ctr),

@@ -108,6 +108,7 @@ struct ChainStats {
 struct Engine {
   pgn_config cfg{};
   std::vector<double> means, log_w;
+  std::vector<double> data_x, data_y;   // LOGREG: X [n_data][d] row-major, y [n_data]
   pgn_explorer_params ep{};
   std::vector<double> std_devs;
   bool have_std = false;
@@ -131,7 +132,8 @@ struct Engine {
     const double* x = r.x.data();
     switch (cfg.target_kind) {
       case PGN_TARGET_FUNNEL:
-      case PGN_TARGET_GMM: {
+      case PGN_TARGET_GMM:
+      case PGN_TARGET_LOGREG: {
         const double iv = cfg.p[5], ls = cfg.p[4];
         return tree_sum(d(), [&](int c) { return -(x[c] * x[c] * iv + LOG2PI) * 0.5 - ls; });
       }
@@ -140,9 +142,79 @@ struct Engine {
       default: return QNAN;
     }
   }
+  // ---- logistic regression (BASELINE config 5; analytic-gradient target in the style of
+  // test/test_custom_gradient.jl:1-33): target = N(0, s^2 I) prior x Bernoulli(sigmoid(X theta)).
+  // Summation orders are part of the arithmetic spec (they are what the device GEMMs do):
+  //   z_n      : sequential fma over c = 0..d-1 starting from 0.0
+  //   sum_n ll : rows in tiles of 128; inside a tile the canonical 32-lane tree
+  //              (lane = row % 32); tile sums added in tile order
+  //   G[c]     : rows in chunks of 4096, sequential fma inside a chunk starting from 0.0,
+  //              chunk partials added in chunk order
+  static constexpr int LR_TILE = 128, LR_CHUNK = 4096;
+  int n_data() const { return (int)cfg.p[0]; }
+  void logreg_z(const double* x, std::vector<double>& z) const {
+    const int n = n_data(), dd = d();
+    z.assign(n, 0.0);
+    // each z_i is ONE sequential fma chain over c; eight rows are interleaved only to give the
+    // CPU independent chains to pipeline (the per-row order is unchanged)
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+      const double* row = &data_x[(size_t)i * dd];
+      double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < dd; ++c) {
+        const double xc = x[c];
+        for (int j = 0; j < 8; ++j) a[j] = std::fma(row[(size_t)j * dd + c], xc, a[j]);
+      }
+      for (int j = 0; j < 8; ++j) z[i + j] = a[j];
+    }
+    for (; i < n; ++i) {
+      const double* row = &data_x[(size_t)i * dd];
+      double acc = 0.0;
+      for (int c = 0; c < dd; ++c) acc = std::fma(row[c], x[c], acc);
+      z[i] = acc;
+    }
+  }
+  static void logreg_terms(double z, double y, double& ll, double& resid) {
+    const double az = z < 0.0 ? -z : z;
+    const double t = exp_(-az);
+    const double sp = (z > 0.0 ? z : 0.0) + log1p_(t);         // softplus(z)
+    const double sig = z >= 0.0 ? 1.0 / (1.0 + t) : t / (1.0 + t);
+    ll = y * z - sp;
+    resid = y - sig;
+  }
+  double logreg_lik(const double* x, double* grad_lik) const {
+    const int n = n_data(), dd = d();
+    std::vector<double> z, ll(n), rs(n);
+    logreg_z(x, z);
+    for (int i = 0; i < n; ++i) logreg_terms(z[i], data_y[i], ll[i], rs[i]);
+    double total = 0.0;
+    for (int t0 = 0; t0 < n; t0 += LR_TILE) {
+      const int len = std::min(LR_TILE, n - t0);
+      total = total + tree_sum(len, [&](int i) { return ll[t0 + i]; });
+    }
+    if (grad_lik) {
+      // G[c] = sum over 4096-row chunks (in order) of the chunk's sequential fma chain over rows;
+      // the loops are ordered row-major for the cache, each G[c] still sees its rows in ascending order
+      std::vector<double> part(dd);
+      for (int c = 0; c < dd; ++c) grad_lik[c] = 0.0;
+      for (int k0 = 0; k0 < n; k0 += LR_CHUNK) {
+        const int k1 = std::min(n, k0 + LR_CHUNK);
+        std::fill(part.begin(), part.end(), 0.0);
+        for (int i = k0; i < k1; ++i) {
+          const double* row = &data_x[(size_t)i * dd];
+          const double ri = rs[i];
+          for (int c = 0; c < dd; ++c) part[c] = std::fma(row[c], ri, part[c]);
+        }
+        for (int c = 0; c < dd; ++c) grad_lik[c] = grad_lik[c] + part[c];
+      }
+    }
+    return total;
+  }
+
   double tgt_density(const Replica& r) const {
     const double* x = r.x.data();
     switch (cfg.target_kind) {
+      case PGN_TARGET_LOGREG: return ref_density(r) + logreg_lik(x, nullptr);
       case PGN_TARGET_FUNNEL: {
         const double y = x[0];
         const double e = exp_(-y);
@@ -182,6 +254,13 @@ struct Engine {
   double tgt_density_grad(const Replica& r, double* g) const {
     const double* x = r.x.data();
     switch (cfg.target_kind) {
+      case PGN_TARGET_LOGREG: {
+        std::vector<double> gl(d());
+        const double lik = logreg_lik(x, gl.data());
+        const double iv = cfg.p[5];
+        for (int c = 0; c < d(); ++c) g[c] = -x[c] * iv + gl[c];
+        return ref_density(r) + lik;
+      }
       case PGN_TARGET_FUNNEL: {
         const double y = x[0];
         const double e = exp_(-y);
@@ -326,7 +405,8 @@ struct Engine {
         break;
       }
       case PGN_TARGET_FUNNEL:
-      case PGN_TARGET_GMM: {       // DistributionLogPotential.jl:26-27 (rand!(rng, MvNormal(0, s^2 I), x))
+      case PGN_TARGET_GMM:
+      case PGN_TARGET_LOGREG: {    // DistributionLogPotential.jl:26-27 (rand!(rng, MvNormal(0, s^2 I), x))
         double sg = cfg.p[3];
         for (int c = 0; c < dd; ++c) r.x[c] = sg * normal_at(r.rng, r.ctr + c);
         r.ctr += dd;
@@ -801,6 +881,8 @@ void run_round(Engine& E, int64_t n_scans, pgn_round_out* out) {
   out->n_ref_equiv_evals = total_ref_evals;
   out->n_density_points = 0;
   out->kernel_ms = 0.0;
+  out->gemm_ms = 0.0;
+  out->batch_steps = 0;
 }
 
 int fail(char** err, int code, const std::string& msg) {
@@ -826,7 +908,8 @@ int orc_create(const pgn_config* cfg, orc_handle** out, char** err) {
   if (cfg->abi_version != PGN_ABI_VERSION) return fail(err, PGN_ERR_INVALID, "ABI version mismatch");
   if (cfg->world_size != 1 || cfg->rank != 0) return fail(err, PGN_ERR_INVALID, "oracle is single-process");
   if (cfg->n_chains < 1) return fail(err, PGN_ERR_INVALID, "n_chains must be >= 1");
-  if (cfg->target_kind == PGN_TARGET_LOGREG) return fail(err, PGN_ERR_INVALID, "LOGREG not implemented");
+  if (cfg->target_kind == PGN_TARGET_LOGREG && (!cfg->data_x || !cfg->data_y || cfg->p[0] < 1))
+    return fail(err, PGN_ERR_INVALID, "LOGREG: data_x / data_y / n_data missing");
   if (cfg->target_kind == PGN_TARGET_GMM && (cfg->n_modes < 1 || cfg->n_modes > 64))
     return fail(err, PGN_ERR_INVALID, "GMM: 1 <= n_modes <= 64");
   if (cfg->target_kind == PGN_TARGET_ISING) {
@@ -839,6 +922,11 @@ int orc_create(const pgn_config* cfg, orc_handle** out, char** err) {
   if (cfg->target_kind == PGN_TARGET_GMM) {
     E.means.assign(cfg->means, cfg->means + (size_t)cfg->n_modes * cfg->dim);
     E.log_w.assign(cfg->log_weights, cfg->log_weights + cfg->n_modes);
+  }
+  if (cfg->target_kind == PGN_TARGET_LOGREG) {
+    const size_t n = (size_t)cfg->p[0];
+    E.data_x.assign(cfg->data_x, cfg->data_x + n * cfg->dim);
+    E.data_y.assign(cfg->data_y, cfg->data_y + n);
   }
   E.cfg.means = E.cfg.log_weights = E.cfg.data_x = E.cfg.data_y = nullptr;
   E.beta.assign(cfg->n_chains, 0.0);

@@ -68,6 +68,7 @@ class pgn_round_out(C.Structure):
         ("index_process", _i32p), ("swap_lr", _dp), ("swap_u", _dp), ("swap_accept", _u8p),
         ("target_trace", _dp),
         ("n_density_points", C.c_int64), ("n_ref_equiv_evals", C.c_int64), ("kernel_ms", C.c_double),
+        ("gemm_ms", C.c_double), ("batch_steps", C.c_int64),
     ]
 
 
@@ -85,7 +86,7 @@ DECLARED_SYMBOLS = [
     "pgn_abi_version", "pgn_create", "pgn_destroy", "pgn_free_string", "pgn_device_info", "pgn_local_range",
     "pgn_set_schedule", "pgn_set_explorer", "pgn_init_replicas", "pgn_get_state", "pgn_set_state",
     "pgn_run_round", "pgn_log_potential", "pgn_logdensity_and_gradient", "pgn_ipc_export", "pgn_ipc_attach",
-    "pgn_peer_attach", "pgn_test_math",
+    "pgn_peer_attach", "pgn_test_math", "pgn_measure_fp64_peak",
 ]
 
 
@@ -141,6 +142,13 @@ class EngineLib:
         rc = self.fn(name)(*args, C.byref(err))
         self.check(rc, err)
 
+    def measure_fp64_peak(self, device: int = 0) -> float:
+        v = C.c_double()
+        f = self.fn("measure_fp64_peak")
+        f.restype = C.c_int
+        self.call("measure_fp64_peak", C.c_int32(device), C.byref(v))
+        return v.value
+
     def test_math(self, op: int, values, seed: int = 1, replica_index: int = 1, device: int = 0) -> np.ndarray:
         v = np.ascontiguousarray(values, dtype=np.float64)
         n = v.size // 2 if op == 6 else v.size
@@ -180,6 +188,8 @@ class RoundResult:
     n_ref_equiv_evals: int
     kernel_ms: float
     wall_s: float = 0.0
+    gemm_ms: float = 0.0
+    batch_steps: int = 0
 
 
 class Engine:
@@ -304,6 +314,7 @@ class Engine:
         res.online_n = out.online_n
         res.n_density_points, res.n_ref_equiv_evals = out.n_density_points, out.n_ref_equiv_evals
         res.kernel_ms = out.kernel_ms
+        res.gemm_ms, res.batch_steps = out.gemm_ms, out.batch_steps
         return res
 
     # -- parity entry points -------------------------------------------------------

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "pgn_kernels.cuh"
+#include "pgn_logreg.cuh"
 
 using namespace pgn;
 
@@ -92,6 +93,14 @@ struct pgn_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool initialised = false;
   unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+  // ---- logistic regression (batched GEMM path)
+  int lr_n_data = 0, lr_n_pad = 0, lr_r_pad = 0, lr_splits = 0;
+  DevBuf<double> lr_Xr, lr_Xt, lr_y, lr_Theta, lr_Thetat, lr_LL, lr_Res, lr_lik, lr_Gp, lr_G;
+  DevBuf<double> lr_P, lr_G0, lr_SX, lr_SP, lr_SG, lr_TP, lr_TG, lr_FX, lr_FG;
+  DevBuf<LrChainState> lr_st;
+  DevBuf<int> lr_n_active;
+  double last_gemm_ms = 0.0;     // device time spent in the two GEMMs during the last round
+  long long last_batch_steps = 0;
 };
 
 namespace {
@@ -120,6 +129,197 @@ void fill_params(pgn_handle* h, Params& P) {
   P.online_mean = h->online_mean.p; P.online_s2 = h->online_s2.p; P.online_n = h->online_n.p;
   P.error_flag = h->error_flag.p;
   P.timeout_ns = h->timeout_ns;
+}
+
+// ===========================================================================
+// logistic regression: batched-GEMM engine (pgn_logreg.cuh)
+// ===========================================================================
+constexpr size_t GEMM_SMEM_BYTES = 2ull * 2 * GEMM_BK * GEMM_BM * sizeof(double);
+
+void logreg_allocate(pgn_handle* h, const pgn_config* cfg) {
+  const int d = cfg->dim, dp = h->d_pad;
+  const int n = (int)cfg->p[0];
+  const int np = (n + 127) / 128 * 128;
+  const int rp = (h->n_local + 127) / 128 * 128;
+  h->lr_n_data = n; h->lr_n_pad = np; h->lr_r_pad = rp;
+  h->lr_splits = (np + LR_CHUNK - 1) / LR_CHUNK;
+  // X row-major padded [np][dp] (K-major operand of the gradient GEMM) and its transpose [dp][np]
+  {
+    std::vector<double> xr((size_t)np * dp, 0.0);
+    for (int i = 0; i < n; ++i) std::memcpy(&xr[(size_t)i * dp], cfg->data_x + (size_t)i * d, sizeof(double) * d);
+    h->lr_Xr.alloc(xr.size(), false);
+    h->lr_Xr.upload(xr.data(), xr.size());
+  }
+  h->lr_Xt.alloc((size_t)dp * np, false);
+  {
+    dim3 grid((dp + 31) / 32, (np + 31) / 32), block(32, 8);
+    logreg_transpose_kernel<<<grid, block>>>(h->lr_Xr.p, np, dp, dp, h->lr_Xt.p, np);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaDeviceSynchronize());
+  }
+  h->lr_y.alloc(np);
+  h->lr_y.upload(cfg->data_y, n);
+  const size_t vec = (size_t)rp * dp;
+  h->lr_Theta.alloc(vec); h->lr_Thetat.alloc(vec);
+  h->lr_LL.alloc((size_t)np * rp, false); h->lr_Res.alloc((size_t)np * rp, false);
+  h->lr_lik.alloc(rp);
+  h->lr_Gp.alloc((size_t)h->lr_splits * dp * rp, false);
+  h->lr_G.alloc(vec);
+  h->lr_P.alloc(vec); h->lr_G0.alloc(vec); h->lr_SX.alloc(vec); h->lr_SP.alloc(vec); h->lr_SG.alloc(vec);
+  h->lr_TP.alloc(vec); h->lr_TG.alloc(vec); h->lr_FX.alloc(vec); h->lr_FG.alloc(vec);
+  h->lr_st.alloc(h->n_local);
+  h->lr_n_active.alloc(1);
+  CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
+}
+
+// Evaluate likelihood and its gradient at the rows of `theta` ([r_pad][d_pad]) for all columns:
+// lr_lik[r], lr_G[r][:].  Returns the device time of the two GEMMs through `gemm_ms`.
+void logreg_eval_batch(pgn_handle* h, const double* theta, cudaEvent_t e0, cudaEvent_t e1) {
+  const int dp = h->d_pad, np = h->lr_n_pad, rp = h->lr_r_pad;
+  {
+    dim3 grid((dp + 31) / 32, (rp + 31) / 32), block(32, 8);
+    logreg_transpose_kernel<<<grid, block, 0, h->stream>>>(theta, rp, dp, dp, h->lr_Thetat.p, rp);
+  }
+  if (e0) CUDA_CHECK(cudaEventRecord(e0, h->stream));
+  {
+    dim3 grid(np / GEMM_BM, rp / GEMM_BN, 1);
+    dgemm_km_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
+        h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, h->lr_Res.p, rp, 0, h->lr_y.p, h->lr_n_data);
+  }
+  logreg_reduce_ll_kernel<<<(rp + 7) / 8, 256, 0, h->stream>>>(h->lr_LL.p, rp, h->lr_n_data, rp, h->lr_lik.p);
+  {
+    dim3 grid(dp / GEMM_BM, rp / GEMM_BN, h->lr_splits);
+    dgemm_km_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
+        h->lr_Xr.p, dp, h->lr_Res.p, rp, np, LR_CHUNK, h->lr_Gp.p, nullptr, rp, (size_t)dp * rp, nullptr, 0);
+  }
+  if (e1) CUDA_CHECK(cudaEventRecord(e1, h->stream));
+  {
+    dim3 grid((dp + 31) / 32, (rp + 31) / 32), block(32, 8);
+    logreg_finalize_grad_kernel<<<grid, block, 0, h->stream>>>(h->lr_Gp.p, h->lr_splits, (size_t)dp * rp, rp, dp, rp,
+                                                              h->lr_G.p);
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void logreg_fill_params(pgn_handle* h, LrParams& P) {
+  std::memset(&P, 0, sizeof(P));
+  P.d = h->cfg.dim; P.d_pad = h->d_pad; P.n_chains = h->cfg.n_chains; P.first_chain = h->first_chain;
+  P.n_local = h->n_local; P.r_pad = h->lr_r_pad;
+  P.explorer_kind = h->ep.kind;
+  P.seed_lo = (unsigned int)(unsigned long long)h->cfg.seed;
+  P.seed_hi = (unsigned int)((unsigned long long)h->cfg.seed >> 32);
+  P.epoch = h->epoch;
+  P.sigma_ref = h->cfg.p[3]; P.ls_ref = h->cfg.p[4]; P.iv_ref = h->cfg.p[5];
+  P.n_refresh = h->ep.n_refresh; P.step_size = h->ep.step_size; P.precond_kind = h->ep.precond_kind;
+  P.mix_p0 = h->ep.mix_p0; P.mix_p01 = h->ep.mix_p01;
+  P.std_devs = h->have_std ? h->std_devs.p : nullptr;
+  P.beta = h->beta.p;
+  P.st = h->lr_st.p;
+  P.X = h->x.p; P.P = h->lr_P.p; P.G0 = h->lr_G0.p; P.SX = h->lr_SX.p; P.SP = h->lr_SP.p; P.SG = h->lr_SG.p;
+  P.TP = h->lr_TP.p; P.TG = h->lr_TG.p; P.FX = h->lr_FX.p; P.FG = h->lr_FG.p; P.TX = h->lr_Theta.p;
+  P.lik = h->lr_lik.p; P.G = h->lr_G.p;
+  P.n_active = h->lr_n_active.p; P.error_flag = h->error_flag.p;
+  P.mail = h->mail.p; P.mail_left = h->mail_left; P.mail_right = h->mail_right; P.slot_bytes = h->slot_bytes;
+  P.online_mean = h->online_mean.p; P.online_s2 = h->online_s2.p; P.online_n = h->online_n.p;
+  P.timeout_ns = 600ull * 1000ull * 1000ull * 1000ull;   // scans take seconds here; neighbours may lag
+}
+
+// run_one_round! for the logistic-regression target
+void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<ChainStatsDev>& st_out, float& total_ms) {
+  const int nl = h->n_local;
+  if (h->ep.kind != PGN_EXPLORER_AUTOMALA && h->ep.kind != PGN_EXPLORER_MALA)
+    throw CudaError{PGN_ERR_INVALID, "LOGREG supports the AutoMALA and MALA explorers"};
+  // chain state from the replica arrays
+  std::vector<int> ri(nl), rt(nl);
+  std::vector<unsigned long long> ctr(nl);
+  h->replica_index.download(ri.data(), nl);
+  h->rng_ctr.download(ctr.data(), nl);
+  std::vector<LrChainState> st(nl);
+  std::memset(st.data(), 0, sizeof(LrChainState) * nl);
+  for (int i = 0; i < nl; ++i) {
+    st[i].phase = LR_SCAN_START;
+    st[i].replica_index = ri[i]; st[i].ctr = ctr[i]; st[i].rt_state = 0;
+    st[i].ls_fwd.value = -INFINITY; st[i].ls_bwd.value = -INFINITY;
+  }
+  h->lr_st.upload(st.data(), nl);
+  CUDA_CHECK(cudaMemsetAsync(h->online_mean.p, 0, sizeof(double) * h->d_pad, h->stream));
+  CUDA_CHECK(cudaMemsetAsync(h->online_s2.p, 0, sizeof(double) * h->d_pad, h->stream));
+  CUDA_CHECK(cudaMemsetAsync(h->online_n.p, 0, sizeof(long long), h->stream));
+  cudaEvent_t g0, g1;
+  CUDA_CHECK(cudaEventCreate(&g0));
+  CUDA_CHECK(cudaEventCreate(&g1));
+  h->last_gemm_ms = 0.0;
+  h->last_batch_steps = 0;
+  const int wpb = 4, grid = (nl + wpb - 1) / wpb;
+  CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  int flag = 0;
+  for (int64_t scan = 1; scan <= n_scans && flag == 0; ++scan) {
+    P.scan = scan;
+    while (true) {
+      CUDA_CHECK(cudaMemsetAsync(h->lr_n_active.p, 0, sizeof(int), h->stream));
+      logreg_controller_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
+      int active = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&active, h->lr_n_active.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_CHECK(cudaMemcpyAsync(&flag, h->error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      if (flag != 0 || active == 0) break;
+      logreg_eval_batch(h, h->lr_Theta.p, g0, g1);
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, g0, g1));
+      h->last_gemm_ms += ms;
+      h->last_batch_steps += 1;
+    }
+    if (flag != 0) break;
+    logreg_post_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
+    logreg_decide_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
+    CUDA_CHECK(cudaMemcpyAsync(&flag, h->error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
+  CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  CUDA_CHECK(cudaEventElapsedTime(&total_ms, h->ev0, h->ev1));
+  cudaEventDestroy(g0);
+  cudaEventDestroy(g1);
+  // replica arrays + statistics back
+  h->lr_st.download(st.data(), nl);
+  st_out.assign(nl, ChainStatsDev{});
+  for (int i = 0; i < nl; ++i) {
+    const LrChainState& s = st[i];
+    ri[i] = s.replica_index; ctr[i] = s.ctr; rt[i] = s.rt_state;
+    ChainStatsDev& o = st_out[i];
+    o.swap_n = s.swap_acc.n; o.swap_mean = s.swap_acc.mu; o.ls_fwd = s.ls_fwd.value; o.ls_bwd = s.ls_bwd.value;
+    o.expl_acc_n = s.expl_acc.n; o.expl_acc_mean = s.expl_acc.mu; o.n_steps = s.n_steps;
+    o.am_n = s.am.n; o.am_mean = s.am.mu; o.rev_n = s.rev.n; o.rev_mean = s.rev.mu;
+    o.n_restarts = s.n_restarts; o.n_round_trips = s.n_trips; o.n_points = s.n_points; o.n_ref_evals = s.n_ref;
+  }
+  h->replica_index.upload(ri.data(), nl);
+  h->rng_ctr.upload(ctr.data(), nl);
+  h->rt_state.upload(rt.data(), nl);
+}
+
+// parity entry points for LOGREG: batches of r_pad points through the same GEMM path
+void logreg_points(pgn_handle* h, const double* x, int n_points, const double* beta, double* lp, double* ld, double* grad) {
+  const int d = h->cfg.dim, dp = h->d_pad, rp = h->lr_r_pad;
+  DevBuf<double> db, dlp, dld, dg;
+  db.alloc(rp); dlp.alloc(rp); dld.alloc(rp); dg.alloc((size_t)rp * d);
+  std::vector<double> stage((size_t)rp * dp);
+  for (int base = 0; base < n_points; base += rp) {
+    const int m = std::min(rp, n_points - base);
+    std::fill(stage.begin(), stage.end(), 0.0);
+    for (int i = 0; i < m; ++i) std::memcpy(&stage[(size_t)i * dp], x + (size_t)(base + i) * d, sizeof(double) * d);
+    h->lr_Theta.upload(stage.data(), stage.size());
+    db.upload(beta + base, m);
+    logreg_eval_batch(h, h->lr_Theta.p, nullptr, nullptr);
+    logreg_points_finish_kernel<<<(m + 3) / 4, 128, 0, h->stream>>>(h->lr_Theta.p, d, dp, m, db.p, h->lr_lik.p, h->lr_G.p,
+                                                                   h->cfg.p[5], h->cfg.p[4], lp ? dlp.p : nullptr,
+                                                                   ld ? dld.p : nullptr, dg.p);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (lp) dlp.download(lp + base, m);
+    if (ld) { dld.download(ld + base, m); dg.download(grad + (size_t)base * d, (size_t)m * d); }
+  }
 }
 
 template <class Chain>
@@ -215,7 +415,10 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
       break;
     }
     case PGN_TARGET_TEST_SWAPPER: break;
-    case PGN_TARGET_LOGREG: return fail(err, PGN_ERR_INVALID, "LOGREG is not implemented in this build");
+    case PGN_TARGET_LOGREG:
+      if (cfg->dim < 1 || cfg->p[0] < 1 || !cfg->data_x || !cfg->data_y)
+        return fail(err, PGN_ERR_INVALID, "LOGREG: dim, n_data, data_x, data_y required");
+      break;
     default: return fail(err, PGN_ERR_INVALID, "unknown target_kind (device targets are a closed family)");
   }
   if (cfg->target_kind == PGN_TARGET_GMM) {
@@ -240,6 +443,11 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
     const int d = cfg->dim;
     if (cfg->target_kind == PGN_TARGET_ISING) { h->cpl = 1; h->d_pad = 64; h->pay_doubles = 32; }
     else if (cfg->target_kind == PGN_TARGET_TEST_SWAPPER) { h->cpl = 1; h->d_pad = 1; h->pay_doubles = 0; }
+    else if (cfg->target_kind == PGN_TARGET_LOGREG) {
+      h->cpl = 0;
+      h->d_pad = (d + 127) / 128 * 128;
+      h->pay_doubles = h->d_pad + 2;
+    }
     else {
       h->cpl = d <= 32 ? 1 : (d <= 64 ? 2 : 4);
       h->d_pad = h->cpl * 32;
@@ -266,6 +474,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
       h->log_w.alloc(cfg->n_modes);
       h->log_w.upload(cfg->log_weights, cfg->n_modes);
     }
+    if (cfg->target_kind == PGN_TARGET_LOGREG) logreg_allocate(h, cfg);
     // default schedule: equally spaced (src/schedules/Schedule.jl:36-44)
     std::vector<double> b(cfg->n_chains);
     for (int i = 0; i < cfg->n_chains; ++i) b[i] = cfg->n_chains == 1 ? 1.0 : (double)i / (cfg->n_chains - 1);
@@ -408,13 +617,16 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
   }
   try {
     use_device(h);
-    void* kernel = select_scan_kernel(h);
-    if (!kernel) throw CudaError{PGN_ERR_INVALID, "explorer not supported for this target on the device"};
+    const bool is_logreg = h->cfg.target_kind == PGN_TARGET_LOGREG;
+    void* kernel = is_logreg ? nullptr : select_scan_kernel(h);
+    if (!kernel && !is_logreg) throw CudaError{PGN_ERR_INVALID, "explorer not supported for this target on the device"};
     const int nl = h->n_local, d = h->cfg.dim;
     h->epoch += 1;
     Params P;
     fill_params(h, P);
     P.n_scans = n_scans;
+    LrParams LP;
+    if (is_logreg) logreg_fill_params(h, LP);
     // optional event logs
     DevBuf<int> d_index;
     DevBuf<double> d_lr, d_u, d_trace;
@@ -427,33 +639,37 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     const bool owns_target = (h->first_chain + nl - 1 == h->cfg.n_chains);
     if (out->target_trace && owns_target) { d_trace.alloc((size_t)n_scans * std::max(d, 1), false); P.target_trace = d_trace.p; }
     CUDA_CHECK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int), h->stream));
-
-    // launch geometry: one warp per chain, all warps co-resident
-    const size_t smem = scan_smem_bytes(h);
-    int wpb = 0, grid = 0;
-    for (int w = 1; w <= 8; w *= 2) {
-      int per_sm = 0;
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, smem));
-      const int g = (nl + w - 1) / w;
-      if ((long long)per_sm * h->n_sms >= g) { wpb = w; grid = g; break; }
-    }
-    if (wpb == 0)
-      throw CudaError{PGN_ERR_INVALID, "too many chains for one GPU: all chains of a shard must be co-resident"};
-    void* args[] = {(void*)&P};
-    CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-    if (n_scans > 0)
-      CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(wpb * 32), args, smem, h->stream));
-    CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
-    CUDA_CHECK(cudaStreamSynchronize(h->stream));
     float ms = 0.f;
-    CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    std::vector<ChainStatsDev> st(nl);
+    if (is_logreg) {
+      LP.index_process = P.index_process; LP.swap_lr = P.swap_lr; LP.swap_u = P.swap_u;
+      LP.swap_accept = P.swap_accept; LP.target_trace = P.target_trace;
+      logreg_run_round(h, n_scans, LP, st, ms);
+    } else {
+      // launch geometry: one warp per chain, all warps co-resident
+      const size_t smem = scan_smem_bytes(h);
+      int wpb = 0, grid = 0;
+      for (int w = 1; w <= 8; w *= 2) {
+        int per_sm = 0;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, smem));
+        const int g = (nl + w - 1) / w;
+        if ((long long)per_sm * h->n_sms >= g) { wpb = w; grid = g; break; }
+      }
+      if (wpb == 0)
+        throw CudaError{PGN_ERR_INVALID, "too many chains for one GPU: all chains of a shard must be co-resident"};
+      void* args[] = {(void*)&P};
+      CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+      if (n_scans > 0)
+        CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(wpb * 32), args, smem, h->stream));
+      CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+      if (n_scans > 0) h->stats.download(st.data(), nl);
+      else std::memset(st.data(), 0, sizeof(ChainStatsDev) * nl);
+    }
     int flag = 0;
     h->error_flag.download(&flag, 1);
 
-    // statistics
-    std::vector<ChainStatsDev> st(nl);
-    if (n_scans > 0) h->stats.download(st.data(), nl);
-    else std::memset(st.data(), 0, sizeof(ChainStatsDev) * nl);
     long long restarts = 0, trips = 0, pts = 0, evals = 0;
     for (int i = 0; i < nl; ++i) {
       const ChainStatsDev& s = st[i];
@@ -475,6 +691,8 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     out->n_density_points = pts;
     out->n_ref_equiv_evals = evals;
     out->kernel_ms = (double)ms;
+    out->gemm_ms = is_logreg ? h->last_gemm_ms : 0.0;
+    out->batch_steps = is_logreg ? h->last_batch_steps : 0;
     out->online_n = 0;
     if (owns_target && n_scans > 0) {
       long long on = 0;
@@ -514,6 +732,10 @@ int pgn_log_potential(pgn_handle* h, const double* x, int32_t n_points, const do
     use_device(h);
     const int d = h->cfg.dim;
     if (h->cfg.target_kind == PGN_TARGET_TEST_SWAPPER) return fail(err, PGN_ERR_INVALID, "TestSwapper has no log_potential");
+    if (h->cfg.target_kind == PGN_TARGET_LOGREG) {
+      logreg_points(h, x, n_points, beta, out, nullptr, nullptr);
+      return PGN_OK;
+    }
     DevBuf<double> dx, db, dout;
     dx.alloc((size_t)n_points * d, false); db.alloc(n_points, false); dout.alloc(n_points, false);
     dx.upload(x, (size_t)n_points * d); db.upload(beta, n_points);
@@ -539,6 +761,10 @@ int pgn_logdensity_and_gradient(pgn_handle* h, const double* x, int32_t n_points
     use_device(h);
     const int d = h->cfg.dim;
     const int tk = h->cfg.target_kind;
+    if (tk == PGN_TARGET_LOGREG) {
+      logreg_points(h, x, n_points, beta, nullptr, logdens, grad);
+      return PGN_OK;
+    }
     if (tk != PGN_TARGET_TOY_MVN && tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM)
       return fail(err, PGN_ERR_INVALID, "target has no gradient");
     DevBuf<double> dx, db, dld, dg;
@@ -596,6 +822,40 @@ int pgn_peer_attach(pgn_handle* h, int32_t side, pgn_handle* neighbour, char** e
       cudaGetLastError();
     }
     if (side == 0) h->mail_left = neighbour->mail.p; else h->mail_right = neighbour->mail.p;
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_measure_fp64_peak(int32_t device, double* tflops, char** err) {
+  try {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+      return fail(err, PGN_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    DevBuf<double> sink;
+    sink.alloc(1);
+    const int iters = 4096, blocks = prop.multiProcessorCount * 4, threads = 256;
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a));
+    CUDA_CHECK(cudaEventCreate(&b));
+    fp64_peak_kernel<<<blocks, threads>>>(sink.p, iters, 1.0000001);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+      CUDA_CHECK(cudaEventRecord(a));
+      fp64_peak_kernel<<<blocks, threads>>>(sink.p, iters, 1.0000001);
+      CUDA_CHECK(cudaEventRecord(b));
+      CUDA_CHECK(cudaEventSynchronize(b));
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+      best = ms < best ? ms : best;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
   } catch (CudaError& e) { return fail(err, e.code, e.msg); }
   return PGN_OK;
 }

@@ -128,6 +128,42 @@ def eight_mode_mixture(dim: int = 128, mu: float = 8.0) -> GaussianMixture:
 
 
 @dataclass
+class LogisticRegression(Target):
+    """BASELINE config 5: Bayesian logistic regression with an analytic gradient (the
+    `BufferedAD` custom-gradient pattern of test/test_custom_gradient.jl:14-24,
+    docs/src/input-julia.md:147-192).  Prior = reference = N(0, prior_sigma^2 I);
+    target = prior x prod_n Bernoulli(y_n | sigmoid(x_n . theta))."""
+    x: np.ndarray                      # [n_data, d]
+    y: np.ndarray                      # [n_data] in {0, 1}
+    prior_sigma: float = 1.0
+    dim: int = field(init=False)
+
+    def __post_init__(self):
+        self.x = np.ascontiguousarray(self.x, dtype=np.float64)
+        self.y = np.ascontiguousarray(self.y, dtype=np.float64)
+        assert self.x.ndim == 2 and self.y.shape == (self.x.shape[0],)
+        self.dim = int(self.x.shape[1])
+
+    def default_explorer(self):
+        from .explorers import AutoMALA
+        return AutoMALA()
+
+    def engine_config(self):
+        p = (float(self.x.shape[0]), 0.0, 0.0) + _normal_ref_params(self.prior_sigma)
+        return dict(target_kind=_capi.TARGET_LOGREG, dim=self.dim, p=p, data_x=self.x, data_y=self.y)
+
+
+def synthetic_logistic_regression(n_data: int, dim: int, seed: int = 2) -> LogisticRegression:
+    """SURVEY.md §8(d) C5 inputs: X ~ N(0,1)/sqrt(d), theta* ~ N(0, I), y ~ Bernoulli(sigmoid(X theta*))."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    x = rng.standard_normal((n_data, dim)) / math.sqrt(dim)
+    theta = rng.standard_normal(dim)
+    pr = 1.0 / (1.0 + np.exp(-(x @ theta)))
+    y = (rng.uniform(size=n_data) < pr).astype(np.float64)
+    return LogisticRegression(x=x, y=y, prior_sigma=1.0)
+
+
+@dataclass
 class IsingLogPotential(Target):
     """examples/ising.jl:6-117: l(state) = beta * sum_<ij> s_i s_j on an L x L
     torus; reference = same with beta = 0 (i.i.d. Bernoulli(1/2) spins)."""

@@ -16,6 +16,9 @@ GOLDEN_CASES = {
                                               n_rounds=5, seed=1),
     # BASELINE config 4 shape, reduced chain count
     "c4_ising32_n8_r4": lambda: dict(target=pg.IsingLogPotential(0.4406867935097715, 32), n_chains=8, n_rounds=4, seed=1),
+    # BASELINE config 5 shape, reduced sizes
+    "c5_logreg_d24_n300_automala_n6_r5": lambda: dict(target=pg.synthetic_logistic_regression(300, 24), explorer=pg.AutoMALA(),
+                                                      n_chains=6, n_rounds=5, seed=1),
     "ising5_n10_r8": lambda: dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=8, seed=1),
 }
 

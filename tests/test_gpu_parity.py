@@ -67,6 +67,9 @@ CASES = {
     "toy10_mala": dict(target=pg.toy_mvn_target(10), explorer=pg.MALA(step_size=0.3), n_chains=6, n_rounds=7, seed=11),
     "funnel16_mala": dict(target=pg.Funnel(16), explorer=pg.MALA(step_size=0.2), n_chains=8, n_rounds=6, seed=12),
     "gmm70_mala_4cpl": dict(target=pg.eight_mode_mixture(70, 4.0), explorer=pg.MALA(step_size=0.5), n_chains=6, n_rounds=5, seed=13),
+    "logreg24_automala": dict(target=pg.synthetic_logistic_regression(300, 24), explorer=pg.AutoMALA(), n_chains=6, n_rounds=5, seed=1),
+    "logreg150_mala": dict(target=pg.synthetic_logistic_regression(4500, 150, seed=3), explorer=pg.MALA(step_size=0.05), n_chains=5,
+                           n_rounds=4, seed=2),
     "ising5": dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=7, seed=1),
     "ising32": dict(target=pg.IsingLogPotential(0.44, 32), n_chains=6, n_rounds=3, seed=2),
     "test_swapper": dict(target=pg.TestSwapper(0.6), n_chains=9, n_rounds=8, seed=7, record=[pg.index_process, pg.swap_trace]),
@@ -93,14 +96,15 @@ def _points(rng, n, d, scale=2.0):
 
 
 @pytest.mark.parametrize("target", [pg.toy_mvn_target(2), pg.toy_mvn_target(77), pg.Funnel(32), pg.Funnel(5),
-                                    pg.eight_mode_mixture(128, 8.0), pg.eight_mode_mixture(40, 2.0)])
+                                    pg.eight_mode_mixture(128, 8.0), pg.eight_mode_mixture(40, 2.0),
+                                    pg.synthetic_logistic_regression(300, 24), pg.synthetic_logistic_regression(4500, 150, seed=3)])
 def test_log_potential_and_gradient_entry_points(target, gpu_lib, oracle_lib):
     """pgn_log_potential / pgn_logdensity_and_gradient against the oracle, incl. beta in {0, 1}."""
     rng = np.random.default_rng(0)
     cfg = target.engine_config()
     eg = pg.Engine(gpu_lib, n_chains=4, seed=1, **cfg)
     eo = pg.Engine(oracle_lib, n_chains=4, seed=1, **cfg)
-    x = _points(rng, 64, target.dim)
+    x = _points(rng, 64, target.dim, 0.7 if isinstance(target, pg.LogisticRegression) else 2.0)
     beta = rng.uniform(0, 1, 64)
     beta[:8] = 0.0
     beta[8:16] = 1.0
@@ -118,7 +122,7 @@ def test_log_potential_and_gradient_entry_points(target, gpu_lib, oracle_lib):
         xp[:, j] += h
         xm[:, j] -= h
         fd = (eg.logdensity_and_gradient(xp, beta)[0] - eg.logdensity_and_gradient(xm, beta)[0]) / (2 * h)
-        np.testing.assert_allclose(gg[:, j], fd, rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(gg[:, j], fd, rtol=2e-5, atol=2e-5 * max(1.0, float(np.max(np.abs(gg)))))
     eg.close(); eo.close()
 
 
