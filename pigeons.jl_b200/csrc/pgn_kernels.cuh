@@ -771,12 +771,6 @@ struct IsingChain {
     if (b == 1.0) return tgt;
     return (1.0 - b) * ref + b * tgt;
   }
-  __device__ __forceinline__ double lp_fast(int s) const {
-    const double tgt = P->p[0] * (double)s;
-    if (beta == 0.0) return 0.0 * (double)s;
-    if (beta == 1.0) return tgt;
-    return beta * tgt;
-  }
   __device__ void sample_iid() {   // examples/ising.jl:49-58
     const unsigned int mask = L >= 32 ? 0xffffffffu : ((1u << L) - 1u);
     row = lane < L ? (bits32_at(rng, rng.ctr + (unsigned long long)lane) & mask) : 0u;
@@ -794,16 +788,11 @@ struct IsingChain {
           const int me = sgn(cur, j);
           const int nb = sgn(up, j) + sgn(dn, j) + sgn(cur, jl) + sgn(cur, jr);
           const int S_new = S + (-me * nb - me * nb);
-          // lp_fast == lp bit for bit up to the sign of zero (adding the reference term
-          // (1-b)*(0.0*S) = +-0 to b*(beta_model*S) changes nothing); and exp_(delta) >= 1
-          // whenever delta >= 0, so that branch accepts without exp and without a draw,
-          // exactly like `accept_ratio < 1 && rand > accept_ratio` (examples/ising.jl:109-110).
-          const double delta = lp_fast(S_new) - lp_fast(S);
+          const double log_pr_before = lp(beta, S);
+          const double log_pr_after = lp(beta, S_new);
+          const double accept_ratio = exp_(log_pr_after - log_pr_before);
           bool reject = false;
-          if (delta < 0.0 || delta != delta) {
-            const double accept_ratio = exp_(delta);
-            if (accept_ratio < 1) reject = next_uniform(rng) > accept_ratio;
-          }
+          if (accept_ratio < 1) reject = next_uniform(rng) > accept_ratio;
           if (!reject) { cur ^= (1u << j); S = S_new; }
         }
         if (lane == i) row = cur;

@@ -53,11 +53,18 @@ dgemm_km_kernel(const double* __restrict__ A, int lda, const double* __restrict_
   const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * GEMM_BN;
   const int k_begin = blockIdx.z * k_chunk;
   const int k_end = min(k_total, k_begin + k_chunk);
-  // loader mapping: 16 threads cover one 128-double row
-  const int lk = tid >> 4, lo = (tid & 15) * 8;
-  // compute mapping: 16 x 16 threads, thread (ty, tx) owns rows ty*8..ty*8+7 and the column pairs
-  // {32 j + 2 tx, 32 j + 2 tx + 1}, j = 0..3 (consecutive lanes read consecutive 16-byte words of Bs)
-  const int ty = tid >> 4, tx = tid & 15;
+  // loader mapping: 16 threads cover one 128-double row, consecutive threads load consecutive
+  // 16-byte words (coalesced global loads, conflict-free shared stores)
+  const int lk = tid >> 4, lo = (tid & 15) * 2;
+  // compute mapping: 16 x 16 logical threads; a warp covers 4 (ty) x 8 (tx) of them so that its
+  // shared-memory reads touch 4 x 64 B of As (broadcast) and 8 x 16 B of Bs per load.
+  // thread (ty, tx) owns the row pairs {32 i + 2 ty, 32 i + 2 ty + 1}, i = 0..3, and the column pairs
+  // {16 j + 2 tx, 16 j + 2 tx + 1}, j = 0..3, within the 64-column half selected by the warp parity
+  // (both shared-memory reads are then 64 / 128 contiguous bytes per warp: one wavefront each).
+  const int warp = tid >> 5, lane = tid & 31;
+  const int ty = 4 * (warp >> 1) + (lane >> 3);
+  const int tx = lane & 7;
+  const int cbase = 64 * (warp & 1);
   double acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -70,15 +77,15 @@ dgemm_km_kernel(const double* __restrict__ A, int lda, const double* __restrict_
     const double* bp = B + (size_t)(kt + lk) * ldb + n0 + lo;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      ra[i] = *reinterpret_cast<const double2*>(ap + 2 * i);
-      rb[i] = *reinterpret_cast<const double2*>(bp + 2 * i);
+      ra[i] = *reinterpret_cast<const double2*>(ap + 32 * i);
+      rb[i] = *reinterpret_cast<const double2*>(bp + 32 * i);
     }
   };
   auto sstore = [&](int buf) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      *reinterpret_cast<double2*>(&As[buf][lk][lo + 2 * i]) = ra[i];
-      *reinterpret_cast<double2*>(&Bs[buf][lk][lo + 2 * i]) = rb[i];
+      *reinterpret_cast<double2*>(&As[buf][lk][lo + 32 * i]) = ra[i];
+      *reinterpret_cast<double2*>(&Bs[buf][lk][lo + 32 * i]) = rb[i];
     }
   };
   int buf = 0;
@@ -95,12 +102,12 @@ dgemm_km_kernel(const double* __restrict__ A, int lda, const double* __restrict_
       double a[8], b[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const double2 t = *reinterpret_cast<const double2*>(&As[buf][kk][ty * 8 + 2 * i]);
+        const double2 t = *reinterpret_cast<const double2*>(&As[buf][kk][32 * i + 2 * ty]);
         a[2 * i] = t.x; a[2 * i + 1] = t.y;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double2 t = *reinterpret_cast<const double2*>(&Bs[buf][kk][32 * j + 2 * tx]);
+        const double2 t = *reinterpret_cast<const double2*>(&Bs[buf][kk][cbase + 16 * j + 2 * tx]);
         b[2 * j] = t.x; b[2 * j + 1] = t.y;
       }
 #pragma unroll
@@ -115,13 +122,13 @@ dgemm_km_kernel(const double* __restrict__ A, int lda, const double* __restrict_
   // epilogue
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int m = m0 + ty * 8 + i;
+    const int m = m0 + 32 * (i >> 1) + 2 * ty + (i & 1);
     if (EPI == 0) {
       double* crow = C0 + (size_t)blockIdx.z * split_stride + (size_t)m * ldc + n0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         double2 v; v.x = acc[i][2 * j]; v.y = acc[i][2 * j + 1];
-        *reinterpret_cast<double2*>(crow + 32 * j + 2 * tx) = v;
+        *reinterpret_cast<double2*>(crow + cbase + 16 * j + 2 * tx) = v;
       }
     } else {
       const bool live = m < n_valid_rows;
@@ -134,8 +141,8 @@ dgemm_km_kernel(const double* __restrict__ A, int lda, const double* __restrict_
         logreg_terms(acc[i][2 * j], y, l.x, r.x);
         logreg_terms(acc[i][2 * j + 1], y, l.y, r.y);
         if (!live) { l.x = l.y = 0.0; r.x = r.y = 0.0; }
-        *reinterpret_cast<double2*>(llrow + 32 * j + 2 * tx) = l;
-        *reinterpret_cast<double2*>(rsrow + 32 * j + 2 * tx) = r;
+        *reinterpret_cast<double2*>(llrow + cbase + 16 * j + 2 * tx) = l;
+        *reinterpret_cast<double2*>(rsrow + cbase + 16 * j + 2 * tx) = r;
       }
     }
   }
