@@ -1,4 +1,4 @@
-"""Multi-GPU parity: the ladder sharded over 2 (and 4) GPUs gives the identical
+"""Multi-GPU parity: the ladder sharded over 2, 4 and 8 GPUs gives the identical
 result to the single-process oracle — the reference's invariance-to-#workers
 guarantee (docs/src/distributed.md:37-55, test/test_parallelism_invariance.jl)."""
 import json
@@ -24,7 +24,7 @@ def free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_ladder_matches_oracle(world, tmp_path):
     if n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
