@@ -266,6 +266,7 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm
+    os.environ["NCCL_DEBUG"] = os.environ.get("PGN_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
     import torch
     torch.cuda.set_device(local_rank)
     comm = pg.SingleProcess()
