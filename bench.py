@@ -48,7 +48,7 @@ CONFIGS = {
                workload="C4: Ising 32x32 torus (examples/ising.jl), beta = log(1+sqrt 2)/2 (critical), "
                         "IsingMetropolis(n_steps=3), 512 chains per GPU (4096 on 8 GPUs)"),
     "c5": dict(chains_per_gpu=256, dim=4096, explorer="AutoMALA", state_bytes=4096 * 8, n_data=65536,
-               kernel="pgn::dgemm_km_kernel<0/1> (two FP64 GEMMs per batched evaluation) + logreg_controller_kernel",
+               kernel="pgn::dgemm_km_dmma_kernel<0/1> (two FP64 tensor-core GEMMs per batched evaluation) + logreg_controller_kernel",
                workload="C5: synthetic logistic regression d=4096, N_data=65536 (X ~ N(0,1)/sqrt d), prior N(0,I), "
                         "AutoMALA defaults, 256 chains per GPU"),
 }
@@ -357,7 +357,9 @@ def main():
         flops_per_batch = 2 * 2.0 * CFG["n_data"] * CFG["dim"] * CHAINS_PER_GPU      # two GEMMs, 2 flops per fma
         fp64_peak = lib.measure_fp64_peak(local_rank)
         line["fp64_roofline"] = {
-            "bound": "fp64 fma (tcgen05 has no FP64 path; SIMT DFMA GEMM with a fixed summation order)",
+            "bound": "fp64 (tcgen05 has no FP64 path; DMMA m8n8k4 GEMM whose summation order equals the sequential-fma spec; "
+                     "PGN_GEMM=simt selects the DFMA kernel)",
+            "gemm": os.environ.get("PGN_GEMM", "dmma"),
             "achieved_tflops": flops_per_batch * batch_steps / (gemm_ms * 1e-3) / 1e12,
             "peak_tflops": fp64_peak, "peak_source": "measured in-run: register-resident DFMA loop on all SMs",
             "frac": flops_per_batch * batch_steps / (gemm_ms * 1e-3) / 1e12 / fp64_peak,

@@ -234,6 +234,13 @@ int pgn_measure_fp64_peak(int32_t device, double* tflops, char** err);
 int pgn_test_math(int32_t device, int32_t op, const double* in, double* out, int64_t n,
                   int64_t seed, int32_t replica_index, char** err);
 
+/* Probe of the FP64 tensor-core instruction mma.sync.m8n8k4.f64 (DMMA): n_trials
+ * independent products D = A(8x4) B(4x8) + C(8x8), row-major inputs, one warp each.
+ * Used to establish the accumulation order of the hardware before it may replace
+ * the SIMT GEMM of the LOGREG path (whose summation order is part of the spec). */
+int pgn_test_dmma(int32_t device, const double* a, const double* b, const double* c, double* d_out,
+                  int32_t n_trials, char** err);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,7 +86,7 @@ DECLARED_SYMBOLS = [
     "pgn_abi_version", "pgn_create", "pgn_destroy", "pgn_free_string", "pgn_device_info", "pgn_local_range",
     "pgn_set_schedule", "pgn_set_explorer", "pgn_init_replicas", "pgn_get_state", "pgn_set_state",
     "pgn_run_round", "pgn_log_potential", "pgn_logdensity_and_gradient", "pgn_ipc_export", "pgn_ipc_attach",
-    "pgn_peer_attach", "pgn_test_math", "pgn_measure_fp64_peak",
+    "pgn_peer_attach", "pgn_test_math", "pgn_measure_fp64_peak", "pgn_test_dmma",
 ]
 
 
@@ -148,6 +148,17 @@ class EngineLib:
         f.restype = C.c_int
         self.call("measure_fp64_peak", C.c_int32(device), C.byref(v))
         return v.value
+
+    def test_dmma(self, a, b, c, device: int = 0) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        n = a.shape[0]
+        assert a.shape == (n, 8, 4) and b.shape == (n, 4, 8) and c.shape == (n, 8, 8)
+        out = np.empty((n, 8, 8), dtype=np.float64)
+        self.fn("test_dmma").restype = C.c_int
+        self.call("test_dmma", C.c_int32(device), _ptr(a, C.c_double), _ptr(b, C.c_double), _ptr(c, C.c_double),
+                  _ptr(out, C.c_double), C.c_int32(n))
+        return out
 
     def test_math(self, op: int, values, seed: int = 1, replica_index: int = 1, device: int = 0) -> np.ndarray:
         v = np.ascontiguousarray(values, dtype=np.float64)

@@ -99,6 +99,7 @@ struct pgn_handle {
   DevBuf<double> lr_P, lr_G0, lr_SX, lr_SP, lr_SG, lr_TP, lr_TG, lr_FX, lr_FG;
   DevBuf<LrChainState> lr_st;
   DevBuf<int> lr_n_active;
+  bool lr_use_dmma = true;       // FP64 tensor-core GEMM (same summation order as the SIMT kernel, see pgn_logreg.cuh)
   double last_gemm_ms = 0.0;     // device time spent in the two GEMMs during the last round
   long long last_batch_steps = 0;
 };
@@ -135,6 +136,7 @@ void fill_params(pgn_handle* h, Params& P) {
 // logistic regression: batched-GEMM engine (pgn_logreg.cuh)
 // ===========================================================================
 constexpr size_t GEMM_SMEM_BYTES = 2ull * 2 * GEMM_BK * GEMM_BM * sizeof(double);
+constexpr size_t DMMA_SMEM_BYTES = 2ull * 2 * GEMM_BK * DMMA_LD * sizeof(double);
 
 void logreg_allocate(pgn_handle* h, const pgn_config* cfg) {
   const int d = cfg->dim, dp = h->d_pad;
@@ -169,6 +171,12 @@ void logreg_allocate(pgn_handle* h, const pgn_config* cfg) {
   h->lr_TP.alloc(vec); h->lr_TG.alloc(vec); h->lr_FX.alloc(vec); h->lr_FG.alloc(vec);
   h->lr_st.alloc(h->n_local);
   h->lr_n_active.alloc(1);
+  {
+    const char* g = std::getenv("PGN_GEMM");   // "simt" selects the DFMA kernel; default: FP64 tensor cores
+    h->lr_use_dmma = !(g != nullptr && std::string(g) == "simt");
+  }
+  CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMMA_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMMA_SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
 }
@@ -184,14 +192,22 @@ void logreg_eval_batch(pgn_handle* h, const double* theta, cudaEvent_t e0, cudaE
   if (e0) CUDA_CHECK(cudaEventRecord(e0, h->stream));
   {
     dim3 grid(np / GEMM_BM, rp / GEMM_BN, 1);
-    dgemm_km_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
-        h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, h->lr_Res.p, rp, 0, h->lr_y.p, h->lr_n_data);
+    if (h->lr_use_dmma)
+      dgemm_km_dmma_kernel<1><<<grid, GEMM_THREADS, DMMA_SMEM_BYTES, h->stream>>>(
+          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, h->lr_Res.p, rp, 0, h->lr_y.p, h->lr_n_data);
+    else
+      dgemm_km_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
+          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, h->lr_Res.p, rp, 0, h->lr_y.p, h->lr_n_data);
   }
   logreg_reduce_ll_kernel<<<(rp + 7) / 8, 256, 0, h->stream>>>(h->lr_LL.p, rp, h->lr_n_data, rp, h->lr_lik.p);
   {
     dim3 grid(dp / GEMM_BM, rp / GEMM_BN, h->lr_splits);
-    dgemm_km_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
-        h->lr_Xr.p, dp, h->lr_Res.p, rp, np, LR_CHUNK, h->lr_Gp.p, nullptr, rp, (size_t)dp * rp, nullptr, 0);
+    if (h->lr_use_dmma)
+      dgemm_km_dmma_kernel<0><<<grid, GEMM_THREADS, DMMA_SMEM_BYTES, h->stream>>>(
+          h->lr_Xr.p, dp, h->lr_Res.p, rp, np, LR_CHUNK, h->lr_Gp.p, nullptr, rp, (size_t)dp * rp, nullptr, 0);
+    else
+      dgemm_km_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
+          h->lr_Xr.p, dp, h->lr_Res.p, rp, np, LR_CHUNK, h->lr_Gp.p, nullptr, rp, (size_t)dp * rp, nullptr, 0);
   }
   if (e1) CUDA_CHECK(cudaEventRecord(e1, h->stream));
   {
@@ -856,6 +872,25 @@ int pgn_measure_fp64_peak(int32_t device, double* tflops, char** err) {
     cudaEventDestroy(b);
     const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
     *tflops = flops / (best * 1e-3) / 1e12;
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_test_dmma(int32_t device, const double* a, const double* b, const double* c, double* d_out, int32_t n_trials,
+                  char** err) {
+  try {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+      return fail(err, PGN_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");
+    CUDA_CHECK(cudaSetDevice(device));
+    DevBuf<double> da, db, dc, dd;
+    da.alloc((size_t)n_trials * 32, false); db.alloc((size_t)n_trials * 32, false);
+    dc.alloc((size_t)n_trials * 64, false); dd.alloc((size_t)n_trials * 64, false);
+    da.upload(a, (size_t)n_trials * 32); db.upload(b, (size_t)n_trials * 32); dc.upload(c, (size_t)n_trials * 64);
+    dmma_probe_kernel<<<(n_trials + 3) / 4, 128>>>(da.p, db.p, dc.p, dd.p, n_trials);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaDeviceSynchronize());
+    dd.download(d_out, (size_t)n_trials * 64);
   } catch (CudaError& e) { return fail(err, e.code, e.msg); }
   return PGN_OK;
 }

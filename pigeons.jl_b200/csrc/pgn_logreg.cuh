@@ -11,11 +11,15 @@
 //     G  = X^T Resid     (d x n_data) (n_data x R)  split-K over 4096-row chunks
 // so X (2 GiB) is streamed once per GEMM for all R chains instead of once per chain.
 //
-// The GEMMs are hand-written SIMT DFMA kernels with a FIXED summation order
-// (sequential fma over k inside a thread, chunk partials added in chunk order),
-// which is part of the arithmetic spec mirrored by the CPU oracle — results stay
-// bit-identical to the oracle, which tensor-core (DMMA) accumulation order would not
-// guarantee.  tcgen05 has no FP64 path, so the FP64 pipe is the roofline here.
+// The GEMMs are hand-written with a FIXED summation order (sequential fma over k for every
+// output element, split-K chunk partials added in chunk order), which is part of the arithmetic
+// spec mirrored by the CPU oracle.  Two implementations produce identical bits:
+//   dgemm_km_dmma_kernel  FP64 tensor cores (mma.sync.m8n8k4.f64 = DMMA.8x8x4), default: the
+//                         hardware accumulates each instruction as an fma chain in ascending k
+//                         (probed and asserted), 76 % of the measured FP64 peak;
+//   dgemm_km_kernel       SIMT DFMA, 8x8 register tiles; limited by shared-memory bandwidth
+//                         (16 operand doubles per 64 fma = 128 B/clk/SM), 56 % of peak.
+// tcgen05 has no FP64 path, so DMMA/DFMA (64 fma/clk/SM) is the roofline here.
 #pragma once
 #include "pgn_kernels.cuh"
 
@@ -143,6 +147,103 @@ dgemm_km_kernel(const double* __restrict__ A, int lda, const double* __restrict_
         if (!live) { l.x = l.y = 0.0; r.x = r.y = 0.0; }
         *reinterpret_cast<double2*>(llrow + cbase + 16 * j + 2 * tx) = l;
         *reinterpret_cast<double2*>(rsrow + cbase + 16 * j + 2 * tx) = r;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Same contraction on the FP64 tensor cores (DMMA, mma.sync.m8n8k4.f64).  Valid as a
+// drop-in ONLY because the hardware accumulates the four k-products of one instruction as
+// a sequential fma chain in ascending k starting from C (established by
+// tools/probe_dmma_order.py and asserted by tests/test_gpu_parity.py::test_dmma_is_a_sequential_fma_chain),
+// so chaining the instructions over k reproduces the spec's summation order bit for bit.
+// Operands come from registers (1 double per lane per 8x4 / 4x8 fragment), which removes the
+// shared-memory bandwidth limit of the SIMT kernel (16 operand doubles per 64 fma).
+// Block tile 128x128, BK = 16, 8 warps; warp tile 32 (M) x 64 (N) = 4 x 8 DMMA tiles.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b, double c0, double c1);
+constexpr int DMMA_LD = 132;   // padded row stride (doubles): 264 words = 8 mod 32 -> conflict-free fragment loads
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS)
+dgemm_km_dmma_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, int k_total,
+                     int k_chunk, double* __restrict__ C0, double* __restrict__ C1, int ldc, size_t split_stride,
+                     const double* __restrict__ yvec, int n_valid_rows) {
+  extern __shared__ double gemm_smem[];
+  double (*As)[GEMM_BK][DMMA_LD] = reinterpret_cast<double (*)[GEMM_BK][DMMA_LD]>(gemm_smem);
+  double (*Bs)[GEMM_BK][DMMA_LD] = reinterpret_cast<double (*)[GEMM_BK][DMMA_LD]>(gemm_smem + 2 * GEMM_BK * DMMA_LD);
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * GEMM_BN;
+  const int k_begin = blockIdx.z * k_chunk;
+  const int k_end = min(k_total, k_begin + k_chunk);
+  const int lk = tid >> 4, lo = (tid & 15) * 2;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp >> 1) * 32;      // warp row offset inside the block tile (4 warp rows)
+  const int wn = (warp & 1) * 64;       // warp column offset (2 warp columns)
+  const int fr = lane >> 2, fk = lane & 3;
+  double acc[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  double2 ra[4], rb[4];
+  auto gload = [&](int kt) {
+    const double* ap = A + (size_t)(kt + lk) * lda + m0 + lo;
+    const double* bp = B + (size_t)(kt + lk) * ldb + n0 + lo;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ra[i] = *reinterpret_cast<const double2*>(ap + 32 * i);
+      rb[i] = *reinterpret_cast<const double2*>(bp + 32 * i);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<double2*>(&As[buf][lk][lo + 32 * i]) = ra[i];
+      *reinterpret_cast<double2*>(&Bs[buf][lk][lo + 32 * i]) = rb[i];
+    }
+  };
+  int buf = 0;
+  if (k_begin < k_end) { gload(k_begin); sstore(0); }
+  __syncthreads();
+  for (int kt = k_begin; kt < k_end; kt += GEMM_BK) {
+    const bool has_next = kt + GEMM_BK < k_end;
+    if (has_next) gload(kt + GEMM_BK);
+#pragma unroll
+    for (int k4 = 0; k4 < GEMM_BK; k4 += 4) {
+      double a[4], b[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[buf][k4 + fk][wm + 8 * i + fr];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = Bs[buf][k4 + fk][wn + 8 * j + fr];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j], acc[i][j][0], acc[i][j][1]);
+    }
+    if (has_next) sstore(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + wm + 8 * i + fr;
+    const bool live = EPI == 0 || m < n_valid_rows;
+    const double y = (EPI == 1 && live) ? yvec[m] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + wn + 8 * j + 2 * fk;
+      if (EPI == 0) {
+        double2 v; v.x = acc[i][j][0]; v.y = acc[i][j][1];
+        *reinterpret_cast<double2*>(C0 + (size_t)blockIdx.z * split_stride + (size_t)m * ldc + n) = v;
+      } else {
+        double2 l, r;
+        logreg_terms(acc[i][j][0], y, l.x, r.x);
+        logreg_terms(acc[i][j][1], y, l.y, r.y);
+        if (!live) { l.x = l.y = 0.0; r.x = r.y = 0.0; }
+        *reinterpret_cast<double2*>(C0 + (size_t)m * ldc + n) = l;
+        *reinterpret_cast<double2*>(C1 + (size_t)m * ldc + n) = r;
       }
     }
   }
@@ -692,6 +793,26 @@ __global__ void logreg_points_finish_kernel(const double* __restrict__ xs, int d
       grad_out[(size_t)w * d + c] = t + gt * b;
     }
   }
+}
+
+// D = A B + C with one mma.sync.m8n8k4.f64 per warp (fragment layout of the PTX ISA:
+// a: row lane/4, col lane%4; b: row lane%4, col lane/4; c/d: row lane/4, cols 2*(lane%4)+{0,1})
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b, double c0, double c1) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+               : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+__global__ void dmma_probe_kernel(const double* A, const double* B, const double* Cm, double* D, int n_trials) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= n_trials) return;
+  const double a = A[(size_t)t * 32 + (lane >> 2) * 4 + (lane & 3)];
+  const double b = B[(size_t)t * 32 + (lane & 3) * 8 + (lane >> 2)];
+  const double c0 = Cm[(size_t)t * 64 + (lane >> 2) * 8 + 2 * (lane & 3)];
+  const double c1 = Cm[(size_t)t * 64 + (lane >> 2) * 8 + 2 * (lane & 3) + 1];
+  double d0, d1;
+  dmma_m8n8k4(d0, d1, a, b, c0, c1);
+  D[(size_t)t * 64 + (lane >> 2) * 8 + 2 * (lane & 3)] = d0;
+  D[(size_t)t * 64 + (lane >> 2) * 8 + 2 * (lane & 3) + 1] = d1;
 }
 
 // 16 independent DFMA chains per thread, register resident: FP64 FMA peak probe

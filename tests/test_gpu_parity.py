@@ -161,3 +161,30 @@ def test_errors_are_reported_not_swallowed(gpu_lib):
 def test_unsupported_configuration_raises(gpu_lib):
     with pytest.raises(pg.EngineError):
         pg.Engine(gpu_lib, n_chains=4, seed=1, **pg.toy_mvn_target(1000).engine_config())
+
+
+def test_dmma_is_a_sequential_fma_chain(gpu_lib):
+    """mma.sync.m8n8k4.f64 accumulates its four products as an fma chain in ascending k starting
+    from C (exactly-rounded reference via rational arithmetic).  This is what makes the
+    tensor-core GEMM a bit-identical replacement for the SIMT one."""
+    from fractions import Fraction
+    rng = np.random.default_rng(0)
+    n = 24
+    scale = lambda shape: rng.normal(0, 1, shape) * np.exp(rng.uniform(-8, 8, shape))   # noqa: E731
+    a, b, c = scale((n, 8, 4)), scale((n, 4, 8)), scale((n, 8, 8))
+    d = gpu_lib.test_dmma(a, b, c)
+    for t in range(n):
+        for i in range(8):
+            for j in range(8):
+                acc = float(c[t, i, j])
+                for k in range(4):
+                    acc = float(Fraction(float(a[t, i, k])) * Fraction(float(b[t, k, j])) + Fraction(acc))
+                assert acc == d[t, i, j]
+
+
+@pytest.mark.parametrize("name", ["logreg24_automala", "logreg150_mala"])
+def test_logreg_parity_with_simt_gemm(name, gpu_lib, oracle_lib, monkeypatch):
+    """PGN_GEMM=simt: the DFMA GEMM (the default is the FP64 tensor-core kernel) gives the same bits."""
+    monkeypatch.setenv("PGN_GEMM", "simt")
+    kw = CASES[name]
+    assert_same(run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw), name + "/simt")
