@@ -205,6 +205,33 @@ def cpu_reference_run(pg, scans_hint, n_chains, threads=0, budget_s=12.0, clone_
     return pt, lib, n_threads, scans
 
 
+def cpu_baseline_c5(pg, threads=0):
+    """C5 on the CPU is far too slow to time whole scans (one density+gradient evaluation streams
+    the 2 GiB design matrix twice per chain).  Bounded sample: T chains (one per host thread) x ONE
+    momentum refreshment of the same autoMALA kernel on the same data, extrapolated linearly to
+    256 chains x 57 refreshments (explore is independent per replica and per refreshment)."""
+    from oracle_adapter import load_oracle
+    import ctypes as C
+    lib = load_oracle()
+    target = pg.synthetic_logistic_regression(CFG["n_data"], CFG["dim"])
+    probe = pg.create_pt(pg.Inputs(target=target, explorer=pg.AutoMALA(), n_chains=2, n_rounds=0, seed=1, engine_lib=lib))
+    max_threads = lib.lib.orc_get_threads(probe.engine._h)
+    probe.close()
+    t_chains = threads or max_threads
+    explorer = pg.AutoMALA(base_n_refresh=1, exponent_n_refresh=0.0, step_size=0.02)
+    pt = pg.create_pt(pg.Inputs(target=target, explorer=explorer, n_chains=t_chains, n_rounds=0, seed=1, engine_lib=lib))
+    lib.lib.orc_set_threads(pt.engine._h, C.c_int(t_chains))
+    pt.engine.set_schedule(pt.shared.tempering.schedule.grids)
+    pt.engine.set_explorer(**explorer.engine_params(CFG["dim"]))
+    r = pt.engine.run_round(2)          # scan 1 has no MH step; time both, count refreshments actually done
+    full_refresh = pg.AutoMALA().n_refresh(CFG["dim"])
+    per_chain_refresh_s = r.wall_s / 2.0          # T chains in parallel on T threads, 1 refreshment per scan
+    scan_s = per_chain_refresh_s * full_refresh * (CHAINS_PER_GPU / t_chains)
+    return {"value": 1.0 / scan_s, "unit": "scans/s", "cores": t_chains, "kind": "port",
+            "sample": f"{t_chains} chains x 2 scans x 1 refreshment of the same kernel and data on {t_chains} threads "
+                      f"({r.wall_s:.1f} s), extrapolated x{full_refresh} refreshments x{CHAINS_PER_GPU}/{t_chains} chains"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -365,6 +392,8 @@ def main():
             "frac": flops_per_batch * batch_steps / (gemm_ms * 1e-3) / 1e12 / fp64_peak,
             "gemm_share_of_kernel_time": gemm_ms / kernel_ms, "batched_evaluations": batch_steps,
             "flops_per_batched_evaluation": flops_per_batch}
+    if not args.no_cpu_baseline and args.gpus == 1 and CFG_NAME == "c5":
+        line["cpu_baseline"] = cpu_baseline_c5(pg, args.cpu_threads)
     if not args.no_cpu_baseline and args.gpus == 1 and CFG_NAME != "c5":
         cpt, clib, n_threads, scans = cpu_reference_run(pg, args.scans, CHAINS_PER_GPU, threads=args.cpu_threads, budget_s=12.0,
                                                           clone_from=pt)

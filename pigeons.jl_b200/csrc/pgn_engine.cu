@@ -193,11 +193,12 @@ void logreg_eval_batch(pgn_handle* h, const double* theta, cudaEvent_t e0, cudaE
   {
     dim3 grid(np / GEMM_BM, rp / GEMM_BN, 1);
     if (h->lr_use_dmma)
-      dgemm_km_dmma_kernel<1><<<grid, GEMM_THREADS, DMMA_SMEM_BYTES, h->stream>>>(
-          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, h->lr_Res.p, rp, 0, h->lr_y.p, h->lr_n_data);
+      dgemm_km_dmma_kernel<0><<<grid, GEMM_THREADS, DMMA_SMEM_BYTES, h->stream>>>(
+          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, nullptr, rp, 0, nullptr, 0);
     else
-      dgemm_km_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
-          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, h->lr_Res.p, rp, 0, h->lr_y.p, h->lr_n_data);
+      dgemm_km_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
+          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, nullptr, rp, 0, nullptr, 0);
+    logreg_bernoulli_kernel<<<h->n_sms * 8, 256, 0, h->stream>>>(h->lr_LL.p, h->lr_Res.p, h->lr_y.p, rp, np, h->lr_n_data);
   }
   logreg_reduce_ll_kernel<<<(rp + 7) / 8, 256, 0, h->stream>>>(h->lr_LL.p, rp, h->lr_n_data, rp, h->lr_lik.p);
   {

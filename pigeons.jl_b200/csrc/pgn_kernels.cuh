@@ -205,6 +205,18 @@ struct VecChain {
     return (1.0 - b) * a0 + b * a1;
   }
 
+  // exp(a[m] - M) for the K <= 8 mixture components: lane m evaluates component m (one SIMT
+  // pass instead of K redundant ones), then the values are broadcast — same bits as K calls.
+  __device__ __forceinline__ void mode_exps(const double (&a)[KMAX_MODES], double M, int K, double (&w)[KMAX_MODES]) const {
+    double mine = a[0];
+#pragma unroll
+    for (int m = 1; m < KMAX_MODES; ++m) mine = ((lane & 7) == m) ? a[m] : mine;
+    const double e = exp_(mine - M);
+#pragma unroll
+    for (int m = 0; m < KMAX_MODES; ++m) w[m] = __shfl_sync(PGN_FULL_MASK, e, m);
+    (void)K;
+  }
+
   // component densities at xx
   __device__ void eval(const double (&xx)[CPL], double& a0, double& a1) {
     n_points += 1;
@@ -253,9 +265,13 @@ struct VecChain {
         a[m] = lw[m] - 0.5 * v[m] * ivm - cst;
         if (a[m] > M) M = a[m];
       }
+      double wexp[KMAX_MODES];
+#pragma unroll
+      for (int m = 0; m < KMAX_MODES; ++m) if (m >= K) a[m] = M;
+      mode_exps(a, M, K, wexp);
       double s = 0.0;
 #pragma unroll
-      for (int m = 0; m < KMAX_MODES; ++m) if (m < K) s = s + exp_(a[m] - M);
+      for (int m = 0; m < KMAX_MODES; ++m) if (m < K) s = s + wexp[m];
       a1 = M + log_(s);
     }
   }
@@ -331,9 +347,17 @@ struct VecChain {
         w[m] = lw[m] - 0.5 * v[m] * ivm - cst;
         if (w[m] > M) M = w[m];
       }
+#pragma unroll
+      for (int m = 0; m < KMAX_MODES; ++m) if (m >= K) w[m] = M;
+      {
+        double wexp[KMAX_MODES];
+        mode_exps(w, M, K, wexp);
+#pragma unroll
+        for (int m = 0; m < KMAX_MODES; ++m) w[m] = wexp[m];
+      }
       double s = 0.0;
 #pragma unroll
-      for (int m = 0; m < KMAX_MODES; ++m) if (m < K) { w[m] = exp_(w[m] - M); s = s + w[m]; }
+      for (int m = 0; m < KMAX_MODES; ++m) if (m < K) s = s + w[m];
       a1 = M + log_(s);
 #pragma unroll
       for (int k = 0; k < CPL; ++k) {

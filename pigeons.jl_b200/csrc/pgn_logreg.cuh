@@ -249,6 +249,28 @@ dgemm_km_dmma_kernel(const double* __restrict__ A, int lda, const double* __rest
   }
 }
 
+// Bernoulli terms, elementwise at full occupancy: Z[m][n] (in LL) -> LL[m][n], RES[m][n];
+// rows m >= n_valid_rows are zeroed.  (Fusing this into the GEMM epilogue costs more: the
+// GEMM runs 8 warps per SM, so ~150 dependent FP64 instructions per element there stall the
+// tensor pipe; measured 0.7 ms fused vs 0.2 ms as a separate pass over 128 MB.)
+__global__ void logreg_bernoulli_kernel(double* __restrict__ LL, double* __restrict__ RES, const double* __restrict__ yvec,
+                                        int ld, int n_rows_pad, int n_valid_rows) {
+  const size_t total2 = (size_t)n_rows_pad * ld / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = 2 * i;
+    const int m = (int)(e / ld);
+    const bool live = m < n_valid_rows;
+    const double y = live ? yvec[m] : 0.0;
+    const double2 z = *reinterpret_cast<const double2*>(LL + e);
+    double2 l, r;
+    logreg_terms(z.x, y, l.x, r.x);
+    logreg_terms(z.y, y, l.y, r.y);
+    if (!live) { l.x = l.y = 0.0; r.x = r.y = 0.0; }
+    *reinterpret_cast<double2*>(LL + e) = l;
+    *reinterpret_cast<double2*>(RES + e) = r;
+  }
+}
+
 // lik[r] = sum over row tiles (in order) of the canonical 32-lane tree over the tile's rows.
 // One warp per chain column; LL is [n_pad][ld].
 __global__ void logreg_reduce_ll_kernel(const double* __restrict__ LL, int ld, int n_data, int n_cols,
