@@ -373,7 +373,7 @@ void* select_scan_kernel(const pgn_handle* h) {
   }
 }
 size_t scan_smem_bytes(const pgn_handle* h) {
-  if (h->cfg.target_kind == PGN_TARGET_GMM) return ((size_t)h->cfg.n_modes * h->d_pad + KMAX_MODES) * sizeof(double);
+  if (h->cfg.target_kind == PGN_TARGET_GMM) return ((size_t)KMAX_MODES * h->d_pad + KMAX_MODES) * sizeof(double);
   return 0;
 }
 

@@ -127,12 +127,17 @@ struct VecChain {
   // target-chain online statistics (OnlineStatsBase.Variance per coordinate)
   double on_mu[CPL], on_s2[CPL];
   long long on_n;
+  double pool;
+  unsigned long long pool_base;
+  bool pool_valid;
 
   static __device__ void stage_shared(const Params& P, double* smem) {
     if (TK == PGN_TARGET_GMM) {
-      const int n = P.n_modes * P.d_pad;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = P.means[i];
-      for (int i = threadIdx.x; i < KMAX_MODES; i += blockDim.x) smem[n + i] = i < P.n_modes ? P.log_w[i] : 0.0;
+      const int n = KMAX_MODES * P.d_pad;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = i < P.n_modes * P.d_pad ? P.means[i] : 0.0;
+      // components beyond K are padded with weight exp(-inf) = 0: their terms add exact zeros, so the
+      // mode loops run over all KMAX_MODES slots without predicates and give the same bits as K terms
+      for (int i = threadIdx.x; i < KMAX_MODES; i += blockDim.x) smem[n + i] = i < P.n_modes ? P.log_w[i] : -PGN_INF;
     }
   }
 
@@ -152,6 +157,7 @@ struct VecChain {
     expl_acc = MeanAcc{0, 0.0}; am = MeanAcc{0, 0.0}; rev = MeanAcc{0, 0.0};
     n_steps = n_points = n_ref = 0;
     err = 0; e0 = e1 = 0.0;
+    pool = 0.0; pool_base = 0; pool_valid = false;
   }
   __device__ void store(int wl) {
 #pragma unroll
@@ -250,28 +256,26 @@ struct VecChain {
         const double xv = xx[k];
         v[KMAX_MODES] = v[KMAX_MODES] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
 #pragma unroll
-        for (int m = 0; m < KMAX_MODES; ++m) if (m < K) {
+        for (int m = 0; m < KMAX_MODES; ++m) {
           double t = xv - sm_means[m * P->d_pad + k * 32 + lane];
           v[m] = v[m] + t * t;
         }
       }
       warp_sum_n<KMAX_MODES + 1>(v);
       a0 = v[KMAX_MODES];
-      const double* lw = sm_means + (size_t)K * P->d_pad;
+      const double* lw = sm_means + (size_t)KMAX_MODES * P->d_pad;
       double a[KMAX_MODES];
       double M = -PGN_INF;
 #pragma unroll
-      for (int m = 0; m < KMAX_MODES; ++m) if (m < K) {
+      for (int m = 0; m < KMAX_MODES; ++m) {
         a[m] = lw[m] - 0.5 * v[m] * ivm - cst;
         if (a[m] > M) M = a[m];
       }
       double wexp[KMAX_MODES];
-#pragma unroll
-      for (int m = 0; m < KMAX_MODES; ++m) if (m >= K) a[m] = M;
       mode_exps(a, M, K, wexp);
       double s = 0.0;
 #pragma unroll
-      for (int m = 0; m < KMAX_MODES; ++m) if (m < K) s = s + wexp[m];
+      for (int m = 0; m < KMAX_MODES; ++m) s = s + wexp[m];
       a1 = M + log_(s);
     }
   }
@@ -332,23 +336,21 @@ struct VecChain {
         const double xv = xx[k];
         v[KMAX_MODES] = v[KMAX_MODES] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
 #pragma unroll
-        for (int m = 0; m < KMAX_MODES; ++m) if (m < K) {
+        for (int m = 0; m < KMAX_MODES; ++m) {
           double t = xv - sm_means[m * P->d_pad + k * 32 + lane];
           v[m] = v[m] + t * t;
         }
       }
       warp_sum_n<KMAX_MODES + 2>(v);
       a0 = v[KMAX_MODES]; extra = v[KMAX_MODES + 1];
-      const double* lw = sm_means + (size_t)K * P->d_pad;
+      const double* lw = sm_means + (size_t)KMAX_MODES * P->d_pad;
       double w[KMAX_MODES];
       double M = -PGN_INF;
 #pragma unroll
-      for (int m = 0; m < KMAX_MODES; ++m) if (m < K) {
+      for (int m = 0; m < KMAX_MODES; ++m) {
         w[m] = lw[m] - 0.5 * v[m] * ivm - cst;
         if (w[m] > M) M = w[m];
       }
-#pragma unroll
-      for (int m = 0; m < KMAX_MODES; ++m) if (m >= K) w[m] = M;
       {
         double wexp[KMAX_MODES];
         mode_exps(w, M, K, wexp);
@@ -357,7 +359,7 @@ struct VecChain {
       }
       double s = 0.0;
 #pragma unroll
-      for (int m = 0; m < KMAX_MODES; ++m) if (m < K) s = s + w[m];
+      for (int m = 0; m < KMAX_MODES; ++m) s = s + w[m];
       a1 = M + log_(s);
 #pragma unroll
       for (int k = 0; k < CPL; ++k) {
@@ -365,7 +367,7 @@ struct VecChain {
         const double xv = xx[k];
         double acc = 0.0;
 #pragma unroll
-        for (int m = 0; m < KMAX_MODES; ++m) if (m < K) acc = acc + w[m] * (sm_means[m * P->d_pad + k * 32 + lane] - xv);
+        for (int m = 0; m < KMAX_MODES; ++m) acc = acc + w[m] * (sm_means[m * P->d_pad + k * 32 + lane] - xv);
         double gt = (acc / s) * ivm;
         double gr = -xv * ivr;
         double t = gr * (1.0 - b);
@@ -427,15 +429,15 @@ struct VecChain {
   __device__ double slice_coord(int lo, double cached_lp) {   // :89-186
     const double w = P->slice_w;
     const double cur = __shfl_sync(PGN_FULL_MASK, x[KO], lo);
-    const double z = cached_lp - next_exponential(rng);
+    const double z = cached_lp - draw_exponential();
     // slice_double :97-126
-    double L = cur - w * next_uniform(rng);
+    double L = cur - w * draw_uniform();
     double R = L + w;
     int K = P->slice_p;
     double lp_L = lp_at<KO>(lo, L);
     double lp_R = lp_at<KO>(lo, R);
     while (K > 0 && ((z < lp_L) || (z < lp_R))) {
-      double V = next_uniform(rng);
+      double V = draw_uniform();
       if (V <= 0.5) { L = L - (R - L); lp_L = lp_at<KO>(lo, L); }
       else { R = R + (R - L); lp_R = lp_at<KO>(lo, R); }
       K -= 1;
@@ -445,7 +447,7 @@ struct VecChain {
     double Lbar = L, Rbar = R;
     int n = 1;
     while (n <= P->slice_max_iter) {
-      double new_position = Lbar + next_uniform(rng) * (Rbar - Lbar);
+      double new_position = Lbar + draw_uniform() * (Rbar - Lbar);
       double new_lp = lp_at<KO>(lo, new_position);
       bool consider = z < new_lp;
       if (consider && slice_accept<KO>(lo, cur, new_position, z, L, R, lp_L, lp_R)) {
@@ -552,7 +554,7 @@ struct VecChain {
       for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : 1.0 / sd[k];
       return false;
     }
-    const double u = next_uniform(rng);
+    const double u = draw_uniform();
     if (u <= P->mix_p0) {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : 1.0 / sd[k];
@@ -562,7 +564,7 @@ struct VecChain {
       for (int k = 0; k < CPL; ++k) pre[k] = 1.0;
       return true;
     } else {
-      const double mix = next_uniform(rng);
+      const double mix = draw_uniform();
       const double rmix = 1.0 - mix;
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : mix + rmix / sd[k];
@@ -572,55 +574,64 @@ struct VecChain {
   // auto_mala! :106-182.  The forward and the reversed step-size searches
   // (auto_step_size :184-248) share ONE inlined copy of run_trial: `dir` selects the
   // start point, `mode` walks initial -> shrink | grow -> (re-evaluate at the chosen
-  // step) exactly as shrink_step_size / grow_step_size do.
-  __device__ void automala(bool use_mh) {
+  // step) exactly as shrink_step_size / grow_step_size do.  The density/gradient at the
+  // scan's starting state goes through the same copy as well (pass i = -1: a "trial" with
+  // zero momentum and eps = 0 lands exactly on x), so the kernel contains a single instance
+  // of the target's density code — this is what keeps the GMM kernel inside the instruction
+  // cache.  n_refresh_eff = 0 gives the densities only (reference chain after sample_iid!).
+  __device__ void automala(bool use_mh, int n_refresh_eff) {
     double pre[CPL];
-    const bool pre_one = build_preconditioner(pre);
-    double g0[CPL];
-    {
-      double dummy = 0.0;
-      double graw[CPL];
-      eval_grad(x, beta, e0, e1, graw, dummy);
+    bool pre_one = true;
+    if (n_refresh_eff > 0) pre_one = build_preconditioner(pre);
+    else {
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) g0[k] = pre_one ? graw[k] : graw[k] / pre[k];
+      for (int k = 0; k < CPL; ++k) pre[k] = 1.0;
     }
-    double lp0 = lp_ad(beta, e0, e1);
+    double g0[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) g0[k] = 0.0;
+    double lp0 = 0.0;
     if (!(P->step_size > 0)) { err = PGN_ERR_INVALID; return; }
     Trial T;
-    for (int i = 0; i < P->n_refresh; ++i) {
-      double p[CPL];
-      double pp = 0.0;
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) {
-        p[k] = valid(k) ? normal_at(rng, rng.ctr + (unsigned long long)(k * 32 + lane)) : 0.0;   // randn!(rng, momentum)
-        pp = valid(k) ? pp + p[k] * p[k] : pp;
-      }
-      rng.ctr += (unsigned long long)d;
-      // a, b (:132-133) and the MH uniform (:173) are the next three ticks of this replica's
-      // stream; lanes 0..2 draw them (and the logs of a, b) in one SIMT pass
-      double mine = uniform_at(rng, rng.ctr + (unsigned long long)(lane < 3 ? lane : 0));
-      double lmine = log_(mine);
-      rng.ctr += use_mh ? 3ull : 2ull;
-      const double a = __shfl_sync(PGN_FULL_MASK, mine, 0), b = __shfl_sync(PGN_FULL_MASK, mine, 1);
-      const double la = __shfl_sync(PGN_FULL_MASK, lmine, 0), lb = __shfl_sync(PGN_FULL_MASK, lmine, 1);
-      const double u_mh = __shfl_sync(PGN_FULL_MASK, mine, 2);
-      const double lower = a < b ? la : lb;     // log(min(a, b))
-      const double upper = a < b ? lb : la;     // log(max(a, b))
-      const double init_joint = lp0 - 0.5 * warp_sum(pp);
-      if (!is_finite(init_joint)) { err = PGN_ERR_NOT_POSITIVE; return; }
-      if (!(lower < upper)) { err = PGN_ERR_INVALID; return; }
-
+    for (int i = -1; i < n_refresh_eff; ++i) {
       double sx[CPL], sp[CPL], sg[CPL];     // start point of the current search
       double fx[CPL], fg[CPL];              // forward proposal (kept across the reversed search)
       double f_a0 = 0.0, f_a1 = 0.0, f_lp = 0.0, h_rev = 0.0;
+      double lower = 0.0, upper = 0.0, u_mh = 0.0, init_joint = 0.0;
       int expo[2] = {0, 0};
-      double h_before = init_joint;
+      if (i >= 0) {
+        double p[CPL];
+        double pp = 0.0;
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) { sx[k] = x[k]; sp[k] = p[k]; sg[k] = g0[k]; fx[k] = 0.0; fg[k] = 0.0; }
-      const int n_dir = use_mh ? 2 : 1;
+        for (int k = 0; k < CPL; ++k) {
+          p[k] = valid(k) ? normal_at(rng, rng.ctr + (unsigned long long)(k * 32 + lane)) : 0.0;   // randn!(rng, momentum)
+          pp = valid(k) ? pp + p[k] * p[k] : pp;
+        }
+        rng.ctr += (unsigned long long)d;
+        // a, b (:132-133) and the MH uniform (:173) are the next three ticks of this replica's
+        // stream; lanes 0..2 draw them (and the logs of a, b) in one SIMT pass
+        double mine = uniform_at(rng, rng.ctr + (unsigned long long)(lane < 3 ? lane : 0));
+        double lmine = log_(mine);
+        rng.ctr += use_mh ? 3ull : 2ull;
+        const double a = __shfl_sync(PGN_FULL_MASK, mine, 0), b = __shfl_sync(PGN_FULL_MASK, mine, 1);
+        const double la = __shfl_sync(PGN_FULL_MASK, lmine, 0), lb = __shfl_sync(PGN_FULL_MASK, lmine, 1);
+        u_mh = __shfl_sync(PGN_FULL_MASK, mine, 2);
+        lower = a < b ? la : lb;     // log(min(a, b))
+        upper = a < b ? lb : la;     // log(max(a, b))
+        init_joint = lp0 - 0.5 * warp_sum(pp);
+        if (!is_finite(init_joint)) { err = PGN_ERR_NOT_POSITIVE; return; }
+        if (!(lower < upper)) { err = PGN_ERR_INVALID; return; }
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) { sx[k] = x[k]; sp[k] = p[k]; sg[k] = g0[k]; fx[k] = 0.0; fg[k] = 0.0; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) { sx[k] = x[k]; sp[k] = 0.0; sg[k] = 0.0; fx[k] = 0.0; fg[k] = 0.0; }
+      }
+      double h_before = init_joint;
+      const int n_dir = (i >= 0 && use_mh) ? 2 : 1;
       for (int dir = 0; dir < n_dir; ++dir) {
-        int mode = 0, n = 0, exponent = 0, nst = 0;
-        double eps = P->step_size;
+        int mode = i >= 0 ? 0 : 4, n = 0, exponent = 0, nst = 0;
+        double eps = i >= 0 ? P->step_size : 0.0;
         while (true) {
           const double diff = run_trial(sx, sp, sg, pre, pre_one, eps, h_before, T);
           bool decided = false;
@@ -636,7 +647,7 @@ struct VecChain {
             if (!is_finite(diff) || diff < upper) { nst = n; exponent = n - 1; decided = true; }
             else { n += 1; eps = eps * 2.0; }
           } else {
-            break;                                        // mode 3: re-evaluated at the chosen step
+            break;                                        // mode 3: re-evaluated at the chosen step; mode 4: densities at x
           }
           if (decided) {
             const double eps_final = P->step_size * pow2(exponent);   // leap_frog! at the chosen step :144-151
@@ -644,6 +655,7 @@ struct VecChain {
             mode = 3; eps = eps_final;
           }
         }
+        if (i < 0) break;
         n_steps += 1 + nst;
         am.fit(pow2(exponent));
         expo[dir] = exponent;
@@ -660,6 +672,12 @@ struct VecChain {
         } else {
           n_ref += 1 + 3 * (1 + nst);
         }
+      }
+      if (i < 0) {   // densities and conditioned gradient at the scan's starting state
+        e0 = T.a0; e1 = T.a1; lp0 = T.lp1;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) g0[k] = T.g1c[k];
+        continue;
       }
       bool accept = true;
       if (use_mh) {
@@ -708,7 +726,7 @@ struct VecChain {
       const double prob = 1.0 < e ? 1.0 : e;
       expl_acc.fit(prob);
       n_ref += 4;
-      if (next_uniform(rng) < prob) {
+      if (draw_uniform() < prob) {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) { x[k] = T.x1[k]; g0[k] = T.g1c[k]; }
         e0 = T.a0; e1 = T.a1; lp0 = T.lp1;
@@ -719,16 +737,36 @@ struct VecChain {
 
   // ---- explore!(pt, replica, explorer) (src/pt/pigeons.jl:101-132) --------------
   __device__ void explore(long long scan, bool is_reference) {
+    if (EX == PGN_EXPLORER_AUTOMALA) {
+      if (is_reference) sample_iid(beta);
+      automala(scan != 1, is_reference ? 0 : P->n_refresh);   // AutoMALA.jl:87,102
+      return;
+    }
     if (is_reference) { sample_iid(beta); eval(x, e0, e1); return; }
     if (EX == PGN_EXPLORER_TOY) { sample_iid(beta); eval(x, e0, e1); }
     else if (EX == PGN_EXPLORER_SLICE) slice_step();
-    else if (EX == PGN_EXPLORER_MALA) mala();
-    else automala(scan != 1);   // AutoMALA.jl:87,102
+    else mala();
   }
   // log_unnormalized_ratio (src/log_potentials/log_potentials.jl:43-51)
   __device__ double log_ratio(double beta_partner) const {
     return lp_call(beta_partner, e0, e1) - lp_call(beta, e0, e1);
   }
+  // Pooled uniforms: the replica's draws are consecutive ticks of one Philox stream, so the next
+  // 32 are produced in one SIMT pass (lane l: tick pool_base + l) and handed out by shuffle —
+  // same stream, values and order as one Philox per draw, without the 10 rounds on the serial path.
+  __device__ __forceinline__ double draw_uniform() {
+    unsigned long long idx = rng.ctr - pool_base;
+    if (!pool_valid || idx >= 32ull) {
+      pool_base = rng.ctr;
+      pool = uniform_at(rng, pool_base + (unsigned long long)lane);
+      pool_valid = true;
+      idx = 0;
+    }
+    rng.ctr += 1;
+    return __shfl_sync(PGN_FULL_MASK, pool, (int)idx);
+  }
+  __device__ __forceinline__ double draw_exponential() { return -log_(1.0 - draw_uniform()); }
+  __device__ __forceinline__ void on_replica_changed() { pool_valid = false; }
 };
 
 // ===========================================================================
@@ -745,8 +783,28 @@ struct IsingChain {
   MeanAcc expl_acc, am, rev;
   long long n_steps, n_points, n_ref;
   int err;
+  // The replica's uniforms are consecutive ticks of one Philox stream, so the next 32 of them
+  // can be generated in ONE SIMT pass (lane l computes tick pool_base + l) and handed out with
+  // a shuffle: the 10-round Philox leaves the serial per-site dependency chain.  Same stream,
+  // same values, same order as drawing them one by one.
+  double pool;
+  unsigned long long pool_base;
+  bool pool_valid;
 
   static __device__ void stage_shared(const Params&, double*) {}
+
+  __device__ __forceinline__ double draw_uniform() {
+    unsigned long long idx = rng.ctr - pool_base;
+    if (!pool_valid || idx >= 32ull) {
+      pool_base = rng.ctr;
+      pool = uniform_at(rng, pool_base + (unsigned long long)lane);
+      pool_valid = true;
+      idx = 0;
+    }
+    rng.ctr += 1;
+    return __shfl_sync(PGN_FULL_MASK, pool, (int)idx);
+  }
+  __device__ __forceinline__ void on_replica_changed() { pool_valid = false; }
 
   __device__ __forceinline__ int sgn(unsigned int r, int j) const { return ((r >> j) & 1u) ? 1 : -1; }
   __device__ void recompute_S() {   // examples/ising.jl:28-36
@@ -770,6 +828,7 @@ struct IsingChain {
     rng.ctr = Pr.rng_ctr[wl];
     expl_acc = MeanAcc{0, 0.0}; am = MeanAcc{0, 0.0}; rev = MeanAcc{0, 0.0};
     n_steps = n_points = n_ref = 0; err = 0;
+    pool = 0.0; pool_base = 0; pool_valid = false;
   }
   __device__ void store(int wl) {
     unsigned int* rows = reinterpret_cast<unsigned int*>(P->x + (size_t)wl * P->d_pad);
@@ -816,7 +875,7 @@ struct IsingChain {
           const double log_pr_after = lp(beta, S_new);
           const double accept_ratio = exp_(log_pr_after - log_pr_before);
           bool reject = false;
-          if (accept_ratio < 1) reject = next_uniform(rng) > accept_ratio;
+          if (accept_ratio < 1) reject = draw_uniform() > accept_ratio;
           if (!reject) { cur ^= (1u << j); S = S_new; }
         }
         if (lane == i) row = cur;
@@ -856,6 +915,8 @@ struct TestSwapperChain {
   __device__ void store_online() const {}
   __device__ void explore(long long, bool) {}
   __device__ double log_ratio(double) const { return 0.0; }
+  __device__ __forceinline__ double draw_uniform() { return next_uniform(rng); }
+  __device__ __forceinline__ void on_replica_changed() {}
 };
 
 // ===========================================================================
@@ -902,7 +963,7 @@ __global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Param
       ch.n_ref += 2;
       if (lr != lr) { err = PGN_ERR_NAN_RATIO; break; }
     }
-    const double u = next_uniform(ch.rng);
+    const double u = ch.draw_uniform();
     const size_t log_at = (size_t)(scan - 1) * P.n_local + wl;
     if (lane == 0) {   // recorded before the swap (swap.jl:110-111)
       if (P.index_process) P.index_process[log_at] = replica_index;
@@ -984,6 +1045,7 @@ __global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Param
         rt_state = __ldcg(&hp->rt_state);
         ch.rng.ctr = __ldcg(&hp->ctr);
         ch.rng.key1 = (unsigned int)replica_index;
+        ch.on_replica_changed();
         ch.adopt(reinterpret_cast<const double*>(src + MAIL_HDR_BYTES));
       }
     }
