@@ -16,6 +16,7 @@
 
 #include "pgn_kernels.cuh"
 #include "pgn_logreg.cuh"
+#include "pgn_memchain.cuh"
 
 using namespace pgn;
 
@@ -93,6 +94,11 @@ struct pgn_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool initialised = false;
   unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+  // ---- memory-resident scan path (any d, any number of chains; pgn_memchain.cuh)
+  bool force_mem = false;
+  DevBuf<MemRec> mem_rec;
+  DevBuf<double> mem_vec[10];
+  bool mem_allocated = false;
   // ---- logistic regression (batched GEMM path)
   int lr_n_data = 0, lr_n_pad = 0, lr_r_pad = 0, lr_splits = 0;
   DevBuf<double> lr_Xr, lr_Xt, lr_y, lr_Theta, lr_Thetat, lr_LL, lr_Res, lr_lik, lr_Gp, lr_G;
@@ -372,6 +378,39 @@ void* select_scan_kernel(const pgn_handle* h) {
     default: return nullptr;
   }
 }
+template <int TK>
+void* mem_kernel_for(int ex) {
+  switch (ex) {
+    case PGN_EXPLORER_TOY: return TK == PGN_TARGET_TOY_MVN ? (void*)scan_kernel_mem<TK, PGN_EXPLORER_TOY> : nullptr;
+    case PGN_EXPLORER_SLICE: return (void*)scan_kernel_mem<TK, PGN_EXPLORER_SLICE>;
+    case PGN_EXPLORER_AUTOMALA: return (void*)scan_kernel_mem<TK, PGN_EXPLORER_AUTOMALA>;
+    case PGN_EXPLORER_MALA: return (void*)scan_kernel_mem<TK, PGN_EXPLORER_MALA>;
+    default: return nullptr;
+  }
+}
+void* select_mem_kernel(const pgn_handle* h) {
+  switch (h->cfg.target_kind) {
+    case PGN_TARGET_TOY_MVN: return mem_kernel_for<PGN_TARGET_TOY_MVN>(h->ep.kind);
+    case PGN_TARGET_FUNNEL: return mem_kernel_for<PGN_TARGET_FUNNEL>(h->ep.kind);
+    case PGN_TARGET_GMM: return mem_kernel_for<PGN_TARGET_GMM>(h->ep.kind);
+    default: return nullptr;
+  }
+}
+void mem_allocate(pgn_handle* h) {
+  if (h->mem_allocated) return;
+  h->mem_rec.alloc(h->n_local);
+  for (int i = 0; i < 10; ++i) h->mem_vec[i].alloc((size_t)h->n_local * h->d_pad);
+  h->mem_allocated = true;
+}
+void mem_fill_params(pgn_handle* h, const Params& P, MemParams& MP) {
+  MP.base = P;
+  MP.rec = h->mem_rec.p;
+  MP.VP = h->mem_vec[0].p; MP.VG0 = h->mem_vec[1].p; MP.VSX = h->mem_vec[2].p; MP.VSP = h->mem_vec[3].p;
+  MP.VSG = h->mem_vec[4].p; MP.VTX = h->mem_vec[5].p; MP.VTP = h->mem_vec[6].p; MP.VTG = h->mem_vec[7].p;
+  MP.VFX = h->mem_vec[8].p; MP.VFG = h->mem_vec[9].p;
+  MP.nslots = h->d_pad / 32;
+}
+
 size_t scan_smem_bytes(const pgn_handle* h) {
   if (h->cfg.target_kind == PGN_TARGET_GMM) return ((size_t)KMAX_MODES * h->d_pad + KMAX_MODES) * sizeof(double);
   return 0;
@@ -383,6 +422,14 @@ void launch_eval_points(pgn_handle* h, const Params& P, const double* xs, const 
   const int wpb = 4;
   const int grid = (n + wpb - 1) / wpb;
   const size_t smem = scan_smem_bytes(h);
+  if (h->cpl == 0) {   // d > 128: memory-resident evaluation; xs / grad are padded [n][d_pad] here
+    MemParams MP;
+    std::memset(&MP, 0, sizeof(MP));
+    MP.base = P;
+    MP.nslots = h->d_pad / 32;
+    eval_points_mem_kernel<TK><<<grid, wpb * 32, 0, h->stream>>>(MP, xs, betas, n, lp, ld, grad);
+    return;
+  }
   switch (h->cpl) {
     case 1: eval_points_kernel<TK, 1><<<grid, wpb * 32, smem, h->stream>>>(P, xs, betas, n, lp, ld, grad); break;
     case 2: eval_points_kernel<TK, 2><<<grid, wpb * 32, smem, h->stream>>>(P, xs, betas, n, lp, ld, grad); break;
@@ -424,7 +471,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
   switch (cfg->target_kind) {
     case PGN_TARGET_TOY_MVN: case PGN_TARGET_FUNNEL: case PGN_TARGET_GMM:
       if (cfg->dim < 1) return fail(err, PGN_ERR_INVALID, "dim must be >= 1");
-      if (cfg->dim > 128) return fail(err, PGN_ERR_INVALID, "register-resident chains support dim <= 128 in this build");
+      if (cfg->dim > (1 << 20)) return fail(err, PGN_ERR_INVALID, "dim too large");
       break;
     case PGN_TARGET_ISING: {
       const int L = (int)cfg->p[1];
@@ -465,10 +512,18 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
       h->d_pad = (d + 127) / 128 * 128;
       h->pay_doubles = h->d_pad + 2;
     }
-    else {
+    else if (d <= 128) {
       h->cpl = d <= 32 ? 1 : (d <= 64 ? 2 : 4);
       h->d_pad = h->cpl * 32;
       h->pay_doubles = h->d_pad;
+    } else {   // memory-resident chains only
+      h->cpl = 0;
+      h->d_pad = (d + 31) / 32 * 32;
+      h->pay_doubles = h->d_pad;
+    }
+    {
+      const char* fm = std::getenv("PGN_FORCE_MEM");
+      h->force_mem = fm != nullptr && std::string(fm) == "1";
     }
     h->slot_bytes = (size_t)MAIL_HDR_BYTES + (size_t)h->pay_doubles * sizeof(double);
     h->slot_bytes = (h->slot_bytes + 127) / 128 * 128;
@@ -483,9 +538,12 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
     h->mail.alloc(h->mail_bytes);
     h->std_devs.alloc(std::max(d, 1));
     if (cfg->target_kind == PGN_TARGET_GMM) {
-      std::vector<double> padded((size_t)cfg->n_modes * h->d_pad, 0.0);
+      // staged layout: [KMAX_MODES][d_pad] means (zero rows beyond K) + KMAX_MODES log weights (-inf beyond K)
+      std::vector<double> padded((size_t)KMAX_MODES * h->d_pad + KMAX_MODES, 0.0);
       for (int k = 0; k < cfg->n_modes; ++k)
         for (int c = 0; c < d; ++c) padded[(size_t)k * h->d_pad + c] = cfg->means[(size_t)k * d + c];
+      for (int k = 0; k < KMAX_MODES; ++k)
+        padded[(size_t)KMAX_MODES * h->d_pad + k] = k < cfg->n_modes ? cfg->log_weights[k] : -INFINITY;
       h->means.alloc(padded.size());
       h->means.upload(padded.data(), padded.size());
       h->log_w.alloc(cfg->n_modes);
@@ -636,7 +694,8 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     use_device(h);
     const bool is_logreg = h->cfg.target_kind == PGN_TARGET_LOGREG;
     void* kernel = is_logreg ? nullptr : select_scan_kernel(h);
-    if (!kernel && !is_logreg) throw CudaError{PGN_ERR_INVALID, "explorer not supported for this target on the device"};
+    if (!kernel && !is_logreg && !select_mem_kernel(h))
+      throw CudaError{PGN_ERR_INVALID, "explorer not supported for this target on the device"};
     const int nl = h->n_local, d = h->cfg.dim;
     h->epoch += 1;
     Params P;
@@ -663,26 +722,78 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
       LP.swap_accept = P.swap_accept; LP.target_trace = P.target_trace;
       logreg_run_round(h, n_scans, LP, st, ms);
     } else {
-      // launch geometry: one warp per chain, all warps co-resident
+      // launch geometry of the register-resident kernel: one warp per chain, all warps co-resident
       const size_t smem = scan_smem_bytes(h);
       int wpb = 0, grid = 0;
-      for (int w = 1; w <= 8; w *= 2) {
-        int per_sm = 0;
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, smem));
-        const int g = (nl + w - 1) / w;
-        if ((long long)per_sm * h->n_sms >= g) { wpb = w; grid = g; break; }
+      const bool vec_target = h->cfg.target_kind == PGN_TARGET_TOY_MVN || h->cfg.target_kind == PGN_TARGET_FUNNEL ||
+                              h->cfg.target_kind == PGN_TARGET_GMM;
+      if (kernel && !(h->force_mem && vec_target)) {
+        for (int w = 1; w <= 8; w *= 2) {
+          int per_sm = 0;
+          CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, smem));
+          const int g = (nl + w - 1) / w;
+          if ((long long)per_sm * h->n_sms >= g) { wpb = w; grid = g; break; }
+        }
       }
-      if (wpb == 0)
-        throw CudaError{PGN_ERR_INVALID, "too many chains for one GPU: all chains of a shard must be co-resident"};
-      void* args[] = {(void*)&P};
-      CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-      if (n_scans > 0)
-        CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(wpb * 32), args, smem, h->stream));
-      CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
-      CUDA_CHECK(cudaStreamSynchronize(h->stream));
-      CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-      if (n_scans > 0) h->stats.download(st.data(), nl);
-      else std::memset(st.data(), 0, sizeof(ChainStatsDev) * nl);
+      if (wpb != 0) {
+        void* args[] = {(void*)&P};
+        CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+        if (n_scans > 0)
+          CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(wpb * 32), args, smem, h->stream));
+        CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        if (n_scans > 0) h->stats.download(st.data(), nl);
+        else std::memset(st.data(), 0, sizeof(ChainStatsDev) * nl);
+      } else {
+        // memory-resident kernel: d > 128, or more chains than fit co-resident, or PGN_FORCE_MEM=1
+        void* mk = vec_target ? select_mem_kernel(h) : nullptr;
+        if (!mk) throw CudaError{PGN_ERR_INVALID, "too many chains for one GPU for this target (no memory-resident variant)"};
+        mem_allocate(h);
+        MemParams MP;
+        mem_fill_params(h, P, MP);
+        std::vector<int> ri(nl);
+        std::vector<unsigned long long> ctr(nl);
+        h->replica_index.download(ri.data(), nl);
+        h->rng_ctr.download(ctr.data(), nl);
+        std::vector<MemRec> rec(nl);
+        std::memset(rec.data(), 0, sizeof(MemRec) * nl);
+        for (int i = 0; i < nl; ++i) {
+          rec[i].ctr = ctr[i]; rec[i].replica_index = ri[i];
+          rec[i].ls_fwd.value = -INFINITY; rec[i].ls_bwd.value = -INFINITY;
+        }
+        h->mem_rec.upload(rec.data(), nl);
+        CUDA_CHECK(cudaMemsetAsync(h->online_mean.p, 0, sizeof(double) * h->d_pad, h->stream));
+        CUDA_CHECK(cudaMemsetAsync(h->online_s2.p, 0, sizeof(double) * h->d_pad, h->stream));
+        CUDA_CHECK(cudaMemsetAsync(h->online_n.p, 0, sizeof(long long), h->stream));
+        const int mwpb = 4;
+        int per_sm = 0;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mk, mwpb * 32, 0));
+        if (per_sm < 1) throw CudaError{PGN_ERR_CUDA, "memory-resident scan kernel does not fit on an SM"};
+        const int max_blocks = per_sm * h->n_sms;
+        const int mgrid = std::min(max_blocks, (nl + mwpb - 1) / mwpb);
+        void* args[] = {(void*)&MP};
+        CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+        if (n_scans > 0)
+          CUDA_CHECK(cudaLaunchCooperativeKernel(mk, dim3(mgrid), dim3(mwpb * 32), args, 0, h->stream));
+        CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->mem_rec.download(rec.data(), nl);
+        std::vector<int> rt(nl);
+        for (int i = 0; i < nl; ++i) {
+          const MemRec& r = rec[i];
+          ri[i] = r.replica_index; ctr[i] = r.ctr; rt[i] = r.rt_state;
+          ChainStatsDev& o = st[i];
+          o.swap_n = r.swap_acc.n; o.swap_mean = r.swap_acc.mu; o.ls_fwd = r.ls_fwd.value; o.ls_bwd = r.ls_bwd.value;
+          o.expl_acc_n = r.expl_acc.n; o.expl_acc_mean = r.expl_acc.mu; o.n_steps = r.n_steps;
+          o.am_n = r.am.n; o.am_mean = r.am.mu; o.rev_n = r.rev.n; o.rev_mean = r.rev.mu;
+          o.n_restarts = r.n_restarts; o.n_round_trips = r.n_trips; o.n_points = r.n_points; o.n_ref_evals = r.n_ref;
+        }
+        h->replica_index.upload(ri.data(), nl);
+        h->rng_ctr.upload(ctr.data(), nl);
+        h->rt_state.upload(rt.data(), nl);
+      }
     }
     int flag = 0;
     h->error_flag.download(&flag, 1);
@@ -754,8 +865,11 @@ int pgn_log_potential(pgn_handle* h, const double* x, int32_t n_points, const do
       return PGN_OK;
     }
     DevBuf<double> dx, db, dout;
-    dx.alloc((size_t)n_points * d, false); db.alloc(n_points, false); dout.alloc(n_points, false);
-    dx.upload(x, (size_t)n_points * d); db.upload(beta, n_points);
+    const int ldx = h->cpl == 0 && h->cfg.target_kind != PGN_TARGET_ISING ? h->d_pad : d;   // d > 128: padded rows
+    dx.alloc((size_t)n_points * ldx, true); db.alloc(n_points, false); dout.alloc(n_points, false);
+    if (ldx == d) dx.upload(x, (size_t)n_points * d);
+    else CUDA_CHECK(cudaMemcpy2D(dx.p, sizeof(double) * ldx, x, sizeof(double) * d, sizeof(double) * d, n_points, cudaMemcpyHostToDevice));
+    db.upload(beta, n_points);
     Params P;
     fill_params(h, P);
     switch (h->cfg.target_kind) {
@@ -785,9 +899,12 @@ int pgn_logdensity_and_gradient(pgn_handle* h, const double* x, int32_t n_points
     if (tk != PGN_TARGET_TOY_MVN && tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM)
       return fail(err, PGN_ERR_INVALID, "target has no gradient");
     DevBuf<double> dx, db, dld, dg;
-    dx.alloc((size_t)n_points * d, false); db.alloc(n_points, false); dld.alloc(n_points, false);
-    dg.alloc((size_t)n_points * d, false);
-    dx.upload(x, (size_t)n_points * d); db.upload(beta, n_points);
+    const int ldx = h->cpl == 0 ? h->d_pad : d;   // d > 128: padded rows
+    dx.alloc((size_t)n_points * ldx, true); db.alloc(n_points, false); dld.alloc(n_points, false);
+    dg.alloc((size_t)n_points * ldx, true);
+    if (ldx == d) dx.upload(x, (size_t)n_points * d);
+    else CUDA_CHECK(cudaMemcpy2D(dx.p, sizeof(double) * ldx, x, sizeof(double) * d, sizeof(double) * d, n_points, cudaMemcpyHostToDevice));
+    db.upload(beta, n_points);
     Params P;
     fill_params(h, P);
     switch (tk) {
@@ -798,7 +915,8 @@ int pgn_logdensity_and_gradient(pgn_handle* h, const double* x, int32_t n_points
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
     dld.download(logdens, n_points);
-    dg.download(grad, (size_t)n_points * d);
+    if (ldx == d) dg.download(grad, (size_t)n_points * d);
+    else CUDA_CHECK(cudaMemcpy2D(grad, sizeof(double) * d, dg.p, sizeof(double) * ldx, sizeof(double) * d, n_points, cudaMemcpyDeviceToHost));
   } catch (CudaError& e) { return fail(err, e.code, e.msg); }
   return PGN_OK;
 }

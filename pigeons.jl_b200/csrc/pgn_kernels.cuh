@@ -133,11 +133,11 @@ struct VecChain {
 
   static __device__ void stage_shared(const Params& P, double* smem) {
     if (TK == PGN_TARGET_GMM) {
-      const int n = KMAX_MODES * P.d_pad;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = i < P.n_modes * P.d_pad ? P.means[i] : 0.0;
-      // components beyond K are padded with weight exp(-inf) = 0: their terms add exact zeros, so the
-      // mode loops run over all KMAX_MODES slots without predicates and give the same bits as K terms
-      for (int i = threadIdx.x; i < KMAX_MODES; i += blockDim.x) smem[n + i] = i < P.n_modes ? P.log_w[i] : -PGN_INF;
+      // P.means is the staged layout [KMAX_MODES][d_pad] followed by KMAX_MODES log weights; components
+      // beyond K are padded with weight exp(-inf) = 0: their terms add exact zeros, so the mode loops
+      // run over all KMAX_MODES slots without predicates and give the same bits as K terms
+      const int n = KMAX_MODES * P.d_pad + KMAX_MODES;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = P.means[i];
     }
   }
 

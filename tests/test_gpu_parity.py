@@ -159,8 +159,58 @@ def test_errors_are_reported_not_swallowed(gpu_lib):
 
 
 def test_unsupported_configuration_raises(gpu_lib):
+    """Device targets are a closed family: a 9-component mixture has no device implementation."""
+    nine = pg.GaussianMixture(means=np.arange(18.0).reshape(9, 2), reference_sigma=3.0)
     with pytest.raises(pg.EngineError):
-        pg.Engine(gpu_lib, n_chains=4, seed=1, **pg.toy_mvn_target(1000).engine_config())
+        pg.Engine(gpu_lib, n_chains=4, seed=1, **nine.engine_config())
+
+
+MEM_FORCED = ["c1_toy_slice", "toy_default_explorer", "toy10_automala", "toy40_slice_2cpl", "toy100_automala_4cpl",
+              "funnel32_automala", "funnel8_slice", "funnel_diag_precond", "gmm128_automala", "gmm6_slice",
+              "gmm2_two_modes", "toy10_mala", "gmm70_mala_4cpl", "single_chain", "two_chains"]
+
+
+@pytest.mark.parametrize("name", MEM_FORCED)
+def test_memory_resident_kernel_parity(name, gpu_lib, oracle_lib, monkeypatch):
+    """PGN_FORCE_MEM=1: the memory-resident scan kernel (any d, any number of chains) reproduces the
+    oracle bit for bit on the same cases as the register-resident kernel."""
+    monkeypatch.setenv("PGN_FORCE_MEM", "1")
+    kw = CASES[name]
+    assert_same(run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw), name + "/mem")
+
+
+BIG_CASES = {
+    # dimensions beyond the register-resident limit (d > 128)
+    "toy1000_automala": dict(target=pg.toy_mvn_target(1000), explorer=pg.AutoMALA(), n_chains=4, n_rounds=5, seed=1),
+    "funnel300_slice": dict(target=pg.Funnel(300), explorer=pg.SliceSampler(), n_chains=3, n_rounds=3, seed=2),
+    "gmm200_automala": dict(target=pg.eight_mode_mixture(200, 4.0), explorer=pg.AutoMALA(), n_chains=5, n_rounds=4, seed=3),
+    "funnel500_mala": dict(target=pg.Funnel(500), explorer=pg.MALA(step_size=0.05), n_chains=4, n_rounds=4, seed=4),
+    # more chains than fit co-resident: one warp serves several chains
+    "toy2_slice_6000_chains": dict(target=pg.toy_mvn_target(2), explorer=pg.SliceSampler(), n_chains=6000, n_rounds=3, seed=5,
+                                   record=[pg.index_process, pg.swap_trace]),
+    "funnel8_automala_5000_chains": dict(target=pg.Funnel(8), explorer=pg.AutoMALA(), n_chains=5000, n_rounds=2, seed=6,
+                                         record=[pg.index_process, pg.swap_trace]),
+}
+
+
+@pytest.mark.parametrize("name", list(BIG_CASES))
+def test_large_dimension_and_many_chains(name, gpu_lib, oracle_lib):
+    kw = BIG_CASES[name]
+    assert_same(run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw), name)
+
+
+def test_entry_points_large_dimension(gpu_lib, oracle_lib):
+    rng = np.random.default_rng(7)
+    for target in (pg.toy_mvn_target(1000), pg.Funnel(300), pg.eight_mode_mixture(200, 4.0)):
+        cfg = target.engine_config()
+        eg = pg.Engine(gpu_lib, n_chains=4, seed=1, **cfg)
+        eo = pg.Engine(oracle_lib, n_chains=4, seed=1, **cfg)
+        x = rng.normal(0, 1, (9, target.dim))
+        beta = np.array([0.0, 1.0, 0.5, 0.1, 0.9, 0.3, 0.7, 0.2, 0.8])
+        assert np.array_equal(eg.log_potential(x, beta), eo.log_potential(x, beta))
+        (ldg, gg), (ldo, go) = eg.logdensity_and_gradient(x, beta), eo.logdensity_and_gradient(x, beta)
+        assert np.array_equal(ldg, ldo) and np.array_equal(gg, go)
+        eg.close(); eo.close()
 
 
 def test_dmma_is_a_sequential_fma_chain(gpu_lib):
