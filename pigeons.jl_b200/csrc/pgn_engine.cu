@@ -80,6 +80,7 @@ struct pgn_handle {
   int cpl = 1, d_pad = 32, pay_doubles = 32;
   size_t slot_bytes = 0, mail_bytes = 0;
   unsigned int epoch = 0;
+  unsigned long long scan_seq = 0;   // scans run so far (all rounds): base of the mailbox tags
   int n_sms = 0;
   DevBuf<double> beta, x, means, log_w, std_devs, online_mean, online_s2;
   DevBuf<int> replica_index, rt_state, error_flag;
@@ -120,6 +121,7 @@ void fill_params(pgn_handle* h, Params& P) {
   P.seed_lo = (unsigned int)(unsigned long long)h->cfg.seed;
   P.seed_hi = (unsigned int)((unsigned long long)h->cfg.seed >> 32);
   P.epoch = h->epoch;
+  P.tag_base = (unsigned int)h->scan_seq;
   for (int i = 0; i < 8; ++i) P.p[i] = h->cfg.p[i];
   P.n_modes = h->cfg.n_modes;
   P.means = h->means.p; P.log_w = h->log_w.p; P.beta = h->beta.p;
@@ -411,9 +413,21 @@ void mem_fill_params(pgn_handle* h, const Params& P, MemParams& MP) {
   MP.nslots = h->d_pad / 32;
 }
 
-size_t scan_smem_bytes(const pgn_handle* h) {
-  if (h->cfg.target_kind == PGN_TARGET_GMM) return ((size_t)KMAX_MODES * h->d_pad + KMAX_MODES) * sizeof(double);
-  return 0;
+bool is_team_kernel(const pgn_handle* h) {   // VecChain<.., AUTOMALA>::kTeam
+  const int tk = h->cfg.target_kind;
+  return h->ep.kind == PGN_EXPLORER_AUTOMALA && h->cpl > 0 &&
+         (tk == PGN_TARGET_TOY_MVN || tk == PGN_TARGET_FUNNEL || tk == PGN_TARGET_GMM);
+}
+// dynamic shared memory of the scan kernel: staged target constants, then (team kernels) the
+// control words and 3 rotating buffers of W trial slots
+size_t scan_smem_bytes(const pgn_handle* h, int team_w = 0, int warps_per_block = 1, int pool_refresh = 0) {
+  size_t n = 0;
+  if (h->cfg.target_kind == PGN_TARGET_GMM) n += (size_t)KMAX_MODES * h->d_pad + KMAX_MODES;
+  if (h->cfg.target_kind == PGN_TARGET_ISING)   // one Metropolis-ratio table per chain (IsingChain::build_table)
+    n += (size_t)warps_per_block * IsingChain::table_doubles((int)h->cfg.p[1]);
+  if (team_w > 0) n += (24 + h->cpl * 32) + (size_t)3 * team_w * (3 * h->cpl * 32 + 8);   // VecChain::TEAM_CTL_DOUBLES + slots
+  if (team_w > 1) n += (size_t)pool_refresh * (h->cpl * 32 + 8);                          // VecChain::POOL_DOUBLES per refreshment
+  return n * sizeof(double);
 }
 
 template <int TK>
@@ -525,7 +539,9 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
       const char* fm = std::getenv("PGN_FORCE_MEM");
       h->force_mem = fm != nullptr && std::string(fm) == "1";
     }
-    h->slot_bytes = (size_t)MAIL_HDR_BYTES + (size_t)h->pay_doubles * sizeof(double);
+    // the scan kernel's flag-in-data words need 16 bytes per payload double (8 header words + 2 words per double);
+    // the logistic-regression and memory-resident kernels use the first 64 + 8 * pay_doubles bytes of a slot
+    h->slot_bytes = (size_t)MAIL_HDR_BYTES + (size_t)h->pay_doubles * 2 * sizeof(double);
     h->slot_bytes = (h->slot_bytes + 127) / 128 * 128;
     h->mail_bytes = (size_t)(h->n_local + 2) * MAIL_RINGS * h->slot_bytes;
     const int nl = h->n_local;
@@ -701,6 +717,7 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     Params P;
     fill_params(h, P);
     P.n_scans = n_scans;
+    h->scan_seq += (unsigned long long)n_scans;   // P.tag_base holds the count before this round
     LrParams LP;
     if (is_logreg) logreg_fill_params(h, LP);
     // optional event logs
@@ -723,16 +740,38 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
       logreg_run_round(h, n_scans, LP, st, ms);
     } else {
       // launch geometry of the register-resident kernel: one warp per chain, all warps co-resident
-      const size_t smem = scan_smem_bytes(h);
+      size_t smem = scan_smem_bytes(h);
       int wpb = 0, grid = 0;
       const bool vec_target = h->cfg.target_kind == PGN_TARGET_TOY_MVN || h->cfg.target_kind == PGN_TARGET_FUNNEL ||
                               h->cfg.target_kind == PGN_TARGET_GMM;
       if (kernel && !(h->force_mem && vec_target)) {
-        for (int w = 1; w <= 8; w *= 2) {
-          int per_sm = 0;
-          CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, smem));
-          const int g = (nl + w - 1) / w;
-          if ((long long)per_sm * h->n_sms >= g) { wpb = w; grid = g; break; }
+        if (is_team_kernel(h)) {
+          // block = the team of W warps serving one chain.  W = the widest team (<= 8) whose blocks are all
+          // co-resident with at most PGN_TEAM_WARPS_PER_SMSP (default 3) warps per scheduler; PGN_TEAM=W pins it.
+          const char* e = std::getenv("PGN_TEAM");
+          const char* e2 = std::getenv("PGN_TEAM_WARPS_PER_SMSP");
+          const int pinned = e ? std::atoi(e) : 0;
+          const int per_smsp = e2 ? std::max(1, std::atoi(e2)) : 3;
+          for (int w = (pinned >= 1 && pinned <= 8) ? pinned : 8; w >= 1; --w) {
+            // a team shares one scan's momentum draws through shared memory when they fit in 64 KB
+            const int pool = (w > 1 && (size_t)h->ep.n_refresh * (h->cpl * 32 + 8) * sizeof(double) <= 64 * 1024) ? h->ep.n_refresh : 0;
+            const size_t sm = scan_smem_bytes(h, w, 1, pool);
+            if (sm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            int per_sm = 0;
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, sm));
+            const bool fits = (long long)per_sm * h->n_sms >= nl;
+            const bool wide_ok = w == 1 || pinned == w || (long long)nl * w <= (long long)per_smsp * 4 * h->n_sms;
+            if (fits && wide_ok) { wpb = w; grid = nl; smem = sm; P.pool_refresh = pool; break; }
+          }
+        } else {
+          for (int w = 1; w <= 8; w *= 2) {
+            const size_t sm = scan_smem_bytes(h, 0, w);
+            if (sm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            int per_sm = 0;
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, sm));
+            const int g = (nl + w - 1) / w;
+            if ((long long)per_sm * h->n_sms >= g) { wpb = w; grid = g; smem = sm; break; }
+          }
         }
       }
       if (wpb != 0) {
@@ -798,6 +837,14 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     int flag = 0;
     h->error_flag.download(&flag, 1);
 
+    if (const char* dump = std::getenv("PGN_TIMING_DUMP")) {   // diagnostics: per-chain explore / partner-wait clocks of this round
+      if (FILE* f = std::fopen(dump, "a")) {
+        for (int i = 0; i < nl; ++i)
+          std::fprintf(f, "%u %d %lld %lld %lld %lld\n", h->epoch, h->first_chain + i, (long long)n_scans, st[i].explore_cycles,
+                       st[i].wait_cycles, st[i].n_points);
+        std::fclose(f);
+      }
+    }
     long long restarts = 0, trips = 0, pts = 0, evals = 0;
     for (int i = 0; i < nl; ++i) {
       const ChainStatsDev& s = st[i];

@@ -49,6 +49,7 @@ struct ChainStatsDev {   // one per local chain, written when the round ends
   long long am_n; double am_mean; long long rev_n; double rev_mean;
   long long n_restarts, n_round_trips;
   long long n_points, n_ref_evals;
+  long long explore_cycles, wait_cycles;   // diagnostics (PGN_TIMING_DUMP): SM clocks spent exploring / waiting for the swap partner
 };
 
 struct MailHdr {   // 32 bytes
@@ -63,6 +64,8 @@ struct Params {
   long long n_scans;
   unsigned int seed_lo, seed_hi;
   unsigned int epoch;
+  int pool_refresh;        // refreshments the team's shared-memory momentum pool has room for (0: no pool)
+  unsigned int tag_base;   // scans run by this handle before this round (mod 2^32): mailbox tag = tag_base + scan
   double p[8];
   int n_modes;
   const double* means;      // [K][d_pad]
@@ -105,6 +108,30 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Flag-in-data mailbox words (the scheme of NCCL's LL protocol): every 8-byte word carries 32 bits of
+// payload and the 32-bit tag of the (round, scan) it belongs to.  An aligned 8-byte store is atomic, so
+// a reader that sees the tag has the payload: posting and polling need no fence and no separate flag,
+// locally (through L2) and across GPUs (peer-mapped stores over NVLink) alike.
+__device__ __forceinline__ void ll_store(unsigned long long* p, unsigned int data, unsigned int tag) {
+  st_relaxed_sys(p, ((unsigned long long)tag << 32) | (unsigned long long)data);
+}
+constexpr unsigned int LL_PAYLOAD_SPIN_LIMIT = 1u << 24;
+// poll one word until it carries `tag`; returns false if it never does (the header of the same post was
+// already seen, so this only guards against a broken peer)
+__device__ __forceinline__ bool ll_load(const unsigned long long* p, unsigned int tag, unsigned int& data) {
+  unsigned long long w = ld_relaxed_sys(p);
+  unsigned int it = 0;
+  while ((unsigned int)(w >> 32) != tag) {
+    if (++it > LL_PAYLOAD_SPIN_LIMIT) { data = 0u; return false; }
+    w = ld_relaxed_sys(p);
+  }
+  data = (unsigned int)w;
+  return true;
+}
+constexpr int LL_HDR_WORDS = 8;   // lr (2), u (2), rng counter (2), replica_index, round-trip state
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
@@ -114,6 +141,19 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 template <int TK, int CPL, int EX>
 struct VecChain {
   static constexpr bool kTestSwapper = false;
+  // autoMALA runs with a TEAM of W warps per chain (block = team): the step-size search evaluates W
+  // candidate steps per round, one per warp, and replays the reference's sequential decisions on the
+  // results (see automala()).  Everything else is executed redundantly by all warps of the team on
+  // identical data; only team warp 0 talks to the mailboxes and writes results.
+  static constexpr bool kTeam = (EX == PGN_EXPLORER_AUTOMALA);
+  static constexpr bool kIsing = false;
+  static constexpr int SLOT_DOUBLES = 3 * CPL * 32 + 8;    // x1 | p1 | g1c | {a0, a1, lp1, h_after, diff, eps, -, -}
+  static constexpr int TEAM_CTL_DOUBLES = 24 + CPL * 32;   // control words + shared copy of an adopted state
+  static constexpr int POOL_DOUBLES = CPL * 32 + 8;        // per refreshment: momentum | a, b, u, -, log a, log b, -, -
+  int tw, W, gen;
+  int e_prev;           // exponent chosen by this chain's previous forward search (candidate placement only)
+  double* slots;        // [3][W][SLOT_DOUBLES] trial results, rotating buffers
+  double* rng_pool;     // [n_refresh][d_pad + 8] a scan's momenta and bound uniforms, drawn by the team in one go (or null)
   const Params* P;
   const double* sm_means;
   int lane, d;
@@ -131,6 +171,14 @@ struct VecChain {
   unsigned long long pool_base;
   bool pool_valid;
 
+  static __host__ __device__ int target_smem_doubles(int d_pad) {
+    return TK == PGN_TARGET_GMM ? KMAX_MODES * d_pad + KMAX_MODES : 0;
+  }
+  __device__ void set_team(int tw_, int W_, double* slots_, double* rng_pool_) { tw = tw_; W = W_; slots = slots_; gen = 0; rng_pool = rng_pool_; }
+  // The running statistics do not feed back into the chain, so each is kept by ONE warp of the team
+  // (the others would only repeat its divisions): statistic j lives in team warp j mod W.
+  __device__ __forceinline__ int own(int j) const { return j % W; }
+  __device__ __forceinline__ double* slot(int buf, int w) const { return slots + ((size_t)buf * W + w) * SLOT_DOUBLES; }
   static __device__ void stage_shared(const Params& P, double* smem) {
     if (TK == PGN_TARGET_GMM) {
       // P.means is the staged layout [KMAX_MODES][d_pad] followed by KMAX_MODES log weights; components
@@ -158,19 +206,40 @@ struct VecChain {
     n_steps = n_points = n_ref = 0;
     err = 0; e0 = e1 = 0.0;
     pool = 0.0; pool_base = 0; pool_valid = false;
+    tw = 0; W = 1; gen = 0; slots = nullptr; e_prev = 0; rng_pool = nullptr;
   }
   __device__ void store(int wl) {
 #pragma unroll
     for (int k = 0; k < CPL; ++k)
       if (valid(k)) P->x[(size_t)wl * P->d_pad + k * 32 + lane] = x[k];
   }
-  __device__ void post(double* pay) const {
+  __device__ void post(unsigned long long* pay, unsigned int tag) const {
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) pay[k * 32 + lane] = x[k];
+    for (int k = 0; k < CPL; ++k) {
+      const unsigned long long b = double_to_bits(x[k]);
+      ll_store(pay + 2 * (k * 32 + lane), (unsigned int)b, tag);
+      ll_store(pay + 2 * (k * 32 + lane) + 1, (unsigned int)(b >> 32), tag);
+    }
   }
-  __device__ void adopt(const double* pay) {
+  __device__ bool adopt(const unsigned long long* pay, unsigned int tag) {
+    bool ok = true;
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) x[k] = __ldcg(pay + k * 32 + lane);
+    for (int k = 0; k < CPL; ++k) {
+      unsigned int lo, hi;
+      ok = ll_load(pay + 2 * (k * 32 + lane), tag, lo) && ok;
+      ok = ll_load(pay + 2 * (k * 32 + lane) + 1, tag, hi) && ok;
+      x[k] = bits_to_double(((unsigned long long)hi << 32) | lo);
+    }
+    return __all_sync(PGN_FULL_MASK, ok);
+  }
+  // the team leader hands the adopted state to the other warps of the team through shared memory
+  __device__ void share_state(double* sm) const {
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) sm[k * 32 + lane] = x[k];
+  }
+  __device__ void load_state(const double* sm) {
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) x[k] = sm[k * 32 + lane];
   }
   __device__ void write_trace(double* row) const {
 #pragma unroll
@@ -571,14 +640,62 @@ struct VecChain {
       return false;
     }
   }
-  // auto_mala! :106-182.  The forward and the reversed step-size searches
-  // (auto_step_size :184-248) share ONE inlined copy of run_trial: `dir` selects the
-  // start point, `mode` walks initial -> shrink | grow -> (re-evaluate at the chosen
-  // step) exactly as shrink_step_size / grow_step_size do.  The density/gradient at the
-  // scan's starting state goes through the same copy as well (pass i = -1: a "trial" with
-  // zero momentum and eps = 0 lands exactly on x), so the kernel contains a single instance
-  // of the target's density code — this is what keeps the GMM kernel inside the instruction
-  // cache.  n_refresh_eff = 0 gives the densities only (reference chain after sample_iid!).
+  // auto_mala! :106-182 with the step-size searches (auto_step_size :184-248) evaluated by the
+  // chain's TEAM of W warps.  The reference walks the candidate steps eps0*2^k one at a time
+  // (k = 0, then -1, -2, ... or +1, +2, ...); every candidate is an independent trial from the same
+  // start point, so a team round evaluates W of them at once — warp w takes offset r1_k(w) in the
+  // first round and the next W offsets of the chosen direction afterwards — publishes the results
+  // in shared memory, and then every warp replays the reference's sequential decisions on the
+  // published log-joint differences.  Results (exponent, chosen trial, every statistic) are the
+  // reference's; only the wall-clock order of the evaluations changes.  The trial at the chosen
+  // step is taken from the published results (the reference re-runs leap_frog! there, :144-151),
+  // and the reversed search stops at its exponent (:160-163 use nothing else).
+  // The forward and the reversed searches share ONE inlined copy of run_trial; the density and
+  // gradient at the scan's starting state go through the same copy (pass i = -1: a "trial" with
+  // zero momentum and eps = 0 lands exactly on x), so the kernel contains a single instance of the
+  // target's density code.  n_refresh_eff = 0 gives the densities only (reference chain after
+  // sample_iid!).
+  // Buffers: round r writes buffer r mod 3 and reads r mod 3 and (r-1) mod 3 after its barrier, so a
+  // warp that has run ahead into round r+1 never touches what a slower team-mate still reads.
+  // First-round candidates: offset 0, n_neg offsets below it and W - 1 - n_neg above it.  Which side gets
+  // the speculative slots is a guess from the exponent this chain's previous forward search ended at
+  // (neighbouring refreshments of a chain want similar steps); the guess changes which trials are
+  // evaluated early, never which one is chosen.
+  __device__ __forceinline__ int r1_n_neg() const {
+    const int S = W - 1;
+    // a search that ends at exponent e < 0 needs the offsets -1..e, one that ends at e >= 0 needs +1..e+1
+    int neg = e_prev < 0 ? 1 - e_prev : 1, pos = e_prev >= 0 ? e_prev + 2 : 1;   // one spare on the predicted side, one slot on the other
+    if (e_prev < 0) { neg = neg < S ? neg : S; pos = pos < S - neg ? pos : S - neg; }
+    else { pos = pos < S ? pos : S; neg = neg < S - pos ? neg : S - pos; }
+    const int left = S - neg - pos;
+    return neg + (e_prev < 0 ? (left + 1) / 2 : left / 2);
+  }
+  __device__ __forceinline__ int r1_k(int w, int n_neg) const { return w == 0 ? 0 : (w <= n_neg ? -w : w - n_neg); }
+  __device__ __forceinline__ int r1_warp(int k, int n_neg) const { return k < 0 ? -k : n_neg + k; }
+  __device__ __forceinline__ void publish(int buf, const Trial& T, double diff) {
+    double* s = slot(buf, tw);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      s[k * 32 + lane] = T.x1[k];
+      s[(CPL + k) * 32 + lane] = T.p1[k];
+      s[(2 * CPL + k) * 32 + lane] = T.g1c[k];
+    }
+    if (lane == 0) {
+      double* h = s + 3 * CPL * 32;
+      h[0] = T.a0; h[1] = T.a1; h[2] = T.lp1; h[3] = T.h_after; h[4] = diff; h[5] = T.eps;
+    }
+  }
+  __device__ __forceinline__ void fetch(int buf, int w, Trial& T) const {
+    const double* s = slot(buf, w);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      T.x1[k] = s[k * 32 + lane];
+      T.p1[k] = s[(CPL + k) * 32 + lane];
+      T.g1c[k] = s[(2 * CPL + k) * 32 + lane];
+    }
+    const double* h = s + 3 * CPL * 32;
+    T.a0 = h[0]; T.a1 = h[1]; T.lp1 = h[2]; T.h_after = h[3]; T.eps = h[5];
+  }
   __device__ void automala(bool use_mh, int n_refresh_eff) {
     double pre[CPL];
     bool pre_one = true;
@@ -592,6 +709,30 @@ struct VecChain {
     for (int k = 0; k < CPL; ++k) g0[k] = 0.0;
     double lp0 = 0.0;
     if (!(P->step_size > 0)) { err = PGN_ERR_INVALID; return; }
+    // A scan's draws are fixed ticks of the replica's stream once the preconditioner has taken its own:
+    // refreshment i uses ticks [c0 + i*stride, +d) for the momentum and the next 2 (3 with MH) for a, b, (u).
+    // The team draws them all now, each warp a share of the SIMT passes, instead of every warp drawing
+    // every one of them again at its refreshment.
+    const bool pooled = rng_pool != nullptr && W > 1 && n_refresh_eff > 0 && n_refresh_eff <= P->pool_refresh;
+    if (pooled) {
+      const unsigned long long c0 = rng.ctr, stride = (unsigned long long)d + (use_mh ? 3ull : 2ull);
+      const int n_norm = n_refresh_eff * CPL, n_uni = (3 * n_refresh_eff + 31) / 32;
+      for (int pass = tw; pass < n_norm + n_uni; pass += W) {
+        if (pass < n_norm) {
+          const int ir = pass / CPL, k = pass - ir * CPL;
+          const double z = valid(k) ? normal_at(rng, c0 + (unsigned long long)ir * stride + (unsigned long long)(k * 32 + lane)) : 0.0;
+          rng_pool[(size_t)ir * POOL_DOUBLES + k * 32 + lane] = z;
+        } else {
+          const int j = (pass - n_norm) * 32 + lane, ir = j / 3, t = j - ir * 3;
+          if (ir < n_refresh_eff) {
+            const double uu = uniform_at(rng, c0 + (unsigned long long)ir * stride + (unsigned long long)(d + t));
+            rng_pool[(size_t)ir * POOL_DOUBLES + CPL * 32 + t] = uu;
+            rng_pool[(size_t)ir * POOL_DOUBLES + CPL * 32 + 4 + t] = log_(uu);
+          }
+        }
+      }
+      __syncthreads();
+    }
     Trial T;
     for (int i = -1; i < n_refresh_eff; ++i) {
       double sx[CPL], sp[CPL], sg[CPL];     // start point of the current search
@@ -602,6 +743,18 @@ struct VecChain {
       if (i >= 0) {
         double p[CPL];
         double pp = 0.0;
+        double a, b, la, lb;
+        if (pooled) {   // this refreshment's draws were made at the start of the scan (same ticks, same values)
+          const double* rp = rng_pool + (size_t)i * POOL_DOUBLES;
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) {
+            p[k] = rp[k * 32 + lane];
+            pp = valid(k) ? pp + p[k] * p[k] : pp;
+          }
+          a = rp[CPL * 32]; b = rp[CPL * 32 + 1]; u_mh = rp[CPL * 32 + 2];
+          la = rp[CPL * 32 + 4]; lb = rp[CPL * 32 + 5];
+          rng.ctr += (unsigned long long)d + (use_mh ? 3ull : 2ull);
+        } else {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
           p[k] = valid(k) ? normal_at(rng, rng.ctr + (unsigned long long)(k * 32 + lane)) : 0.0;   // randn!(rng, momentum)
@@ -613,9 +766,10 @@ struct VecChain {
         double mine = uniform_at(rng, rng.ctr + (unsigned long long)(lane < 3 ? lane : 0));
         double lmine = log_(mine);
         rng.ctr += use_mh ? 3ull : 2ull;
-        const double a = __shfl_sync(PGN_FULL_MASK, mine, 0), b = __shfl_sync(PGN_FULL_MASK, mine, 1);
-        const double la = __shfl_sync(PGN_FULL_MASK, lmine, 0), lb = __shfl_sync(PGN_FULL_MASK, lmine, 1);
+        a = __shfl_sync(PGN_FULL_MASK, mine, 0); b = __shfl_sync(PGN_FULL_MASK, mine, 1);
+        la = __shfl_sync(PGN_FULL_MASK, lmine, 0); lb = __shfl_sync(PGN_FULL_MASK, lmine, 1);
         u_mh = __shfl_sync(PGN_FULL_MASK, mine, 2);
+        }
         lower = a < b ? la : lb;     // log(min(a, b))
         upper = a < b ? lb : la;     // log(max(a, b))
         init_joint = lp0 - 0.5 * warp_sum(pp);
@@ -630,36 +784,72 @@ struct VecChain {
       double h_before = init_joint;
       const int n_dir = (i >= 0 && use_mh) ? 2 : 1;
       for (int dir = 0; dir < n_dir; ++dir) {
-        int mode = i >= 0 ? 0 : 4, n = 0, exponent = 0, nst = 0;
-        double eps = i >= 0 ? P->step_size : 0.0;
+        // phase 0: first team round; 1: later rounds in direction sgn; 2: one trial evaluated by every
+        // warp for itself (densities at x, or the chosen step when it is not among the candidates)
+        int phase = i >= 0 ? 0 : 2;
+        int sgn = 0, m = 0, exponent = 0, nst = 0;
+        int prev_buf = 0, prev_w = 0;        // slot of the candidate examined last
+        const int n_neg = r1_n_neg();
+        double eps_m = P->step_size;         // step of the farthest candidate examined in direction sgn
+        double eps = 0.0;
+        if (i >= 0) {
+          const int k0 = r1_k(tw, n_neg);
+          eps = P->step_size;
+          for (int j = 0; j < (k0 < 0 ? -k0 : k0); ++j) eps = eps * (k0 < 0 ? 0.5 : 2.0);   // x * 0.5 == x / 2.0 for every double
+        }
         while (true) {
           const double diff = run_trial(sx, sp, sg, pre, pre_one, eps, h_before, T);
+          if (phase == 2) break;
+          const int buf = gen;
+          gen = gen == 2 ? 0 : gen + 1;
+          publish(buf, T, diff);
+          __syncthreads();
           bool decided = false;
-          if (mode == 0) {
-            if (!is_finite(diff) || diff < lower) { mode = 1; n = 1; eps = eps / 2.0; }
-            else if (diff > upper) { mode = 2; n = 1; eps = eps * 2.0; }
+          int win_buf = buf, win_w = 0;
+          int n_first, n_last;
+          if (phase == 0) {
+            const double d0 = slot(buf, 0)[3 * CPL * 32 + 4];
+            if (!is_finite(d0) || d0 < lower) sgn = -1;            // auto_step_size :203-209
+            else if (d0 > upper) sgn = 1;
             else decided = true;
-          } else if (mode == 1) {                         // shrink_step_size :228-248
-            if (eps == 0.0) { err = PGN_ERR_STEP_UNDERFLOW; return; }
-            if (diff > lower) { nst = n; exponent = -n; decided = true; }
-            else { n += 1; eps = eps / 2.0; }
-          } else if (mode == 2) {                         // grow_step_size :216-226
-            if (!is_finite(diff) || diff < upper) { nst = n; exponent = n - 1; decided = true; }
-            else { n += 1; eps = eps * 2.0; }
+            prev_buf = buf; prev_w = 0;
+            n_first = 1; n_last = decided ? 0 : (sgn < 0 ? n_neg : W - 1 - n_neg);
           } else {
-            break;                                        // mode 3: re-evaluated at the chosen step; mode 4: densities at x
+            n_first = m + 1; n_last = m + W;
           }
+          for (int n = n_first; n <= n_last && !decided; ++n) {
+            const int w = phase == 0 ? r1_warp(sgn * n, n_neg) : n - n_first;
+            const double* hh = slot(buf, w) + 3 * CPL * 32;
+            const double dn = hh[4], en = hh[5];
+            if (sgn < 0) {                                         // shrink_step_size :228-248
+              if (en == 0.0) { err = PGN_ERR_STEP_UNDERFLOW; return; }
+              if (dn > lower) { decided = true; nst = n; exponent = -n; win_buf = buf; win_w = w; }
+            } else {                                               // grow_step_size :216-226
+              if (!is_finite(dn) || dn < upper) { decided = true; nst = n; exponent = n - 1; win_buf = prev_buf; win_w = prev_w; }
+            }
+            prev_buf = buf; prev_w = w; eps_m = en;
+          }
+          m = n_last;
           if (decided) {
+            if (dir == 1) break;                                   // reversed search: only the exponent is used (:160-163)
             const double eps_final = P->step_size * pow2(exponent);   // leap_frog! at the chosen step :144-151
-            if (T.eps == eps_final) break;
-            mode = 3; eps = eps_final;
+            if (slot(win_buf, win_w)[3 * CPL * 32 + 5] == eps_final) {
+              if (!(win_buf == buf && win_w == tw)) fetch(win_buf, win_w, T);
+              break;
+            }
+            phase = 2; eps = eps_final;
+          } else {
+            phase = 1;
+            eps = eps_m;
+            for (int j = 0; j <= tw; ++j) eps = eps * (sgn < 0 ? 0.5 : 2.0);
           }
         }
         if (i < 0) break;
         n_steps += 1 + nst;
-        am.fit(pow2(exponent));
+        if (tw == own(1)) am.fit(pow2(exponent));
         expo[dir] = exponent;
         if (dir == 0) {
+          e_prev = exponent;
           n_ref += 1 + 1 + 3 * (1 + nst) + 2;
           h_rev = T.h_after;      // log_joint at (x1, -p1): same partial sums as h_after
           h_before = h_rev;
@@ -682,10 +872,10 @@ struct VecChain {
       bool accept = true;
       if (use_mh) {
         const bool passed = (expo[1] == expo[0]);
-        rev.fit(passed ? 1.0 : 0.0);
+        if (tw == own(2)) rev.fit(passed ? 1.0 : 0.0);
         double prob = 0.0;
         if (passed) { double e = exp_(h_rev - init_joint); prob = 1.0 < e ? 1.0 : e; n_ref += 1; }
-        expl_acc.fit(prob);
+        if (tw == own(3)) expl_acc.fit(prob);
         accept = u_mh < prob;
       }
       if (accept) {
@@ -774,6 +964,8 @@ struct VecChain {
 // ===========================================================================
 struct IsingChain {
   static constexpr bool kTestSwapper = false;
+  static constexpr bool kTeam = false;
+  static constexpr bool kIsing = true;
   const Params* P;
   int lane, L;
   double beta;
@@ -791,7 +983,18 @@ struct IsingChain {
   unsigned long long pool_base;
   bool pool_valid;
 
+  // A chain keeps its beta for the whole round, and a single flip changes S by dS in {0, +-4, +-8}
+  // with S = 2 L^2 - 4 m, so the Metropolis ratio exp(lp(S + dS) - lp(S)) takes (L^2 + 1) x 4 values
+  // per round.  The two dS that LOWER lp (the only ones whose ratio can be < 1: lp is monotone in S and
+  // exp_ of a non-negative argument is >= 1) are tabulated in shared memory when the round starts —
+  // the very expression the reference evaluates per site (examples/ising.jl:107-109), evaluated once
+  // per (S, dS) instead of once per site.
+  const double* tbl;   // [(L^2 + 1)][2]: |dS| = 4, 8
+  int sig;             // sign of the dS that lowers lp
+  int S0;              // 2 L^2
+  static __host__ __device__ int table_doubles(int L_) { return (L_ * L_ + 1) * 2; }
   static __device__ void stage_shared(const Params&, double*) {}
+  __device__ __forceinline__ int own(int) const { return 0; }
 
   __device__ __forceinline__ double draw_uniform() {
     unsigned long long idx = rng.ctr - pool_base;
@@ -830,15 +1033,32 @@ struct IsingChain {
     n_steps = n_points = n_ref = 0; err = 0;
     pool = 0.0; pool_base = 0; pool_valid = false;
   }
+  __device__ void build_table(double* smem) {
+    double* t = smem + (size_t)(threadIdx.x >> 5) * table_doubles(L);
+    const double c = P->p[0];
+    const bool decreasing = (beta > 0.0 && c < 0.0) || (beta < 0.0 && c > 0.0);   // lp decreasing in S
+    sig = decreasing ? 1 : -1;
+    S0 = 2 * L * L;
+    for (int idx = lane; idx < table_doubles(L); idx += 32) {
+      const int s_old = S0 - 4 * (idx >> 1);
+      const int s_new = s_old + sig * 4 * ((idx & 1) + 1);
+      t[idx] = exp_(lp(beta, s_new) - lp(beta, s_old));
+    }
+    tbl = t;
+    __syncwarp();
+  }
   __device__ void store(int wl) {
     unsigned int* rows = reinterpret_cast<unsigned int*>(P->x + (size_t)wl * P->d_pad);
     if (lane < L) rows[lane] = row;
   }
-  __device__ void post(double* pay) const { reinterpret_cast<unsigned int*>(pay)[lane] = row; }
-  __device__ void adopt(const double* pay) {
-    row = __ldcg(reinterpret_cast<const unsigned int*>(pay) + lane);
+  __device__ void post(unsigned long long* pay, unsigned int tag) const { ll_store(pay + lane, row, tag); }
+  __device__ bool adopt(const unsigned long long* pay, unsigned int tag) {
+    const bool ok = ll_load(pay + lane, tag, row);
     recompute_S();
+    return __all_sync(PGN_FULL_MASK, ok);
   }
+  __device__ void share_state(double*) const {}
+  __device__ void load_state(const double*) {}
   __device__ void write_trace(double* out) const {
     if (lane < L)
       for (int j = 0; j < L; ++j) out[lane * L + j] = ((row >> j) & 1u) ? 1.0 : 0.0;
@@ -866,17 +1086,20 @@ struct IsingChain {
         const unsigned int up = __shfl_sync(PGN_FULL_MASK, row, (i + L - 1) % L);
         const unsigned int dn = __shfl_sync(PGN_FULL_MASK, row, (i + 1) % L);
         unsigned int cur = __shfl_sync(PGN_FULL_MASK, row, i);
+        // bit j = 1 where the vertical neighbour equals site (i, j); a site's own bit is untouched until it is visited
+        const unsigned int eq_up = ~(cur ^ up), eq_dn = ~(cur ^ dn);
         for (int j = 0; j < L; ++j) {
           const int jl = j == 0 ? L - 1 : j - 1, jr = j == L - 1 ? 0 : j + 1;
-          const int me = sgn(cur, j);
-          const int nb = sgn(up, j) + sgn(dn, j) + sgn(cur, jl) + sgn(cur, jr);
-          const int S_new = S + (-me * nb - me * nb);
-          const double log_pr_before = lp(beta, S);
-          const double log_pr_after = lp(beta, S_new);
-          const double accept_ratio = exp_(log_pr_after - log_pr_before);
+          const unsigned int b = (cur >> j) & 1u;
+          // a = neighbours equal to the site: me * sum(neighbours) = 2a - 4, so S_new - S = 8 - 4a
+          const int a = (int)(((eq_up >> j) & 1u) + ((eq_dn >> j) & 1u) + (((cur >> jl) ^ b ^ 1u) & 1u) + (((cur >> jr) ^ b ^ 1u) & 1u));
+          const int dS = 8 - 4 * a;
           bool reject = false;
-          if (accept_ratio < 1) reject = draw_uniform() > accept_ratio;
-          if (!reject) { cur ^= (1u << j); S = S_new; }
+          if (dS != 0 && ((dS < 0) == (sig < 0))) {     // lp goes down: accept_ratio = exp(lp_after - lp_before) may be < 1
+            const double accept_ratio = tbl[((S0 - S) >> 2) * 2 + ((a & 3) == 0 ? 1 : 0)];
+            if (accept_ratio < 1) reject = draw_uniform() > accept_ratio;
+          }
+          if (!reject) { cur ^= (1u << j); S += dS; }
         }
         if (lane == i) row = cur;
       }
@@ -894,12 +1117,15 @@ struct IsingChain {
 // ===========================================================================
 struct TestSwapperChain {
   static constexpr bool kTestSwapper = true;
+  static constexpr bool kTeam = false;
+  static constexpr bool kIsing = false;
   const Params* P;
   Rng rng;
   MeanAcc expl_acc, am, rev;
   long long n_steps, n_points, n_ref;
   int err;
   static __device__ void stage_shared(const Params&, double*) {}
+  __device__ __forceinline__ int own(int) const { return 0; }
   __device__ void init(const Params& Pr, const double*, int wl, int, int replica_index) {
     P = &Pr;
     rng.key0 = Pr.seed_lo; rng.key1 = (unsigned int)replica_index; rng.c2 = Pr.seed_hi; rng.c3 = 0u;
@@ -908,8 +1134,10 @@ struct TestSwapperChain {
     n_steps = n_points = n_ref = 0; err = 0;
   }
   __device__ void store(int) {}
-  __device__ void post(double*) const {}
-  __device__ void adopt(const double*) {}
+  __device__ void post(unsigned long long*, unsigned int) const {}
+  __device__ bool adopt(const unsigned long long*, unsigned int) { return true; }
+  __device__ void share_state(double*) const {}
+  __device__ void load_state(const double*) {}
   __device__ void write_trace(double*) const {}
   __device__ void online_fit() {}
   __device__ void store_online() const {}
@@ -928,8 +1156,13 @@ __global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Param
   Chain::stage_shared(P, smem);
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int wl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // team kernels (autoMALA): block = the W warps serving one chain; otherwise one warp per chain
+  const int tw = Chain::kTeam ? (int)(threadIdx.x >> 5) : 0;
+  const int wl = Chain::kTeam ? (int)blockIdx.x : (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   if (wl >= P.n_local) return;
+  // team control words: [2] evaluation counter, [3] payload status, [8..23] partner header (two alternating
+  // sets of 8), [24..] the adopted state for the other warps of the team
+  long long* team_ctl = nullptr;
   const int N = P.n_chains;
   const int chain = P.first_chain + wl;   // 1-based global chain index
   const int last_local = P.first_chain + P.n_local - 1;
@@ -937,20 +1170,34 @@ __global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Param
   int rt_state = 0;   // recorders are emptied at every round (recorders.jl:113-118)
   Chain ch;
   ch.init(P, smem, wl, lane, replica_index);
+  if constexpr (Chain::kIsing) ch.build_table(smem);
+  if constexpr (Chain::kTeam) {
+    double* team_base = smem + Chain::target_smem_doubles(P.d_pad);
+    team_ctl = reinterpret_cast<long long*>(team_base);
+    const int tW = (int)(blockDim.x >> 5);
+    double* slots = team_base + Chain::TEAM_CTL_DOUBLES;
+    // the momentum pool follows the trial slots when the launch reserved room for it (P.pool_refresh > 0)
+    ch.set_team(tw, tW, slots, P.pool_refresh > 0 ? slots + (size_t)3 * tW * Chain::SLOT_DOUBLES : nullptr);
+    if (threadIdx.x == 0) team_ctl[2] = 0;
+    __syncthreads();
+  }
   MeanAcc swap_acc{0, 0.0};
   LogSumAcc ls_fwd{0, -PGN_INF}, ls_bwd{0, -PGN_INF};
   long long n_restarts = 0, n_trips = 0;
+  long long explore_cycles = 0, wait_cycles = 0;
   const bool is_ref = (chain == 1 && N > 1);   // DEO.jl:13
   const bool is_tgt = (chain == N);            // DEO.jl:14
   int err = 0;
 
   for (long long scan = 1; scan <= P.n_scans; ++scan) {
     // ---------------- explore ----------------
+    const long long t_explore0 = clock64();
     ch.explore(scan, is_ref);
+    explore_cycles += clock64() - t_explore0;
     if (ch.err) { err = ch.err; break; }
     if (is_tgt) {   // pigeons.jl:110-131
-      ch.online_fit();
-      if (P.target_trace) ch.write_trace(P.target_trace + (size_t)(scan - 1) * P.d);
+      if (tw == ch.own(4)) ch.online_fit();
+      if (P.target_trace && tw == 0) ch.write_trace(P.target_trace + (size_t)(scan - 1) * P.d);
     }
     // ---------------- swap ----------------
     const bool even = (scan & 1LL) == 0;                                   // DEO.jl:12
@@ -965,7 +1212,7 @@ __global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Param
     }
     const double u = ch.draw_uniform();
     const size_t log_at = (size_t)(scan - 1) * P.n_local + wl;
-    if (lane == 0) {   // recorded before the swap (swap.jl:110-111)
+    if (lane == 0 && tw == 0) {   // recorded before the swap (swap.jl:110-111)
       if (P.index_process) P.index_process[log_at] = replica_index;
       if (P.swap_lr) P.swap_lr[log_at] = lr;
       if (P.swap_u) P.swap_u[log_at] = u;
@@ -977,9 +1224,9 @@ __global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Param
     bool accepted = false;
     if (partner != chain) {
       const int ring = (int)((P.epoch & 1u) * 4u + (unsigned int)(scan & 3LL));
-      const unsigned long long tag = ((unsigned long long)P.epoch << 32) | (unsigned long long)scan;
+      const unsigned int tag = P.tag_base + (unsigned int)scan;
       const bool remote = partner < P.first_chain || partner > last_local;
-      // ---- post my SwapStat + replica where my partner will look for it
+      // ---- where I post my SwapStat + replica, and where my partner posts theirs
       char* dst;
       const char* src;
       if (!remote) {
@@ -992,39 +1239,71 @@ __global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Param
         dst = P.mail_left + ((size_t)1 * MAIL_RINGS + ring) * P.slot_bytes;
         src = P.mail + ((size_t)0 * MAIL_RINGS + ring) * P.slot_bytes;
       }
-      if (lane == 0) {
-        MailHdr* h = reinterpret_cast<MailHdr*>(dst + 32);
-        h->lr = lr; h->u = u; h->ctr = ch.rng.ctr; h->replica_index = replica_index; h->rt_state = rt_state;
-      }
-      ch.post(reinterpret_cast<double*>(dst + MAIL_HDR_BYTES));
-      __syncwarp();
-      if (lane == 0) {
-        if (remote) st_release_sys(reinterpret_cast<unsigned long long*>(dst), tag);
-        else st_release_gpu(reinterpret_cast<unsigned long long*>(dst), tag);
-      }
-      // ---- wait for the partner's post
+      unsigned long long* dstw = reinterpret_cast<unsigned long long*>(dst);
+      const unsigned long long* srcw = reinterpret_cast<const unsigned long long*>(src);
       int status = 0;
-      if (lane == 0) {
-        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(src);
+      double lr_p = 0.0, u_p = 0.0;
+      unsigned long long ctr_p = 0ull;
+      int ri_p = 0, rt_p = 0;
+      const long long t_wait0 = clock64();
+      if (tw == 0) {
+        {   // post: header words from lanes 0..7, then the replica
+          const unsigned long long lb = double_to_bits(lr), ub = double_to_bits(u), cb = ch.rng.ctr;
+          unsigned int hv = (unsigned int)lb;
+          hv = lane == 1 ? (unsigned int)(lb >> 32) : hv;
+          hv = lane == 2 ? (unsigned int)ub : hv;
+          hv = lane == 3 ? (unsigned int)(ub >> 32) : hv;
+          hv = lane == 4 ? (unsigned int)cb : hv;
+          hv = lane == 5 ? (unsigned int)(cb >> 32) : hv;
+          hv = lane == 6 ? (unsigned int)replica_index : hv;
+          hv = lane == 7 ? (unsigned int)rt_state : hv;
+          if (lane < LL_HDR_WORDS) ll_store(dstw + lane, hv, tag);
+          ch.post(dstw + LL_HDR_WORDS, tag);
+        }
+        // ---- wait for the partner's header
+        unsigned long long w = 0ull;
         unsigned long long t0 = 0;
         unsigned int it = 0;
-        while (ld_relaxed_sys(flag) != tag) {
+        while (true) {
+          if (lane < LL_HDR_WORDS) w = ld_relaxed_sys(srcw + lane);
+          const bool ok = lane >= LL_HDR_WORDS || (unsigned int)(w >> 32) == tag;
+          if (__all_sync(PGN_FULL_MASK, ok)) break;
           ++it;
           if ((it & 255u) == 0u) {
-            if (*reinterpret_cast<volatile int*>(P.error_flag) != 0) { status = 1; break; }
-            const unsigned long long now = globaltimer_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > P.timeout_ns) { status = 2; break; }
+            if (lane == 0) {
+              if (*reinterpret_cast<volatile int*>(P.error_flag) != 0) status = 1;
+              const unsigned long long now = globaltimer_ns();
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > P.timeout_ns) status = 2;
+            }
+            status = __shfl_sync(PGN_FULL_MASK, status, 0);
+            if (status != 0) break;
             if (it > 65536u) __nanosleep(200);
           }
         }
-        if (remote) fence_acq_rel_sys(); else fence_acq_rel_gpu();
+        const unsigned int lo = (unsigned int)w;
+        const unsigned int h0 = __shfl_sync(PGN_FULL_MASK, lo, 0), h1 = __shfl_sync(PGN_FULL_MASK, lo, 1);
+        const unsigned int h2 = __shfl_sync(PGN_FULL_MASK, lo, 2), h3 = __shfl_sync(PGN_FULL_MASK, lo, 3);
+        const unsigned int h4 = __shfl_sync(PGN_FULL_MASK, lo, 4), h5 = __shfl_sync(PGN_FULL_MASK, lo, 5);
+        ri_p = (int)__shfl_sync(PGN_FULL_MASK, lo, 6);
+        rt_p = (int)__shfl_sync(PGN_FULL_MASK, lo, 7);
+        lr_p = bits_to_double(((unsigned long long)h1 << 32) | h0);
+        u_p = bits_to_double(((unsigned long long)h3 << 32) | h2);
+        ctr_p = ((unsigned long long)h5 << 32) | h4;
       }
-      status = __shfl_sync(PGN_FULL_MASK, status, 0);
+      if constexpr (Chain::kTeam) {   // team warp 0 did the hand-shake and hands the header to the team
+        long long* tc = team_ctl + 8 + 8 * (int)(scan & 1LL);
+        if (threadIdx.x == 0) {
+          tc[0] = status; tc[1] = (long long)double_to_bits(lr_p); tc[2] = (long long)double_to_bits(u_p);
+          tc[3] = (long long)ctr_p; tc[4] = ri_p; tc[5] = rt_p;
+        }
+        __syncthreads();
+        status = (int)tc[0];
+        lr_p = bits_to_double((unsigned long long)tc[1]); u_p = bits_to_double((unsigned long long)tc[2]);
+        ctr_p = (unsigned long long)tc[3]; ri_p = (int)tc[4]; rt_p = (int)tc[5];
+      }
+      wait_cycles += clock64() - t_wait0;
       if (status != 0) { err = status == 2 ? PGN_ERR_TIMEOUT : -1; break; }
-      const MailHdr* hp = reinterpret_cast<const MailHdr*>(src + 32);
-      const double lr_p = __ldcg(&hp->lr);
-      const double u_p = __ldcg(&hp->u);
       // ---- decision (identical on both sides; swap_decision pair_swapper.jl:81-88)
       const bool lower = chain < partner;
       double acceptance_pr;
@@ -1034,28 +1313,54 @@ __global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Param
         const double e = lower ? exp_(lr + lr_p) : exp_(lr_p + lr);
         acceptance_pr = 1.0 < e ? 1.0 : e;
         if (lower) {   // record_swap_stats! :59-66, by the replica holding the lower chain
-          swap_acc.fit(acceptance_pr);
-          ls_fwd.fit(lr);
-          ls_bwd.fit(lr_p);
+          if (tw == ch.own(1)) swap_acc.fit(acceptance_pr);
+          if (tw == ch.own(2)) ls_fwd.fit(lr);
+          if (tw == ch.own(3)) ls_bwd.fit(lr_p);
         }
       }
       accepted = (lower ? u : u_p) < acceptance_pr;
       if (accepted) {   // adopt the partner's replica (states move, chains stay)
-        replica_index = __ldcg(&hp->replica_index);
-        rt_state = __ldcg(&hp->rt_state);
-        ch.rng.ctr = __ldcg(&hp->ctr);
+        replica_index = ri_p;
+        rt_state = rt_p;
+        ch.rng.ctr = ctr_p;
         ch.rng.key1 = (unsigned int)replica_index;
         ch.on_replica_changed();
-        ch.adopt(reinterpret_cast<const double*>(src + MAIL_HDR_BYTES));
+        bool got = true;
+        if (tw == 0) got = ch.adopt(srcw + LL_HDR_WORDS, tag);
+        if constexpr (Chain::kTeam) {
+          double* sx = reinterpret_cast<double*>(team_ctl + 24);
+          if (tw == 0) { ch.share_state(sx); if (lane == 0) team_ctl[3] = got ? 1 : 0; }
+          __syncthreads();
+          if (tw != 0) ch.load_state(sx);
+          got = team_ctl[3] != 0;
+        }
+        if (!got) { err = PGN_ERR_TIMEOUT; break; }
       }
     }
-    if (lane == 0 && P.swap_accept) P.swap_accept[log_at] = accepted ? 1 : 0;
+    if (lane == 0 && tw == 0 && P.swap_accept) P.swap_accept[log_at] = accepted ? 1 : 0;
   }
 
   if (err > 0 && lane == 0) atomicCAS(P.error_flag, 0, err);
   // ---------------- epilogue: replica back to HBM, statistics out ----------------
+  if constexpr (Chain::kTeam) {   // collect what the other warps of the team hold: their statistics and evaluation counts
+    double* ex = reinterpret_cast<double*>(team_ctl + 24);
+    long long* exl = reinterpret_cast<long long*>(ex);
+    if (is_tgt && tw == ch.own(4)) ch.store_online();
+    if (lane == 0) {
+      if (tw != 0) atomicAdd(reinterpret_cast<unsigned long long*>(team_ctl + 2), (unsigned long long)ch.n_points);
+      if (tw == ch.own(1)) { exl[0] = ch.am.n; ex[1] = ch.am.mu; exl[2] = swap_acc.n; ex[3] = swap_acc.mu; }
+      if (tw == ch.own(2)) { exl[4] = ch.rev.n; ex[5] = ch.rev.mu; exl[6] = ls_fwd.n; ex[7] = ls_fwd.value; }
+      if (tw == ch.own(3)) { exl[8] = ch.expl_acc.n; ex[9] = ch.expl_acc.mu; exl[10] = ls_bwd.n; ex[11] = ls_bwd.value; }
+    }
+    __syncthreads();
+    if (tw != 0) return;
+    ch.n_points += team_ctl[2];
+    ch.am.n = exl[0]; ch.am.mu = ex[1]; swap_acc.n = exl[2]; swap_acc.mu = ex[3];
+    ch.rev.n = exl[4]; ch.rev.mu = ex[5]; ls_fwd.n = exl[6]; ls_fwd.value = ex[7];
+    ch.expl_acc.n = exl[8]; ch.expl_acc.mu = ex[9]; ls_bwd.n = exl[10]; ls_bwd.value = ex[11];
+  }
   ch.store(wl);
-  if (is_tgt) ch.store_online();
+  if (is_tgt && !Chain::kTeam) ch.store_online();
   if (lane == 0) {
     P.replica_index[wl] = replica_index;
     P.rng_ctr[wl] = ch.rng.ctr;
@@ -1066,6 +1371,7 @@ __global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Param
     s.am_n = ch.am.n; s.am_mean = ch.am.mu; s.rev_n = ch.rev.n; s.rev_mean = ch.rev.mu;
     s.n_restarts = n_restarts; s.n_round_trips = n_trips;
     s.n_points = ch.n_points; s.n_ref_evals = ch.n_ref;
+    s.explore_cycles = explore_cycles; s.wait_cycles = wait_cycles;
     P.stats[wl] = s;
   }
 }

@@ -165,6 +165,33 @@ def test_unsupported_configuration_raises(gpu_lib):
         pg.Engine(gpu_lib, n_chains=4, seed=1, **nine.engine_config())
 
 
+_ORACLE_CACHE = {}
+
+
+def oracle_result(name, oracle_lib):
+    if name not in _ORACLE_CACHE:
+        _ORACLE_CACHE[name] = run_pt(oracle_lib, **CASES[name])
+    return _ORACLE_CACHE[name]
+
+
+@pytest.mark.parametrize("team", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("name", ["funnel32_automala", "toy100_automala_4cpl", "gmm2_two_modes", "two_chains", "funnel_diag_precond"])
+def test_automala_team_width_parity(name, team, gpu_lib, oracle_lib, monkeypatch):
+    """PGN_TEAM=W: the autoMALA step-size search evaluated W candidate steps at a time by a team of W
+    warps per chain gives the reference's sequential result bit for bit, for every team width."""
+    monkeypatch.setenv("PGN_TEAM", str(team))
+    assert_same(run_pt(gpu_lib, **CASES[name]), oracle_result(name, oracle_lib), f"{name}/team{team}")
+
+
+def test_ising_antiferromagnetic_and_large_ladder(gpu_lib, oracle_lib):
+    """The tabulated Metropolis ratios (one table per chain and round) against the per-site
+    evaluation of the oracle: negative coupling (the lowering moves change sign) and a 40-chain ladder."""
+    for kw in (dict(target=pg.IsingLogPotential(-0.7, 8), n_chains=7, n_rounds=6, seed=3),
+               dict(target=pg.IsingLogPotential(0.4406867935097715, 32), n_chains=40, n_rounds=4, seed=4),
+               dict(target=pg.IsingLogPotential(1e-9, 6), n_chains=4, n_rounds=5, seed=5)):
+        assert_same(run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw), f"ising {kw['target']}")
+
+
 MEM_FORCED = ["c1_toy_slice", "toy_default_explorer", "toy10_automala", "toy40_slice_2cpl", "toy100_automala_4cpl",
               "funnel32_automala", "funnel8_slice", "funnel_diag_precond", "gmm128_automala", "gmm6_slice",
               "gmm2_two_modes", "toy10_mala", "gmm70_mala_4cpl", "single_chain", "two_chains"]
