@@ -752,7 +752,10 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
           const char* e2 = std::getenv("PGN_TEAM_WARPS_PER_SMSP");
           const int pinned = e ? std::atoi(e) : 0;
           const int per_smsp = e2 ? std::max(1, std::atoi(e2)) : 3;
-          for (int w = (pinned >= 1 && pinned <= 8) ? pinned : 8; w >= 1; --w) {
+          cudaFuncAttributes fa;
+          CUDA_CHECK(cudaFuncGetAttributes(&fa, kernel));
+          const int w_max = std::min(8, fa.maxThreadsPerBlock / 32);   // the kernel's launch bounds
+          for (int w = std::min(w_max, (pinned >= 1 && pinned <= 8) ? pinned : 8); w >= 1; --w) {
             // a team shares one scan's momentum draws through shared memory when they fit in 64 KB
             const int pool = (w > 1 && (size_t)h->ep.n_refresh * (h->cpl * 32 + 8) * sizeof(double) <= 64 * 1024) ? h->ep.n_refresh : 0;
             const size_t sm = scan_smem_bytes(h, w, 1, pool);

@@ -35,12 +35,14 @@ constexpr int MAIL_HDR_BYTES = 64; // [flag u64 | pad | MailHdr 32B]
 struct MeanAcc {   // OnlineStatsBase.Mean (EqualWeight)
   long long n;
   double mu;
-  __device__ __forceinline__ void fit(double x) { n += 1; mu = mu + (1.0 / (double)n) * (x - mu); }
+  template <bool COMPACT = false>
+  __device__ __forceinline__ void fit(double x) { n += 1; mu = mu + div_<COMPACT>(1.0, (double)n) * (x - mu); }
 };
 struct LogSumAcc {  // src/recorders/LogSum.jl:1-24
   long long n;
   double value;
-  __device__ __forceinline__ void fit(double y) { value = logaddexp_(value, y); n += 1; }
+  template <bool COMPACT = false>
+  __device__ __forceinline__ void fit(double y) { value = logaddexp_<COMPACT>(value, y); n += 1; }
 };
 
 struct ChainStatsDev {   // one per local chain, written when the round ends
@@ -147,10 +149,15 @@ struct VecChain {
   // identical data; only team warp 0 talks to the mailboxes and writes results.
   static constexpr bool kTeam = (EX == PGN_EXPLORER_AUTOMALA);
   static constexpr bool kIsing = false;
+  // one coordinate per lane: teams of up to 6 warps, two teams per SM (168 registers per thread)
+  static constexpr int kMaxThreads = (kTeam && CPL == 1) ? 192 : 256;
+  static constexpr int kMinBlocksPerSM = (kTeam && CPL == 1) ? 2 : 1;
+  static constexpr bool kCompact = CPL > 1;                  // large kernels call divisions / generators out of line (instruction cache)
   static constexpr int SLOT_DOUBLES = 3 * CPL * 32 + 8;    // x1 | p1 | g1c | {a0, a1, lp1, h_after, diff, eps, -, -}
   static constexpr int TEAM_CTL_DOUBLES = 24 + CPL * 32;   // control words + shared copy of an adopted state
   static constexpr int POOL_DOUBLES = CPL * 32 + 8;        // per refreshment: momentum | a, b, u, -, log a, log b, -, -
   int tw, W, gen;
+  int own1, own2, own3, own4;   // team warp keeping statistic j (j mod W)
   int e_prev;           // exponent chosen by this chain's previous forward search (candidate placement only)
   double* slots;        // [3][W][SLOT_DOUBLES] trial results, rotating buffers
   double* rng_pool;     // [n_refresh][d_pad + 8] a scan's momenta and bound uniforms, drawn by the team in one go (or null)
@@ -174,10 +181,12 @@ struct VecChain {
   static __host__ __device__ int target_smem_doubles(int d_pad) {
     return TK == PGN_TARGET_GMM ? KMAX_MODES * d_pad + KMAX_MODES : 0;
   }
-  __device__ void set_team(int tw_, int W_, double* slots_, double* rng_pool_) { tw = tw_; W = W_; slots = slots_; gen = 0; rng_pool = rng_pool_; }
+  __device__ void set_team(int tw_, int W_, double* slots_, double* rng_pool_) { tw = tw_; W = W_; slots = slots_; gen = 0; rng_pool = rng_pool_;
+    own1 = 1 % W_; own2 = 2 % W_; own3 = 3 % W_; own4 = 4 % W_;
+  }
   // The running statistics do not feed back into the chain, so each is kept by ONE warp of the team
   // (the others would only repeat its divisions): statistic j lives in team warp j mod W.
-  __device__ __forceinline__ int own(int j) const { return j % W; }
+  __device__ __forceinline__ int own(int j) const { return j == 1 ? own1 : (j == 2 ? own2 : (j == 3 ? own3 : (j == 4 ? own4 : 0))); }
   __device__ __forceinline__ double* slot(int buf, int w) const { return slots + ((size_t)buf * W + w) * SLOT_DOUBLES; }
   static __device__ void stage_shared(const Params& P, double* smem) {
     if (TK == PGN_TARGET_GMM) {
@@ -190,6 +199,12 @@ struct VecChain {
   }
 
   __device__ __forceinline__ bool valid(int k) const { return k * 32 + lane < d; }
+  // one standard normal at tick `ctr` of this replica's stream; with several coordinates per lane the
+  // generator is called out of line (CPL unrolled copies of Philox + Box-Muller are ~15 KB of code)
+  __device__ __forceinline__ double normal_tick(unsigned long long ctr) const {
+    if (CPL > 1) return normal_at_ni(rng.key0, rng.key1, rng.c2, rng.c3, ctr);
+    return normal_at(rng, ctr);
+  }
 
   __device__ void init(const Params& Pr, const double* smem, int wl, int lane_, int replica_index) {
     P = &Pr; sm_means = smem; lane = lane_; d = Pr.d;
@@ -207,6 +222,7 @@ struct VecChain {
     err = 0; e0 = e1 = 0.0;
     pool = 0.0; pool_base = 0; pool_valid = false;
     tw = 0; W = 1; gen = 0; slots = nullptr; e_prev = 0; rng_pool = nullptr;
+    own1 = own2 = own3 = own4 = 0;
   }
   __device__ void store(int wl) {
 #pragma unroll
@@ -223,12 +239,15 @@ struct VecChain {
   }
   __device__ bool adopt(const unsigned long long* pay, unsigned int tag) {
     bool ok = true;
+#pragma unroll 1
+    for (int j = 0; j < 2 * CPL; ++j) {   // wait until every word of the post has landed ...
+      unsigned int dummy;
+      ok = ll_load(pay + 2 * ((j >> 1) * 32 + lane) + (j & 1), tag, dummy) && ok;
+    }
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-      unsigned int lo, hi;
-      ok = ll_load(pay + 2 * (k * 32 + lane), tag, lo) && ok;
-      ok = ll_load(pay + 2 * (k * 32 + lane) + 1, tag, hi) && ok;
-      x[k] = bits_to_double(((unsigned long long)hi << 32) | lo);
+    for (int k = 0; k < CPL; ++k) {       // ... then take them
+      const unsigned long long lo = ld_relaxed_sys(pay + 2 * (k * 32 + lane)), hi = ld_relaxed_sys(pay + 2 * (k * 32 + lane) + 1);
+      x[k] = bits_to_double((hi << 32) | (lo & 0xffffffffull));
     }
     return __all_sync(PGN_FULL_MASK, ok);
   }
@@ -248,7 +267,7 @@ struct VecChain {
   }
   __device__ void online_fit() {
     on_n += 1;
-    const double g = 1.0 / (double)on_n;
+    const double g = div_<kCompact>(1.0, (double)on_n);
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
       double mu_old = on_mu[k];
@@ -450,7 +469,7 @@ struct VecChain {
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
       if (!valid(k)) continue;
-      double z = normal_at(rng, rng.ctr + (unsigned long long)(k * 32 + lane));
+      double z = normal_tick(rng.ctr + (unsigned long long)(k * 32 + lane));
       if (TK == PGN_TARGET_TOY_MVN) x[k] = z / sqrt(toy_precision(b));   // toy_mvn_target.jl:18-21
       else x[k] = P->p[3] * z;                                           // rand!(rng, MvNormal(0, s^2 I), x)
     }
@@ -577,7 +596,7 @@ struct VecChain {
                                               double eps, double h_before, Trial& T) {
     double ph[CPL];
     double pp = 0.0;
-    const double half_eps = eps / 2;
+    const double half_eps = eps * 0.5;   // == eps / 2 for every double
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
       ph[k] = ps[k] + half_eps * gs[k];
@@ -620,13 +639,13 @@ struct VecChain {
     for (int k = 0; k < CPL; ++k) sd[k] = valid(k) ? P->std_devs[k * 32 + lane] : 0.0;
     if (P->precond_kind == PGN_PRECOND_DIAGONAL) {
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : 1.0 / sd[k];
+      for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : div_<kCompact>(1.0, sd[k]);
       return false;
     }
     const double u = draw_uniform();
     if (u <= P->mix_p0) {
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : 1.0 / sd[k];
+      for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : div_<kCompact>(1.0, sd[k]);
       return false;
     } else if (u <= P->mix_p01) {
 #pragma unroll
@@ -636,7 +655,7 @@ struct VecChain {
       const double mix = draw_uniform();
       const double rmix = 1.0 - mix;
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : mix + rmix / sd[k];
+      for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : mix + div_<kCompact>(rmix, sd[k]);
       return false;
     }
   }
@@ -720,7 +739,7 @@ struct VecChain {
       for (int pass = tw; pass < n_norm + n_uni; pass += W) {
         if (pass < n_norm) {
           const int ir = pass / CPL, k = pass - ir * CPL;
-          const double z = valid(k) ? normal_at(rng, c0 + (unsigned long long)ir * stride + (unsigned long long)(k * 32 + lane)) : 0.0;
+          const double z = valid(k) ? normal_tick(c0 + (unsigned long long)ir * stride + (unsigned long long)(k * 32 + lane)) : 0.0;
           rng_pool[(size_t)ir * POOL_DOUBLES + k * 32 + lane] = z;
         } else {
           const int j = (pass - n_norm) * 32 + lane, ir = j / 3, t = j - ir * 3;
@@ -734,12 +753,13 @@ struct VecChain {
       __syncthreads();
     }
     Trial T;
+#pragma unroll 1
     for (int i = -1; i < n_refresh_eff; ++i) {
       double sx[CPL], sp[CPL], sg[CPL];     // start point of the current search
       double fx[CPL], fg[CPL];              // forward proposal (kept across the reversed search)
       double f_a0 = 0.0, f_a1 = 0.0, f_lp = 0.0, h_rev = 0.0;
       double lower = 0.0, upper = 0.0, u_mh = 0.0, init_joint = 0.0;
-      int expo[2] = {0, 0};
+      int expo_fwd = 0, expo_rev = 0;
       if (i >= 0) {
         double p[CPL];
         double pp = 0.0;
@@ -757,7 +777,7 @@ struct VecChain {
         } else {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
-          p[k] = valid(k) ? normal_at(rng, rng.ctr + (unsigned long long)(k * 32 + lane)) : 0.0;   // randn!(rng, momentum)
+          p[k] = valid(k) ? normal_tick(rng.ctr + (unsigned long long)(k * 32 + lane)) : 0.0;   // randn!(rng, momentum)
           pp = valid(k) ? pp + p[k] * p[k] : pp;
         }
         rng.ctr += (unsigned long long)d;
@@ -783,6 +803,7 @@ struct VecChain {
       }
       double h_before = init_joint;
       const int n_dir = (i >= 0 && use_mh) ? 2 : 1;
+#pragma unroll 1
       for (int dir = 0; dir < n_dir; ++dir) {
         // phase 0: first team round; 1: later rounds in direction sgn; 2: one trial evaluated by every
         // warp for itself (densities at x, or the chosen step when it is not among the candidates)
@@ -794,9 +815,16 @@ struct VecChain {
         double eps = 0.0;
         if (i >= 0) {
           const int k0 = r1_k(tw, n_neg);
-          eps = P->step_size;
-          for (int j = 0; j < (k0 < 0 ? -k0 : k0); ++j) eps = eps * (k0 < 0 ? 0.5 : 2.0);   // x * 0.5 == x / 2.0 for every double
+          // the reference halves / doubles the step one factor at a time (:216-248); while every intermediate is
+          // a normal number that is the exact product with 2^k0, otherwise walk the same way it does
+          eps = P->step_size * pow2i(k0);
+          const unsigned int ebits = (unsigned int)(double_to_bits(eps) >> 52) & 0x7ffu;
+          if (ebits == 0u || ebits == 0x7ffu) {
+            eps = P->step_size;
+            for (int j = 0; j < (k0 < 0 ? -k0 : k0); ++j) eps = eps * (k0 < 0 ? 0.5 : 2.0);   // x * 0.5 == x / 2.0 for every double
+          }
         }
+#pragma unroll 1
         while (true) {
           const double diff = run_trial(sx, sp, sg, pre, pre_one, eps, h_before, T);
           if (phase == 2) break;
@@ -846,8 +874,8 @@ struct VecChain {
         }
         if (i < 0) break;
         n_steps += 1 + nst;
-        if (tw == own(1)) am.fit(pow2(exponent));
-        expo[dir] = exponent;
+        if (tw == own(1)) am.template fit<kCompact>(pow2(exponent));
+        if (dir == 0) expo_fwd = exponent; else expo_rev = exponent;
         if (dir == 0) {
           e_prev = exponent;
           n_ref += 1 + 1 + 3 * (1 + nst) + 2;
@@ -871,11 +899,11 @@ struct VecChain {
       }
       bool accept = true;
       if (use_mh) {
-        const bool passed = (expo[1] == expo[0]);
-        if (tw == own(2)) rev.fit(passed ? 1.0 : 0.0);
+        const bool passed = (expo_rev == expo_fwd);
+        if (tw == own(2)) rev.template fit<kCompact>(passed ? 1.0 : 0.0);
         double prob = 0.0;
         if (passed) { double e = exp_(h_rev - init_joint); prob = 1.0 < e ? 1.0 : e; n_ref += 1; }
-        if (tw == own(3)) expl_acc.fit(prob);
+        if (tw == own(3)) expl_acc.template fit<kCompact>(prob);
         accept = u_mh < prob;
       }
       if (accept) {
@@ -905,7 +933,7 @@ struct VecChain {
       double pp = 0.0;
 #pragma unroll
       for (int k = 0; k < CPL; ++k) {
-        p[k] = valid(k) ? normal_at(rng, rng.ctr + (unsigned long long)(k * 32 + lane)) : 0.0;
+        p[k] = valid(k) ? normal_tick(rng.ctr + (unsigned long long)(k * 32 + lane)) : 0.0;
         pp = valid(k) ? pp + p[k] * p[k] : pp;
       }
       rng.ctr += (unsigned long long)d;
@@ -966,6 +994,9 @@ struct IsingChain {
   static constexpr bool kTestSwapper = false;
   static constexpr bool kTeam = false;
   static constexpr bool kIsing = true;
+  static constexpr int kMaxThreads = 256;
+  static constexpr int kMinBlocksPerSM = 1;
+  static constexpr bool kCompact = false;
   const Params* P;
   int lane, L;
   double beta;
@@ -1119,6 +1150,9 @@ struct TestSwapperChain {
   static constexpr bool kTestSwapper = true;
   static constexpr bool kTeam = false;
   static constexpr bool kIsing = false;
+  static constexpr int kMaxThreads = 256;
+  static constexpr int kMinBlocksPerSM = 1;
+  static constexpr bool kCompact = false;
   const Params* P;
   Rng rng;
   MeanAcc expl_acc, am, rev;
@@ -1151,7 +1185,7 @@ struct TestSwapperChain {
 // The scan kernel
 // ===========================================================================
 template <class Chain>
-__global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) scan_kernel(const __grid_constant__ Params P) {
   extern __shared__ double smem[];
   Chain::stage_shared(P, smem);
   __syncthreads();
@@ -1269,6 +1303,7 @@ __global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Param
           const bool ok = lane >= LL_HDR_WORDS || (unsigned int)(w >> 32) == tag;
           if (__all_sync(PGN_FULL_MASK, ok)) break;
           ++it;
+          if (it > 4u) __nanosleep(it < 64u ? 32 : 256);   // a sleeping warp leaves its scheduler's issue slots to the working ones
           if ((it & 255u) == 0u) {
             if (lane == 0) {
               if (*reinterpret_cast<volatile int*>(P.error_flag) != 0) status = 1;
@@ -1278,7 +1313,6 @@ __global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Param
             }
             status = __shfl_sync(PGN_FULL_MASK, status, 0);
             if (status != 0) break;
-            if (it > 65536u) __nanosleep(200);
           }
         }
         const unsigned int lo = (unsigned int)w;
@@ -1313,9 +1347,9 @@ __global__ void __launch_bounds__(256) scan_kernel(const __grid_constant__ Param
         const double e = lower ? exp_(lr + lr_p) : exp_(lr_p + lr);
         acceptance_pr = 1.0 < e ? 1.0 : e;
         if (lower) {   // record_swap_stats! :59-66, by the replica holding the lower chain
-          if (tw == ch.own(1)) swap_acc.fit(acceptance_pr);
-          if (tw == ch.own(2)) ls_fwd.fit(lr);
-          if (tw == ch.own(3)) ls_bwd.fit(lr_p);
+          if (tw == ch.own(1)) swap_acc.template fit<Chain::kCompact>(acceptance_pr);
+          if (tw == ch.own(2)) ls_fwd.template fit<Chain::kCompact>(lr);
+          if (tw == ch.own(3)) ls_bwd.template fit<Chain::kCompact>(lr_p);
         }
       }
       accepted = (lower ? u : u_p) < acceptance_pr;

@@ -158,19 +158,35 @@ __device__ __forceinline__ double cospi_(double t) {
   return qi == 0 ? c : (qi == 1 ? -s : (qi == 2 ? -c : s));
 }
 
+// Out-of-line copies for code that runs once per scan or per refreshment rather than once per density
+// evaluation: an inlined fp64 division is ~50 instructions and log_/exp_ ~80, and the scan kernels are
+// large enough for their instruction-cache footprint to matter (same operations, same results).
+__device__ __noinline__ double ddiv_(double a, double b) { return a / b; }
+__device__ __noinline__ double log_ni(double x) { return log_(x); }
+__device__ __noinline__ double exp_ni(double x) { return exp_(x); }
+
+// COMPACT selects the out-of-line copies (kernels whose code size matters more than a call)
+template <bool COMPACT>
+__device__ __forceinline__ double div_(double a, double b) {
+  if constexpr (COMPACT) return ddiv_(a, b); else return a / b;
+}
+template <bool COMPACT = false>
 __device__ __forceinline__ double log1p_(double t) {
   double w = 1.0 + t;
   if (w == 1.0) return t;
-  return log_(w) * (t / (w - 1.0));
+  if constexpr (COMPACT) return log_ni(w) * ddiv_(t, w - 1.0);
+  else return log_(w) * (t / (w - 1.0));
 }
 // LogExpFunctions.logaddexp as used by LogSum (src/recorders/LogSum.jl:10-18)
+template <bool COMPACT = false>
 __device__ __forceinline__ double logaddexp_(double a, double b) {
   if (a == -PGN_INF) return b;
   if (b == -PGN_INF) return a;
   double m = a > b ? a : b;
   double dlt = a > b ? b - a : a - b;
   if (a == b) dlt = 0.0;
-  return m + log1p_(exp_(dlt));
+  if constexpr (COMPACT) return m + log1p_<true>(exp_ni(dlt));
+  else return m + log1p_<false>(exp_(dlt));
 }
 
 // ---- Philox4x32-10 ----------------------------------------------------------
@@ -216,6 +232,11 @@ __device__ __forceinline__ double normal_at(const Rng& g, unsigned long long ctr
   double t = 2.0 * u52(o[2], o[3]);
   double rad = sqrt(-2.0 * log_(u1));
   return rad * cospi_(t);
+}
+__device__ __noinline__ double normal_at_ni(unsigned int key0, unsigned int key1, unsigned int c2, unsigned int c3,
+                                            unsigned long long ctr) {
+  Rng g{key0, key1, c2, c3, 0ull};
+  return normal_at(g, ctr);
 }
 __device__ __forceinline__ unsigned int bits32_at(const Rng& g, unsigned long long ctr) {
   unsigned int o[4]; philox_tick(g, ctr, o);

@@ -40,7 +40,7 @@ def main():
     syms = subprocess.run(["readelf", "-sW", cubin], capture_output=True, text=True).stdout
     idx = None
     for ln in syms.splitlines():
-        if " FUNC " in ln and a.kernel in ln:
+        if " FUNC " in ln and " GLOBAL " in ln and a.kernel in ln:
             idx = int(ln.split(":")[0])
             name = ln.split()[-1]
             break
