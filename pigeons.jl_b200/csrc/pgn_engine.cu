@@ -843,8 +843,8 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     if (const char* dump = std::getenv("PGN_TIMING_DUMP")) {   // diagnostics: per-chain explore / partner-wait clocks of this round
       if (FILE* f = std::fopen(dump, "a")) {
         for (int i = 0; i < nl; ++i)
-          std::fprintf(f, "%u %d %lld %lld %lld %lld\n", h->epoch, h->first_chain + i, (long long)n_scans, st[i].explore_cycles,
-                       st[i].wait_cycles, st[i].n_points);
+          std::fprintf(f, "%u %d %lld %lld %lld %lld %lld %lld %lld\n", h->epoch, h->first_chain + i, (long long)n_scans, st[i].explore_cycles,
+                       st[i].wait_cycles, st[i].n_points, st[i].trial_cycles, st[i].barrier_cycles, st[i].decide_cycles);
         std::fclose(f);
       }
     }

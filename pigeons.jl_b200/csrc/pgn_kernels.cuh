@@ -51,6 +51,7 @@ struct ChainStatsDev {   // one per local chain, written when the round ends
   long long am_n; double am_mean; long long rev_n; double rev_mean;
   long long n_restarts, n_round_trips;
   long long n_points, n_ref_evals;
+  long long trial_cycles, barrier_cycles, decide_cycles;   // diagnostics: autoMALA search phases of team warp 0
   long long explore_cycles, wait_cycles;   // diagnostics (PGN_TIMING_DUMP): SM clocks spent exploring / waiting for the swap partner
 };
 
@@ -155,8 +156,9 @@ struct VecChain {
   static constexpr bool kCompact = CPL > 1;                  // large kernels call divisions / generators out of line (instruction cache)
   static constexpr int SLOT_DOUBLES = 3 * CPL * 32 + 8;    // x1 | p1 | g1c | {a0, a1, lp1, h_after, diff, eps, -, -}
   static constexpr int TEAM_CTL_DOUBLES = 24 + CPL * 32;   // control words + shared copy of an adopted state
-  static constexpr int POOL_DOUBLES = CPL * 32 + 8;        // per refreshment: momentum | a, b, u, -, log a, log b, -, -
+  static constexpr int POOL_DOUBLES = CPL * 32 + 8;        // per refreshment: momentum | a, b, u, |p|^2, log a, log b, -, -
   int tw, W, gen;
+  long long t_trial, t_barrier, t_decide;   // diagnostics (clock64 deltas)
   int own1, own2, own3, own4;   // team warp keeping statistic j (j mod W)
   int e_prev;           // exponent chosen by this chain's previous forward search (candidate placement only)
   double* slots;        // [3][W][SLOT_DOUBLES] trial results, rotating buffers
@@ -223,6 +225,7 @@ struct VecChain {
     pool = 0.0; pool_base = 0; pool_valid = false;
     tw = 0; W = 1; gen = 0; slots = nullptr; e_prev = 0; rng_pool = nullptr;
     own1 = own2 = own3 = own4 = 0;
+    t_trial = t_barrier = t_decide = 0;
   }
   __device__ void store(int wl) {
 #pragma unroll
@@ -735,20 +738,21 @@ struct VecChain {
     const bool pooled = rng_pool != nullptr && W > 1 && n_refresh_eff > 0 && n_refresh_eff <= P->pool_refresh;
     if (pooled) {
       const unsigned long long c0 = rng.ctr, stride = (unsigned long long)d + (use_mh ? 3ull : 2ull);
-      const int n_norm = n_refresh_eff * CPL, n_uni = (3 * n_refresh_eff + 31) / 32;
-      for (int pass = tw; pass < n_norm + n_uni; pass += W) {
-        if (pass < n_norm) {
-          const int ir = pass / CPL, k = pass - ir * CPL;
-          const double z = valid(k) ? normal_tick(c0 + (unsigned long long)ir * stride + (unsigned long long)(k * 32 + lane)) : 0.0;
-          rng_pool[(size_t)ir * POOL_DOUBLES + k * 32 + lane] = z;
-        } else {
-          const int j = (pass - n_norm) * 32 + lane, ir = j / 3, t = j - ir * 3;
-          if (ir < n_refresh_eff) {
-            const double uu = uniform_at(rng, c0 + (unsigned long long)ir * stride + (unsigned long long)(d + t));
-            rng_pool[(size_t)ir * POOL_DOUBLES + CPL * 32 + t] = uu;
-            rng_pool[(size_t)ir * POOL_DOUBLES + CPL * 32 + 4 + t] = log_(uu);
-          }
+      for (int ir = tw; ir < n_refresh_eff; ir += W) {   // team warp w draws for refreshments w, w + W, ...
+        double* rp = rng_pool + (size_t)ir * POOL_DOUBLES;
+        const unsigned long long cr = c0 + (unsigned long long)ir * stride;
+        double pp = 0.0;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          const double z = valid(k) ? normal_tick(cr + (unsigned long long)(k * 32 + lane)) : 0.0;
+          rp[k * 32 + lane] = z;
+          pp = valid(k) ? pp + z * z : pp;
         }
+        const double uu = uniform_at(rng, cr + (unsigned long long)(d + (lane < 3 ? lane : 0)));
+        const double lu = log_(uu);
+        const double spp = warp_sum(pp);                 // the momentum's squared norm, same tree as at the refreshment
+        if (lane < 3) { rp[CPL * 32 + lane] = uu; rp[CPL * 32 + 4 + lane] = lu; }
+        if (lane == 3) rp[CPL * 32 + 3] = spp;
       }
       __syncthreads();
     }
@@ -763,15 +767,12 @@ struct VecChain {
       if (i >= 0) {
         double p[CPL];
         double pp = 0.0;
-        double a, b, la, lb;
+        double a, b, la, lb, spp = 0.0;
         if (pooled) {   // this refreshment's draws were made at the start of the scan (same ticks, same values)
           const double* rp = rng_pool + (size_t)i * POOL_DOUBLES;
 #pragma unroll
-          for (int k = 0; k < CPL; ++k) {
-            p[k] = rp[k * 32 + lane];
-            pp = valid(k) ? pp + p[k] * p[k] : pp;
-          }
-          a = rp[CPL * 32]; b = rp[CPL * 32 + 1]; u_mh = rp[CPL * 32 + 2];
+          for (int k = 0; k < CPL; ++k) p[k] = rp[k * 32 + lane];
+          a = rp[CPL * 32]; b = rp[CPL * 32 + 1]; u_mh = rp[CPL * 32 + 2]; spp = rp[CPL * 32 + 3];
           la = rp[CPL * 32 + 4]; lb = rp[CPL * 32 + 5];
           rng.ctr += (unsigned long long)d + (use_mh ? 3ull : 2ull);
         } else {
@@ -792,7 +793,7 @@ struct VecChain {
         }
         lower = a < b ? la : lb;     // log(min(a, b))
         upper = a < b ? lb : la;     // log(max(a, b))
-        init_joint = lp0 - 0.5 * warp_sum(pp);
+        init_joint = lp0 - 0.5 * (pooled ? spp : warp_sum(pp));
         if (!is_finite(init_joint)) { err = PGN_ERR_NOT_POSITIVE; return; }
         if (!(lower < upper)) { err = PGN_ERR_INVALID; return; }
 #pragma unroll
@@ -826,38 +827,60 @@ struct VecChain {
         }
 #pragma unroll 1
         while (true) {
+          const long long tc0 = clock64();
           const double diff = run_trial(sx, sp, sg, pre, pre_one, eps, h_before, T);
+          const long long tc1 = clock64();
+          t_trial += tc1 - tc0;
           if (phase == 2) break;
           const int buf = gen;
           gen = gen == 2 ? 0 : gen + 1;
           publish(buf, T, diff);
           __syncthreads();
+          const long long tc2 = clock64();
+          t_barrier += tc2 - tc1;
+          // Replay of the reference's sequential walk over the published candidates: lane l holds candidate l of
+          // this round, a ballot finds the first one that stops the walk.
           bool decided = false;
           int win_buf = buf, win_w = 0;
-          int n_first, n_last;
+          const double* hh = slot(buf, lane < W ? lane : 0) + 3 * CPL * 32;
+          const double dn = hh[4], en = hh[5];
+          const unsigned int team_mask = (1u << W) - 1u;
+          int first_w, last_w;                 // candidates examined this round, in walk order
           if (phase == 0) {
-            const double d0 = slot(buf, 0)[3 * CPL * 32 + 4];
+            const double d0 = __shfl_sync(PGN_FULL_MASK, dn, 0);
             if (!is_finite(d0) || d0 < lower) sgn = -1;            // auto_step_size :203-209
             else if (d0 > upper) sgn = 1;
             else decided = true;
             prev_buf = buf; prev_w = 0;
-            n_first = 1; n_last = decided ? 0 : (sgn < 0 ? n_neg : W - 1 - n_neg);
+            first_w = sgn < 0 ? 1 : n_neg + 1;                      // offsets -1..-n_neg sit in warps 1..n_neg, +1.. after them
+            last_w = decided ? 0 : (sgn < 0 ? n_neg : W - 1);
           } else {
-            n_first = m + 1; n_last = m + W;
+            first_w = 0; last_w = W - 1;
           }
-          for (int n = n_first; n <= n_last && !decided; ++n) {
-            const int w = phase == 0 ? r1_warp(sgn * n, n_neg) : n - n_first;
-            const double* hh = slot(buf, w) + 3 * CPL * 32;
-            const double dn = hh[4], en = hh[5];
-            if (sgn < 0) {                                         // shrink_step_size :228-248
-              if (en == 0.0) { err = PGN_ERR_STEP_UNDERFLOW; return; }
-              if (dn > lower) { decided = true; nst = n; exponent = -n; win_buf = buf; win_w = w; }
-            } else {                                               // grow_step_size :216-226
-              if (!is_finite(dn) || dn < upper) { decided = true; nst = n; exponent = n - 1; win_buf = prev_buf; win_w = prev_w; }
+          if (!decided && last_w >= first_w) {
+            // shrink_step_size :228-248 stops at eps == 0 (error) or diff > lower; grow_step_size :216-226 at a
+            // non-finite diff or diff < upper
+            const bool stop = sgn < 0 ? (en == 0.0 || dn > lower) : (!is_finite(dn) || dn < upper);
+            const unsigned int range = (team_mask >> first_w << first_w) & (0xffffffffu >> (31 - last_w));
+            const unsigned int hit = __ballot_sync(PGN_FULL_MASK, stop) & range;
+            if (hit != 0u) {
+              const int w = __ffs((int)hit) - 1;
+              const int n = m + (w - first_w) + 1;
+              if (sgn < 0) {
+                if (__shfl_sync(PGN_FULL_MASK, en, w) == 0.0) { err = PGN_ERR_STEP_UNDERFLOW; return; }
+                nst = n; exponent = -n; win_buf = buf; win_w = w;
+              } else {
+                nst = n; exponent = n - 1;
+                if (w == first_w) { win_buf = prev_buf; win_w = prev_w; } else { win_buf = buf; win_w = w - 1; }
+              }
+              decided = true;
+            } else {
+              m += last_w - first_w + 1;
+              prev_buf = buf; prev_w = last_w;
+              eps_m = __shfl_sync(PGN_FULL_MASK, en, last_w);
             }
-            prev_buf = buf; prev_w = w; eps_m = en;
           }
-          m = n_last;
+          t_decide += clock64() - tc2;
           if (decided) {
             if (dir == 1) break;                                   // reversed search: only the exponent is used (:160-163)
             const double eps_final = P->step_size * pow2(exponent);   // leap_frog! at the chosen step :144-151
@@ -1111,29 +1134,74 @@ struct IsingChain {
     rng.ctr += (unsigned long long)L;
     recompute_S();
   }
+  // One raster-order sweep site: flip (i, j) unless the Metropolis test rejects it.  `a` = neighbours equal
+  // to the site (me * sum(neighbours) = 2a - 4, so S_new - S = 8 - 4a and the table row moves by a - 2);
+  // `low` says the move lowers lp (only then can accept_ratio be < 1), `q` picks |dS| = 8.  Returns "flipped".
+  __device__ __forceinline__ bool site(int a, bool low, int q, int& m, int& k) {
+    if (k == 32) {   // next block of this replica's uniforms (same stream, see draw_uniform)
+      pool_base += 32ull;
+      pool = uniform_at(rng, pool_base + (unsigned long long)lane);
+      k = 0;
+    }
+    const double accept_ratio = tbl[2 * m + q];
+    const double u = __shfl_sync(PGN_FULL_MASK, pool, k);
+    const bool draws = low && accept_ratio < 1;           // rand(rng) only if accept_ratio < 1 (examples/ising.jl:110)
+    const bool reject = draws && u > accept_ratio;
+    k += draws ? 1 : 0;
+    m += reject ? 0 : a - 2;
+    return !reject;
+  }
   __device__ void metropolis() {   // examples/ising.jl:98-117
-    for (int k = 0; k < P->ising_n_steps; ++k)
+    // the sweep's draws come from the pooled stream; k = index of the next one inside the pool
+    if (!pool_valid || rng.ctr - pool_base > 32ull) {
+      pool_base = rng.ctr;
+      pool = uniform_at(rng, pool_base + (unsigned long long)lane);
+      pool_valid = true;
+    }
+    int k = (int)(rng.ctr - pool_base);
+    int m = (S0 - S) >> 2;                                 // table row of the current S = S0 - 4 m
+    const int jl_me = lane == 0 ? L - 1 : lane - 1, jr_me = lane >= L - 1 ? 0 : lane + 1;
+    const bool down = sig < 0;                             // lp falls when S falls
+    for (int sweep = 0; sweep < P->ising_n_steps; ++sweep)
       for (int i = 0; i < L; ++i) {
         const unsigned int up = __shfl_sync(PGN_FULL_MASK, row, (i + L - 1) % L);
         const unsigned int dn = __shfl_sync(PGN_FULL_MASK, row, (i + 1) % L);
-        unsigned int cur = __shfl_sync(PGN_FULL_MASK, row, i);
-        // bit j = 1 where the vertical neighbour equals site (i, j); a site's own bit is untouched until it is visited
-        const unsigned int eq_up = ~(cur ^ up), eq_dn = ~(cur ^ dn);
-        for (int j = 0; j < L; ++j) {
-          const int jl = j == 0 ? L - 1 : j - 1, jr = j == L - 1 ? 0 : j + 1;
-          const unsigned int b = (cur >> j) & 1u;
-          // a = neighbours equal to the site: me * sum(neighbours) = 2a - 4, so S_new - S = 8 - 4a
-          const int a = (int)(((eq_up >> j) & 1u) + ((eq_dn >> j) & 1u) + (((cur >> jl) ^ b ^ 1u) & 1u) + (((cur >> jr) ^ b ^ 1u) & 1u));
-          const int dS = 8 - 4 * a;
-          bool reject = false;
-          if (dS != 0 && ((dS < 0) == (sig < 0))) {     // lp goes down: accept_ratio = exp(lp_after - lp_before) may be < 1
-            const double accept_ratio = tbl[((S0 - S) >> 2) * 2 + ((a & 3) == 0 ? 1 : 0)];
-            if (accept_ratio < 1) reject = draw_uniform() > accept_ratio;
-          }
-          if (!reject) { cur ^= (1u << j); S += dS; }
+        const unsigned int cur0 = __shfl_sync(PGN_FULL_MASK, row, i);
+        // Lane j prepares site (i, j) from the row as it is now: its vertical neighbours are final, its right
+        // neighbour is visited later, and its left neighbour is either untouched (f = 0) or flipped (f = 1) by
+        // the time the sweep gets there — both cases are encoded, the sequential pass below only selects.
+        unsigned int code;
+        {
+          const unsigned int me = (cur0 >> lane) & 1u;
+          const int v = (int)((((cur0 ^ up) >> lane) & 1u) ^ 1u) + (int)((((cur0 ^ dn) >> lane) & 1u) ^ 1u);
+          const int eL = (int)((((cur0 >> jl_me) & 1u) ^ me) ^ 1u), eR = (int)((((cur0 >> jr_me) & 1u) ^ me) ^ 1u);
+          const int a0 = v + eL + eR, a1 = v + (1 - eL) + eR;
+          const unsigned int c0 = (unsigned int)a0 | ((down ? a0 >= 3 : a0 <= 1) ? 8u : 0u) | ((a0 & 3) == 0 ? 16u : 0u);
+          const unsigned int c1 = (unsigned int)a1 | ((down ? a1 >= 3 : a1 <= 1) ? 8u : 0u) | ((a1 & 3) == 0 ? 16u : 0u);
+          code = c0 | (c1 << 8);
         }
-        if (lane == i) row = cur;
+        unsigned int flips = 0u;
+        bool f = false;                                     // did the site to the left flip?
+        for (int j = 0; j < L - 1; ++j) {
+          unsigned int c = __shfl_sync(PGN_FULL_MASK, code, j);
+          c = f ? (c >> 8) : c;
+          f = site((int)(c & 7u), (c & 8u) != 0u, (int)((c >> 4) & 1u), m, k);
+          flips |= f ? (1u << j) : 0u;
+        }
+        {   // last site of the row: its right neighbour is site 0 of the same row, already visited
+          const int j = L - 1;
+          const unsigned int cur = cur0 ^ flips;
+          const int jl = j == 0 ? L - 1 : j - 1, jr = 0;
+          const unsigned int me = (cur >> j) & 1u;
+          const int a = (int)(((((cur0 ^ up) >> j) & 1u) ^ 1u) + ((((cur0 ^ dn) >> j) & 1u) ^ 1u) + ((((cur >> jl) ^ me) & 1u) ^ 1u) +
+                              ((((cur >> jr) ^ me) & 1u) ^ 1u));
+          f = site(a, down ? a >= 3 : a <= 1, (a & 3) == 0 ? 1 : 0, m, k);
+          flips |= f ? (1u << j) : 0u;
+        }
+        if (lane == i) row = cur0 ^ flips;
       }
+    S = S0 - 4 * m;
+    rng.ctr = pool_base + (unsigned long long)k;
     n_ref += 2LL * P->ising_n_steps * L * L;
     n_points += (long long)P->ising_n_steps * L * L;
   }
@@ -1406,6 +1474,8 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
     s.n_restarts = n_restarts; s.n_round_trips = n_trips;
     s.n_points = ch.n_points; s.n_ref_evals = ch.n_ref;
     s.explore_cycles = explore_cycles; s.wait_cycles = wait_cycles;
+    if constexpr (Chain::kTeam) { s.trial_cycles = ch.t_trial; s.barrier_cycles = ch.t_barrier; s.decide_cycles = ch.t_decide; }
+    else { s.trial_cycles = s.barrier_cycles = s.decide_cycles = 0; }
     P.stats[wl] = s;
   }
 }
