@@ -103,7 +103,7 @@ struct pgn_handle {
   // ---- logistic regression (batched GEMM path)
   int lr_n_data = 0, lr_n_pad = 0, lr_r_pad = 0, lr_splits = 0;
   DevBuf<double> lr_Xr, lr_Xt, lr_y, lr_Theta, lr_Thetat, lr_LL, lr_Res, lr_lik, lr_Gp, lr_G;
-  DevBuf<double> lr_P, lr_G0, lr_SX, lr_SP, lr_SG, lr_TP, lr_TG, lr_FX, lr_FG;
+  DevBuf<double> lr_P, lr_G0, lr_SX, lr_SP, lr_SG, lr_TP, lr_TG, lr_FX, lr_FG, lr_QX, lr_QP, lr_QG;
   DevBuf<LrChainState> lr_st;
   DevBuf<int> lr_n_active;
   bool lr_use_dmma = true;       // FP64 tensor-core GEMM (same summation order as the SIMT kernel, see pgn_logreg.cuh)
@@ -177,6 +177,7 @@ void logreg_allocate(pgn_handle* h, const pgn_config* cfg) {
   h->lr_G.alloc(vec);
   h->lr_P.alloc(vec); h->lr_G0.alloc(vec); h->lr_SX.alloc(vec); h->lr_SP.alloc(vec); h->lr_SG.alloc(vec);
   h->lr_TP.alloc(vec); h->lr_TG.alloc(vec); h->lr_FX.alloc(vec); h->lr_FG.alloc(vec);
+  h->lr_QX.alloc(vec); h->lr_QP.alloc(vec); h->lr_QG.alloc(vec);
   h->lr_st.alloc(h->n_local);
   h->lr_n_active.alloc(1);
   {
@@ -243,6 +244,7 @@ void logreg_fill_params(pgn_handle* h, LrParams& P) {
   P.st = h->lr_st.p;
   P.X = h->x.p; P.P = h->lr_P.p; P.G0 = h->lr_G0.p; P.SX = h->lr_SX.p; P.SP = h->lr_SP.p; P.SG = h->lr_SG.p;
   P.TP = h->lr_TP.p; P.TG = h->lr_TG.p; P.FX = h->lr_FX.p; P.FG = h->lr_FG.p; P.TX = h->lr_Theta.p;
+  P.QX = h->lr_QX.p; P.QP = h->lr_QP.p; P.QG = h->lr_QG.p;
   P.lik = h->lr_lik.p; P.G = h->lr_G.p;
   P.n_active = h->lr_n_active.p; P.error_flag = h->error_flag.p;
   P.mail = h->mail.p; P.mail_left = h->mail_left; P.mail_right = h->mail_right; P.slot_bytes = h->slot_bytes;

@@ -340,6 +340,7 @@ struct LrChainState {
   double e0, e1, lp0;                 // densities at x
   double f_a0, f_a1, f_lp, h_rev;     // forward proposal
   double t_a0, t_a1, t_lp1, t_h_after, t_eps, pp;   // current trial
+  double q_a0, q_a1, q_lp1, q_h_after, q_eps;       // previous trial of a growing search (its candidate one step back)
   // replica
   int replica_index, rt_state;
   unsigned long long ctr;
@@ -363,6 +364,7 @@ struct LrParams {
   const double* beta;
   LrChainState* st;
   double *X, *P, *G0, *SX, *SP, *SG, *TP, *TG, *FX, *FG, *TX;   // [r_pad][d_pad]
+  double *QX, *QP, *QG;   // the previous trial's point, momentum and gradient (grow_step_size steps back to it)
   const double* lik;   // [r_pad]
   const double* G;     // [r_pad][d_pad] likelihood gradient at TX
   int* n_active;
@@ -536,11 +538,15 @@ struct LrCtx {
       return;
     }
 
-    // ---- autoMALA step-size search (same transitions as VecChain::automala)
+    // ---- autoMALA step-size search (same transitions as VecChain::automala).  grow_step_size :216-226 ends one
+    // step back from the candidate that stopped it, so a growing search keeps its previous trial and returns
+    // to it instead of evaluating that step a second time; the reversed search (:160-163) only needs its
+    // exponent, so it never re-evaluates.
     bool decided = false;
+    bool keep = false;   // the search goes on growing: this trial becomes "the previous one"
     if (s.mode == 0) {
       if (!is_finite(diff) || diff < s.lower) { s.mode = 1; s.n = 1; s.eps = eps / 2.0; }
-      else if (diff > s.upper) { s.mode = 2; s.n = 1; s.eps = eps * 2.0; }
+      else if (diff > s.upper) { s.mode = 2; s.n = 1; s.eps = eps * 2.0; keep = true; }
       else decided = true;
     } else if (s.mode == 1) {
       if (eps == 0.0) { s.err = PGN_ERR_STEP_UNDERFLOW; return; }
@@ -548,14 +554,29 @@ struct LrCtx {
       else { s.n += 1; s.eps = eps / 2.0; }
     } else if (s.mode == 2) {
       if (!is_finite(diff) || diff < s.upper) { s.nst = s.n; s.exponent = s.n - 1; decided = true; }
-      else { s.n += 1; s.eps = eps * 2.0; }
+      else { s.n += 1; s.eps = eps * 2.0; keep = true; }
     } else {
       decided = true;   // mode 3: re-evaluated at the chosen step
     }
-    if (!decided) { emit_trial(); return; }
-    if (s.mode != 3) {
+    if (!decided) {
+      if (keep && s.dir == 0) {
+        copy(row(P.QX), tx); copy(row(P.QP), tp); copy(row(P.QG), tg);
+        s.q_a0 = s.t_a0; s.q_a1 = s.t_a1; s.q_lp1 = s.t_lp1; s.q_h_after = s.t_h_after; s.q_eps = s.t_eps;
+      }
+      emit_trial();
+      return;
+    }
+    if (s.mode != 3 && s.dir == 0) {
       const double eps_final = P.step_size * pow2(s.exponent);
-      if (s.t_eps != eps_final) { s.mode = 3; s.eps = eps_final; emit_trial(); return; }
+      if (s.t_eps != eps_final) {
+        if (s.mode == 2 && s.q_eps == eps_final) {   // back to the previous trial: it is the leap_frog! at the chosen step :144-151
+          double* txw = row(P.TX);
+          copy(txw, row(P.QX)); copy(tp, row(P.QP)); copy(tg, row(P.QG));
+          s.t_a0 = s.q_a0; s.t_a1 = s.q_a1; s.t_lp1 = s.q_lp1; s.t_h_after = s.q_h_after; s.t_eps = s.q_eps;
+        } else {
+          s.mode = 3; s.eps = eps_final; emit_trial(); return;
+        }
+      }
     }
     // search finished
     s.n_steps += 1 + s.nst;
