@@ -1046,7 +1046,8 @@ struct IsingChain {
   const double* tbl;   // [(L^2 + 1)][2]: |dS| = 4, 8
   int sig;             // sign of the dS that lowers lp
   int S0;              // 2 L^2
-  static __host__ __device__ int table_doubles(int L_) { return (L_ * L_ + 1) * 2; }
+  static constexpr int TBL_PAD = 10;   // rows on either side for the wrong guesses of the speculative sweep (5 sites x +-2)
+  static __host__ __device__ int table_doubles(int L_) { return (L_ * L_ + 1 + 2 * TBL_PAD) * 2; }
   static __device__ void stage_shared(const Params&, double*) {}
   __device__ __forceinline__ int own(int) const { return 0; }
 
@@ -1094,10 +1095,16 @@ struct IsingChain {
     sig = decreasing ? 1 : -1;
     S0 = 2 * L * L;
     for (int idx = lane; idx < table_doubles(L); idx += 32) {
-      const int s_old = S0 - 4 * (idx >> 1);
-      const int s_new = s_old + sig * 4 * ((idx & 1) + 1);
-      t[idx] = exp_(lp(beta, s_new) - lp(beta, s_old));
+      const int row_m = (idx >> 1) - TBL_PAD;
+      double v = 1.0;                                    // padding rows are never used by the true trajectory
+      if (row_m >= 0 && row_m <= L * L) {
+        const int s_old = S0 - 4 * row_m;
+        const int s_new = s_old + sig * 4 * ((idx & 1) + 1);
+        v = exp_(lp(beta, s_new) - lp(beta, s_old));
+      }
+      t[idx] = v;
     }
+    t += 2 * TBL_PAD;
     tbl = t;
     __syncwarp();
   }
@@ -1180,13 +1187,66 @@ struct IsingChain {
           const unsigned int c1 = (unsigned int)a1 | ((down ? a1 >= 3 : a1 <= 1) ? 8u : 0u) | ((a1 & 3) == 0 ? 16u : 0u);
           code = c0 | (c1 << 8);
         }
+        // The sites of a row are visited in order, each depending on whether its left neighbour just flipped, on
+        // the running S and on how many uniforms were consumed so far.  Five sites at a time, lane h GUESSES the
+        // five flip outcomes (bit t of h), walks the block under that guess — table row, draw index and
+        // neighbour state all follow from the guess, so nothing waits for a comparison — and checks every
+        // outcome against the guess.  Exactly one lane is consistent (the first wrong bit of any other guess is
+        // refuted by the true outcome at that site): its state is the sequential sweep's.
         unsigned int flips = 0u;
-        bool f = false;                                     // did the site to the left flip?
-        for (int j = 0; j < L - 1; ++j) {
-          unsigned int c = __shfl_sync(PGN_FULL_MASK, code, j);
+        bool f = false;                                     // did the site to the left of the block flip?
+        int j0 = 0;
+        for (; j0 + 5 <= L - 1; j0 += 5) {
+          if (k > 27) {   // room for five draws: restart the pool at the current tick of the stream
+            pool_base += (unsigned long long)k;
+            pool = uniform_at(rng, pool_base + (unsigned long long)lane);
+            k = 0;
+          }
+          // straight-line on purpose: the five table reads and the five draws of a guess are independent
+          unsigned int cc[5];
+#pragma unroll
+          for (int t = 0; t < 5; ++t) cc[t] = __shfl_sync(PGN_FULL_MASK, code, j0 + t);
+          int row_at[5];
+          bool low[5];
+          {
+            int mm = m;
+            bool fl = f;
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+              const unsigned int c = fl ? (cc[t] >> 8) : cc[t];
+              const bool g = ((lane >> t) & 1) != 0;
+              row_at[t] = 2 * mm + (int)((c >> 4) & 1u);
+              low[t] = (c & 8u) != 0u;
+              mm += g ? (int)(c & 7u) - 2 : 0;
+              fl = g;
+            }
+            row_at[0] += 0;
+            cc[0] = (unsigned int)mm;   // the guess's table row after the block
+          }
+          double ratio[5];
+#pragma unroll
+          for (int t = 0; t < 5; ++t) ratio[t] = tbl[row_at[t]];
+          int kk = k;
+          bool ok = true;
+#pragma unroll
+          for (int t = 0; t < 5; ++t) {
+            const bool draws = low[t] & (ratio[t] < 1);               // rand(rng) only if accept_ratio < 1 (examples/ising.jl:110)
+            const double u = __shfl_sync(PGN_FULL_MASK, pool, kk);
+            const bool flipped = !(draws & (u > ratio[t]));
+            ok = ok & (flipped == (((lane >> t) & 1) != 0));
+            kk += draws ? 1 : 0;
+          }
+          const int win = __ffs((int)__ballot_sync(PGN_FULL_MASK, ok)) - 1;
+          m = (int)__shfl_sync(PGN_FULL_MASK, cc[0], win);
+          k = __shfl_sync(PGN_FULL_MASK, kk, win);
+          flips |= (unsigned int)win << j0;
+          f = ((win >> 4) & 1) != 0;
+        }
+        for (; j0 < L - 1; ++j0) {   // the sites left over by the blocks of five, one at a time
+          unsigned int c = __shfl_sync(PGN_FULL_MASK, code, j0);
           c = f ? (c >> 8) : c;
           f = site((int)(c & 7u), (c & 8u) != 0u, (int)((c >> 4) & 1u), m, k);
-          flips |= f ? (1u << j) : 0u;
+          flips |= f ? (1u << j0) : 0u;
         }
         {   // last site of the row: its right neighbour is site 0 of the same row, already visited
           const int j = L - 1;

@@ -7,7 +7,7 @@ not the CUDA line they came from; `nvdisasm -gi` knows the lines (the library is
 warp-instructions and stall samples — by innermost line and by the line of a chosen outer function
 (the call site inside it), so a hot inlined helper is attributed to its callers too.
 
-usage: ncu_lines.py REPORT.ncu-rep MANGLED_KERNEL_SUBSTRING [--so LIB] [--top N] [--outer LO:HI]
+usage: ncu_lines.py REPORT.ncu-rep|SOURCE_PAGE.csv MANGLED_KERNEL_SUBSTRING [--so LIB] [--top N] [--outer LO:HI]
 """
 import argparse
 import csv
@@ -65,7 +65,8 @@ def main():
             frames = []
         elif ln.startswith("//---") and insts:
             break
-    rep = sh(["ncu", "-i", a.report, "--page", "source", "--csv"])
+    # REPORT is an .ncu-rep, or the CSV already exported from one with `ncu -i X.ncu-rep --page source --csv`
+    rep = open(a.report).read() if a.report.endswith(".csv") else sh(["ncu", "-i", a.report, "--page", "source", "--csv"])
     rows = list(csv.reader(io.StringIO(rep)))
     h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     col = {n: i for i, n in enumerate(rows[h])}
