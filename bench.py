@@ -83,6 +83,18 @@ def algorithmic_bytes_per_scan(n_chains, dim=None):
     return 3 * n_chains * CFG["state_bytes"] + 64 * n_chains
 
 
+def read_ncu_traffic(cfg_name):
+    """DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json); None when no capture of this config is committed."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            e = json.load(f).get(cfg_name)
+        return (e["dram_bytes_per_launch"], e["scans_in_captured_launch"], e["source"]) if e else (None, None, None)
+    except Exception:
+        return None, None, None
+
+
 def read_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -358,6 +370,7 @@ def main():
     launch_ms = kernel_ms / args.steps
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     n_local = pt.engine.n_local
+    traffic, traffic_scans, traffic_src = read_ncu_traffic(CFG_NAME)
     line = {
         "metric": "pt_scans_per_s", "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak",
@@ -372,7 +385,10 @@ def main():
                 "note": "wall clock around set_schedule + set_explorer + pgn_run_round (host buffers in, statistics out)"},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_note": (f"DRAM bytes of one {traffic_scans}-scan launch, {traffic_src}; the replica "
+                                                          "state stays in registers for the whole launch, so the traffic does not "
+                                                          "grow with the number of scans" if traffic is not None else None),
+                     "peak_source": peak_src,
                      "kernel": CFG["kernel"] + " (one persistent launch per step)",
                      "algorithmic_bytes_per_scan": algorithmic_bytes_per_scan(CHAINS_PER_GPU, DIM),
                      "note": "the working set is register-resident for the whole round: the path is bound by the dependency "
