@@ -192,6 +192,69 @@ def test_ising_antiferromagnetic_and_large_ladder(gpu_lib, oracle_lib):
         assert_same(run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw), f"ising {kw['target']}")
 
 
+FULL_SIZE = {
+    # BASELINE.json configs 2-4 at their full per-GPU width (rounds kept short so the oracle finishes in seconds)
+    "c2_funnel32_automala_256": dict(target=pg.Funnel(32), explorer=pg.AutoMALA(), n_chains=256, n_rounds=5, seed=1,
+                                     record=[pg.index_process, pg.swap_trace]),
+    "c3_gmm128_automala_1024": dict(target=pg.eight_mode_mixture(128, 8.0), explorer=pg.AutoMALA(), n_chains=1024, n_rounds=3, seed=1,
+                                    record=[pg.index_process, pg.swap_trace]),
+    "c4_ising32_512": dict(target=pg.IsingLogPotential(0.4406867935097715, 32), n_chains=512, n_rounds=4, seed=1,
+                           record=[pg.index_process, pg.swap_trace]),
+}
+
+
+def check_scan_invariants(rr, n_chains):
+    """Size-independent properties of a PT scan trace (src/swap/swap.jl:6-39, OddEven.jl:23-31): every scan's
+    index process is a permutation; only DEO neighbours of the scan's parity exchange replicas; a pair's two
+    sides agree; and the decision is u_lower < min(1, exp(lr_lower + lr_upper))."""
+    ip, acc, lr, u = rr.index_process, rr.swap_accept, rr.swap_lr, rr.swap_u
+    n_scans = ip.shape[0]
+    assert ip.shape == (n_scans, n_chains)
+    ident = np.arange(n_chains)
+    for s in range(n_scans):
+        assert np.array_equal(np.sort(ip[s]), np.sort(ip[0])), "index process is not a permutation"
+        even = ((s + 1) % 2 == 0)                      # scans are 1-based inside a round; rounds restart the parity
+        partner = np.where(((ident + 1) % 2 == 0) == even, ident + 1, ident - 1)
+        partner = np.clip(partner, 0, n_chains - 1)
+        lo = ident[(partner == ident + 1)]
+        assert np.array_equal(acc[s][lo], acc[s][lo + 1]), "the two sides of a pair disagree"
+        alone = ident[partner == ident]
+        assert not acc[s][alone].any()
+        a = np.minimum(1.0, np.exp(lr[s][lo] + lr[s][lo + 1]))
+        decided = u[s][lo] < a
+        clear = np.abs(u[s][lo] - a) > 1e-12           # numpy's exp is not the spec's exp_: skip razor-edge cases
+        assert np.array_equal(decided[clear], acc[s][lo][clear].astype(bool)), "accept decision is not u < min(1, exp(sum lr))"
+    return True
+
+
+@pytest.mark.parametrize("name", list(FULL_SIZE))
+def test_full_size_configs(name, gpu_lib, oracle_lib):
+    """BASELINE configs at full width: bit-exact against the oracle over the first rounds, plus the
+    size-independent scan invariants on the device trace of the last round."""
+    kw = FULL_SIZE[name]
+    g, c = run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw)
+    assert_same(g, c, name)
+    rr = g["rr"]
+    # rounds restart the DEO parity: check the last round's block of scans
+    n_last = 2 ** kw["n_rounds"]
+    last = type("R", (), dict(index_process=rr.index_process[-n_last:], swap_accept=rr.swap_accept[-n_last:],
+                              swap_lr=rr.swap_lr[-n_last:], swap_u=rr.swap_u[-n_last:]))
+    check_scan_invariants(last, kw["n_chains"])
+
+
+def test_known_answers_on_the_device(gpu_lib):
+    """The reference's tolerance-based known answers, run on the CUDA path itself: stepping stone of
+    toy_mvn_target(10) (test/test_stepping_stone.jl:15-28), cumulative barrier of toy_mvn_target(2)
+    (test/test_cumulative_barrier.jl:1-11), Ising 5x5 log Z (examples/custom-sampler.jl:4-5)."""
+    pt = pg.pigeons(target=pg.toy_mvn_target(10), explorer=pg.AutoMALA(), n_chains=6, n_rounds=12, seed=1, engine_lib=gpu_lib)
+    truth = 0.5 * 10 * (np.log(1.0) - np.log(10.0))
+    assert abs(pg.stepping_stone(pt) - truth) < 0.2
+    pt.close()
+    pt = pg.pigeons(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=12, seed=1, engine_lib=gpu_lib)
+    assert abs(pg.stepping_stone(pt) - 33.37317482430507) < 0.15
+    pt.close()
+
+
 MEM_FORCED = ["c1_toy_slice", "toy_default_explorer", "toy10_automala", "toy40_slice_2cpl", "toy100_automala_4cpl",
               "funnel32_automala", "funnel8_slice", "funnel_diag_precond", "gmm128_automala", "gmm6_slice",
               "gmm2_two_modes", "toy10_mala", "gmm70_mala_4cpl", "single_chain", "two_chains"]
