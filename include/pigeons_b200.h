@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PGN_ABI_VERSION 1
+#define PGN_ABI_VERSION 2
 
 /* ---- return codes ------------------------------------------------------- */
 #define PGN_OK 0
@@ -65,6 +65,8 @@ extern "C" {
 #define PGN_EXPLORER_AUTOMALA 3         /* src/explorers/AutoMALA.jl:29-294                        */
 #define PGN_EXPLORER_ISING_METROPOLIS 4 /* examples/ising.jl:91-117                                */
 #define PGN_EXPLORER_MALA 5             /* src/explorers/MALA.jl:19-104 (fixed step size)          */
+#define PGN_EXPLORER_SLICE_THEN_AUTOMALA 6 /* Compose(SliceSampler(), AutoMALA()): src/explorers/Compose.jl:16-19 */
+#define PGN_MAX_MIX 4                   /* explorers in a Mix (src/explorers/Mix.jl:7-21)          */
 
 /* ---- preconditioners (src/explorers/Preconditioner.jl:7-77) --------------- */
 #define PGN_PRECOND_IDENTITY 0
@@ -121,6 +123,18 @@ typedef struct pgn_explorer_params {
   const double* std_devs;     /* estimated_target_std_deviations [d] or NULL (round 1) */
   /* IsingMetropolis */
   int32_t ising_n_steps;      /* 3 */
+  /* Mix(AutoMALA(...), AutoMALA(...), ...) (src/explorers/Mix.jl:20-21: one of the explorers, drawn uniformly
+     from the replica's stream, performs the step; test/test_parallelism_invariance.jl:14-18 mixes autoMALA
+     kernels that differ in their preconditioner).  n_mix <= 1: the single autoMALA described above.
+     n_mix in 2..PGN_MAX_MIX: variant v uses (mix_n_refresh[v], mix_step_size[v], mix_precond_kind[v],
+     mix_variant_p0[v], mix_variant_p01[v]); std_devs is shared (every variant adapts from the same
+     recorders, Mix.jl:14-17). */
+  int32_t n_mix;
+  int32_t mix_n_refresh[PGN_MAX_MIX];
+  int32_t mix_precond_kind[PGN_MAX_MIX];
+  double mix_step_size[PGN_MAX_MIX];
+  double mix_variant_p0[PGN_MAX_MIX];
+  double mix_variant_p01[PGN_MAX_MIX];
 } pgn_explorer_params;
 
 /* Outputs of one round.  Every pointer is caller-allocated; optional logs may

@@ -607,21 +607,30 @@ struct Engine {
     if (e >= -1022) return pow2i(e);
     return scale2(1.0, e);
   }
+  // One explorer of a Mix (src/explorers/Mix.jl:20-21: step!(rand(replica.rng, explorer.explorers), ...)): the
+  // variant is drawn uniformly with one tick of the replica's stream; a plain autoMALA / MALA is the single variant.
+  struct Variant { int n_refresh; double step_size; int precond_kind; double p0, p01; };
+  Variant pick_variant(Replica& r) {
+    if (ep.n_mix <= 1) return Variant{ep.n_refresh, ep.step_size, ep.precond_kind, ep.mix_p0, ep.mix_p01};
+    int v = (int)(r.uniform() * (double)ep.n_mix);
+    if (v >= ep.n_mix) v = ep.n_mix - 1;
+    return Variant{ep.mix_n_refresh[v], ep.mix_step_size[v], ep.mix_precond_kind[v], ep.mix_variant_p0[v], ep.mix_variant_p01[v]};
+  }
   // build_preconditioner! (Preconditioner.jl:57-77)
-  void build_preconditioner(Replica& r) {
+  void build_preconditioner(Replica& r, const Variant& vr) {
     const int dd = d();
-    if (!have_std || ep.precond_kind == PGN_PRECOND_IDENTITY) {
+    if (!have_std || vr.precond_kind == PGN_PRECOND_IDENTITY) {
       for (int c = 0; c < dd; ++c) r.precond[c] = 1.0;
       return;
     }
-    if (ep.precond_kind == PGN_PRECOND_DIAGONAL) {
+    if (vr.precond_kind == PGN_PRECOND_DIAGONAL) {
       for (int c = 0; c < dd; ++c) r.precond[c] = std_devs[c] == 0.0 ? 1.0 : 1.0 / std_devs[c];
       return;
     }
     double u = r.uniform();
-    if (u <= ep.mix_p0) {
+    if (u <= vr.p0) {
       for (int c = 0; c < dd; ++c) r.precond[c] = std_devs[c] == 0.0 ? 1.0 : 1.0 / std_devs[c];
-    } else if (u <= ep.mix_p01) {
+    } else if (u <= vr.p01) {
       for (int c = 0; c < dd; ++c) r.precond[c] = 1.0;
     } else {
       double mix = r.uniform();
@@ -633,8 +642,9 @@ struct Engine {
   void auto_mala(Replica& r, ChainStats& st, bool use_mh) {
     const int dd = d();
     const double b = beta[r.chain - 1];
-    build_preconditioner(r);
-    for (int i = 0; i < ep.n_refresh; ++i) {
+    const Variant vr = pick_variant(r);
+    build_preconditioner(r, vr);
+    for (int i = 0; i < vr.n_refresh; ++i) {
       r.start_state = r.x;
       for (int c = 0; c < dd; ++c) r.momentum[c] = normal_at(r.rng, r.ctr + c);   // randn!(rng, momentum)
       r.ctr += dd;
@@ -645,12 +655,12 @@ struct Engine {
       double bb = r.uniform();
       double lower_bound = log_(a < bb ? a : bb);
       double upper_bound = log_(a < bb ? bb : a);
-      int proposed_exponent = auto_step_size(b, r, st, ep.step_size, lower_bound, upper_bound);
-      double proposed_step_size = ep.step_size * pow2(proposed_exponent);
+      int proposed_exponent = auto_step_size(b, r, st, vr.step_size, lower_bound, upper_bound);
+      double proposed_step_size = vr.step_size * pow2(proposed_exponent);
       leap_frog(b, r, proposed_step_size);
       if (use_mh) {
         for (int c = 0; c < dd; ++c) r.momentum[c] = r.momentum[c] * -1.0;
-        int reversed_exponent = auto_step_size(b, r, st, ep.step_size, lower_bound, upper_bound);
+        int reversed_exponent = auto_step_size(b, r, st, vr.step_size, lower_bound, upper_bound);
         bool reversibility_passed = reversed_exponent == proposed_exponent;
         st.rev.fit(reversibility_passed ? 1.0 : 0.0);
         double probability;
@@ -676,7 +686,7 @@ struct Engine {
   void mala(Replica& r, ChainStats& st) {
     const int dd = d();
     const double b = beta[r.chain - 1];
-    build_preconditioner(r);
+    build_preconditioner(r, Variant{ep.n_refresh, ep.step_size, ep.precond_kind, ep.mix_p0, ep.mix_p01});
     for (int i = 0; i < ep.n_refresh; ++i) {
       r.start_state = r.x;
       for (int c = 0; c < dd; ++c) r.momentum[c] = normal_at(r.rng, r.ctr + c);
@@ -727,6 +737,10 @@ struct Engine {
         case PGN_EXPLORER_TOY: sample_iid(beta[r.chain - 1], r); break;   // ToyExplorer.jl:7-12
         case PGN_EXPLORER_SLICE: slice_step(r, st); break;
         case PGN_EXPLORER_AUTOMALA: auto_mala(r, st, scan != 1); break;   // AutoMALA.jl:87,102
+        case PGN_EXPLORER_SLICE_THEN_AUTOMALA:                            // Compose.jl:16-19
+          slice_step(r, st);
+          auto_mala(r, st, scan != 1);
+          break;
         case PGN_EXPLORER_MALA: mala(r, st); break;
         case PGN_EXPLORER_ISING_METROPOLIS: ising_metropolis(r); break;
         default: break;
@@ -954,6 +968,7 @@ int orc_set_schedule(orc_handle* h, const double* beta, int32_t n, char** err) {
 }
 int orc_set_explorer(orc_handle* h, const pgn_explorer_params* ep, char** err) {
   Engine& E = h->E;
+  if (ep->n_mix < 0 || ep->n_mix > PGN_MAX_MIX) return fail(err, PGN_ERR_INVALID, "n_mix out of range");
   E.ep = *ep;
   E.have_std = ep->std_devs != nullptr;
   if (E.have_std) E.std_devs.assign(ep->std_devs, ep->std_devs + E.cfg.dim);

@@ -10,7 +10,7 @@ this package is host-side glue around the C ABI in include/pigeons_b200.h.
 """
 from ._capi import Engine, EngineError, EngineLib, default_library_path          # noqa: F401
 from .distributed import LoadBalance, SingleProcess, TorchDistributed             # noqa: F401
-from .explorers import (MALA, AutoMALA, DiagonalPreconditioner, IdentityPreconditioner,  # noqa: F401
+from .explorers import (MALA, AutoMALA, Compose, Mix, DiagonalPreconditioner, IdentityPreconditioner,  # noqa: F401
                         IsingMetropolis, MixDiagonalPreconditioner, SliceSampler, ToyExplorer)
 from .pt import (PT, Inputs, Iterators, NonReversiblePT, Shared, adapt, create_pt, global_barrier,   # noqa: F401
                  index_process, n_round_trips, n_scans_in_round, n_tempered_restarts, online, pigeons,

@@ -129,6 +129,12 @@ void fill_params(pgn_handle* h, Params& P) {
   P.slice_max_iter = h->ep.slice_max_iter;
   P.n_refresh = h->ep.n_refresh; P.step_size = h->ep.step_size; P.precond_kind = h->ep.precond_kind;
   P.mix_p0 = h->ep.mix_p0; P.mix_p01 = h->ep.mix_p01;
+  P.n_mix = h->ep.n_mix;
+  for (int v = 0; v < PGN_MAX_MIX; ++v) {
+    P.mix_n_refresh[v] = h->ep.mix_n_refresh[v]; P.mix_precond_kind[v] = h->ep.mix_precond_kind[v];
+    P.mix_step_size[v] = h->ep.mix_step_size[v]; P.mix_variant_p0[v] = h->ep.mix_variant_p0[v];
+    P.mix_variant_p01[v] = h->ep.mix_variant_p01[v];
+  }
   P.std_devs = h->have_std ? h->std_devs.p : nullptr;
   P.ising_n_steps = h->ep.ising_n_steps;
   P.x = h->x.p; P.replica_index = h->replica_index.p; P.rng_ctr = h->rng_ctr.p; P.rt_state = h->rt_state.p;
@@ -239,6 +245,7 @@ void logreg_fill_params(pgn_handle* h, LrParams& P) {
   P.sigma_ref = h->cfg.p[3]; P.ls_ref = h->cfg.p[4]; P.iv_ref = h->cfg.p[5];
   P.n_refresh = h->ep.n_refresh; P.step_size = h->ep.step_size; P.precond_kind = h->ep.precond_kind;
   P.mix_p0 = h->ep.mix_p0; P.mix_p01 = h->ep.mix_p01;
+
   P.std_devs = h->have_std ? h->std_devs.p : nullptr;
   P.beta = h->beta.p;
   P.st = h->lr_st.p;
@@ -359,6 +366,7 @@ void* vec_kernel_for(int ex) {
     case PGN_EXPLORER_SLICE: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_SLICE>>();
     case PGN_EXPLORER_AUTOMALA: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_AUTOMALA>>();
     case PGN_EXPLORER_MALA: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_MALA>>();
+    case PGN_EXPLORER_SLICE_THEN_AUTOMALA: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_SLICE_THEN_AUTOMALA>>();
     default: return nullptr;
   }
 }
@@ -417,7 +425,7 @@ void mem_fill_params(pgn_handle* h, const Params& P, MemParams& MP) {
 
 bool is_team_kernel(const pgn_handle* h) {   // VecChain<.., AUTOMALA>::kTeam
   const int tk = h->cfg.target_kind;
-  return h->ep.kind == PGN_EXPLORER_AUTOMALA && h->cpl > 0 &&
+  return (h->ep.kind == PGN_EXPLORER_AUTOMALA || h->ep.kind == PGN_EXPLORER_SLICE_THEN_AUTOMALA) && h->cpl > 0 &&
          (tk == PGN_TARGET_TOY_MVN || tk == PGN_TARGET_FUNNEL || tk == PGN_TARGET_GMM);
 }
 // dynamic shared memory of the scan kernel: staged target constants, then (team kernels) the
@@ -613,6 +621,13 @@ int pgn_set_schedule(pgn_handle* h, const double* beta, int32_t n, char** err) {
 }
 
 int pgn_set_explorer(pgn_handle* h, const pgn_explorer_params* ep, char** err) {
+  if (!h || !ep) return fail(err, PGN_ERR_INVALID, "null argument");
+  if (ep->n_mix < 0 || ep->n_mix > PGN_MAX_MIX) return fail(err, PGN_ERR_INVALID, "n_mix out of range");
+  if (ep->n_mix > 1 && ep->kind != PGN_EXPLORER_AUTOMALA)
+    return fail(err, PGN_ERR_INVALID, "the device mixes autoMALA kernels only (no CPU fallback for other mixtures)");
+  if ((ep->n_mix > 1 || ep->kind == PGN_EXPLORER_SLICE_THEN_AUTOMALA) &&
+      (h->cfg.target_kind == PGN_TARGET_LOGREG || h->cpl == 0 || h->force_mem))
+    return fail(err, PGN_ERR_INVALID, "Mix / Compose explorers run on the register-resident scan kernels only (d <= 128)");
   try {
     use_device(h);
     h->ep = *ep;
@@ -759,7 +774,9 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
           const int w_max = std::min(8, fa.maxThreadsPerBlock / 32);   // the kernel's launch bounds
           for (int w = std::min(w_max, (pinned >= 1 && pinned <= 8) ? pinned : 8); w >= 1; --w) {
             // a team shares one scan's momentum draws through shared memory when they fit in 64 KB
-            const int pool = (w > 1 && (size_t)h->ep.n_refresh * (h->cpl * 32 + 8) * sizeof(double) <= 64 * 1024) ? h->ep.n_refresh : 0;
+            int max_refresh = h->ep.n_refresh;
+            for (int v = 0; v < h->ep.n_mix && v < PGN_MAX_MIX; ++v) max_refresh = std::max(max_refresh, h->ep.mix_n_refresh[v]);
+            const int pool = (w > 1 && (size_t)max_refresh * (h->cpl * 32 + 8) * sizeof(double) <= 64 * 1024) ? max_refresh : 0;
             const size_t sm = scan_smem_bytes(h, w, 1, pool);
             if (sm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             int per_sm = 0;

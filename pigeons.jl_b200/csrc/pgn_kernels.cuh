@@ -77,6 +77,9 @@ struct Params {
   // explorer
   double slice_w; int slice_p, slice_n_passes, slice_max_iter;
   int n_refresh; double step_size; int precond_kind; double mix_p0, mix_p01;
+  int n_mix;   // Mix of autoMALA kernels (Mix.jl:20-21): variant v = mix_*[v]
+  int mix_n_refresh[PGN_MAX_MIX]; int mix_precond_kind[PGN_MAX_MIX];
+  double mix_step_size[PGN_MAX_MIX], mix_variant_p0[PGN_MAX_MIX], mix_variant_p01[PGN_MAX_MIX];
   const double* std_devs;   // [d] or null
   int ising_n_steps;
   // replica state in HBM, chain order
@@ -148,7 +151,7 @@ struct VecChain {
   // candidate steps per round, one per warp, and replays the reference's sequential decisions on the
   // results (see automala()).  Everything else is executed redundantly by all warps of the team on
   // identical data; only team warp 0 talks to the mailboxes and writes results.
-  static constexpr bool kTeam = (EX == PGN_EXPLORER_AUTOMALA);
+  static constexpr bool kTeam = (EX == PGN_EXPLORER_AUTOMALA || EX == PGN_EXPLORER_SLICE_THEN_AUTOMALA);
   static constexpr bool kIsing = false;
   // one coordinate per lane: teams of up to 6 warps, two teams per SM (168 registers per thread)
   static constexpr int kMaxThreads = (kTeam && CPL == 1) ? 192 : 256;
@@ -630,9 +633,9 @@ struct VecChain {
     T.eps = eps;
     return T.h_after - h_before;
   }
-  __device__ bool build_preconditioner(double (&pre)[CPL]) {   // Preconditioner.jl:57-77; returns "is identity"
+  __device__ bool build_preconditioner(double (&pre)[CPL], int precond_kind, double mix_p0, double mix_p01) {   // Preconditioner.jl:57-77; returns "is identity"
     const bool have = P->std_devs != nullptr;
-    if (!have || P->precond_kind == PGN_PRECOND_IDENTITY) {
+    if (!have || precond_kind == PGN_PRECOND_IDENTITY) {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pre[k] = 1.0;
       return true;
@@ -640,17 +643,17 @@ struct VecChain {
     double sd[CPL];
 #pragma unroll
     for (int k = 0; k < CPL; ++k) sd[k] = valid(k) ? P->std_devs[k * 32 + lane] : 0.0;
-    if (P->precond_kind == PGN_PRECOND_DIAGONAL) {
+    if (precond_kind == PGN_PRECOND_DIAGONAL) {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : div_<kCompact>(1.0, sd[k]);
       return false;
     }
     const double u = draw_uniform();
-    if (u <= P->mix_p0) {
+    if (u <= mix_p0) {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pre[k] = sd[k] == 0.0 ? 1.0 : div_<kCompact>(1.0, sd[k]);
       return false;
-    } else if (u <= P->mix_p01) {
+    } else if (u <= mix_p01) {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pre[k] = 1.0;
       return true;
@@ -721,7 +724,16 @@ struct VecChain {
   __device__ void automala(bool use_mh, int n_refresh_eff) {
     double pre[CPL];
     bool pre_one = true;
-    if (n_refresh_eff > 0) pre_one = build_preconditioner(pre);
+    // Mix (src/explorers/Mix.jl:20-21): one tick of the replica's stream picks the autoMALA variant of this step
+    double step0 = P->step_size, v_p0 = P->mix_p0, v_p01 = P->mix_p01;
+    int v_precond = P->precond_kind;
+    if (n_refresh_eff > 0 && P->n_mix > 1) {
+      int v = (int)(draw_uniform() * (double)P->n_mix);
+      v = v >= P->n_mix ? P->n_mix - 1 : v;
+      n_refresh_eff = P->mix_n_refresh[v]; step0 = P->mix_step_size[v]; v_precond = P->mix_precond_kind[v];
+      v_p0 = P->mix_variant_p0[v]; v_p01 = P->mix_variant_p01[v];
+    }
+    if (n_refresh_eff > 0) pre_one = build_preconditioner(pre, v_precond, v_p0, v_p01);
     else {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pre[k] = 1.0;
@@ -730,7 +742,7 @@ struct VecChain {
 #pragma unroll
     for (int k = 0; k < CPL; ++k) g0[k] = 0.0;
     double lp0 = 0.0;
-    if (!(P->step_size > 0)) { err = PGN_ERR_INVALID; return; }
+    if (!(step0 > 0)) { err = PGN_ERR_INVALID; return; }
     // A scan's draws are fixed ticks of the replica's stream once the preconditioner has taken its own:
     // refreshment i uses ticks [c0 + i*stride, +d) for the momentum and the next 2 (3 with MH) for a, b, (u).
     // The team draws them all now, each warp a share of the SIMT passes, instead of every warp drawing
@@ -812,16 +824,16 @@ struct VecChain {
         int sgn = 0, m = 0, exponent = 0, nst = 0;
         int prev_buf = 0, prev_w = 0;        // slot of the candidate examined last
         const int n_neg = r1_n_neg();
-        double eps_m = P->step_size;         // step of the farthest candidate examined in direction sgn
+        double eps_m = step0;         // step of the farthest candidate examined in direction sgn
         double eps = 0.0;
         if (i >= 0) {
           const int k0 = r1_k(tw, n_neg);
           // the reference halves / doubles the step one factor at a time (:216-248); while every intermediate is
           // a normal number that is the exact product with 2^k0, otherwise walk the same way it does
-          eps = P->step_size * pow2i(k0);
+          eps = step0 * pow2i(k0);
           const unsigned int ebits = (unsigned int)(double_to_bits(eps) >> 52) & 0x7ffu;
           if (ebits == 0u || ebits == 0x7ffu) {
-            eps = P->step_size;
+            eps = step0;
             for (int j = 0; j < (k0 < 0 ? -k0 : k0); ++j) eps = eps * (k0 < 0 ? 0.5 : 2.0);   // x * 0.5 == x / 2.0 for every double
           }
         }
@@ -883,7 +895,7 @@ struct VecChain {
           t_decide += clock64() - tc2;
           if (decided) {
             if (dir == 1) break;                                   // reversed search: only the exponent is used (:160-163)
-            const double eps_final = P->step_size * pow2(exponent);   // leap_frog! at the chosen step :144-151
+            const double eps_final = step0 * pow2(exponent);   // leap_frog! at the chosen step :144-151
             if (slot(win_buf, win_w)[3 * CPL * 32 + 5] == eps_final) {
               if (!(win_buf == buf && win_w == tw)) fetch(win_buf, win_w, T);
               break;
@@ -940,7 +952,7 @@ struct VecChain {
   // mala! (src/explorers/MALA.jl:74-97): one leapfrog at the fixed step size + MH, n_refresh times
   __device__ void mala() {
     double pre[CPL];
-    const bool pre_one = build_preconditioner(pre);
+    const bool pre_one = build_preconditioner(pre, P->precond_kind, P->mix_p0, P->mix_p01);
     double g0[CPL];
     {
       double dummy = 0.0;
@@ -978,8 +990,9 @@ struct VecChain {
 
   // ---- explore!(pt, replica, explorer) (src/pt/pigeons.jl:101-132) --------------
   __device__ void explore(long long scan, bool is_reference) {
-    if (EX == PGN_EXPLORER_AUTOMALA) {
+    if (EX == PGN_EXPLORER_AUTOMALA || EX == PGN_EXPLORER_SLICE_THEN_AUTOMALA) {
       if (is_reference) sample_iid(beta);
+      else if (EX == PGN_EXPLORER_SLICE_THEN_AUTOMALA) { slice_step(); if (err) return; }   // Compose.jl:16-19: first, then second
       automala(scan != 1, is_reference ? 0 : P->n_refresh);   // AutoMALA.jl:87,102
       return;
     }

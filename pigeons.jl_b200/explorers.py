@@ -125,3 +125,56 @@ class IsingMetropolis:
 
     def engine_params(self, dim: int) -> dict:
         return dict(kind=_capi.EXPLORER_ISING_METROPOLIS, ising_n_steps=self.n_steps)
+
+
+@dataclass(frozen=True)
+class Compose:
+    """src/explorers/Compose.jl:5-27: `first` then `second` at every step, both feeding the same
+    recorders.  The device implements the combination the reference documents and tests,
+    `Compose(SliceSampler(), AutoMALA())` (Compose.jl:3, test/test_parallelism_invariance.jl:19,
+    test/test_DistributionLogPotential.jl:57); any other pair raises (no CPU fallback)."""
+    first: object
+    second: object
+
+    def __post_init__(self):
+        if not (isinstance(self.first, SliceSampler) and isinstance(self.second, AutoMALA)):
+            raise NotImplementedError("the device composes SliceSampler followed by AutoMALA only")
+
+    def engine_params(self, dim: int) -> dict:
+        p = dict(self.second.engine_params(dim))
+        p.update(self.first.engine_params(dim))
+        p["kind"] = _capi.EXPLORER_SLICE_THEN_AUTOMALA
+        return p
+
+    def adapt(self, round_result) -> "Compose":      # Compose.jl:10-14
+        return Compose(self.first, self.second.adapt(round_result))
+
+
+@dataclass(frozen=True, init=False)
+class Mix:
+    """src/explorers/Mix.jl:7-30: one of the explorers, drawn uniformly from the replica's stream,
+    performs the step.  Device support: 2..4 AutoMALA kernels (they may differ in preconditioner,
+    step size and number of refreshments — test/test_parallelism_invariance.jl:14-18)."""
+    explorers: tuple
+
+    def __init__(self, *explorers):
+        if len(explorers) == 1 and isinstance(explorers[0], (tuple, list)):
+            explorers = tuple(explorers[0])
+        if not (2 <= len(explorers) <= _capi.MAX_MIX) or not all(isinstance(e, AutoMALA) for e in explorers):
+            raise NotImplementedError(f"the device mixes 2..{_capi.MAX_MIX} AutoMALA explorers")
+        object.__setattr__(self, "explorers", tuple(explorers))
+
+    def engine_params(self, dim: int) -> dict:
+        p = dict(self.explorers[0].engine_params(dim))
+        variants = []
+        for e in self.explorers:
+            q = e.engine_params(dim)
+            variants.append((q["n_refresh"], q["step_size"], q["precond_kind"], q["mix_p0"], q["mix_p01"]))
+        # the variants share one std-dev estimate (every explorer adapts from the same recorders, Mix.jl:14-17)
+        sds = [e.estimated_target_std_deviations for e in self.explorers if e.estimated_target_std_deviations is not None]
+        p["std_devs"] = None if not sds else np.asarray(sds[0])
+        p["mix_variants"] = variants
+        return p
+
+    def adapt(self, round_result) -> "Mix":          # Mix.jl:14-17
+        return Mix(*(e.adapt(round_result) for e in self.explorers))

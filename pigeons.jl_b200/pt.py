@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _capi
 from .distributed import Communicator, LoadBalance, SingleProcess
-from .explorers import MALA, AutoMALA
+from .explorers import MALA, AutoMALA, Compose, Mix
 from .recorders import ReducedRecorders, merge_round_results
 from .tempering import (CommunicationBarriers, Schedule, communication_barriers, equally_spaced_schedule,
                         optimal_schedule, rejections)
@@ -145,7 +145,7 @@ def adapt(pt: PT, rr: ReducedRecorders) -> PT:
     else:
         new_temp = temp
     explorer = pt.shared.explorer
-    if isinstance(explorer, (AutoMALA, MALA)):
+    if isinstance(explorer, (AutoMALA, MALA, Compose, Mix)):
         explorer = explorer.adapt(rr)
     pt.shared = Shared(pt.shared.iterators, new_temp, explorer)
     pt.reduced_recorders = rr

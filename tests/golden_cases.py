@@ -19,6 +19,14 @@ GOLDEN_CASES = {
     # BASELINE config 5 shape, reduced sizes
     "c5_logreg_d24_n300_automala_n6_r5": lambda: dict(target=pg.synthetic_logistic_regression(300, 24), explorer=pg.AutoMALA(),
                                                       n_chains=6, n_rounds=5, seed=1),
+    # the explorer combinations of test/test_parallelism_invariance.jl:14-19
+    "toy3_compose_slice_automala_n4_r8": lambda: dict(target=pg.toy_mvn_target(3), explorer=pg.Compose(pg.SliceSampler(), pg.AutoMALA()),
+                                                      n_chains=4, n_rounds=8, seed=1),
+    "funnel8_mix_automala_n6_r7": lambda: dict(
+        target=pg.Funnel(8), n_chains=6, n_rounds=7, seed=1,
+        explorer=pg.Mix(pg.AutoMALA(preconditioner=pg.IdentityPreconditioner(), base_n_refresh=1),
+                        pg.AutoMALA(preconditioner=pg.MixDiagonalPreconditioner(0.0, 0.0), base_n_refresh=1),
+                        pg.AutoMALA(preconditioner=pg.DiagonalPreconditioner(), base_n_refresh=1))),
     "ising5_n10_r8": lambda: dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=8, seed=1),
 }
 

@@ -73,6 +73,16 @@ CASES = {
     "ising5": dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=7, seed=1),
     "ising32": dict(target=pg.IsingLogPotential(0.44, 32), n_chains=6, n_rounds=3, seed=2),
     "test_swapper": dict(target=pg.TestSwapper(0.6), n_chains=9, n_rounds=8, seed=7, record=[pg.index_process, pg.swap_trace]),
+    "toy3_compose_slice_automala": dict(target=pg.toy_mvn_target(3), explorer=pg.Compose(pg.SliceSampler(), pg.AutoMALA()),
+                                        n_chains=4, n_rounds=8, seed=1),
+    "gmm70_compose_4cpl": dict(target=pg.eight_mode_mixture(70, 4.0), explorer=pg.Compose(pg.SliceSampler(), pg.AutoMALA()),
+                               n_chains=5, n_rounds=4, seed=2),
+    "funnel8_mix_automala": dict(target=pg.Funnel(8), n_chains=6, n_rounds=7, seed=1,
+                                 explorer=pg.Mix(pg.AutoMALA(preconditioner=pg.IdentityPreconditioner(), base_n_refresh=1),
+                                                 pg.AutoMALA(preconditioner=pg.MixDiagonalPreconditioner(0.0, 0.0), base_n_refresh=1),
+                                                 pg.AutoMALA(preconditioner=pg.DiagonalPreconditioner(), base_n_refresh=1))),
+    "toy40_mix_two_step_sizes": dict(target=pg.toy_mvn_target(40), n_chains=5, n_rounds=6, seed=3,
+                                     explorer=pg.Mix(pg.AutoMALA(step_size=0.5), pg.AutoMALA(step_size=2.0, base_n_refresh=2))),
     "single_chain": dict(target=pg.toy_mvn_target(4), explorer=pg.SliceSampler(), n_chains=1, n_rounds=5, seed=1),
     "two_chains": dict(target=pg.toy_mvn_target(2), explorer=pg.AutoMALA(), n_chains=2, n_rounds=6, seed=8),
 }
@@ -175,7 +185,8 @@ def oracle_result(name, oracle_lib):
 
 
 @pytest.mark.parametrize("team", [1, 2, 3, 4, 5, 8])
-@pytest.mark.parametrize("name", ["funnel32_automala", "toy100_automala_4cpl", "gmm2_two_modes", "two_chains", "funnel_diag_precond"])
+@pytest.mark.parametrize("name", ["funnel32_automala", "toy100_automala_4cpl", "gmm2_two_modes", "two_chains", "funnel_diag_precond",
+                                  "toy3_compose_slice_automala", "funnel8_mix_automala"])
 def test_automala_team_width_parity(name, team, gpu_lib, oracle_lib, monkeypatch):
     """PGN_TEAM=W: the autoMALA step-size search evaluated W candidate steps at a time by a team of W
     warps per chain gives the reference's sequential result bit for bit, for every team width."""

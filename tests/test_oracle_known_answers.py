@@ -70,7 +70,13 @@ def test_stepping_stone(explorer, oracle_lib):
     assert abs(p[0] - truth) < 0.2 and abs(p[1] - truth) < 0.2
 
 
-@pytest.mark.parametrize("explorer", [None, pg.SliceSampler(), pg.AutoMALA(), pg.MALA(step_size=0.25)])
+MIXED_AM = pg.Mix(pg.AutoMALA(preconditioner=pg.IdentityPreconditioner(), base_n_refresh=1),      # test_parallelism_invariance.jl:14-18
+                  pg.AutoMALA(preconditioner=pg.MixDiagonalPreconditioner(0.0, 0.0), base_n_refresh=1),
+                  pg.AutoMALA(preconditioner=pg.DiagonalPreconditioner(), base_n_refresh=1))
+
+
+@pytest.mark.parametrize("explorer", [None, pg.SliceSampler(), pg.AutoMALA(), pg.MALA(step_size=0.25),
+                                      pg.Compose(pg.SliceSampler(), pg.AutoMALA()), MIXED_AM])
 def test_moments(explorer, oracle_lib):
     """test/test_moments.jl:1-27 and test/test_mala.jl: toy MVN d=2, mean 0 +- 0.03, var 0.1 +- 0.03."""
     kw = dict(target=pg.toy_mvn_target(2), n_chains=2, n_rounds=10 if explorer is None else 12, record=[pg.online],
