@@ -4,6 +4,8 @@
 mkdir -p gpurun_out/prof
 cd "$(dirname "$0")/.."
 O=gpurun_out/prof
+( timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ) > $O/smoke.log 2>&1
+( timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 ) > $O/pytest_gpu.log 2>&1
 timeout 900 python bench.py > $O/bench_n1_c2.json 2> $O/bench_n1_c2.err
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_n1_c2_reference.json 2> $O/bench_n1_c2_reference.err
 for c in c1 c3 c4; do timeout 600 python bench.py --config $c --no-cpu-baseline > $O/bench_n1_$c.json 2> $O/bench_n1_$c.err; done
@@ -17,4 +19,4 @@ for k in c2_funnel_automala c3_gmm_automala c4_ising; do   # keep the CSV pages,
   ncu -i $O/$k.ncu-rep --page source --csv > $O/${k}_ncu_source.csv 2>/dev/null
   rm -f $O/$k.ncu-rep
 done
-ls -la $O; cut -c1-120 $O/bench_n1_*.json
+tail -2 $O/smoke.log $O/pytest_gpu.log; cut -c1-120 $O/bench_n1_*.json
