@@ -759,6 +759,9 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
       // launch geometry of the register-resident kernel: one warp per chain, all warps co-resident
       size_t smem = scan_smem_bytes(h);
       int wpb = 0, grid = 0;
+      // every rank must pick the same kernel family (the register-resident kernels and the memory-resident one lay
+      // their mailbox slots out differently), so co-residency is judged on the largest shard of the ladder
+      const int nl_max = (h->cfg.n_chains + std::max(h->cfg.world_size, 1) - 1) / std::max(h->cfg.world_size, 1);
       const bool vec_target = h->cfg.target_kind == PGN_TARGET_TOY_MVN || h->cfg.target_kind == PGN_TARGET_FUNNEL ||
                               h->cfg.target_kind == PGN_TARGET_GMM;
       if (kernel && !(h->force_mem && vec_target)) {
@@ -781,7 +784,7 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
             if (sm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             int per_sm = 0;
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, sm));
-            const bool fits = (long long)per_sm * h->n_sms >= nl;
+            const bool fits = (long long)per_sm * h->n_sms >= nl_max;
             const bool wide_ok = w == 1 || pinned == w || (long long)nl * w <= (long long)per_smsp * 4 * h->n_sms;
             if (fits && wide_ok) { wpb = w; grid = nl; smem = sm; P.pool_refresh = pool; break; }
           }
@@ -792,7 +795,7 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
             int per_sm = 0;
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, sm));
             const int g = (nl + w - 1) / w;
-            if ((long long)per_sm * h->n_sms >= g) { wpb = w; grid = g; smem = sm; break; }
+            if ((long long)per_sm * h->n_sms >= (nl_max + w - 1) / w) { wpb = w; grid = g; smem = sm; break; }
           }
         }
       }
