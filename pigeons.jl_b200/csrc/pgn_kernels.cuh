@@ -1221,8 +1221,8 @@ struct IsingChain {
           for (int t = 0; t < 5; ++t) cc[t] = __shfl_sync(PGN_FULL_MASK, code, j0 + t);
           int row_at[5];
           bool low[5];
+          int mm = m;                  // the guess's table row, walked through the block
           {
-            int mm = m;
             bool fl = f;
 #pragma unroll
             for (int t = 0; t < 5; ++t) {
@@ -1233,8 +1233,6 @@ struct IsingChain {
               mm += g ? (int)(c & 7u) - 2 : 0;
               fl = g;
             }
-            row_at[0] += 0;
-            cc[0] = (unsigned int)mm;   // the guess's table row after the block
           }
           double ratio[5];
 #pragma unroll
@@ -1250,7 +1248,7 @@ struct IsingChain {
             kk += draws ? 1 : 0;
           }
           const int win = __ffs((int)__ballot_sync(PGN_FULL_MASK, ok)) - 1;
-          m = (int)__shfl_sync(PGN_FULL_MASK, cc[0], win);
+          m = __shfl_sync(PGN_FULL_MASK, mm, win);
           k = __shfl_sync(PGN_FULL_MASK, kk, win);
           flips |= (unsigned int)win << j0;
           f = ((win >> 4) & 1) != 0;
