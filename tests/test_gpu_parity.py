@@ -339,3 +339,14 @@ def test_logreg_parity_with_simt_gemm(name, gpu_lib, oracle_lib, monkeypatch):
     monkeypatch.setenv("PGN_GEMM", "simt")
     kw = CASES[name]
     assert_same(run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw), name + "/simt")
+
+
+@pytest.mark.parametrize("target", [pg.toy_mvn_target(10), pg.Funnel(8), pg.eight_mode_mixture(6, 3.0)])
+def test_leapfrog_involution_on_the_device(target, gpu_lib):
+    """test/test_auto_mala.jl:51-85 with the gradients of the CUDA entry point."""
+    from test_oracle_known_answers import leapfrog_involution_error
+    e = pg.Engine(gpu_lib, n_chains=2, seed=1, **target.engine_config())
+    for beta in (0.0, 0.37, 1.0):
+        dx, dp, moved = leapfrog_involution_error(e, target, beta)
+        assert moved > 1e-3 and dx < 1e-9 and dp < 1e-9
+    e.close()

@@ -170,3 +170,37 @@ def test_logistic_regression_density_and_gradient(oracle_lib):
     pt = pg.pigeons(target=t, explorer=pg.AutoMALA(), n_chains=6, n_rounds=8, record=[pg.online], engine_lib=oracle_lib)
     assert np.isfinite(pg.stepping_stone(pt))
     assert pt.reduced_recorders.expl_acc_mean[1:].min() > 0.2
+
+
+def leapfrog_involution_error(engine, target, beta, n_steps=40, eps=0.01, seed=0):
+    """test/test_auto_mala.jl:51-85: n leapfrog steps, momentum flip, n more steps, flip — back at the start.
+    The integrator is written here in numpy on top of the engine's logdensity_and_gradient entry point
+    (the LogDensityProblems contract the reference's hamiltonian_dynamics! consumes, hamiltonian_dynamics.jl:39-84)."""
+    rng = np.random.default_rng(seed)
+    x0 = rng.normal(0.0, 0.3, size=(1, target.dim))
+    p0 = rng.normal(0.0, 1.0, size=(1, target.dim))
+    b = np.array([beta])
+    grad = lambda x: engine.logdensity_and_gradient(x, b)[1]          # noqa: E731
+
+    def run(x, p):
+        g = grad(x)
+        for _ in range(n_steps):
+            p = p + 0.5 * eps * g
+            x = x + eps * p
+            g = grad(x)
+            p = p + 0.5 * eps * g
+        return x, p
+    x1, p1 = run(x0.copy(), p0.copy())
+    x2, p2 = run(x1, -p1)
+    return float(np.max(np.abs(x2 - x0))), float(np.max(np.abs(-p2 - p0))), float(np.max(np.abs(x1 - x0)))
+
+
+@pytest.mark.parametrize("target", [pg.toy_mvn_target(10), pg.Funnel(8), pg.eight_mode_mixture(6, 3.0),
+                                    pg.synthetic_logistic_regression(300, 24)])
+def test_leapfrog_involution(target, oracle_lib):
+    e = pg.Engine(oracle_lib, n_chains=2, seed=1, **target.engine_config())
+    for beta in (0.0, 0.37, 1.0):
+        dx, dp, moved = leapfrog_involution_error(e, target, beta)
+        assert moved > 1e-3                       # the trajectory went somewhere
+        assert dx < 1e-9 and dp < 1e-9            # and came back (isapprox in the reference)
+    e.close()
