@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(256) scan_kernel_mem(const __grid_constant__ M
   for (long long scan = 1; scan <= P.n_scans && err == 0; ++scan) {
     const bool even = (scan & 1LL) == 0;
     const int ring = (int)((P.epoch & 1u) * 4u + (unsigned int)(scan & 3LL));
-    const unsigned long long tag = ((unsigned long long)P.epoch << 32) | (unsigned long long)scan;
+    const unsigned int tag = P.tag_base + (unsigned int)scan;   // flag-in-data mailbox words, as in scan_kernel
     // ---------------- phase A: explore + post, for every chain this warp serves ----------------
     for (int cl = w; cl < P.n_local && err == 0; cl += W) {
       const int chain = P.first_chain + cl;
@@ -560,16 +560,23 @@ __global__ void __launch_bounds__(256) scan_kernel_mem(const __grid_constant__ M
         if (!remote) dst = P.mail + ((size_t)(2 + cl) * MAIL_RINGS + ring) * P.slot_bytes;
         else if (partner > chain) dst = P.mail_right + ((size_t)0 * MAIL_RINGS + ring) * P.slot_bytes;
         else dst = P.mail_left + ((size_t)1 * MAIL_RINGS + ring) * P.slot_bytes;
-        if (lane == 0) {
-          MailHdr* h = reinterpret_cast<MailHdr*>(dst + 32);
-          h->lr = lr; h->u = u; h->ctr = r.ctr; h->replica_index = r.replica_index; h->rt_state = r.rt_state;
+        unsigned long long* dstw = reinterpret_cast<unsigned long long*>(dst);
+        {
+          const unsigned long long lb = double_to_bits(lr), ub = double_to_bits(u), cb = r.ctr;
+          unsigned int hv = (unsigned int)lb;
+          hv = lane == 1 ? (unsigned int)(lb >> 32) : hv;
+          hv = lane == 2 ? (unsigned int)ub : hv;
+          hv = lane == 3 ? (unsigned int)(ub >> 32) : hv;
+          hv = lane == 4 ? (unsigned int)cb : hv;
+          hv = lane == 5 ? (unsigned int)(cb >> 32) : hv;
+          hv = lane == 6 ? (unsigned int)r.replica_index : hv;
+          hv = lane == 7 ? (unsigned int)r.rt_state : hv;
+          if (lane < LL_HDR_WORDS) ll_store(dstw + lane, hv, tag);
         }
-        double* pay = reinterpret_cast<double*>(dst + MAIL_HDR_BYTES);
-        for (int c = lane; c < P.d_pad; c += 32) pay[c] = x[c];
-        __syncwarp();
-        if (lane == 0) {
-          if (remote) st_release_sys(reinterpret_cast<unsigned long long*>(dst), tag);
-          else st_release_gpu(reinterpret_cast<unsigned long long*>(dst), tag);
+        for (int c = lane; c < P.d_pad; c += 32) {
+          const unsigned long long b = double_to_bits(x[c]);
+          ll_store(dstw + LL_HDR_WORDS + 2 * c, (unsigned int)b, tag);
+          ll_store(dstw + LL_HDR_WORDS + 2 * c + 1, (unsigned int)(b >> 32), tag);
         }
       }
       if (lane == 0) MP.rec[cl] = r;
@@ -591,39 +598,56 @@ __global__ void __launch_bounds__(256) scan_kernel_mem(const __grid_constant__ M
         if (!remote) src = P.mail + ((size_t)(2 + (partner - P.first_chain)) * MAIL_RINGS + ring) * P.slot_bytes;
         else if (partner > chain) src = P.mail + ((size_t)1 * MAIL_RINGS + ring) * P.slot_bytes;
         else src = P.mail + ((size_t)0 * MAIL_RINGS + ring) * P.slot_bytes;
+        const unsigned long long* srcw = reinterpret_cast<const unsigned long long*>(src);
         int status = 0;
-        if (lane == 0) {
-          const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(src);
+        unsigned long long hw = 0ull;
+        {
           unsigned long long t0 = 0;
           unsigned int it = 0;
-          while (ld_relaxed_sys(flag) != tag) {
+          while (true) {
+            if (lane < LL_HDR_WORDS) hw = ld_relaxed_sys(srcw + lane);
+            const bool ok = lane >= LL_HDR_WORDS || (unsigned int)(hw >> 32) == tag;
+            if (__all_sync(PGN_FULL_MASK, ok)) break;
             ++it;
+            if (it > 4u) __nanosleep(it < 64u ? 32 : 256);
             if ((it & 255u) == 0u) {
-              if (*reinterpret_cast<volatile int*>(P.error_flag) != 0) { status = 1; break; }
-              const unsigned long long now = globaltimer_ns();
-              if (t0 == 0) t0 = now;
-              else if (now - t0 > P.timeout_ns) { status = 2; break; }
-              if (it > 65536u) __nanosleep(200);
+              if (lane == 0) {
+                if (*reinterpret_cast<volatile int*>(P.error_flag) != 0) status = 1;
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > P.timeout_ns) status = 2;
+              }
+              status = __shfl_sync(PGN_FULL_MASK, status, 0);
+              if (status != 0) break;
             }
           }
-          if (remote) fence_acq_rel_sys(); else fence_acq_rel_gpu();
         }
-        status = __shfl_sync(PGN_FULL_MASK, status, 0);
         if (status != 0) { err = status == 2 ? PGN_ERR_TIMEOUT : -1; break; }
-        const MailHdr* hp = reinterpret_cast<const MailHdr*>(src + 32);
-        const double lr_p = __ldcg(&hp->lr), u_p = __ldcg(&hp->u);
+        const unsigned int lo = (unsigned int)hw;
+        const unsigned int h0 = __shfl_sync(PGN_FULL_MASK, lo, 0), h1 = __shfl_sync(PGN_FULL_MASK, lo, 1);
+        const unsigned int h2 = __shfl_sync(PGN_FULL_MASK, lo, 2), h3 = __shfl_sync(PGN_FULL_MASK, lo, 3);
+        const unsigned int h4 = __shfl_sync(PGN_FULL_MASK, lo, 4), h5 = __shfl_sync(PGN_FULL_MASK, lo, 5);
+        const int ri_p = (int)__shfl_sync(PGN_FULL_MASK, lo, 6), rt_p = (int)__shfl_sync(PGN_FULL_MASK, lo, 7);
+        const double lr_p = bits_to_double(((unsigned long long)h1 << 32) | h0);
+        const double u_p = bits_to_double(((unsigned long long)h3 << 32) | h2);
         const bool lower = chain < partner;
         const double e = lower ? exp_(r.lr + lr_p) : exp_(lr_p + r.lr);
         const double acceptance_pr = 1.0 < e ? 1.0 : e;
         if (lower) { r.swap_acc.fit(acceptance_pr); r.ls_fwd.fit(r.lr); r.ls_bwd.fit(lr_p); }
         accepted = (lower ? r.u : u_p) < acceptance_pr;
         if (accepted) {
-          r.replica_index = __ldcg(&hp->replica_index);
-          r.rt_state = __ldcg(&hp->rt_state);
-          r.ctr = __ldcg(&hp->ctr);
-          const double* pay = reinterpret_cast<const double*>(src + MAIL_HDR_BYTES);
+          r.replica_index = ri_p;
+          r.rt_state = rt_p;
+          r.ctr = ((unsigned long long)h5 << 32) | h4;
           double* x = P.x + (size_t)cl * P.d_pad;
-          for (int c = lane; c < P.d_pad; c += 32) x[c] = __ldcg(pay + c);
+          bool got = true;
+          for (int c = lane; c < P.d_pad; c += 32) {
+            unsigned int xlo, xhi;
+            got = ll_load(srcw + LL_HDR_WORDS + 2 * c, tag, xlo) && got;
+            got = ll_load(srcw + LL_HDR_WORDS + 2 * c + 1, tag, xhi) && got;
+            x[c] = bits_to_double(((unsigned long long)xhi << 32) | xlo);
+          }
+          if (!__all_sync(PGN_FULL_MASK, got)) { err = PGN_ERR_TIMEOUT; break; }
         }
         if (lane == 0) MP.rec[cl] = r;
         __syncwarp();
