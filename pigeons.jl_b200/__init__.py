@@ -13,7 +13,7 @@ from .distributed import LoadBalance, SingleProcess, TorchDistributed           
 from .explorers import (MALA, AutoMALA, Compose, Mix, DiagonalPreconditioner, IdentityPreconditioner,  # noqa: F401
                         IsingMetropolis, MixDiagonalPreconditioner, SliceSampler, ToyExplorer)
 from .pt import (PT, Inputs, Iterators, NonReversiblePT, Shared, adapt, create_pt, global_barrier,   # noqa: F401
-                 index_process, n_round_trips, n_scans_in_round, n_tempered_restarts, online, pigeons,
+                 index_process, n_round_trips, n_scans_in_round, n_tempered_restarts, online, pigeons, resume, write_checkpoint,
                  pigeons_pt, round_trip, run_one_round, sample_array, stepping_stone, stepping_stone_pair,
                  swap_trace, traces)
 from .recorders import ReducedRecorders                                            # noqa: F401

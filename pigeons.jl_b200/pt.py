@@ -170,6 +170,33 @@ def pigeons_pt(pt: PT) -> PT:
     return pt
 
 
+def write_checkpoint(pt: PT) -> dict:
+    """write_checkpoint (src/pt/checkpoint.jl:110-145) for the harness: everything a later `resume` needs to
+    continue the run bit for bit — `Shared` (round counter, schedule, adapted explorer) and the `Replica`s
+    (state, chain <-> replica index, RNG position, round-trip state; `pgn_get_state`).  A plain dict of numpy
+    arrays / dataclasses, not the reference's `.jls` wire format."""
+    return dict(round=pt.shared.iterators.round, grids=pt.shared.tempering.schedule.grids.copy(),
+                communication_barriers=pt.shared.tempering.communication_barriers, explorer=pt.shared.explorer,
+                replicas=pt.engine.get_state(), n_chains=pt.inputs.n_chains, seed=pt.inputs.seed)
+
+
+def resume(checkpoint: dict, inputs: Inputs) -> PT:
+    """PT(exec_folder) + pigeons(pt) (src/pt/PT.jl:56-92, checkpoint.jl:18-60): rebuild the PT from a
+    checkpoint and run rounds `checkpoint round + 1 .. inputs.n_rounds`.  `inputs` supplies what a
+    checkpoint does not serialise in the reference either (the target and the engine handle are rebuilt,
+    `ext/PigeonsBridgeStanExt/interface.jl:27-48`)."""
+    if inputs.n_chains != checkpoint["n_chains"] or inputs.seed != checkpoint["seed"]:
+        raise ValueError("the checkpoint was written by a run with a different n_chains / seed")
+    pt = create_pt(inputs)
+    st = checkpoint["replicas"]
+    pt.engine.set_state(x=st["x"] if st["x"].size else None, replica_index=st["replica_index"],
+                        rng_counter=st["rng_counter"], round_trip_state=st["round_trip_state"])
+    sched = Schedule(np.asarray(checkpoint["grids"], dtype=np.float64).copy())
+    pt.shared = Shared(Iterators(round=checkpoint["round"]), NonReversiblePT(sched, checkpoint["communication_barriers"]),
+                       checkpoint["explorer"])
+    return pigeons_pt(pt)
+
+
 def pigeons(**kwargs) -> PT:
     """pigeons(; target, n_chains, explorer, ...) (src/api.jl:16-19)."""
     return pigeons_pt(create_pt(Inputs(**kwargs)))

@@ -114,3 +114,33 @@ def test_package_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "liborc" not in text and "oracle_adapter" not in text and "orc_engine" not in text, f
+
+
+@pytest.mark.parametrize("kw", [
+    dict(target=pg.toy_mvn_target(3), explorer=pg.SliceSampler(), n_chains=5, seed=2),
+    dict(target=pg.Funnel(6), explorer=pg.AutoMALA(), n_chains=6, seed=3),
+    dict(target=pg.IsingLogPotential(0.6, 5), n_chains=5, seed=4),
+    dict(target=pg.toy_mvn_target(4), explorer=pg.Compose(pg.SliceSampler(), pg.AutoMALA()), n_chains=4, seed=5),
+], ids=["toy_slice", "funnel_automala", "ising", "toy_compose"])
+def test_checkpoint_resume_is_bit_identical(kw):
+    """test/test_resume.jl / test_checkpoint.jl: stopping after round 5 and resuming to round 8 gives the run
+    that went straight to round 8 — schedule, explorer, statistics and every replica, bit for bit
+    (Shared + Replica state through pgn_get_state / pgn_set_state, on the CPU engine here)."""
+    from oracle_adapter import load_oracle
+    lib = load_oracle()
+    rec = [pg.index_process, pg.swap_trace]
+    straight = pg.pigeons(engine_lib=lib, n_rounds=8, record=rec, **kw)
+    first = pg.pigeons(engine_lib=lib, n_rounds=5, record=rec, **kw)
+    ckpt = pg.write_checkpoint(first)
+    first.close()
+    resumed = pg.resume(ckpt, pg.Inputs(engine_lib=lib, n_rounds=8, record=rec, **kw))
+    a, b = straight.reduced_recorders, resumed.reduced_recorders
+    for k in ("index_process", "swap_lr", "swap_u", "swap_accept", "swap_mean", "logsum_fwd", "logsum_bwd", "expl_n_steps"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.array_equal(straight.shared.tempering.schedule.grids, resumed.shared.tempering.schedule.grids)
+    assert straight.shared.explorer == resumed.shared.explorer
+    sa, sb = straight.engine.get_state(), resumed.engine.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    assert pg.stepping_stone(straight) == pg.stepping_stone(resumed)
+    straight.close(); resumed.close()
