@@ -144,3 +144,16 @@ def test_checkpoint_resume_is_bit_identical(kw):
         assert np.array_equal(sa[k], sb[k]), k
     assert pg.stepping_stone(straight) == pg.stepping_stone(resumed)
     straight.close(); resumed.close()
+
+
+def test_report_shape_of_a_default_run():
+    """test/test_apis.jl:12-20: a default run (10 chains, 10 rounds) reports 10 rounds x 9 swap pairs."""
+    from oracle_adapter import load_oracle
+    pt = pg.pigeons(target=pg.toy_mvn_target(2), engine_lib=load_oracle())
+    assert pt.inputs.n_chains == 10 and pt.inputs.n_rounds == 10 and len(pt.round_log) == 10
+    rr = pt.reduced_recorders
+    assert rr.n_scans == 2 ** 10
+    pairs = int(np.sum(rr.swap_n > 0))
+    assert pairs == 9 and rr.swap_n[-1] == 0        # pair (i, i+1) is kept by chain i; chain N has none
+    assert np.all(rr.swap_n[:9] == 2 ** 9)          # every pair is proposed on every other scan
+    pt.close()
