@@ -10,7 +10,7 @@ looping over scans on the host it makes ONE C-ABI call per round
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, replace
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np
@@ -152,6 +152,41 @@ def adapt(pt: PT, rr: ReducedRecorders) -> PT:
     return pt
 
 
+class ChecksFailed(AssertionError):
+    """check_against_serial found a difference (src/pt/checks.jl:52-78)."""
+
+
+def run_checks(pt: PT) -> None:
+    """run_checks / check_against_serial (src/pt/checks.jl:5-78, the oracle of
+    test/test_parallelism_invariance.jl): after round `checked_round`, rank 0 re-runs rounds 1..checked_round
+    in ONE process on one device — a fresh engine of the same library holding the whole ladder — and the
+    sharded run must agree with it field by field: every replica (state, chain <-> replica index, RNG
+    position, round-trip state), the adapted schedule and the adapted explorer.  With one process this is
+    the determinism check of the reference's serial re-run."""
+    inputs, it = pt.inputs, pt.shared.iterators
+    if inputs.checked_round <= 0 or it.round != inputs.checked_round:
+        return
+    comm = inputs.comm
+    st = pt.engine.get_state()
+    whole = {k: np.concatenate(comm.all_gather_array(np.ascontiguousarray(v)), axis=0) for k, v in st.items()}
+    bad = []
+    if comm.rank == 0:
+        serial = replace(inputs, comm=SingleProcess(), n_rounds=inputs.checked_round, checked_round=0,
+                         engine_factory=None, show_report=False)
+        ref = pigeons_pt(create_pt(serial))
+        rs = ref.engine.get_state()
+        bad = [k for k in whole if not np.array_equal(whole[k].reshape(rs[k].shape), rs[k])]
+        if not np.array_equal(pt.shared.tempering.schedule.grids, ref.shared.tempering.schedule.grids):
+            bad.append("schedule")
+        if pt.shared.explorer != ref.shared.explorer:
+            bad.append("explorer")
+        ref.close()
+    verdicts = comm.all_gather_array(np.array([len(bad)], dtype=np.int64))     # every rank learns rank 0's verdict
+    if int(verdicts[0][0]) != 0:
+        raise ChecksFailed(f"round {it.round}: the run on {comm.world_size} process(es) differs from the serial run"
+                           + (f" in {bad}" if bad else ""))
+
+
 def pigeons_pt(pt: PT) -> PT:
     """pigeons(pt::PT) (pigeons.jl:12-28)."""
     it = pt.shared.iterators
@@ -163,6 +198,7 @@ def pigeons_pt(pt: PT) -> PT:
                                  wall_s=rr.wall_s, global_barrier=global_barrier(pt) if pt.inputs.n_chains > 1 and rr.has_swap_stats else float("nan"),
                                  stepping_stone=stepping_stone(pt) if rr.has_swap_stats else float("nan"),
                                  n_round_trips=rr.n_round_trips))
+        run_checks(pt)
         if pt.inputs.show_report:
             r = pt.round_log[-1]
             print(f"round {r['round']:3d}  scans {r['n_scans']:8d}  Λ {r['global_barrier']:.4g}  "

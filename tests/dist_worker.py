@@ -36,6 +36,11 @@ class ShardedOracleView:
     def __getattr__(self, name):          # set_schedule, set_explorer, init_replicas, close ...
         return getattr(self.full, name)
 
+    def get_state(self):
+        st = self.full.get_state()
+        lo, hi = self.first_chain - 1, self.first_chain - 1 + self.n_local
+        return {k: np.ascontiguousarray(v[lo:hi]) for k, v in st.items()}
+
     def ipc_export(self):
         return (b"mailbox-of-rank-%d" % self.rank).ljust(64, b"\0")
 
@@ -85,7 +90,8 @@ def main():
             views.append(v)
             return v
         rec = [pg.index_process, pg.swap_trace, pg.traces]
-        pt = pg.pigeons(engine_factory=factory, comm=comm, record=rec, **kw)
+        # checked_round: after round 3 rank 0 re-runs rounds 1..3 in one process and compares (src/pt/checks.jl:36-78)
+        pt = pg.pigeons(engine_factory=factory, engine_lib=lib, comm=comm, record=rec, checked_round=3, **kw)
         v = views[0]
         # neighbour plumbing: every rank attached exactly its neighbours' handles
         want = {}

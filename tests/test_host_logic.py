@@ -157,3 +157,27 @@ def test_report_shape_of_a_default_run():
     assert pairs == 9 and rr.swap_n[-1] == 0        # pair (i, i+1) is kept by chain i; chain N has none
     assert np.all(rr.swap_n[:9] == 2 ** 9)          # every pair is proposed on every other scan
     pt.close()
+
+
+def test_checked_round_serial_rerun_and_failure_detection():
+    """src/pt/checks.jl:36-78: `checked_round = k` re-runs rounds 1..k serially and compares every replica,
+    the schedule and the explorer; a run that differs raises."""
+    from oracle_adapter import load_oracle
+    lib = load_oracle()
+    kw = dict(target=pg.Funnel(6), explorer=pg.AutoMALA(), n_chains=5, n_rounds=5, seed=7, engine_lib=lib)
+    pt = pg.pigeons(checked_round=3, **kw)            # passes silently
+    pt.close()
+
+    class Drifting:                                    # an engine whose replicas' RNG positions are off by one
+        def __init__(self, **cfg):
+            self.e = pg.Engine(lib, **cfg)
+
+        def __getattr__(self, name):
+            return getattr(self.e, name)
+
+        def get_state(self):
+            st = self.e.get_state()
+            st["rng_counter"] = st["rng_counter"] + np.uint64(1)
+            return st
+    with pytest.raises(pg.ChecksFailed):
+        pg.pigeons(checked_round=2, engine_factory=lambda **cfg: Drifting(**cfg), **kw)
