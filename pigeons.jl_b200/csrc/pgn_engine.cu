@@ -1,38 +1,15 @@
-// pgn_engine.cu — host side of libpigeons_b200.so: device memory, kernel
-// dispatch, and the C ABI declared in include/pigeons_b200.h.
+// pgn_engine.cu — the C ABI declared in include/pigeons_b200.h: handle lifecycle, kernel
+// selection and launch geometry.
 //
 // One handle = one shard of the chain ladder on one GPU.  `pgn_run_round`
 // is the single call per round that replaces the reference's host scan loop
-// (src/pt/pigeons.jl:46-55).
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "pgn_kernels.cuh"
-#include "pgn_logreg.cuh"
-#include "pgn_memchain.cuh"
+// (src/pt/pigeons.jl:46-55).  The kernels live in the other translation units
+// (pgn_scan_vec.cu, pgn_scan_misc.cu, pgn_scan_mem.cu, pgn_logreg_host.cu; see pgn_host.hpp).
+#include "pgn_host.hpp"
 
 using namespace pgn;
 
 namespace {
-
-struct CudaError {
-  int code;
-  std::string msg;
-};
-
-#define CUDA_CHECK(expr)                                                                          \
-  do {                                                                                            \
-    cudaError_t e_ = (expr);                                                                      \
-    if (e_ != cudaSuccess)                                                                        \
-      throw CudaError{PGN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)};          \
-  } while (0)
 
 int fail(char** err, int code, const std::string& msg) {
   if (err) {
@@ -42,26 +19,6 @@ int fail(char** err, int code, const std::string& msg) {
   return code;
 }
 
-template <class T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t n = 0;
-  void alloc(size_t count, bool zero = true) {
-    release();
-    n = count;
-    if (count == 0) count = 1;
-    CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
-    if (zero) CUDA_CHECK(cudaMemset(p, 0, count * sizeof(T)));
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr; n = 0;
-  }
-  void upload(const T* h, size_t count) { CUDA_CHECK(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice)); }
-  void download(T* h, size_t count) const { CUDA_CHECK(cudaMemcpy(h, p, count * sizeof(T), cudaMemcpyDeviceToHost)); }
-  ~DevBuf() { release(); }
-};
-
 // LoadBalance (src/mpi_utils/LoadBalance.jl:70-73,119-128), 0-based rank
 void shard_range(int n_chains, int world, int rank, int& first_chain, int& n_local) {
   const int basic = n_chains / world, extras = n_chains % world;
@@ -69,49 +26,6 @@ void shard_range(int n_chains, int world, int rank, int& first_chain, int& n_loc
   const int with_extra = std::min(rank, extras);
   first_chain = 1 + (rank - with_extra) * basic + with_extra * (basic + 1);
 }
-
-}  // namespace
-
-struct pgn_handle {
-  pgn_config cfg{};
-  pgn_explorer_params ep{};
-  bool have_std = false;
-  int first_chain = 1, n_local = 0;
-  int cpl = 1, d_pad = 32, pay_doubles = 32;
-  size_t slot_bytes = 0, mail_bytes = 0;
-  unsigned int epoch = 0;
-  unsigned long long scan_seq = 0;   // scans run so far (all rounds): base of the mailbox tags
-  int n_sms = 0;
-  DevBuf<double> beta, x, means, log_w, std_devs, online_mean, online_s2;
-  DevBuf<int> replica_index, rt_state, error_flag;
-  DevBuf<unsigned long long> rng_ctr;
-  DevBuf<long long> online_n;
-  DevBuf<ChainStatsDev> stats;
-  DevBuf<char> mail;
-  char* mail_left = nullptr;
-  char* mail_right = nullptr;
-  bool left_is_ipc = false, right_is_ipc = false;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool initialised = false;
-  unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
-  // ---- memory-resident scan path (any d, any number of chains; pgn_memchain.cuh)
-  bool force_mem = false;
-  DevBuf<MemRec> mem_rec;
-  DevBuf<double> mem_vec[10];
-  bool mem_allocated = false;
-  // ---- logistic regression (batched GEMM path)
-  int lr_n_data = 0, lr_n_pad = 0, lr_r_pad = 0, lr_splits = 0;
-  DevBuf<double> lr_Xr, lr_Xt, lr_y, lr_Theta, lr_Thetat, lr_LL, lr_Res, lr_lik, lr_Gp, lr_G;
-  DevBuf<double> lr_P, lr_G0, lr_SX, lr_SP, lr_SG, lr_TP, lr_TG, lr_FX, lr_FG, lr_QX, lr_QP, lr_QG;
-  DevBuf<LrChainState> lr_st;
-  DevBuf<int> lr_n_active;
-  bool lr_use_dmma = true;       // FP64 tensor-core GEMM (same summation order as the SIMT kernel, see pgn_logreg.cuh)
-  double last_gemm_ms = 0.0;     // device time spent in the two GEMMs during the last round
-  long long last_batch_steps = 0;
-};
-
-namespace {
 
 void fill_params(pgn_handle* h, Params& P) {
   std::memset(&P, 0, sizeof(P));
@@ -146,268 +60,18 @@ void fill_params(pgn_handle* h, Params& P) {
   P.timeout_ns = h->timeout_ns;
 }
 
-// ===========================================================================
-// logistic regression: batched-GEMM engine (pgn_logreg.cuh)
-// ===========================================================================
-constexpr size_t GEMM_SMEM_BYTES = 2ull * 2 * GEMM_BK * GEMM_BM * sizeof(double);
-constexpr size_t DMMA_SMEM_BYTES = 2ull * 2 * GEMM_BK * DMMA_LD * sizeof(double);
-
-void logreg_allocate(pgn_handle* h, const pgn_config* cfg) {
-  const int d = cfg->dim, dp = h->d_pad;
-  const int n = (int)cfg->p[0];
-  const int np = (n + 127) / 128 * 128;
-  const int rp = (h->n_local + 127) / 128 * 128;
-  h->lr_n_data = n; h->lr_n_pad = np; h->lr_r_pad = rp;
-  h->lr_splits = (np + LR_CHUNK - 1) / LR_CHUNK;
-  // X row-major padded [np][dp] (K-major operand of the gradient GEMM) and its transpose [dp][np]
-  {
-    std::vector<double> xr((size_t)np * dp, 0.0);
-    for (int i = 0; i < n; ++i) std::memcpy(&xr[(size_t)i * dp], cfg->data_x + (size_t)i * d, sizeof(double) * d);
-    h->lr_Xr.alloc(xr.size(), false);
-    h->lr_Xr.upload(xr.data(), xr.size());
-  }
-  h->lr_Xt.alloc((size_t)dp * np, false);
-  {
-    dim3 grid((dp + 31) / 32, (np + 31) / 32), block(32, 8);
-    logreg_transpose_kernel<<<grid, block>>>(h->lr_Xr.p, np, dp, dp, h->lr_Xt.p, np);
-    CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaDeviceSynchronize());
-  }
-  h->lr_y.alloc(np);
-  h->lr_y.upload(cfg->data_y, n);
-  const size_t vec = (size_t)rp * dp;
-  h->lr_Theta.alloc(vec); h->lr_Thetat.alloc(vec);
-  h->lr_LL.alloc((size_t)np * rp, false); h->lr_Res.alloc((size_t)np * rp, false);
-  h->lr_lik.alloc(rp);
-  h->lr_Gp.alloc((size_t)h->lr_splits * dp * rp, false);
-  h->lr_G.alloc(vec);
-  h->lr_P.alloc(vec); h->lr_G0.alloc(vec); h->lr_SX.alloc(vec); h->lr_SP.alloc(vec); h->lr_SG.alloc(vec);
-  h->lr_TP.alloc(vec); h->lr_TG.alloc(vec); h->lr_FX.alloc(vec); h->lr_FG.alloc(vec);
-  h->lr_QX.alloc(vec); h->lr_QP.alloc(vec); h->lr_QG.alloc(vec);
-  h->lr_st.alloc(h->n_local);
-  h->lr_n_active.alloc(1);
-  {
-    const char* g = std::getenv("PGN_GEMM");   // "simt" selects the DFMA kernel; default: FP64 tensor cores
-    h->lr_use_dmma = !(g != nullptr && std::string(g) == "simt");
-  }
-  CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMMA_SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMMA_SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
-}
-
-// Evaluate likelihood and its gradient at the rows of `theta` ([r_pad][d_pad]) for all columns:
-// lr_lik[r], lr_G[r][:].  Returns the device time of the two GEMMs through `gemm_ms`.
-void logreg_eval_batch(pgn_handle* h, const double* theta, cudaEvent_t e0, cudaEvent_t e1) {
-  const int dp = h->d_pad, np = h->lr_n_pad, rp = h->lr_r_pad;
-  {
-    dim3 grid((dp + 31) / 32, (rp + 31) / 32), block(32, 8);
-    logreg_transpose_kernel<<<grid, block, 0, h->stream>>>(theta, rp, dp, dp, h->lr_Thetat.p, rp);
-  }
-  if (e0) CUDA_CHECK(cudaEventRecord(e0, h->stream));
-  {
-    dim3 grid(np / GEMM_BM, rp / GEMM_BN, 1);
-    if (h->lr_use_dmma)
-      dgemm_km_dmma_kernel<0><<<grid, GEMM_THREADS, DMMA_SMEM_BYTES, h->stream>>>(
-          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, nullptr, rp, 0, nullptr, 0);
-    else
-      dgemm_km_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
-          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, nullptr, rp, 0, nullptr, 0);
-    logreg_bernoulli_kernel<<<h->n_sms * 8, 256, 0, h->stream>>>(h->lr_LL.p, h->lr_Res.p, h->lr_y.p, rp, np, h->lr_n_data);
-  }
-  logreg_reduce_ll_kernel<<<(rp + 7) / 8, 256, 0, h->stream>>>(h->lr_LL.p, rp, h->lr_n_data, rp, h->lr_lik.p);
-  {
-    dim3 grid(dp / GEMM_BM, rp / GEMM_BN, h->lr_splits);
-    if (h->lr_use_dmma)
-      dgemm_km_dmma_kernel<0><<<grid, GEMM_THREADS, DMMA_SMEM_BYTES, h->stream>>>(
-          h->lr_Xr.p, dp, h->lr_Res.p, rp, np, LR_CHUNK, h->lr_Gp.p, nullptr, rp, (size_t)dp * rp, nullptr, 0);
-    else
-      dgemm_km_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
-          h->lr_Xr.p, dp, h->lr_Res.p, rp, np, LR_CHUNK, h->lr_Gp.p, nullptr, rp, (size_t)dp * rp, nullptr, 0);
-  }
-  if (e1) CUDA_CHECK(cudaEventRecord(e1, h->stream));
-  {
-    dim3 grid((dp + 31) / 32, (rp + 31) / 32), block(32, 8);
-    logreg_finalize_grad_kernel<<<grid, block, 0, h->stream>>>(h->lr_Gp.p, h->lr_splits, (size_t)dp * rp, rp, dp, rp,
-                                                              h->lr_G.p);
-  }
-  CUDA_CHECK(cudaGetLastError());
-}
-
-void logreg_fill_params(pgn_handle* h, LrParams& P) {
-  std::memset(&P, 0, sizeof(P));
-  P.d = h->cfg.dim; P.d_pad = h->d_pad; P.n_chains = h->cfg.n_chains; P.first_chain = h->first_chain;
-  P.n_local = h->n_local; P.r_pad = h->lr_r_pad;
-  P.explorer_kind = h->ep.kind;
-  P.seed_lo = (unsigned int)(unsigned long long)h->cfg.seed;
-  P.seed_hi = (unsigned int)((unsigned long long)h->cfg.seed >> 32);
-  P.epoch = h->epoch;
-  P.sigma_ref = h->cfg.p[3]; P.ls_ref = h->cfg.p[4]; P.iv_ref = h->cfg.p[5];
-  P.n_refresh = h->ep.n_refresh; P.step_size = h->ep.step_size; P.precond_kind = h->ep.precond_kind;
-  P.mix_p0 = h->ep.mix_p0; P.mix_p01 = h->ep.mix_p01;
-
-  P.std_devs = h->have_std ? h->std_devs.p : nullptr;
-  P.beta = h->beta.p;
-  P.st = h->lr_st.p;
-  P.X = h->x.p; P.P = h->lr_P.p; P.G0 = h->lr_G0.p; P.SX = h->lr_SX.p; P.SP = h->lr_SP.p; P.SG = h->lr_SG.p;
-  P.TP = h->lr_TP.p; P.TG = h->lr_TG.p; P.FX = h->lr_FX.p; P.FG = h->lr_FG.p; P.TX = h->lr_Theta.p;
-  P.QX = h->lr_QX.p; P.QP = h->lr_QP.p; P.QG = h->lr_QG.p;
-  P.lik = h->lr_lik.p; P.G = h->lr_G.p;
-  P.n_active = h->lr_n_active.p; P.error_flag = h->error_flag.p;
-  P.mail = h->mail.p; P.mail_left = h->mail_left; P.mail_right = h->mail_right; P.slot_bytes = h->slot_bytes;
-  P.online_mean = h->online_mean.p; P.online_s2 = h->online_s2.p; P.online_n = h->online_n.p;
-  P.timeout_ns = 600ull * 1000ull * 1000ull * 1000ull;   // scans take seconds here; neighbours may lag
-}
-
-// run_one_round! for the logistic-regression target
-void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<ChainStatsDev>& st_out, float& total_ms) {
-  const int nl = h->n_local;
-  if (h->ep.kind != PGN_EXPLORER_AUTOMALA && h->ep.kind != PGN_EXPLORER_MALA)
-    throw CudaError{PGN_ERR_INVALID, "LOGREG supports the AutoMALA and MALA explorers"};
-  // chain state from the replica arrays
-  std::vector<int> ri(nl), rt(nl);
-  std::vector<unsigned long long> ctr(nl);
-  h->replica_index.download(ri.data(), nl);
-  h->rng_ctr.download(ctr.data(), nl);
-  std::vector<LrChainState> st(nl);
-  std::memset(st.data(), 0, sizeof(LrChainState) * nl);
-  for (int i = 0; i < nl; ++i) {
-    st[i].phase = LR_SCAN_START;
-    st[i].replica_index = ri[i]; st[i].ctr = ctr[i]; st[i].rt_state = 0;
-    st[i].ls_fwd.value = -INFINITY; st[i].ls_bwd.value = -INFINITY;
-  }
-  h->lr_st.upload(st.data(), nl);
-  CUDA_CHECK(cudaMemsetAsync(h->online_mean.p, 0, sizeof(double) * h->d_pad, h->stream));
-  CUDA_CHECK(cudaMemsetAsync(h->online_s2.p, 0, sizeof(double) * h->d_pad, h->stream));
-  CUDA_CHECK(cudaMemsetAsync(h->online_n.p, 0, sizeof(long long), h->stream));
-  cudaEvent_t g0, g1;
-  CUDA_CHECK(cudaEventCreate(&g0));
-  CUDA_CHECK(cudaEventCreate(&g1));
-  h->last_gemm_ms = 0.0;
-  h->last_batch_steps = 0;
-  const int wpb = 4, grid = (nl + wpb - 1) / wpb;
-  CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-  int flag = 0;
-  for (int64_t scan = 1; scan <= n_scans && flag == 0; ++scan) {
-    P.scan = scan;
-    while (true) {
-      CUDA_CHECK(cudaMemsetAsync(h->lr_n_active.p, 0, sizeof(int), h->stream));
-      logreg_controller_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
-      int active = 0;
-      CUDA_CHECK(cudaMemcpyAsync(&active, h->lr_n_active.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      CUDA_CHECK(cudaMemcpyAsync(&flag, h->error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      CUDA_CHECK(cudaStreamSynchronize(h->stream));
-      if (flag != 0 || active == 0) break;
-      logreg_eval_batch(h, h->lr_Theta.p, g0, g1);
-      CUDA_CHECK(cudaStreamSynchronize(h->stream));
-      float ms = 0.f;
-      CUDA_CHECK(cudaEventElapsedTime(&ms, g0, g1));
-      h->last_gemm_ms += ms;
-      h->last_batch_steps += 1;
-    }
-    if (flag != 0) break;
-    logreg_post_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
-    logreg_decide_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
-    CUDA_CHECK(cudaMemcpyAsync(&flag, h->error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  }
-  CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
-  CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  CUDA_CHECK(cudaEventElapsedTime(&total_ms, h->ev0, h->ev1));
-  cudaEventDestroy(g0);
-  cudaEventDestroy(g1);
-  // replica arrays + statistics back
-  h->lr_st.download(st.data(), nl);
-  st_out.assign(nl, ChainStatsDev{});
-  for (int i = 0; i < nl; ++i) {
-    const LrChainState& s = st[i];
-    ri[i] = s.replica_index; ctr[i] = s.ctr; rt[i] = s.rt_state;
-    ChainStatsDev& o = st_out[i];
-    o.swap_n = s.swap_acc.n; o.swap_mean = s.swap_acc.mu; o.ls_fwd = s.ls_fwd.value; o.ls_bwd = s.ls_bwd.value;
-    o.expl_acc_n = s.expl_acc.n; o.expl_acc_mean = s.expl_acc.mu; o.n_steps = s.n_steps;
-    o.am_n = s.am.n; o.am_mean = s.am.mu; o.rev_n = s.rev.n; o.rev_mean = s.rev.mu;
-    o.n_restarts = s.n_restarts; o.n_round_trips = s.n_trips; o.n_points = s.n_points; o.n_ref_evals = s.n_ref;
-  }
-  h->replica_index.upload(ri.data(), nl);
-  h->rng_ctr.upload(ctr.data(), nl);
-  h->rt_state.upload(rt.data(), nl);
-}
-
-// parity entry points for LOGREG: batches of r_pad points through the same GEMM path
-void logreg_points(pgn_handle* h, const double* x, int n_points, const double* beta, double* lp, double* ld, double* grad) {
-  const int d = h->cfg.dim, dp = h->d_pad, rp = h->lr_r_pad;
-  DevBuf<double> db, dlp, dld, dg;
-  db.alloc(rp); dlp.alloc(rp); dld.alloc(rp); dg.alloc((size_t)rp * d);
-  std::vector<double> stage((size_t)rp * dp);
-  for (int base = 0; base < n_points; base += rp) {
-    const int m = std::min(rp, n_points - base);
-    std::fill(stage.begin(), stage.end(), 0.0);
-    for (int i = 0; i < m; ++i) std::memcpy(&stage[(size_t)i * dp], x + (size_t)(base + i) * d, sizeof(double) * d);
-    h->lr_Theta.upload(stage.data(), stage.size());
-    db.upload(beta + base, m);
-    logreg_eval_batch(h, h->lr_Theta.p, nullptr, nullptr);
-    logreg_points_finish_kernel<<<(m + 3) / 4, 128, 0, h->stream>>>(h->lr_Theta.p, d, dp, m, db.p, h->lr_lik.p, h->lr_G.p,
-                                                                   h->cfg.p[5], h->cfg.p[4], lp ? dlp.p : nullptr,
-                                                                   ld ? dld.p : nullptr, dg.p);
-    CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    if (lp) dlp.download(lp + base, m);
-    if (ld) { dld.download(ld + base, m); dg.download(grad + (size_t)base * d, (size_t)m * d); }
-  }
-}
-
-template <class Chain>
-void* scan_kernel_ptr() { return (void*)scan_kernel<Chain>; }
-
-template <int TK, int CPL>
-void* vec_kernel_for(int ex) {
-  switch (ex) {
-    case PGN_EXPLORER_TOY: return TK == PGN_TARGET_TOY_MVN ? scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_TOY>>() : nullptr;
-    case PGN_EXPLORER_SLICE: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_SLICE>>();
-    case PGN_EXPLORER_AUTOMALA: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_AUTOMALA>>();
-    case PGN_EXPLORER_MALA: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_MALA>>();
-    case PGN_EXPLORER_SLICE_THEN_AUTOMALA: return scan_kernel_ptr<VecChain<TK, CPL, PGN_EXPLORER_SLICE_THEN_AUTOMALA>>();
-    default: return nullptr;
-  }
-}
-template <int TK>
-void* vec_kernel_cpl(int cpl, int ex) {
-  switch (cpl) {
-    case 1: return vec_kernel_for<TK, 1>(ex);
-    case 2: return vec_kernel_for<TK, 2>(ex);
-    case 4: return vec_kernel_for<TK, 4>(ex);
-    default: return nullptr;
-  }
-}
 void* select_scan_kernel(const pgn_handle* h) {
   const int ex = h->ep.kind;
   switch (h->cfg.target_kind) {
-    case PGN_TARGET_TOY_MVN: return vec_kernel_cpl<PGN_TARGET_TOY_MVN>(h->cpl, ex);
-    case PGN_TARGET_FUNNEL: return vec_kernel_cpl<PGN_TARGET_FUNNEL>(h->cpl, ex);
-    case PGN_TARGET_GMM: return vec_kernel_cpl<PGN_TARGET_GMM>(h->cpl, ex);
-    case PGN_TARGET_ISING: return ex == PGN_EXPLORER_ISING_METROPOLIS ? scan_kernel_ptr<IsingChain>() : nullptr;
-    case PGN_TARGET_TEST_SWAPPER: return ex == PGN_EXPLORER_NONE ? scan_kernel_ptr<TestSwapperChain>() : nullptr;
+    case PGN_TARGET_TOY_MVN: return vec_scan_kernel_toy(h->cpl, ex);
+    case PGN_TARGET_FUNNEL: return vec_scan_kernel_funnel(h->cpl, ex);
+    case PGN_TARGET_GMM: return vec_scan_kernel_gmm(h->cpl, ex);
+    case PGN_TARGET_ISING: return ex == PGN_EXPLORER_ISING_METROPOLIS ? ising_scan_kernel() : nullptr;
+    case PGN_TARGET_TEST_SWAPPER: return ex == PGN_EXPLORER_NONE ? test_swapper_scan_kernel() : nullptr;
     default: return nullptr;
   }
 }
-template <int TK>
-void* mem_kernel_for(int ex) {
-  switch (ex) {
-    case PGN_EXPLORER_TOY: return TK == PGN_TARGET_TOY_MVN ? (void*)scan_kernel_mem<TK, PGN_EXPLORER_TOY> : nullptr;
-    case PGN_EXPLORER_SLICE: return (void*)scan_kernel_mem<TK, PGN_EXPLORER_SLICE>;
-    case PGN_EXPLORER_AUTOMALA: return (void*)scan_kernel_mem<TK, PGN_EXPLORER_AUTOMALA>;
-    case PGN_EXPLORER_MALA: return (void*)scan_kernel_mem<TK, PGN_EXPLORER_MALA>;
-    default: return nullptr;
-  }
-}
-void* select_mem_kernel(const pgn_handle* h) {
-  switch (h->cfg.target_kind) {
-    case PGN_TARGET_TOY_MVN: return mem_kernel_for<PGN_TARGET_TOY_MVN>(h->ep.kind);
-    case PGN_TARGET_FUNNEL: return mem_kernel_for<PGN_TARGET_FUNNEL>(h->ep.kind);
-    case PGN_TARGET_GMM: return mem_kernel_for<PGN_TARGET_GMM>(h->ep.kind);
-    default: return nullptr;
-  }
-}
+void* select_mem_kernel(const pgn_handle* h) { return mem_scan_kernel(h->cfg.target_kind, h->ep.kind); }
 void mem_allocate(pgn_handle* h) {
   if (h->mem_allocated) return;
   h->mem_rec.alloc(h->n_local);
@@ -440,25 +104,25 @@ size_t scan_smem_bytes(const pgn_handle* h, int team_w = 0, int warps_per_block 
   return n * sizeof(double);
 }
 
-template <int TK>
 void launch_eval_points(pgn_handle* h, const Params& P, const double* xs, const double* betas, int n, double* lp,
                         double* ld, double* grad) {
   const int wpb = 4;
   const int grid = (n + wpb - 1) / wpb;
   const size_t smem = scan_smem_bytes(h);
+  const int tk = h->cfg.target_kind;
   if (h->cpl == 0) {   // d > 128: memory-resident evaluation; xs / grad are padded [n][d_pad] here
     MemParams MP;
     std::memset(&MP, 0, sizeof(MP));
     MP.base = P;
     MP.nslots = h->d_pad / 32;
-    eval_points_mem_kernel<TK><<<grid, wpb * 32, 0, h->stream>>>(MP, xs, betas, n, lp, ld, grad);
+    launch_eval_points_mem(tk, grid, wpb * 32, h->stream, MP, xs, betas, n, lp, ld, grad);
     return;
   }
-  switch (h->cpl) {
-    case 1: eval_points_kernel<TK, 1><<<grid, wpb * 32, smem, h->stream>>>(P, xs, betas, n, lp, ld, grad); break;
-    case 2: eval_points_kernel<TK, 2><<<grid, wpb * 32, smem, h->stream>>>(P, xs, betas, n, lp, ld, grad); break;
-    case 4: eval_points_kernel<TK, 4><<<grid, wpb * 32, smem, h->stream>>>(P, xs, betas, n, lp, ld, grad); break;
-    default: throw CudaError{PGN_ERR_INVALID, "unsupported dimension"};
+  switch (tk) {
+    case PGN_TARGET_TOY_MVN: launch_eval_points_toy(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
+    case PGN_TARGET_FUNNEL: launch_eval_points_funnel(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
+    case PGN_TARGET_GMM: launch_eval_points_gmm(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
+    default: throw CudaError{PGN_ERR_INVALID, "unsupported target"};
   }
 }
 
@@ -653,7 +317,7 @@ int pgn_init_replicas(pgn_handle* h, char** err) {
       Params P;
       fill_params(h, P);
       const int wpb = 4;
-      init_toy_kernel<<<(nl + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>(P);
+      launch_init_toy((nl + wpb - 1) / wpb, wpb * 32, h->stream, P);
       CUDA_CHECK(cudaGetLastError());
       CUDA_CHECK(cudaStreamSynchronize(h->stream));
     }
@@ -945,10 +609,9 @@ int pgn_log_potential(pgn_handle* h, const double* x, int32_t n_points, const do
     Params P;
     fill_params(h, P);
     switch (h->cfg.target_kind) {
-      case PGN_TARGET_TOY_MVN: launch_eval_points<PGN_TARGET_TOY_MVN>(h, P, dx.p, db.p, n_points, dout.p, nullptr, nullptr); break;
-      case PGN_TARGET_FUNNEL: launch_eval_points<PGN_TARGET_FUNNEL>(h, P, dx.p, db.p, n_points, dout.p, nullptr, nullptr); break;
-      case PGN_TARGET_GMM: launch_eval_points<PGN_TARGET_GMM>(h, P, dx.p, db.p, n_points, dout.p, nullptr, nullptr); break;
-      case PGN_TARGET_ISING: ising_lp_kernel<<<(n_points + 3) / 4, 128, 0, h->stream>>>(P, dx.p, db.p, n_points, dout.p); break;
+      case PGN_TARGET_TOY_MVN: case PGN_TARGET_FUNNEL: case PGN_TARGET_GMM:
+        launch_eval_points(h, P, dx.p, db.p, n_points, dout.p, nullptr, nullptr); break;
+      case PGN_TARGET_ISING: launch_ising_lp((n_points + 3) / 4, 128, h->stream, P, dx.p, db.p, n_points, dout.p); break;
       default: return fail(err, PGN_ERR_INVALID, "unsupported target");
     }
     CUDA_CHECK(cudaGetLastError());
@@ -979,11 +642,7 @@ int pgn_logdensity_and_gradient(pgn_handle* h, const double* x, int32_t n_points
     db.upload(beta, n_points);
     Params P;
     fill_params(h, P);
-    switch (tk) {
-      case PGN_TARGET_TOY_MVN: launch_eval_points<PGN_TARGET_TOY_MVN>(h, P, dx.p, db.p, n_points, nullptr, dld.p, dg.p); break;
-      case PGN_TARGET_FUNNEL: launch_eval_points<PGN_TARGET_FUNNEL>(h, P, dx.p, db.p, n_points, nullptr, dld.p, dg.p); break;
-      default: launch_eval_points<PGN_TARGET_GMM>(h, P, dx.p, db.p, n_points, nullptr, dld.p, dg.p); break;
-    }
+    launch_eval_points(h, P, dx.p, db.p, n_points, nullptr, dld.p, dg.p);
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
     dld.download(logdens, n_points);
@@ -1038,31 +697,7 @@ int pgn_measure_fp64_peak(int32_t device, double* tflops, char** err) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
       return fail(err, PGN_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");
-    CUDA_CHECK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    DevBuf<double> sink;
-    sink.alloc(1);
-    const int iters = 4096, blocks = prop.multiProcessorCount * 4, threads = 256;
-    cudaEvent_t a, b;
-    CUDA_CHECK(cudaEventCreate(&a));
-    CUDA_CHECK(cudaEventCreate(&b));
-    fp64_peak_kernel<<<blocks, threads>>>(sink.p, iters, 1.0000001);
-    CUDA_CHECK(cudaDeviceSynchronize());
-    float best = 1e30f;
-    for (int rep = 0; rep < 5; ++rep) {
-      CUDA_CHECK(cudaEventRecord(a));
-      fp64_peak_kernel<<<blocks, threads>>>(sink.p, iters, 1.0000001);
-      CUDA_CHECK(cudaEventRecord(b));
-      CUDA_CHECK(cudaEventSynchronize(b));
-      float ms = 0.f;
-      CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
-      best = ms < best ? ms : best;
-    }
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
-    const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
-    *tflops = flops / (best * 1e-3) / 1e12;
+    *tflops = logreg_measure_fp64_peak(device);
   } catch (CudaError& e) { return fail(err, e.code, e.msg); }
   return PGN_OK;
 }
@@ -1074,14 +709,7 @@ int pgn_test_dmma(int32_t device, const double* a, const double* b, const double
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
       return fail(err, PGN_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");
     CUDA_CHECK(cudaSetDevice(device));
-    DevBuf<double> da, db, dc, dd;
-    da.alloc((size_t)n_trials * 32, false); db.alloc((size_t)n_trials * 32, false);
-    dc.alloc((size_t)n_trials * 64, false); dd.alloc((size_t)n_trials * 64, false);
-    da.upload(a, (size_t)n_trials * 32); db.upload(b, (size_t)n_trials * 32); dc.upload(c, (size_t)n_trials * 64);
-    dmma_probe_kernel<<<(n_trials + 3) / 4, 128>>>(da.p, db.p, dc.p, dd.p, n_trials);
-    CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaDeviceSynchronize());
-    dd.download(d_out, (size_t)n_trials * 64);
+    logreg_test_dmma(a, b, c, d_out, n_trials);
   } catch (CudaError& e) { return fail(err, e.code, e.msg); }
   return PGN_OK;
 }
@@ -1097,9 +725,8 @@ int pgn_test_math(int32_t device, int32_t op, const double* in, double* out, int
     DevBuf<double> din, dout;
     din.alloc(nin, false); dout.alloc(n, false);
     din.upload(in, nin);
-    test_math_kernel<<<(unsigned)((n + 127) / 128), 128>>>(op, din.p, dout.p, n, (unsigned int)(unsigned long long)seed,
-                                                            (unsigned int)((unsigned long long)seed >> 32),
-                                                            (unsigned int)replica_index);
+    launch_test_math((int)((n + 127) / 128), 128, op, din.p, dout.p, n, (unsigned int)(unsigned long long)seed,
+                     (unsigned int)((unsigned long long)seed >> 32), (unsigned int)replica_index);
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaDeviceSynchronize());
     dout.download(out, n);

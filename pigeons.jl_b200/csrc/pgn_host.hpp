@@ -1,0 +1,133 @@
+// pgn_host.hpp — host-side types shared by the translation units of libpigeons_b200.so:
+// the engine handle, device buffers, error plumbing, and the functions through which
+// pgn_engine.cu (the C ABI) reaches the kernels compiled in the other translation units.
+//
+// The library is built from several .cu files (csrc/Makefile) so that the heavy kernel
+// families compile in parallel; every kernel is launched from the translation unit that
+// defines it (no relocatable device code).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pgn_kernels.cuh"
+#include "pgn_logreg_types.cuh"
+#include "pgn_memchain_types.cuh"
+
+namespace pgn {
+
+struct CudaError {
+  int code;
+  std::string msg;
+};
+
+#define CUDA_CHECK(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      throw ::pgn::CudaError{PGN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)};   \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count, bool zero = true) {
+    release();
+    n = count;
+    if (count == 0) count = 1;
+    CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    if (zero) CUDA_CHECK(cudaMemset(p, 0, count * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  void upload(const T* h, size_t count) { CUDA_CHECK(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice)); }
+  void download(T* h, size_t count) const { CUDA_CHECK(cudaMemcpy(h, p, count * sizeof(T), cudaMemcpyDeviceToHost)); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+};
+
+}  // namespace pgn
+
+struct pgn_handle {
+  pgn_config cfg{};
+  pgn_explorer_params ep{};
+  bool have_std = false;
+  int first_chain = 1, n_local = 0;
+  int cpl = 1, d_pad = 32, pay_doubles = 32;
+  size_t slot_bytes = 0, mail_bytes = 0;
+  unsigned int epoch = 0;
+  unsigned long long scan_seq = 0;   // scans run so far (all rounds): base of the mailbox tags
+  int n_sms = 0;
+  pgn::DevBuf<double> beta, x, means, log_w, std_devs, online_mean, online_s2;
+  pgn::DevBuf<int> replica_index, rt_state, error_flag;
+  pgn::DevBuf<unsigned long long> rng_ctr;
+  pgn::DevBuf<long long> online_n;
+  pgn::DevBuf<pgn::ChainStatsDev> stats;
+  pgn::DevBuf<char> mail;
+  char* mail_left = nullptr;
+  char* mail_right = nullptr;
+  bool left_is_ipc = false, right_is_ipc = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool initialised = false;
+  unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+  // ---- memory-resident scan path (any d, any number of chains; pgn_memchain.cuh)
+  bool force_mem = false;
+  pgn::DevBuf<pgn::MemRec> mem_rec;
+  pgn::DevBuf<double> mem_vec[10];
+  bool mem_allocated = false;
+  // ---- logistic regression (batched GEMM path, pgn_logreg_host.cu)
+  int lr_n_data = 0, lr_n_pad = 0, lr_r_pad = 0, lr_splits = 0;
+  pgn::DevBuf<double> lr_Xr, lr_Xt, lr_y, lr_Theta, lr_Thetat, lr_LL, lr_Res, lr_lik, lr_Gp, lr_G;
+  pgn::DevBuf<double> lr_P, lr_G0, lr_SX, lr_SP, lr_SG, lr_TP, lr_TG, lr_FX, lr_FG, lr_QX, lr_QP, lr_QG;
+  pgn::DevBuf<pgn::LrChainState> lr_st;
+  pgn::DevBuf<int> lr_n_active;
+  bool lr_use_dmma = true;       // FP64 tensor-core GEMM (same summation order as the SIMT kernel, see pgn_logreg.cuh)
+  double last_gemm_ms = 0.0;     // device time spent in the two GEMMs during the last round
+  long long last_batch_steps = 0;
+};
+
+namespace pgn {
+
+// ---- kernels compiled in the other translation units -------------------------------------------
+// scan kernels (pgn_scan_vec.cu, one object per target family; pgn_scan_misc.cu; pgn_scan_mem.cu)
+void* vec_scan_kernel_toy(int cpl, int ex);
+void* vec_scan_kernel_funnel(int cpl, int ex);
+void* vec_scan_kernel_gmm(int cpl, int ex);
+void* ising_scan_kernel();
+void* test_swapper_scan_kernel();
+void* mem_scan_kernel(int target_kind, int ex);
+// parity entry points
+void launch_eval_points_toy(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
+                            const double* betas, int n, double* lp, double* ld, double* grad);
+void launch_eval_points_funnel(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
+                               const double* betas, int n, double* lp, double* ld, double* grad);
+void launch_eval_points_gmm(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
+                            const double* betas, int n, double* lp, double* ld, double* grad);
+void launch_eval_points_mem(int target_kind, int grid, int block, cudaStream_t s, const MemParams& MP, const double* xs,
+                            const double* betas, int n, double* lp, double* ld, double* grad);
+void launch_init_toy(int grid, int block, cudaStream_t s, const Params& P);
+void launch_ising_lp(int grid, int block, cudaStream_t s, const Params& P, const double* xs, const double* betas, int n,
+                     double* lp);
+void launch_test_math(int grid, int block, int op, const double* in, double* out, long long n, unsigned int seed_lo,
+                      unsigned int seed_hi, unsigned int replica_index);
+// logistic regression (pgn_logreg_host.cu)
+void logreg_allocate(pgn_handle* h, const pgn_config* cfg);
+void logreg_fill_params(pgn_handle* h, LrParams& P);
+void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<ChainStatsDev>& st_out, float& total_ms);
+void logreg_points(pgn_handle* h, const double* x, int n_points, const double* beta, double* lp, double* ld, double* grad);
+double logreg_measure_fp64_peak(int device);
+void logreg_test_dmma(const double* a, const double* b, const double* c, double* d_out, int n_trials);
+
+}  // namespace pgn

@@ -1552,20 +1552,8 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
 }
 
 // ===========================================================================
-// Small helper kernels
+// Parity entry points (the other small helper kernels live in pgn_scan_misc.cu)
 // ===========================================================================
-// initialization(target, rng, replica_index) for toy MVN (toy_mvn_target.jl:10-11):
-// x = randn(rng, dim) / sqrt(precision1); one warp per replica.
-__global__ void init_toy_kernel(const __grid_constant__ Params P) {
-  const int lane = threadIdx.x & 31;
-  const int wl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (wl >= P.n_local) return;
-  Rng rng{P.seed_lo, (unsigned int)(P.first_chain + wl), P.seed_hi, 0u, 0ull};
-  const double sq = sqrt(P.p[1]);
-  for (int c = lane; c < P.d; c += 32) P.x[(size_t)wl * P.d_pad + c] = normal_at(rng, (unsigned long long)c) / sq;
-  if (lane == 0) P.rng_ctr[wl] = (unsigned long long)P.d;
-}
-
 // parity entry points: one warp per point
 template <int TK, int CPL>
 __global__ void eval_points_kernel(const __grid_constant__ Params P, const double* xs, const double* betas, int n_points, double* lp_out,
@@ -1598,40 +1586,6 @@ __global__ void eval_points_kernel(const __grid_constant__ Params P, const doubl
     for (int k = 0; k < CPL; ++k)
       if (k * 32 + lane < P.d) grad_out[(size_t)w * P.d + k * 32 + lane] = g[k];
   }
-}
-
-__global__ void ising_lp_kernel(const __grid_constant__ Params P, const double* xs, const double* betas, int n_points, double* lp_out) {
-  const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= n_points) return;
-  IsingChain ch;
-  ch.P = &P; ch.lane = lane; ch.L = (int)P.p[1];
-  unsigned int r = 0u;
-  if (lane < ch.L)
-    for (int j = 0; j < ch.L; ++j)
-      if (xs[(size_t)w * P.d + lane * ch.L + j] != 0.0) r |= (1u << j);
-  ch.row = r;
-  ch.recompute_S();
-  if (lane == 0) lp_out[w] = ch.lp(betas[w], ch.S);
-}
-
-__global__ void test_math_kernel(int op, const double* in, double* out, long long n, unsigned int seed_lo,
-                                 unsigned int seed_hi, unsigned int replica_index) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Rng g{seed_lo, replica_index, seed_hi, 0u, 0ull};
-  double r;
-  switch (op) {
-    case 0: r = exp_(in[i]); break;
-    case 1: r = log_(in[i]); break;
-    case 2: r = cospi_(in[i]); break;
-    case 3: r = normal_at(g, (unsigned long long)in[i]); break;
-    case 4: r = uniform_at(g, (unsigned long long)in[i]); break;
-    case 5: r = exponential_at(g, (unsigned long long)in[i]); break;
-    case 6: r = logaddexp_(in[2 * i], in[2 * i + 1]); break;
-    default: r = PGN_NAN;
-  }
-  out[i] = r;
 }
 
 }  // namespace pgn

@@ -161,9 +161,9 @@ __device__ __forceinline__ double cospi_(double t) {
 // Out-of-line copies for code that runs once per scan or per refreshment rather than once per density
 // evaluation: an inlined fp64 division is ~50 instructions and log_/exp_ ~80, and the scan kernels are
 // large enough for their instruction-cache footprint to matter (same operations, same results).
-__device__ __noinline__ double ddiv_(double a, double b) { return a / b; }
-__device__ __noinline__ double log_ni(double x) { return log_(x); }
-__device__ __noinline__ double exp_ni(double x) { return exp_(x); }
+static __device__ __noinline__ double ddiv_(double a, double b) { return a / b; }
+static __device__ __noinline__ double log_ni(double x) { return log_(x); }
+static __device__ __noinline__ double exp_ni(double x) { return exp_(x); }
 
 // COMPACT selects the out-of-line copies (kernels whose code size matters more than a call)
 template <bool COMPACT>
@@ -233,7 +233,7 @@ __device__ __forceinline__ double normal_at(const Rng& g, unsigned long long ctr
   double rad = sqrt(-2.0 * log_(u1));
   return rad * cospi_(t);
 }
-__device__ __noinline__ double normal_at_ni(unsigned int key0, unsigned int key1, unsigned int c2, unsigned int c3,
+static __device__ __noinline__ double normal_at_ni(unsigned int key0, unsigned int key1, unsigned int c2, unsigned int c3,
                                             unsigned long long ctr) {
   Rng g{key0, key1, c2, c3, 0ull};
   return normal_at(g, ctr);
