@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PGN_ABI_VERSION 2
+#define PGN_ABI_VERSION 3
 
 /* ---- return codes ------------------------------------------------------- */
 #define PGN_OK 0
@@ -177,6 +177,9 @@ typedef struct pgn_round_out {
   double kernel_ms;           /* CUDA-event duration of the scan kernel(s) of this round */
   double gemm_ms;             /* LOGREG: device time inside the two FP64 GEMMs of this round (0 otherwise) */
   int64_t batch_steps;        /* LOGREG: number of batched density/gradient evaluations (0 otherwise) */
+  int64_t n_launches;         /* kernels of this library launched for the round (1 for the persistent scan kernels) */
+  int64_t active_columns;     /* LOGREG: sum over batch steps of the chains whose pending point was evaluated */
+  int64_t gemm_columns;       /* LOGREG: sum over batch steps of the columns the GEMMs multiplied (tiles of 128) */
 } pgn_round_out;
 
 /* Replica state for checkpoint / inspection, in chain order:

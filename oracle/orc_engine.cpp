@@ -897,6 +897,9 @@ void run_round(Engine& E, int64_t n_scans, pgn_round_out* out) {
   out->kernel_ms = 0.0;
   out->gemm_ms = 0.0;
   out->batch_steps = 0;
+  out->n_launches = 0;
+  out->active_columns = 0;
+  out->gemm_columns = 0;
 }
 
 int fail(char** err, int code, const std::string& msg) {

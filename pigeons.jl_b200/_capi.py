@@ -19,7 +19,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # return codes (include/pigeons_b200.h)
 PGN_OK = 0
@@ -74,6 +74,7 @@ class pgn_round_out(C.Structure):
         ("target_trace", _dp),
         ("n_density_points", C.c_int64), ("n_ref_equiv_evals", C.c_int64), ("kernel_ms", C.c_double),
         ("gemm_ms", C.c_double), ("batch_steps", C.c_int64),
+        ("n_launches", C.c_int64), ("active_columns", C.c_int64), ("gemm_columns", C.c_int64),
     ]
 
 
@@ -86,7 +87,7 @@ class pgn_device_info_t(C.Structure):
                 ("global_mem_bytes", C.c_int64), ("max_resident_chains", C.c_int32), ("name", C.c_char * 128)]
 
 
-# every symbol include/pigeons_b200.h declares (checked by tests/test_capi_symbols.py)
+# every symbol include/pigeons_b200.h declares (checked by tests/test_host_logic.py::test_capi_library_loads_and_exports_every_symbol)
 DECLARED_SYMBOLS = [
     "pgn_abi_version", "pgn_create", "pgn_destroy", "pgn_free_string", "pgn_device_info", "pgn_local_range",
     "pgn_set_schedule", "pgn_set_explorer", "pgn_init_replicas", "pgn_get_state", "pgn_set_state",
@@ -206,6 +207,9 @@ class RoundResult:
     wall_s: float = 0.0
     gemm_ms: float = 0.0
     batch_steps: int = 0
+    n_launches: int = 0
+    active_columns: int = 0
+    gemm_columns: int = 0
 
 
 class Engine:
@@ -294,10 +298,23 @@ class Engine:
         return {"x": x, "replica_index": ri, "rng_counter": ctr, "round_trip_state": rt}
 
     def set_state(self, x=None, replica_index=None, rng_counter=None, round_trip_state=None):
-        def prep(a, dt):
-            return None if a is None else np.ascontiguousarray(a, dtype=dt)
-        x, ri = prep(x, np.float64), prep(replica_index, np.int32)
-        ctr, rt = prep(rng_counter, np.uint64), prep(round_trip_state, np.int32)
+        # pgn_set_state copies n_local rows from every buffer it is given: a buffer of any other size would make the
+        # library read past it (or silently assign the wrong replicas to chains), so the shapes are checked here
+        def prep(a, dt, shape, name):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dt)
+            if a.shape != shape:
+                raise ValueError(f"set_state: {name} has shape {a.shape}, this shard holds {shape} "
+                                 f"(chains {self.first_chain}..{self.first_chain + self.n_local - 1}, dim {self.dim})")
+            return a
+        n, d = self.n_local, self.dim
+        x = prep(x, np.float64, (n, d), "x")
+        ri = prep(replica_index, np.int32, (n,), "replica_index")
+        ctr = prep(rng_counter, np.uint64, (n,), "rng_counter")
+        rt = prep(round_trip_state, np.int32, (n,), "round_trip_state")
+        if ri is not None and (ri.min(initial=1) < 1 or ri.max(initial=1) > self.n_chains):
+            raise ValueError("set_state: replica_index entries must lie in 1..n_chains")
         st = pgn_replica_state(_ptr(x, C.c_double), _ptr(ri, C.c_int32), _ptr(ctr, C.c_uint64), _ptr(rt, C.c_int32))
         self.lib.call("set_state", self._h, C.byref(st))
 
@@ -339,6 +356,7 @@ class Engine:
         res.n_density_points, res.n_ref_equiv_evals = out.n_density_points, out.n_ref_equiv_evals
         res.kernel_ms = out.kernel_ms
         res.gemm_ms, res.batch_steps = out.gemm_ms, out.batch_steps
+        res.n_launches, res.active_columns, res.gemm_columns = out.n_launches, out.active_columns, out.gemm_columns
         return res
 
     # -- parity entry points -------------------------------------------------------

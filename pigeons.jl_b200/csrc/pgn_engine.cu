@@ -557,6 +557,9 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     out->kernel_ms = (double)ms;
     out->gemm_ms = is_logreg ? h->last_gemm_ms : 0.0;
     out->batch_steps = is_logreg ? h->last_batch_steps : 0;
+    out->n_launches = is_logreg ? h->last_launches : (n_scans > 0 ? 1 : 0);
+    out->active_columns = is_logreg ? h->last_active_cols : 0;
+    out->gemm_columns = is_logreg ? h->last_gemm_cols : 0;
     out->online_n = 0;
     if (owns_target && n_scans > 0) {
       long long on = 0;

@@ -96,6 +96,9 @@ struct pgn_handle {
   bool lr_use_dmma = true;       // FP64 tensor-core GEMM (same summation order as the SIMT kernel, see pgn_logreg.cuh)
   double last_gemm_ms = 0.0;     // device time spent in the two GEMMs during the last round
   long long last_batch_steps = 0;
+  long long last_launches = 0;      // kernels launched during the last round
+  long long last_active_cols = 0;   // sum over batch steps of the number of chains that asked for an evaluation
+  long long last_gemm_cols = 0;     // sum over batch steps of the number of columns the GEMMs multiplied
 };
 
 namespace pgn {

@@ -145,6 +145,9 @@ void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<C
   CUDA_CHECK(cudaEventCreate(&g1));
   h->last_gemm_ms = 0.0;
   h->last_batch_steps = 0;
+  h->last_launches = 0;
+  h->last_active_cols = 0;
+  h->last_gemm_cols = 0;
   const int wpb = 4, grid = (nl + wpb - 1) / wpb;
   CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
   int flag = 0;
@@ -164,10 +167,14 @@ void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<C
       CUDA_CHECK(cudaEventElapsedTime(&ms, g0, g1));
       h->last_gemm_ms += ms;
       h->last_batch_steps += 1;
+      h->last_launches += 1 + 7;          // controller + transpose, 2 GEMMs, Bernoulli, reduce, finalize (+ the memset)
+      h->last_active_cols += active;
+      h->last_gemm_cols += h->lr_r_pad;
     }
     if (flag != 0) break;
     logreg_post_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
     logreg_decide_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
+    h->last_launches += 3;              // the last controller pass of the scan + post + decide
     CUDA_CHECK(cudaMemcpyAsync(&flag, h->error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
   }

@@ -128,3 +128,76 @@ class TorchDistributed(Communicator):
 
     def barrier(self):
         self.dist.barrier()
+
+
+class ThreadGroup:
+    """Several shards driven from ONE process, one host thread per shard (the counterpart of a
+    multi-threaded host that owns several GPUs, or several handles on one GPU).  Neighbouring
+    handles are connected with `pgn_peer_attach` — the mailboxes are ordinary device pointers of
+    the same process, so no CUDA IPC is involved — and the per-round gathers are plain copies
+    between the threads."""
+
+    def __init__(self, world_size: int):
+        import threading
+        self.world_size = int(world_size)
+        self.barrier = threading.Barrier(self.world_size)
+        self.slots = [None] * self.world_size
+        self.engines = [None] * self.world_size
+
+    def comm(self, rank: int) -> "ThreadComm":
+        return ThreadComm(self, rank)
+
+    def run(self, fn):
+        """Run `fn(comm)` on world_size threads; returns the list of results in rank order.  The first
+        exception aborts the barrier (so no thread is left waiting) and is re-raised."""
+        import threading
+        results, errors = [None] * self.world_size, [None] * self.world_size
+
+        def work(r):
+            try:
+                results[r] = fn(self.comm(r))
+            except BaseException as e:      # noqa: BLE001 - re-raised below
+                errors[r] = e
+                self.barrier.abort()
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(self.world_size)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        import threading as _t
+        first = [e for e in errors if e is not None and not isinstance(e, _t.BrokenBarrierError)]
+        if first:
+            raise first[0]
+        if any(e is not None for e in errors):
+            raise [e for e in errors if e is not None][0]
+        return results
+
+
+class ThreadComm(Communicator):
+    def __init__(self, group: ThreadGroup, rank: int):
+        self.group, self.rank, self.world_size = group, int(rank), group.world_size
+
+    def all_gather_array(self, a: np.ndarray) -> List[np.ndarray]:
+        g = self.group
+        g.slots[self.rank] = np.array(a, copy=True)
+        g.barrier.wait()
+        out = [np.array(s, copy=True) for s in g.slots]
+        g.barrier.wait()
+        return out
+
+    def all_gather_bytes(self, payload: bytes) -> List[bytes]:
+        return [x.tobytes() for x in self.all_gather_array(np.frombuffer(payload, dtype=np.uint8))]
+
+    def connect_neighbours(self, engine) -> None:
+        g = self.group
+        g.engines[self.rank] = engine
+        g.barrier.wait()
+        if self.rank > 0:
+            engine.peer_attach(0, g.engines[self.rank - 1])
+        if self.rank < self.world_size - 1:
+            engine.peer_attach(1, g.engines[self.rank + 1])
+        g.barrier.wait()
+
+    def barrier(self) -> None:
+        self.group.barrier.wait()

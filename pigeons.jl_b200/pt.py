@@ -138,7 +138,7 @@ def adapt(pt: PT, rr: ReducedRecorders) -> PT:
     """adapt (pigeons.jl:152-162): adapt_tempering (NonReversiblePT.jl:52-66) then adapt_explorer."""
     temp = pt.shared.tempering
     n = temp.schedule.n_chains
-    if n > 1 and rr.has_swap_stats:
+    if n > 1:     # adaptation.jl:103-112: a pair that never recorded counts as acceptance 0.5
         rej = rejections(rr.swap_n, rr.swap_mean, n)
         new_temp = NonReversiblePT(optimal_schedule(rej, temp.schedule),
                                    communication_barriers(rej, temp.schedule.grids))
@@ -169,20 +169,27 @@ def run_checks(pt: PT) -> None:
     comm = inputs.comm
     st = pt.engine.get_state()
     whole = {k: np.concatenate(comm.all_gather_array(np.ascontiguousarray(v)), axis=0) for k, v in st.items()}
-    bad = []
+    bad, failure = [], ""
     if comm.rank == 0:
-        serial = replace(inputs, comm=SingleProcess(), n_rounds=inputs.checked_round, checked_round=0,
-                         engine_factory=None, show_report=False)
-        ref = pigeons_pt(create_pt(serial))
-        rs = ref.engine.get_state()
-        bad = [k for k in whole if not np.array_equal(whole[k].reshape(rs[k].shape), rs[k])]
-        if not np.array_equal(pt.shared.tempering.schedule.grids, ref.shared.tempering.schedule.grids):
-            bad.append("schedule")
-        if pt.shared.explorer != ref.shared.explorer:
-            bad.append("explorer")
-        ref.close()
-    verdicts = comm.all_gather_array(np.array([len(bad)], dtype=np.int64))     # every rank learns rank 0's verdict
-    if int(verdicts[0][0]) != 0:
+        try:
+            # the serial re-run uses the same engine library / factory as the run it checks
+            serial = replace(inputs, comm=SingleProcess(), n_rounds=inputs.checked_round, checked_round=0, show_report=False)
+            ref = pigeons_pt(create_pt(serial))
+            rs = ref.engine.get_state()
+            bad = [k for k in whole if not np.array_equal(whole[k].reshape(rs[k].shape), rs[k])]
+            if not np.array_equal(pt.shared.tempering.schedule.grids, ref.shared.tempering.schedule.grids):
+                bad.append("schedule")
+            if pt.shared.explorer != ref.shared.explorer:
+                bad.append("explorer")
+            ref.close()
+        except Exception as e:      # noqa: BLE001 - the other ranks wait in the gather below: tell them instead of hanging them
+            failure = f"{type(e).__name__}: {e}"
+    code = -1 if failure else len(bad)
+    verdicts = comm.all_gather_array(np.array([code], dtype=np.int64))     # every rank learns rank 0's verdict
+    v = int(verdicts[0][0])
+    if v < 0:
+        raise ChecksFailed(f"round {it.round}: the serial re-run on rank 0 failed" + (f" ({failure})" if failure else ""))
+    if v != 0:
         raise ChecksFailed(f"round {it.round}: the run on {comm.world_size} process(es) differs from the serial run"
                            + (f" in {bad}" if bad else ""))
 
@@ -195,7 +202,7 @@ def pigeons_pt(pt: PT) -> PT:
         rr = run_one_round(pt)
         pt = adapt(pt, rr)
         pt.round_log.append(dict(round=it.round, n_scans=n_scans_in_round(it), kernel_ms=rr.kernel_ms,
-                                 wall_s=rr.wall_s, global_barrier=global_barrier(pt) if pt.inputs.n_chains > 1 and rr.has_swap_stats else float("nan"),
+                                 wall_s=rr.wall_s, global_barrier=global_barrier(pt),
                                  stepping_stone=stepping_stone(pt) if rr.has_swap_stats else float("nan"),
                                  n_round_trips=rr.n_round_trips))
         run_checks(pt)
@@ -206,6 +213,12 @@ def pigeons_pt(pt: PT) -> PT:
     return pt
 
 
+def _target_fingerprint(target) -> tuple:
+    """(kind, dim, scalar parameters) of the device target: enough to refuse a checkpoint of another model."""
+    cfg = target.engine_config()
+    return (int(cfg["target_kind"]), int(cfg["dim"]), tuple(float(v) for v in cfg.get("p", ())))
+
+
 def write_checkpoint(pt: PT) -> dict:
     """write_checkpoint (src/pt/checkpoint.jl:110-145) for the harness: everything a later `resume` needs to
     continue the run bit for bit — `Shared` (round counter, schedule, adapted explorer) and the `Replica`s
@@ -213,7 +226,9 @@ def write_checkpoint(pt: PT) -> dict:
     arrays / dataclasses, not the reference's `.jls` wire format."""
     return dict(round=pt.shared.iterators.round, grids=pt.shared.tempering.schedule.grids.copy(),
                 communication_barriers=pt.shared.tempering.communication_barriers, explorer=pt.shared.explorer,
-                replicas=pt.engine.get_state(), n_chains=pt.inputs.n_chains, seed=pt.inputs.seed)
+                replicas=pt.engine.get_state(), n_chains=pt.inputs.n_chains, seed=pt.inputs.seed,
+                world_size=pt.inputs.comm.world_size, rank=pt.inputs.comm.rank, first_chain=pt.engine.first_chain,
+                n_local=pt.engine.n_local, dim=pt.inputs.target.dim, target_config=_target_fingerprint(pt.inputs.target))
 
 
 def resume(checkpoint: dict, inputs: Inputs) -> PT:
@@ -223,7 +238,15 @@ def resume(checkpoint: dict, inputs: Inputs) -> PT:
     `ext/PigeonsBridgeStanExt/interface.jl:27-48`)."""
     if inputs.n_chains != checkpoint["n_chains"] or inputs.seed != checkpoint["seed"]:
         raise ValueError("the checkpoint was written by a run with a different n_chains / seed")
+    if checkpoint.get("target_config") is not None and checkpoint["target_config"] != _target_fingerprint(inputs.target):
+        raise ValueError("the checkpoint was written for a different target")
     pt = create_pt(inputs)
+    # a checkpoint holds ONE shard: it can only be loaded by the same shard of the same layout
+    for key, have in (("world_size", inputs.comm.world_size), ("rank", inputs.comm.rank),
+                      ("first_chain", pt.engine.first_chain), ("n_local", pt.engine.n_local), ("dim", inputs.target.dim)):
+        if key in checkpoint and checkpoint[key] != have:
+            pt.close()
+            raise ValueError(f"the checkpoint was written by a shard with {key} = {checkpoint[key]}, this one has {have}")
     st = checkpoint["replicas"]
     pt.engine.set_state(x=st["x"] if st["x"].size else None, replica_index=st["replica_index"],
                         rng_counter=st["rng_counter"], round_trip_state=st["round_trip_state"])
@@ -262,7 +285,10 @@ def stepping_stone(pt: PT) -> float:
 
 
 def global_barrier(pt: PT) -> float:        # NonReversiblePT.jl:74
-    return pt.shared.tempering.communication_barriers.globalbarrier
+    cb = pt.shared.tempering.communication_barriers
+    if cb is None:      # a single chain (or no round run yet): the reference leaves the tempering untouched
+        return float("nan")
+    return cb.globalbarrier
 
 
 def n_round_trips(pt: PT) -> int:           # RoundTripRecorder.jl:23

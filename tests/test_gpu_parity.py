@@ -350,3 +350,107 @@ def test_leapfrog_involution_on_the_device(target, gpu_lib):
         dx, dp, moved = leapfrog_involution_error(e, target, beta)
         assert moved > 1e-3 and dx < 1e-9 and dp < 1e-9
     e.close()
+
+
+RESUME_CASES = {
+    "toy_slice": dict(target=pg.toy_mvn_target(3), explorer=pg.SliceSampler(), n_chains=5, seed=2),
+    "funnel_automala_team": dict(target=pg.Funnel(32), explorer=pg.AutoMALA(), n_chains=12, seed=3),
+    "gmm_automala": dict(target=pg.eight_mode_mixture(128, 8.0), explorer=pg.AutoMALA(), n_chains=6, seed=4),
+    "ising": dict(target=pg.IsingLogPotential(0.6, 5), n_chains=5, seed=4),
+    "logreg": dict(target=pg.synthetic_logistic_regression(300, 24), explorer=pg.AutoMALA(), n_chains=5, seed=5),
+    "toy300_mem": dict(target=pg.toy_mvn_target(300), explorer=pg.MALA(step_size=0.1), n_chains=4, seed=6),
+    "test_swapper": dict(target=pg.TestSwapper(0.7), n_chains=6, seed=7),
+}
+
+
+@pytest.mark.parametrize("name", list(RESUME_CASES))
+def test_device_resume_is_bit_identical(name, gpu_lib, oracle_lib):
+    """test/test_resume.jl on the DEVICE: pgn_get_state after round 4 -> a NEW handle -> pgn_set_state -> rounds 5..6
+    gives the run that went straight to round 6 bit for bit, and both equal the oracle's straight run."""
+    kw = RESUME_CASES[name]
+    rec = [pg.index_process, pg.swap_trace]
+    straight = pg.pigeons(engine_lib=gpu_lib, n_rounds=6, record=rec, **kw)
+    first = pg.pigeons(engine_lib=gpu_lib, n_rounds=4, record=rec, **kw)
+    ckpt = pg.write_checkpoint(first)
+    first.close()                                    # the handle is gone: only the checkpoint survives
+    resumed = pg.resume(ckpt, pg.Inputs(engine_lib=gpu_lib, n_rounds=6, record=rec, **kw))
+    ref = pg.pigeons(engine_lib=oracle_lib, n_rounds=6, record=rec, **kw)
+    for other, label in ((resumed, "resumed"), (ref, "oracle")):
+        a, b = straight.reduced_recorders, other.reduced_recorders
+        for k in ("index_process", "swap_lr", "swap_u", "swap_accept", "swap_mean", "logsum_fwd", "logsum_bwd", "expl_n_steps",
+                  "expl_acc_mean", "am_mean", "rev_mean"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), f"{name}/{label}: {k}"
+        assert np.array_equal(straight.shared.tempering.schedule.grids, other.shared.tempering.schedule.grids)
+        assert straight.shared.explorer == other.shared.explorer
+        sa, sb = straight.engine.get_state(), other.engine.get_state()
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k]), f"{name}/{label}: replica {k}"
+        assert a.n_round_trips == b.n_round_trips
+    straight.close(); resumed.close(); ref.close()
+
+
+def test_set_state_is_validated_on_the_device_binding(gpu_lib):
+    t = pg.toy_mvn_target(3)
+    e = pg.Engine(gpu_lib, n_chains=5, seed=1, **t.engine_config())
+    e.init_replicas()
+    with pytest.raises(ValueError):
+        e.set_state(x=np.zeros((4, 3)))
+    with pytest.raises(ValueError):
+        e.set_state(rng_counter=np.zeros(6, dtype=np.uint64))
+    e.close()
+
+
+# ---- BASELINE config 5 at its full shape (d = 4096, n_data = 65536) ---------------------------------------------------
+@pytest.fixture(scope="module")
+def c5(oracle_lib):
+    """The C5 data set (2 GiB design matrix) and the oracle's answers on three points, computed once."""
+    target = pg.synthetic_logistic_regression(65536, 4096)
+    rng = np.random.default_rng(5)
+    x = rng.normal(0.0, 0.05, size=(3, 4096))
+    x[1] *= 10.0                                      # larger |z|: both branches of the Bernoulli terms
+    beta = np.array([0.0, 0.37, 1.0])
+    eo = pg.Engine(oracle_lib, n_chains=4, seed=1, **target.engine_config())
+    out = dict(target=target, x=x, beta=beta, lp=eo.log_potential(x, beta), ldg=eo.logdensity_and_gradient(x, beta))
+    eo.close()
+    return out
+
+
+@pytest.mark.parametrize("gemm", ["dmma", "simt"])
+def test_c5_full_shape_entry_points(gemm, c5, gpu_lib, monkeypatch):
+    """pgn_log_potential / pgn_logdensity_and_gradient at d = 4096, n_data = 65536 (16 split-K chunks, 512 row tiles):
+    the FP64 tensor-core GEMM and the SIMT GEMM against the oracle's sequential-fma statement, bit for bit."""
+    monkeypatch.setenv("PGN_GEMM", gemm)
+    eg = pg.Engine(gpu_lib, n_chains=4, seed=1, **c5["target"].engine_config())
+    lp = eg.log_potential(c5["x"], c5["beta"])
+    ld, g = eg.logdensity_and_gradient(c5["x"], c5["beta"])
+    eg.close()
+    np.testing.assert_allclose(lp, c5["lp"], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(ld, c5["ldg"][0], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(g, c5["ldg"][1], rtol=RTOL, atol=1e-300)
+    assert np.array_equal(lp, c5["lp"]) and np.array_equal(ld, c5["ldg"][0]) and np.array_equal(g, c5["ldg"][1])
+
+
+def test_c5_full_shape_round(c5, gpu_lib, oracle_lib):
+    """A 4-chain LOGREG ladder at the full C5 shape, driven through the C ABI directly: 3 scans (MH and the reversed
+    search active from scan 2) with one refreshment per scan so that the oracle finishes in seconds, on a schedule whose
+    first pairs are close enough to exchange their 32 KB states; every output and the final replicas bit for bit."""
+    betas = np.array([0.0, 2e-6, 5e-6, 1.0])
+    ex = pg.AutoMALA(base_n_refresh=1, exponent_n_refresh=0.0, step_size=0.02)
+    outs = []
+    for lib in (gpu_lib, oracle_lib):
+        e = pg.Engine(lib, n_chains=4, seed=1, **c5["target"].engine_config())
+        e.init_replicas()
+        e.set_schedule(betas)
+        e.set_explorer(**ex.engine_params(4096))
+        r = e.run_round(3, log_index_process=True, log_swaps=True, log_target_trace=True)
+        outs.append((r, e.get_state()))
+        e.close()
+    (rg, sg), (ro, so) = outs
+    assert ro.swap_accept.sum() > 0, "the schedule was meant to produce accepted swaps"
+    for k in ("index_process", "swap_accept", "swap_u", "swap_lr", "swap_n", "swap_mean", "logsum_fwd", "logsum_bwd",
+              "expl_acc_n", "expl_acc_mean", "expl_n_steps", "am_n", "am_mean", "rev_n", "rev_mean", "online_mean",
+              "online_var", "target_trace"):
+        assert np.array_equal(getattr(rg, k), getattr(ro, k)), f"c5 full shape: {k}"
+    assert rg.n_ref_equiv_evals == ro.n_ref_equiv_evals and rg.n_round_trips == ro.n_round_trips
+    for k in sg:
+        assert np.array_equal(sg[k], so[k]), f"c5 full shape: final replica {k}"

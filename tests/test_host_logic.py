@@ -93,7 +93,7 @@ def test_capi_library_loads_and_exports_every_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), name
     lib.pgn_abi_version.restype = C.c_int
-    assert lib.pgn_abi_version() == pg._capi.ABI_VERSION == 2
+    assert lib.pgn_abi_version() == pg._capi.ABI_VERSION == 3
 
 
 def test_product_fails_loudly_without_gpu():
@@ -169,15 +169,85 @@ def test_checked_round_serial_rerun_and_failure_detection():
     pt.close()
 
     class Drifting:                                    # an engine whose replicas' RNG positions are off by one
+        built = 0
+
         def __init__(self, **cfg):
             self.e = pg.Engine(lib, **cfg)
+            Drifting.built += 1
+            self.drift = Drifting.built == 1           # the checked run drifts; the serial re-run (same factory) does not
 
         def __getattr__(self, name):
             return getattr(self.e, name)
 
         def get_state(self):
             st = self.e.get_state()
-            st["rng_counter"] = st["rng_counter"] + np.uint64(1)
+            if self.drift:
+                st["rng_counter"] = st["rng_counter"] + np.uint64(1)
             return st
     with pytest.raises(pg.ChecksFailed):
         pg.pigeons(checked_round=2, engine_factory=lambda **cfg: Drifting(**cfg), **kw)
+
+
+def test_serial_rerun_failure_reaches_every_rank():
+    """A serial re-run that raises on rank 0 must come back as ChecksFailed (through the verdict gather), not as a hang
+    of the other ranks."""
+    from oracle_adapter import load_oracle
+    lib = load_oracle()
+    kw = dict(target=pg.toy_mvn_target(2), explorer=pg.SliceSampler(), n_chains=4, n_rounds=3, seed=1, engine_lib=lib)
+    built = []
+
+    def factory(**cfg):
+        built.append(1)
+        if len(built) > 1:
+            raise RuntimeError("no room for the serial ladder")
+        return pg.Engine(lib, **cfg)
+    with pytest.raises(pg.ChecksFailed, match="serial re-run on rank 0 failed"):
+        pg.pigeons(checked_round=2, engine_factory=factory, **kw)
+
+
+def test_set_state_rejects_wrong_shapes_and_resume_rejects_another_layout():
+    """pgn_set_state copies n_local rows unconditionally, so the binding refuses buffers of any other size;
+    `resume` refuses a checkpoint written by another shard layout or another target."""
+    from oracle_adapter import load_oracle
+    lib = load_oracle()
+    kw = dict(target=pg.toy_mvn_target(3), explorer=pg.SliceSampler(), n_chains=5, seed=2)
+    pt = pg.pigeons(engine_lib=lib, n_rounds=2, **kw)
+    st = pt.engine.get_state()
+    with pytest.raises(ValueError):
+        pt.engine.set_state(x=st["x"][:-1])
+    with pytest.raises(ValueError):
+        pt.engine.set_state(replica_index=np.arange(1, 7, dtype=np.int32))
+    with pytest.raises(ValueError):
+        pt.engine.set_state(replica_index=np.array([0, 1, 2, 3, 4], dtype=np.int32))
+    with pytest.raises(ValueError):
+        pt.engine.set_state(x=np.zeros((5, 4)))
+    ck = pg.write_checkpoint(pt)
+    pt.close()
+    assert ck["world_size"] == 1 and ck["n_local"] == 5 and ck["dim"] == 3
+    with pytest.raises(ValueError):
+        pg.resume(ck, pg.Inputs(engine_lib=lib, n_rounds=3, **{**kw, "target": pg.toy_mvn_target(4)}))
+    bad = dict(ck, world_size=2)
+    with pytest.raises(ValueError):
+        pg.resume(bad, pg.Inputs(engine_lib=lib, n_rounds=3, **kw))
+
+
+def test_adaptation_without_swap_statistics():
+    """adaptation.jl:103-112: with no swap recorded a pair counts as acceptance 0.5, so the barriers exist
+    (global barrier 0.5 (N-1)); a single chain leaves the tempering untouched."""
+    from oracle_adapter import load_oracle
+    lib = load_oracle()
+    pt = pg.pigeons(target=pg.toy_mvn_target(2), explorer=pg.SliceSampler(), n_chains=1, n_rounds=2, engine_lib=lib)
+    assert np.isnan(pg.global_barrier(pt))
+    pt.close()
+    from pigeons_jl_b200.pt import adapt
+    pt = pg.create_pt(pg.Inputs(target=pg.toy_mvn_target(2), explorer=pg.SliceSampler(), n_chains=5, n_rounds=0, engine_lib=lib))
+    pt.shared.iterators.round = 1
+    pt.engine.set_schedule(pt.shared.tempering.schedule.grids)
+    pt.engine.set_explorer(**pt.shared.explorer.engine_params(2))
+    from pigeons_jl_b200.recorders import merge_round_results
+    res = pt.engine.run_round(0)       # a round with no scans records nothing
+    rr = merge_round_results(pt.inputs.comm, res, 5, 2)
+    assert not rr.has_swap_stats
+    pt = adapt(pt, rr)
+    assert pg.global_barrier(pt) == pytest.approx(0.5 * 4)
+    pt.close()
