@@ -63,9 +63,9 @@ void fill_params(pgn_handle* h, Params& P) {
 void* select_scan_kernel(const pgn_handle* h) {
   const int ex = h->ep.kind;
   switch (h->cfg.target_kind) {
-    case PGN_TARGET_TOY_MVN: return vec_scan_kernel_toy(h->cpl, ex);
-    case PGN_TARGET_FUNNEL: return vec_scan_kernel_funnel(h->cpl, ex);
-    case PGN_TARGET_GMM: return vec_scan_kernel_gmm(h->cpl, ex);
+    case PGN_TARGET_TOY_MVN: return vec_scan_kernel_toy(h->cpl, ex, h->regcap);
+    case PGN_TARGET_FUNNEL: return vec_scan_kernel_funnel(h->cpl, ex, h->regcap);
+    case PGN_TARGET_GMM: return vec_scan_kernel_gmm(h->cpl, ex, h->regcap);
     case PGN_TARGET_ISING: return ex == PGN_EXPLORER_ISING_METROPOLIS ? ising_scan_kernel() : nullptr;
     case PGN_TARGET_TEST_SWAPPER: return ex == PGN_EXPLORER_NONE ? test_swapper_scan_kernel() : nullptr;
     default: return nullptr;
@@ -74,8 +74,8 @@ void* select_scan_kernel(const pgn_handle* h) {
 void* select_mem_kernel(const pgn_handle* h) { return mem_scan_kernel(h->cfg.target_kind, h->ep.kind); }
 void mem_allocate(pgn_handle* h) {
   if (h->mem_allocated) return;
-  h->mem_rec.alloc(h->n_local);
-  for (int i = 0; i < 10; ++i) h->mem_vec[i].alloc((size_t)h->n_local * h->d_pad);
+  h->mem_rec.alloc_on(h->n_local, h->stream);
+  for (int i = 0; i < 10; ++i) h->mem_vec[i].alloc_on((size_t)h->n_local * h->d_pad, h->stream);
   h->mem_allocated = true;
 }
 void mem_fill_params(pgn_handle* h, const Params& P, MemParams& MP) {
@@ -212,6 +212,8 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
     {
       const char* fm = std::getenv("PGN_FORCE_MEM");
       h->force_mem = fm != nullptr && std::string(fm) == "1";
+      const char* rc = std::getenv("PGN_REGCAP");
+      h->regcap = rc ? std::atoi(rc) : 0;
     }
     // the scan kernel's flag-in-data words need 16 bytes per payload double (8 header words + 2 words per double);
     // the logistic-regression and memory-resident kernels use the first 64 + 8 * pay_doubles bytes of a slot
@@ -247,6 +249,14 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
     h->ep = pgn_explorer_params{};
     h->ep.kind = PGN_EXPLORER_NONE;
     CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {   // per-round scratch comes from the stream-ordered pool; keep what it has freed instead of returning it to the OS
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+    }
     CUDA_CHECK(cudaEventCreate(&h->ev0));
     CUDA_CHECK(cudaEventCreate(&h->ev1));
   } catch (CudaError& e) {
@@ -264,7 +274,9 @@ int pgn_destroy(pgn_handle* h) {
   if (h->right_is_ipc && h->mail_right) cudaIpcCloseMemHandle(h->mail_right);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  h->mem_rec.release();                       // stream-ordered allocations go back while their stream still exists
+  for (auto& v : h->mem_vec) v.release();
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   delete h;
   return PGN_OK;
 }
@@ -279,7 +291,7 @@ int pgn_set_schedule(pgn_handle* h, const double* beta, int32_t n, char** err) {
   if (n != h->cfg.n_chains) return fail(err, PGN_ERR_INVALID, "schedule length != n_chains");
   try {
     use_device(h);
-    h->beta.upload(beta, n);
+    h->beta.upload(beta, n, h->stream);
   } catch (CudaError& e) { return fail(err, e.code, e.msg); }
   return PGN_OK;
 }
@@ -296,7 +308,7 @@ int pgn_set_explorer(pgn_handle* h, const pgn_explorer_params* ep, char** err) {
     use_device(h);
     h->ep = *ep;
     h->have_std = ep->std_devs != nullptr;
-    if (h->have_std) h->std_devs.upload(ep->std_devs, h->cfg.dim);
+    if (h->have_std) h->std_devs.upload(ep->std_devs, h->cfg.dim, h->stream);
     h->ep.std_devs = nullptr;
   } catch (CudaError& e) { return fail(err, e.code, e.msg); }
   return PGN_OK;
@@ -309,10 +321,10 @@ int pgn_init_replicas(pgn_handle* h, char** err) {
     std::vector<int> ri(nl), rt(nl, 0);
     std::vector<unsigned long long> ctr(nl, 0ull);
     for (int i = 0; i < nl; ++i) ri[i] = h->first_chain + i;
-    h->replica_index.upload(ri.data(), nl);
-    h->rt_state.upload(rt.data(), nl);
-    h->rng_ctr.upload(ctr.data(), nl);
-    CUDA_CHECK(cudaMemset(h->x.p, 0, std::max<size_t>(1, (size_t)nl * h->d_pad) * sizeof(double)));
+    h->replica_index.upload(ri.data(), nl, h->stream);
+    h->rt_state.upload(rt.data(), nl, h->stream);
+    h->rng_ctr.upload(ctr.data(), nl, h->stream);
+    CUDA_CHECK(cudaMemsetAsync(h->x.p, 0, std::max<size_t>(1, (size_t)nl * h->d_pad) * sizeof(double), h->stream));
     if (h->cfg.target_kind == PGN_TARGET_TOY_MVN) {
       Params P;
       fill_params(h, P);
@@ -332,7 +344,7 @@ int pgn_get_state(pgn_handle* h, pgn_replica_state* out, char** err) {
     const int nl = h->n_local, d = h->cfg.dim;
     if (out->x && d > 0) {
       std::vector<double> raw((size_t)nl * h->d_pad);
-      h->x.download(raw.data(), raw.size());
+      h->x.download(raw.data(), raw.size(), h->stream);
       if (h->cfg.target_kind == PGN_TARGET_ISING) {
         const int L = (int)h->cfg.p[1];
         for (int i = 0; i < nl; ++i) {
@@ -344,9 +356,9 @@ int pgn_get_state(pgn_handle* h, pgn_replica_state* out, char** err) {
         for (int i = 0; i < nl; ++i) std::memcpy(out->x + (size_t)i * d, &raw[(size_t)i * h->d_pad], sizeof(double) * d);
       }
     }
-    if (out->replica_index) h->replica_index.download(out->replica_index, nl);
-    if (out->rng_counter) h->rng_ctr.download(reinterpret_cast<unsigned long long*>(out->rng_counter), nl);
-    if (out->round_trip_state) h->rt_state.download(out->round_trip_state, nl);
+    if (out->replica_index) h->replica_index.download(out->replica_index, nl, h->stream);
+    if (out->rng_counter) h->rng_ctr.download(reinterpret_cast<unsigned long long*>(out->rng_counter), nl, h->stream);
+    if (out->round_trip_state) h->rt_state.download(out->round_trip_state, nl, h->stream);
   } catch (CudaError& e) { return fail(err, e.code, e.msg); }
   return PGN_OK;
 }
@@ -369,11 +381,11 @@ int pgn_set_state(pgn_handle* h, const pgn_replica_state* in, char** err) {
       } else {
         for (int i = 0; i < nl; ++i) std::memcpy(&raw[(size_t)i * h->d_pad], in->x + (size_t)i * d, sizeof(double) * d);
       }
-      h->x.upload(raw.data(), raw.size());
+      h->x.upload(raw.data(), raw.size(), h->stream);
     }
-    if (in->replica_index) h->replica_index.upload(in->replica_index, nl);
-    if (in->rng_counter) h->rng_ctr.upload(reinterpret_cast<const unsigned long long*>(in->rng_counter), nl);
-    if (in->round_trip_state) h->rt_state.upload(in->round_trip_state, nl);
+    if (in->replica_index) h->replica_index.upload(in->replica_index, nl, h->stream);
+    if (in->rng_counter) h->rng_ctr.upload(reinterpret_cast<const unsigned long long*>(in->rng_counter), nl, h->stream);
+    if (in->round_trip_state) h->rt_state.upload(in->round_trip_state, nl, h->stream);
   } catch (CudaError& e) { return fail(err, e.code, e.msg); }
   return PGN_OK;
 }
@@ -402,16 +414,16 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     LrParams LP;
     if (is_logreg) logreg_fill_params(h, LP);
     // optional event logs
-    DevBuf<int> d_index;
-    DevBuf<double> d_lr, d_u, d_trace;
-    DevBuf<unsigned char> d_acc;
+    StreamBuf<int> d_index;          // stream-ordered: see StreamBuf in pgn_host.hpp
+    StreamBuf<double> d_lr, d_u, d_trace;
+    StreamBuf<unsigned char> d_acc;
     const size_t nlog = (size_t)n_scans * nl;
-    if (out->index_process) { d_index.alloc(nlog, false); P.index_process = d_index.p; }
-    if (out->swap_lr) { d_lr.alloc(nlog, false); P.swap_lr = d_lr.p; }
-    if (out->swap_u) { d_u.alloc(nlog, false); P.swap_u = d_u.p; }
-    if (out->swap_accept) { d_acc.alloc(nlog, false); P.swap_accept = d_acc.p; }
+    if (out->index_process) { d_index.alloc(nlog, h->stream); P.index_process = d_index.p; }
+    if (out->swap_lr) { d_lr.alloc(nlog, h->stream); P.swap_lr = d_lr.p; }
+    if (out->swap_u) { d_u.alloc(nlog, h->stream); P.swap_u = d_u.p; }
+    if (out->swap_accept) { d_acc.alloc(nlog, h->stream); P.swap_accept = d_acc.p; }
     const bool owns_target = (h->first_chain + nl - 1 == h->cfg.n_chains);
-    if (out->target_trace && owns_target) { d_trace.alloc((size_t)n_scans * std::max(d, 1), false); P.target_trace = d_trace.p; }
+    if (out->target_trace && owns_target) { d_trace.alloc((size_t)n_scans * std::max(d, 1), h->stream); P.target_trace = d_trace.p; }
     CUDA_CHECK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int), h->stream));
     float ms = 0.f;
     std::vector<ChainStatsDev> st(nl);
@@ -443,14 +455,18 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
             // a team shares one scan's momentum draws through shared memory when they fit in 64 KB
             int max_refresh = h->ep.n_refresh;
             for (int v = 0; v < h->ep.n_mix && v < PGN_MAX_MIX; ++v) max_refresh = std::max(max_refresh, h->ep.mix_n_refresh[v]);
-            const int pool = (w > 1 && (size_t)max_refresh * (h->cpl * 32 + 8) * sizeof(double) <= 64 * 1024) ? max_refresh : 0;
-            const size_t sm = scan_smem_bytes(h, w, 1, pool);
-            if (sm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            int per_sm = 0;
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, sm));
-            const bool fits = (long long)per_sm * h->n_sms >= nl_max;
+            const int pool_max = (w > 1 && (size_t)max_refresh * (h->cpl * 32 + 8) * sizeof(double) <= 64 * 1024) ? max_refresh : 0;
             const bool wide_ok = w == 1 || pinned == w || (long long)nl * w <= (long long)per_smsp * 4 * h->n_sms;
-            if (fits && wide_ok) { wpb = w; grid = nl; smem = sm; P.pool_refresh = pool; break; }
+            bool chosen = false;
+            for (int pool = pool_max; pool >= 0 && !chosen; pool = pool > 0 ? 0 : -1) {   // with the momentum pool if it fits, else without
+              const size_t sm = scan_smem_bytes(h, w, 1, pool);
+              if (sm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+              int per_sm = 0;
+              CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, sm));
+              const bool fits = (long long)per_sm * h->n_sms >= nl_max;
+              if (fits && wide_ok) { wpb = w; grid = nl; smem = sm; P.pool_refresh = pool; chosen = true; }
+            }
+            if (chosen) break;
           }
         } else {
           for (int w = 1; w <= 8; w *= 2) {
@@ -471,7 +487,7 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
         CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-        if (n_scans > 0) h->stats.download(st.data(), nl);
+        if (n_scans > 0) h->stats.download(st.data(), nl, h->stream);
         else std::memset(st.data(), 0, sizeof(ChainStatsDev) * nl);
       } else {
         // memory-resident kernel: d > 128, or more chains than fit co-resident, or PGN_FORCE_MEM=1
@@ -482,15 +498,15 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
         mem_fill_params(h, P, MP);
         std::vector<int> ri(nl);
         std::vector<unsigned long long> ctr(nl);
-        h->replica_index.download(ri.data(), nl);
-        h->rng_ctr.download(ctr.data(), nl);
+        h->replica_index.download(ri.data(), nl, h->stream);
+        h->rng_ctr.download(ctr.data(), nl, h->stream);
         std::vector<MemRec> rec(nl);
         std::memset(rec.data(), 0, sizeof(MemRec) * nl);
         for (int i = 0; i < nl; ++i) {
           rec[i].ctr = ctr[i]; rec[i].replica_index = ri[i];
           rec[i].ls_fwd.value = -INFINITY; rec[i].ls_bwd.value = -INFINITY;
         }
-        h->mem_rec.upload(rec.data(), nl);
+        h->mem_rec.upload(rec.data(), nl, h->stream);
         CUDA_CHECK(cudaMemsetAsync(h->online_mean.p, 0, sizeof(double) * h->d_pad, h->stream));
         CUDA_CHECK(cudaMemsetAsync(h->online_s2.p, 0, sizeof(double) * h->d_pad, h->stream));
         CUDA_CHECK(cudaMemsetAsync(h->online_n.p, 0, sizeof(long long), h->stream));
@@ -507,7 +523,7 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
         CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
         CUDA_CHECK(cudaStreamSynchronize(h->stream));
         CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-        h->mem_rec.download(rec.data(), nl);
+        h->mem_rec.download(rec.data(), nl, h->stream);
         std::vector<int> rt(nl);
         for (int i = 0; i < nl; ++i) {
           const MemRec& r = rec[i];
@@ -518,13 +534,13 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
           o.am_n = r.am.n; o.am_mean = r.am.mu; o.rev_n = r.rev.n; o.rev_mean = r.rev.mu;
           o.n_restarts = r.n_restarts; o.n_round_trips = r.n_trips; o.n_points = r.n_points; o.n_ref_evals = r.n_ref;
         }
-        h->replica_index.upload(ri.data(), nl);
-        h->rng_ctr.upload(ctr.data(), nl);
-        h->rt_state.upload(rt.data(), nl);
+        h->replica_index.upload(ri.data(), nl, h->stream);
+        h->rng_ctr.upload(ctr.data(), nl, h->stream);
+        h->rt_state.upload(rt.data(), nl, h->stream);
       }
     }
     int flag = 0;
-    h->error_flag.download(&flag, 1);
+    h->error_flag.download(&flag, 1, h->stream);
 
     if (const char* dump = std::getenv("PGN_TIMING_DUMP")) {   // diagnostics: per-chain explore / partner-wait clocks of this round
       if (FILE* f = std::fopen(dump, "a")) {
@@ -563,13 +579,13 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     out->online_n = 0;
     if (owns_target && n_scans > 0) {
       long long on = 0;
-      h->online_n.download(&on, 1);
+      h->online_n.download(&on, 1, h->stream);
       const bool vec = h->cfg.target_kind != PGN_TARGET_ISING && h->cfg.target_kind != PGN_TARGET_TEST_SWAPPER;
       out->online_n = vec ? on : n_scans;
       if (vec && d > 0) {
         std::vector<double> mu(h->d_pad), s2(h->d_pad);
-        h->online_mean.download(mu.data(), h->d_pad);
-        h->online_s2.download(s2.data(), h->d_pad);
+        h->online_mean.download(mu.data(), h->d_pad, h->stream);
+        h->online_s2.download(s2.data(), h->d_pad, h->stream);
         for (int c = 0; c < d; ++c) {
           if (out->online_mean) out->online_mean[c] = mu[c];
           if (out->online_var) out->online_var[c] = on > 1 ? s2[c] * ((double)on / (double)(on - 1)) : 1.0;

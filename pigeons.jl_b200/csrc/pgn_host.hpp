@@ -45,16 +45,69 @@ struct DevBuf {
     CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
     if (zero) CUDA_CHECK(cudaMemset(p, 0, count * sizeof(T)));
   }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr; n = 0;
+  // stream-ordered allocation (first use inside a round: must not wait for another handle's kernel, see StreamBuf)
+  void alloc_on(size_t count, cudaStream_t s) {
+    release();
+    n = count; async_stream = s; is_async = true;
+    if (count == 0) count = 1;
+    CUDA_CHECK(cudaMallocAsync(&p, count * sizeof(T), s));
+    CUDA_CHECK(cudaMemsetAsync(p, 0, count * sizeof(T), s));
   }
+  void release() {
+    if (p) { if (is_async) cudaFreeAsync(p, async_stream); else cudaFree(p); }
+    p = nullptr; n = 0; is_async = false;
+  }
+  cudaStream_t async_stream = nullptr;
+  bool is_async = false;
   void upload(const T* h, size_t count) { CUDA_CHECK(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice)); }
   void download(T* h, size_t count) const { CUDA_CHECK(cudaMemcpy(h, p, count * sizeof(T), cudaMemcpyDeviceToHost)); }
+  // the same on a stream of the caller's (followed by a wait for THAT stream only, not for the device)
+  void upload(const T* h, size_t count, cudaStream_t s) {
+    CUDA_CHECK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  void download(T* h, size_t count, cudaStream_t s) const {
+    CUDA_CHECK(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
+};
+
+// Per-round scratch (event logs, parity entry points), allocated and released in stream order on the handle's own
+// stream (cudaMallocAsync / cudaFreeAsync): unlike cudaMalloc / cudaFree, which may wait for the whole device, these
+// never wait for the kernel of ANOTHER handle — several handles of one process run their rounds concurrently and
+// their kernels wait for each other's mailbox posts (pgn_peer_attach).
+template <class T>
+struct StreamBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = nullptr;
+  void alloc(size_t count, cudaStream_t stream, bool zero = false) {
+    release();
+    n = count; s = stream;
+    if (count == 0) count = 1;
+    CUDA_CHECK(cudaMallocAsync(&p, count * sizeof(T), stream));
+    if (zero) CUDA_CHECK(cudaMemsetAsync(p, 0, count * sizeof(T), stream));
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr; n = 0;
+  }
+  void upload(const T* h, size_t count) {
+    CUDA_CHECK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  void download(T* h, size_t count) const {
+    CUDA_CHECK(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  StreamBuf() = default;
+  StreamBuf(const StreamBuf&) = delete;
+  StreamBuf& operator=(const StreamBuf&) = delete;
+  ~StreamBuf() { release(); }
 };
 
 }  // namespace pgn
@@ -84,6 +137,7 @@ struct pgn_handle {
   unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
   // ---- memory-resident scan path (any d, any number of chains; pgn_memchain.cuh)
   bool force_mem = false;
+  int regcap = 0;                // PGN_REGCAP: register cap of the d > 64 autoMALA team kernel (0: none, 128: room for teams of two)
   pgn::DevBuf<pgn::MemRec> mem_rec;
   pgn::DevBuf<double> mem_vec[10];
   bool mem_allocated = false;
@@ -92,7 +146,8 @@ struct pgn_handle {
   pgn::DevBuf<double> lr_Xr, lr_Xt, lr_y, lr_Theta, lr_Thetat, lr_LL, lr_Res, lr_lik, lr_Gp, lr_G;
   pgn::DevBuf<double> lr_P, lr_G0, lr_SX, lr_SP, lr_SG, lr_TP, lr_TG, lr_FX, lr_FG, lr_QX, lr_QP, lr_QG;
   pgn::DevBuf<pgn::LrChainState> lr_st;
-  pgn::DevBuf<int> lr_n_active;
+  pgn::DevBuf<int> lr_cols;              // compacted list of the chains whose pending point is evaluated in this batch step
+  pgn::DevBuf<pgn::LrControl> lr_ctl;    // device-side counters of the batched evaluation loop
   bool lr_use_dmma = true;       // FP64 tensor-core GEMM (same summation order as the SIMT kernel, see pgn_logreg.cuh)
   double last_gemm_ms = 0.0;     // device time spent in the two GEMMs during the last round
   long long last_batch_steps = 0;
@@ -105,9 +160,9 @@ namespace pgn {
 
 // ---- kernels compiled in the other translation units -------------------------------------------
 // scan kernels (pgn_scan_vec.cu, one object per target family; pgn_scan_misc.cu; pgn_scan_mem.cu)
-void* vec_scan_kernel_toy(int cpl, int ex);
-void* vec_scan_kernel_funnel(int cpl, int ex);
-void* vec_scan_kernel_gmm(int cpl, int ex);
+void* vec_scan_kernel_toy(int cpl, int ex, int regcap);
+void* vec_scan_kernel_funnel(int cpl, int ex, int regcap);
+void* vec_scan_kernel_gmm(int cpl, int ex, int regcap);
 void* ising_scan_kernel();
 void* test_swapper_scan_kernel();
 void* mem_scan_kernel(int target_kind, int ex);

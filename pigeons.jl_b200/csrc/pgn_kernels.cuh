@@ -1320,6 +1320,15 @@ struct TestSwapperChain {
   __device__ __forceinline__ void on_replica_changed() {}
 };
 
+// A chain type with other launch bounds: the same code compiled for fewer registers per thread, so that more warps
+// (wider teams) are co-resident.  MAXT threads per block at most, MINB blocks per SM at least -> 65536 / (MAXT * MINB)
+// registers per thread.
+template <class Base, int MAXT, int MINB>
+struct CappedChain : Base {
+  static constexpr int kMaxThreads = MAXT;
+  static constexpr int kMinBlocksPerSM = MINB;
+};
+
 // ===========================================================================
 // The scan kernel
 // ===========================================================================

@@ -47,7 +47,10 @@ template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS)
 dgemm_km_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, int k_total,
                 int k_chunk, double* __restrict__ C0, double* __restrict__ C1, int ldc, size_t split_stride,
-                const double* __restrict__ yvec, int n_valid_rows) {
+                const double* __restrict__ yvec, int n_valid_rows, const int* __restrict__ n_cols_ptr) {
+  // column tiles beyond the compacted list of this batch step have nothing to multiply (the count lives on the device,
+  // the host launched the full grid without knowing it)
+  if ((int)blockIdx.y * GEMM_BN >= *n_cols_ptr) return;
   extern __shared__ double gemm_smem[];
   double (*As)[GEMM_BK][GEMM_BM] = reinterpret_cast<double (*)[GEMM_BK][GEMM_BM]>(gemm_smem);
   double (*Bs)[GEMM_BK][GEMM_BN] = reinterpret_cast<double (*)[GEMM_BK][GEMM_BN]>(gemm_smem + 2 * GEMM_BK * GEMM_BM);
@@ -165,8 +168,11 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS)
 dgemm_km_dmma_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, int k_total,
-                     int k_chunk, double* __restrict__ C0, double* __restrict__ C1, int ldc, size_t split_stride,
-                     const double* __restrict__ yvec, int n_valid_rows) {
+                int k_chunk, double* __restrict__ C0, double* __restrict__ C1, int ldc, size_t split_stride,
+                const double* __restrict__ yvec, int n_valid_rows, const int* __restrict__ n_cols_ptr) {
+  // column tiles beyond the compacted list of this batch step have nothing to multiply (the count lives on the device,
+  // the host launched the full grid without knowing it)
+  if ((int)blockIdx.y * GEMM_BN >= *n_cols_ptr) return;
   extern __shared__ double gemm_smem[];
   double (*As)[GEMM_BK][DMMA_LD] = reinterpret_cast<double (*)[GEMM_BK][DMMA_LD]>(gemm_smem);
   double (*Bs)[GEMM_BK][DMMA_LD] = reinterpret_cast<double (*)[GEMM_BK][DMMA_LD]>(gemm_smem + 2 * GEMM_BK * DMMA_LD);
@@ -251,11 +257,13 @@ dgemm_km_dmma_kernel(const double* __restrict__ A, int lda, const double* __rest
 // GEMM runs 8 warps per SM, so ~150 dependent FP64 instructions per element there stall the
 // tensor pipe; measured 0.7 ms fused vs 0.2 ms as a separate pass over 128 MB.)
 __global__ void logreg_bernoulli_kernel(double* __restrict__ LL, double* __restrict__ RES, const double* __restrict__ yvec,
-                                        int ld, int n_rows_pad, int n_valid_rows) {
-  const size_t total2 = (size_t)n_rows_pad * ld / 2;
+                                        int ld, int n_rows_pad, int n_valid_rows, const int* __restrict__ n_cols_ptr) {
+  const int ncp = (*n_cols_ptr + GEMM_BN - 1) / GEMM_BN * GEMM_BN;   // the column tiles the GEMM filled
+  const int half = ncp / 2;
+  const size_t total2 = (size_t)n_rows_pad * half;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t e = 2 * i;
-    const int m = (int)(e / ld);
+    const int m = (int)(i / half);
+    const size_t e = (size_t)m * ld + 2 * (i - (size_t)m * half);
     const bool live = m < n_valid_rows;
     const double y = live ? yvec[m] : 0.0;
     const double2 z = *reinterpret_cast<const double2*>(LL + e);
@@ -270,26 +278,29 @@ __global__ void logreg_bernoulli_kernel(double* __restrict__ LL, double* __restr
 
 // lik[r] = sum over row tiles (in order) of the canonical 32-lane tree over the tile's rows.
 // One warp per chain column; LL is [n_pad][ld].
-__global__ void logreg_reduce_ll_kernel(const double* __restrict__ LL, int ld, int n_data, int n_cols,
-                                        double* __restrict__ lik) {
+__global__ void logreg_reduce_ll_kernel(const double* __restrict__ LL, int ld, int n_data, const int* __restrict__ n_cols_ptr,
+                                        const int* __restrict__ cols, double* __restrict__ lik) {
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= n_cols) return;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= *n_cols_ptr) return;
   double total = 0.0;
   for (int t0 = 0; t0 < n_data; t0 += LR_TILE) {
     const int len = min(LR_TILE, n_data - t0);
     double acc = 0.0;
-    for (int i = lane; i < len; i += 32) acc = acc + LL[(size_t)(t0 + i) * ld + r];
+    for (int i = lane; i < len; i += 32) acc = acc + LL[(size_t)(t0 + i) * ld + j];
     total = total + warp_sum(acc);
   }
-  if (lane == 0) lik[r] = total;
+  if (lane == 0) lik[cols[j]] = total;
 }
 
 // G[r][c] = sum over split-K chunks (in order) of Gp[s][c][r]  (also transposes)
 __global__ void logreg_finalize_grad_kernel(const double* __restrict__ Gp, int n_splits, size_t split_stride, int ldp,
-                                            int d_pad, int n_cols, double* __restrict__ G) {
+                                            int d_pad, const int* __restrict__ n_cols_ptr, const int* __restrict__ cols,
+                                            double* __restrict__ G) {
   __shared__ double tile[32][33];
+  const int n_cols = *n_cols_ptr;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  if (r0 >= n_cols) return;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, r = r0 + tx;
@@ -301,7 +312,62 @@ __global__ void logreg_finalize_grad_kernel(const double* __restrict__ Gp, int n
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int r = r0 + i, c = c0 + tx;
-    if (r < n_cols && c < d_pad) G[(size_t)r * d_pad + c] = tile[tx][i];
+    if (r < n_cols && c < d_pad) G[(size_t)cols[r] * d_pad + c] = tile[tx][i];
+  }
+}
+
+// Thetat[c][j] = Theta[cols[j]][c] for the compacted columns j < n_cols; the rest of the last column tile is zero-filled
+__global__ void logreg_gather_transpose_kernel(const double* __restrict__ src, int cols_dim, int ld_src, const int* __restrict__ n_cols_ptr,
+                                               const int* __restrict__ cols, double* __restrict__ dst, int ld_dst) {
+  __shared__ double tile[32][33];
+  const int n_cols = *n_cols_ptr;
+  const int ncp = (n_cols + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  if (r0 >= ncp) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int j = r0 + i, c = c0 + tx;
+    tile[i][tx] = (j < n_cols && c < cols_dim) ? src[(size_t)cols[j] * ld_src + c] : 0.0;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, j = r0 + tx;
+    if (c < cols_dim) dst[(size_t)c * ld_dst + j] = tile[tx][i];
+  }
+}
+
+// The chains whose state machine emitted a point in this batch step, in chain order: cols[0..n_cols).  One block.
+// Also keeps the round's counters (batch steps that evaluated something, columns requested, columns multiplied)
+// and the per-step history the host reads once per chunk of steps.
+__global__ void logreg_compact_kernel(const LrChainState* __restrict__ st, int n_local, int* __restrict__ cols, LrControl* ctl,
+                                      int step_in_chunk) {
+  __shared__ int warp_count[32];
+  __shared__ int base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (int r0 = 0; r0 < n_local; r0 += blockDim.x) {
+    const int r = r0 + tid;
+    const bool want = r < n_local && st[r].phase != LR_DONE && st[r].phase != LR_SCAN_START && st[r].err == 0;
+    const unsigned int m = __ballot_sync(PGN_FULL_MASK, want);
+    if (lane == 0) warp_count[warp] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_count[w];
+    if (want) cols[off + __popc(m & ((1u << lane) - 1u))] = r;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < n_warps; ++w) t += warp_count[w]; base += t; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int n = base;
+    ctl->n_cols = n;
+    ctl->hist[step_in_chunk] = n;
+    if (n > 0) {
+      ctl->steps += 1;
+      ctl->sum_active += n;
+      ctl->sum_gemm_cols += (n + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
+    }
   }
 }
 
@@ -615,7 +681,6 @@ __global__ void logreg_controller_kernel(const __grid_constant__ LrParams P) {
   if (lane == 0) {
     P.st[r] = s;
     if (s.err != 0) atomicCAS(P.error_flag, 0, s.err);
-    else if (s.phase != LR_DONE) atomicAdd(P.n_active, 1);
   }
 }
 

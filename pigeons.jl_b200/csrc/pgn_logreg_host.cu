@@ -45,7 +45,8 @@ void logreg_allocate(pgn_handle* h, const pgn_config* cfg) {
   h->lr_TP.alloc(vec); h->lr_TG.alloc(vec); h->lr_FX.alloc(vec); h->lr_FG.alloc(vec);
   h->lr_QX.alloc(vec); h->lr_QP.alloc(vec); h->lr_QG.alloc(vec);
   h->lr_st.alloc(h->n_local);
-  h->lr_n_active.alloc(1);
+  h->lr_cols.alloc(rp);
+  h->lr_ctl.alloc(1);
   {
     const char* g = std::getenv("PGN_GEMM");   // "simt" selects the DFMA kernel; default: FP64 tensor cores
     h->lr_use_dmma = !(g != nullptr && std::string(g) == "simt");
@@ -56,43 +57,48 @@ void logreg_allocate(pgn_handle* h, const pgn_config* cfg) {
   CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
 }
 
-// Evaluate likelihood and its gradient at the rows of `theta` ([r_pad][d_pad]) for all columns:
-// lr_lik[r], lr_G[r][:].  Returns the device time of the two GEMMs through `gemm_ms`.
+// Evaluate likelihood and its gradient at the rows cols[0..n_cols) of `theta` ([r_pad][d_pad]); results land in
+// lr_lik[cols[j]] and lr_G[cols[j]][:].  n_cols and cols live on the device (LrControl / lr_cols, written by
+// logreg_compact_kernel or by the parity entry point): the host launches the full grids, blocks of column tiles
+// beyond n_cols return at once.  [e0, e1] brackets the two GEMMs (and the Bernoulli / reduction passes between them).
 void logreg_eval_batch(pgn_handle* h, const double* theta, cudaEvent_t e0, cudaEvent_t e1) {
   const int dp = h->d_pad, np = h->lr_n_pad, rp = h->lr_r_pad;
+  const int* ncp = &h->lr_ctl.p->n_cols;
+  const int* cols = h->lr_cols.p;
   {
     dim3 grid((dp + 31) / 32, (rp + 31) / 32), block(32, 8);
-    logreg_transpose_kernel<<<grid, block, 0, h->stream>>>(theta, rp, dp, dp, h->lr_Thetat.p, rp);
+    logreg_gather_transpose_kernel<<<grid, block, 0, h->stream>>>(theta, dp, dp, ncp, cols, h->lr_Thetat.p, rp);
   }
   if (e0) CUDA_CHECK(cudaEventRecord(e0, h->stream));
   {
     dim3 grid(np / GEMM_BM, rp / GEMM_BN, 1);
     if (h->lr_use_dmma)
       dgemm_km_dmma_kernel<0><<<grid, GEMM_THREADS, DMMA_SMEM_BYTES, h->stream>>>(
-          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, nullptr, rp, 0, nullptr, 0);
+          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, nullptr, rp, 0, nullptr, 0, ncp);
     else
       dgemm_km_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
-          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, nullptr, rp, 0, nullptr, 0);
-    logreg_bernoulli_kernel<<<h->n_sms * 8, 256, 0, h->stream>>>(h->lr_LL.p, h->lr_Res.p, h->lr_y.p, rp, np, h->lr_n_data);
+          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, nullptr, rp, 0, nullptr, 0, ncp);
+    logreg_bernoulli_kernel<<<h->n_sms * 8, 256, 0, h->stream>>>(h->lr_LL.p, h->lr_Res.p, h->lr_y.p, rp, np, h->lr_n_data, ncp);
   }
-  logreg_reduce_ll_kernel<<<(rp + 7) / 8, 256, 0, h->stream>>>(h->lr_LL.p, rp, h->lr_n_data, rp, h->lr_lik.p);
+  logreg_reduce_ll_kernel<<<(rp + 7) / 8, 256, 0, h->stream>>>(h->lr_LL.p, rp, h->lr_n_data, ncp, cols, h->lr_lik.p);
   {
     dim3 grid(dp / GEMM_BM, rp / GEMM_BN, h->lr_splits);
     if (h->lr_use_dmma)
       dgemm_km_dmma_kernel<0><<<grid, GEMM_THREADS, DMMA_SMEM_BYTES, h->stream>>>(
-          h->lr_Xr.p, dp, h->lr_Res.p, rp, np, LR_CHUNK, h->lr_Gp.p, nullptr, rp, (size_t)dp * rp, nullptr, 0);
+          h->lr_Xr.p, dp, h->lr_Res.p, rp, np, LR_CHUNK, h->lr_Gp.p, nullptr, rp, (size_t)dp * rp, nullptr, 0, ncp);
     else
       dgemm_km_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
-          h->lr_Xr.p, dp, h->lr_Res.p, rp, np, LR_CHUNK, h->lr_Gp.p, nullptr, rp, (size_t)dp * rp, nullptr, 0);
+          h->lr_Xr.p, dp, h->lr_Res.p, rp, np, LR_CHUNK, h->lr_Gp.p, nullptr, rp, (size_t)dp * rp, nullptr, 0, ncp);
   }
   if (e1) CUDA_CHECK(cudaEventRecord(e1, h->stream));
   {
     dim3 grid((dp + 31) / 32, (rp + 31) / 32), block(32, 8);
-    logreg_finalize_grad_kernel<<<grid, block, 0, h->stream>>>(h->lr_Gp.p, h->lr_splits, (size_t)dp * rp, rp, dp, rp,
+    logreg_finalize_grad_kernel<<<grid, block, 0, h->stream>>>(h->lr_Gp.p, h->lr_splits, (size_t)dp * rp, rp, dp, ncp, cols,
                                                               h->lr_G.p);
   }
   CUDA_CHECK(cudaGetLastError());
 }
+constexpr int LR_EVAL_LAUNCHES = 7;   // gather/transpose, GEMM, Bernoulli, reduce, GEMM, finalize + the compaction before them
 
 void logreg_fill_params(pgn_handle* h, LrParams& P) {
   std::memset(&P, 0, sizeof(P));
@@ -113,7 +119,7 @@ void logreg_fill_params(pgn_handle* h, LrParams& P) {
   P.TP = h->lr_TP.p; P.TG = h->lr_TG.p; P.FX = h->lr_FX.p; P.FG = h->lr_FG.p; P.TX = h->lr_Theta.p;
   P.QX = h->lr_QX.p; P.QP = h->lr_QP.p; P.QG = h->lr_QG.p;
   P.lik = h->lr_lik.p; P.G = h->lr_G.p;
-  P.n_active = h->lr_n_active.p; P.error_flag = h->error_flag.p;
+  P.error_flag = h->error_flag.p;
   P.mail = h->mail.p; P.mail_left = h->mail_left; P.mail_right = h->mail_right; P.slot_bytes = h->slot_bytes;
   P.online_mean = h->online_mean.p; P.online_s2 = h->online_s2.p; P.online_n = h->online_n.p;
   P.timeout_ns = 600ull * 1000ull * 1000ull * 1000ull;   // scans take seconds here; neighbours may lag
@@ -127,8 +133,8 @@ void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<C
   // chain state from the replica arrays
   std::vector<int> ri(nl), rt(nl);
   std::vector<unsigned long long> ctr(nl);
-  h->replica_index.download(ri.data(), nl);
-  h->rng_ctr.download(ctr.data(), nl);
+  h->replica_index.download(ri.data(), nl, h->stream);
+  h->rng_ctr.download(ctr.data(), nl, h->stream);
   std::vector<LrChainState> st(nl);
   std::memset(st.data(), 0, sizeof(LrChainState) * nl);
   for (int i = 0; i < nl; ++i) {
@@ -136,55 +142,63 @@ void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<C
     st[i].replica_index = ri[i]; st[i].ctr = ctr[i]; st[i].rt_state = 0;
     st[i].ls_fwd.value = -INFINITY; st[i].ls_bwd.value = -INFINITY;
   }
-  h->lr_st.upload(st.data(), nl);
+  h->lr_st.upload(st.data(), nl, h->stream);
   CUDA_CHECK(cudaMemsetAsync(h->online_mean.p, 0, sizeof(double) * h->d_pad, h->stream));
   CUDA_CHECK(cudaMemsetAsync(h->online_s2.p, 0, sizeof(double) * h->d_pad, h->stream));
   CUDA_CHECK(cudaMemsetAsync(h->online_n.p, 0, sizeof(long long), h->stream));
-  cudaEvent_t g0, g1;
-  CUDA_CHECK(cudaEventCreate(&g0));
-  CUDA_CHECK(cudaEventCreate(&g1));
+  // The batched evaluation loop.  Per batch step: controller (every chain consumes the evaluation of its pending point
+  // and emits the next one) -> compaction of the chains that emitted a point -> the two GEMMs over those columns only.
+  // The host enqueues LR_STEP_CHUNK steps at a time and looks at the device-side counters once per chunk: steps after
+  // the last chain finished its scan find n_cols = 0 and every kernel of them returns at once.
+  cudaEvent_t ge[2 * LR_STEP_CHUNK];
+  for (auto& e : ge) CUDA_CHECK(cudaEventCreate(&e));
   h->last_gemm_ms = 0.0;
   h->last_batch_steps = 0;
   h->last_launches = 0;
   h->last_active_cols = 0;
   h->last_gemm_cols = 0;
+  CUDA_CHECK(cudaMemsetAsync(h->lr_ctl.p, 0, sizeof(LrControl), h->stream));
   const int wpb = 4, grid = (nl + wpb - 1) / wpb;
   CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
   int flag = 0;
+  LrControl ctl;
   for (int64_t scan = 1; scan <= n_scans && flag == 0; ++scan) {
     P.scan = scan;
-    while (true) {
-      CUDA_CHECK(cudaMemsetAsync(h->lr_n_active.p, 0, sizeof(int), h->stream));
-      logreg_controller_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
-      int active = 0;
-      CUDA_CHECK(cudaMemcpyAsync(&active, h->lr_n_active.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    bool scan_done = false;
+    while (!scan_done && flag == 0) {
+      for (int k = 0; k < LR_STEP_CHUNK; ++k) {
+        logreg_controller_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
+        logreg_compact_kernel<<<1, 1024, 0, h->stream>>>(h->lr_st.p, nl, h->lr_cols.p, h->lr_ctl.p, k);
+        logreg_eval_batch(h, h->lr_Theta.p, ge[2 * k], ge[2 * k + 1]);
+      }
+      h->last_launches += (long long)LR_STEP_CHUNK * (1 + LR_EVAL_LAUNCHES);
+      CUDA_CHECK(cudaMemcpyAsync(&ctl, h->lr_ctl.p, sizeof(LrControl), cudaMemcpyDeviceToHost, h->stream));
       CUDA_CHECK(cudaMemcpyAsync(&flag, h->error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CUDA_CHECK(cudaStreamSynchronize(h->stream));
-      if (flag != 0 || active == 0) break;
-      logreg_eval_batch(h, h->lr_Theta.p, g0, g1);
-      CUDA_CHECK(cudaStreamSynchronize(h->stream));
-      float ms = 0.f;
-      CUDA_CHECK(cudaEventElapsedTime(&ms, g0, g1));
-      h->last_gemm_ms += ms;
-      h->last_batch_steps += 1;
-      h->last_launches += 1 + 7;          // controller + transpose, 2 GEMMs, Bernoulli, reduce, finalize (+ the memset)
-      h->last_active_cols += active;
-      h->last_gemm_cols += h->lr_r_pad;
+      for (int k = 0; k < LR_STEP_CHUNK; ++k) {
+        if (ctl.hist[k] == 0) { scan_done = true; continue; }
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, ge[2 * k], ge[2 * k + 1]));
+        h->last_gemm_ms += ms;
+      }
     }
     if (flag != 0) break;
     logreg_post_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
     logreg_decide_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
-    h->last_launches += 3;              // the last controller pass of the scan + post + decide
+    h->last_launches += 2;
     CUDA_CHECK(cudaMemcpyAsync(&flag, h->error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
   }
   CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   CUDA_CHECK(cudaEventElapsedTime(&total_ms, h->ev0, h->ev1));
-  cudaEventDestroy(g0);
-  cudaEventDestroy(g1);
+  for (auto& e : ge) cudaEventDestroy(e);
+  h->lr_ctl.download(&ctl, 1, h->stream);
+  h->last_batch_steps = ctl.steps;
+  h->last_active_cols = ctl.sum_active;
+  h->last_gemm_cols = ctl.sum_gemm_cols;
   // replica arrays + statistics back
-  h->lr_st.download(st.data(), nl);
+  h->lr_st.download(st.data(), nl, h->stream);
   st_out.assign(nl, ChainStatsDev{});
   for (int i = 0; i < nl; ++i) {
     const LrChainState& s = st[i];
@@ -195,9 +209,9 @@ void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<C
     o.am_n = s.am.n; o.am_mean = s.am.mu; o.rev_n = s.rev.n; o.rev_mean = s.rev.mu;
     o.n_restarts = s.n_restarts; o.n_round_trips = s.n_trips; o.n_points = s.n_points; o.n_ref_evals = s.n_ref;
   }
-  h->replica_index.upload(ri.data(), nl);
-  h->rng_ctr.upload(ctr.data(), nl);
-  h->rt_state.upload(rt.data(), nl);
+  h->replica_index.upload(ri.data(), nl, h->stream);
+  h->rng_ctr.upload(ctr.data(), nl, h->stream);
+  h->rt_state.upload(rt.data(), nl, h->stream);
 }
 
 // parity entry points for LOGREG: batches of r_pad points through the same GEMM path
@@ -212,6 +226,15 @@ void logreg_points(pgn_handle* h, const double* x, int n_points, const double* b
     for (int i = 0; i < m; ++i) std::memcpy(&stage[(size_t)i * dp], x + (size_t)(base + i) * d, sizeof(double) * d);
     h->lr_Theta.upload(stage.data(), stage.size());
     db.upload(beta + base, m);
+    {   // the points are the columns 0..m-1
+      std::vector<int> ident(rp);
+      for (int i = 0; i < rp; ++i) ident[i] = i;
+      h->lr_cols.upload(ident.data(), rp);
+      LrControl c;
+      std::memset(&c, 0, sizeof(c));
+      c.n_cols = m;
+      CUDA_CHECK(cudaMemcpy(h->lr_ctl.p, &c, sizeof(c), cudaMemcpyHostToDevice));
+    }
     logreg_eval_batch(h, h->lr_Theta.p, nullptr, nullptr);
     logreg_points_finish_kernel<<<(m + 3) / 4, 128, 0, h->stream>>>(h->lr_Theta.p, d, dp, m, db.p, h->lr_lik.p, h->lr_G.p,
                                                                    h->cfg.p[5], h->cfg.p[4], lp ? dlp.p : nullptr,

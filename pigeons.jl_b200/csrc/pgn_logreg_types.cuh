@@ -34,6 +34,16 @@ struct LrChainState {
   int accepted;
 };
 
+constexpr int LR_STEP_CHUNK = 8;   // batch steps the host enqueues between two looks at the device-side counters
+
+struct LrControl {   // device-side bookkeeping of the batched evaluation loop
+  int n_cols;                   // columns of the current batch step (chains with a pending point)
+  int hist[LR_STEP_CHUNK];      // n_cols of every step of the chunk in flight
+  long long steps;              // batch steps of this round that evaluated at least one column
+  long long sum_active;         // columns requested, summed over the steps
+  long long sum_gemm_cols;      // columns multiplied (whole tiles of GEMM_BN), summed over the steps
+};
+
 struct LrParams {
   int d, d_pad, n_chains, first_chain, n_local, r_pad;
   int explorer_kind;
@@ -48,7 +58,6 @@ struct LrParams {
   double *QX, *QP, *QG;   // the previous trial's point, momentum and gradient (grow_step_size steps back to it)
   const double* lik;   // [r_pad]
   const double* G;     // [r_pad][d_pad] likelihood gradient at TX
-  int* n_active;
   int* error_flag;
   // swap / logs
   char* mail; char* mail_left; char* mail_right; unsigned long long slot_bytes;

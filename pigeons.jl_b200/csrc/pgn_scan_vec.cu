@@ -36,7 +36,11 @@ void eval_points_launch(int grid, int block, size_t smem, cudaStream_t s, const 
 }
 #else
 template <int CPL>
-void* team_kernel_for(int ex) {
+void* team_kernel_for(int ex, int regcap) {
+  // four coordinates per lane at 128 registers per thread (instead of 255): twice the co-resident warps, i.e. room for
+  // teams of two where the uncapped kernel fits one warp per chain (BASELINE config 3: 1024 chains of d = 128)
+  if (CPL == 4 && PGN_TK != PGN_TARGET_FUNNEL && ex == PGN_EXPLORER_AUTOMALA && regcap == 128)
+    return scan_kernel_ptr<CappedChain<VecChain<PGN_TK, (CPL == 4 ? 4 : 1), PGN_EXPLORER_AUTOMALA>, 128, 4>>();
   switch (ex) {
     case PGN_EXPLORER_AUTOMALA: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_AUTOMALA>>();
     case PGN_EXPLORER_SLICE_THEN_AUTOMALA: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_SLICE_THEN_AUTOMALA>>();
@@ -74,11 +78,11 @@ void PGN_FAMILY(launch_eval_points)(int cpl, int grid, int block, size_t smem, c
   }
 }
 #else
-void* PGN_FAMILY(vec_team_kernel)(int cpl, int ex) {
+void* PGN_FAMILY(vec_team_kernel)(int cpl, int ex, int regcap) {
   switch (cpl) {
-    case 1: return team_kernel_for<1>(ex);
-    case 2: return team_kernel_for<2>(ex);
-    case 4: return team_kernel_for<4>(ex);
+    case 1: return team_kernel_for<1>(ex, regcap);
+    case 2: return team_kernel_for<2>(ex, regcap);
+    case 4: return team_kernel_for<4>(ex, regcap);
     default: return nullptr;
   }
 }
