@@ -185,9 +185,19 @@ def one_step(pt, scans):
     return eng.run_round(scans)
 
 
-def config_dict(name, gpus, scans, burn):
+def ladder_chains(name, gpus, scaling):
+    cpg = CONFIGS[name]["chains_per_gpu"]
+    return cpg if scaling == "strong" else cpg * gpus
+
+
+def config_dict(name, gpus, scans, burn, scaling="weak"):
     cfg = CONFIGS[name]
     cpg = cfg["chains_per_gpu"]
+    if scaling == "strong":
+        return {"workload": cfg["workload"], "name": name, "n_chains": cpg, "dim": cfg["dim"], "explorer": cfg["explorer"],
+                "scans_per_step": scans, "burn_in_rounds": burn, "parallelism": f"chains/{gpus}",
+                "scan_unit": f"one PT scan of the {cpg}-chain ladder, split contiguously over the N GPUs (strong scaling)",
+                "l2": "flushed between timed steps (256 MiB write); the working set is register-resident"}
     return {"workload": cfg["workload"], "name": name, "n_chains": cpg * gpus, "dim": cfg["dim"], "explorer": cfg["explorer"],
             "scans_per_step": scans, "burn_in_rounds": burn, "parallelism": f"chains/{gpus}",
             "scan_unit": f"one PT scan of {cpg} chains; with N GPUs the ladder has {cpg}*N chains and value = N * ladder scans/s",
@@ -284,16 +294,18 @@ def reference_record(pg, name, args, budget_s):
     """`--impl reference` for one config: the oracle port on the host cores, same config dict as the GPU arm."""
     cfg = CONFIGS[name]
     gpus = max(args.gpus, 1)
-    n_chains = cfg["chains_per_gpu"] * gpus
+    n_chains = ladder_chains(name, gpus, args.scaling)
     scans_cfg = args.scans if (args.scans and name == args.config) else cfg["scans"]
     burn = args.burn_rounds if (args.burn_rounds is not None and name == args.config) else cfg["burn"]
-    config = config_dict(name, gpus, scans_cfg, burn)
+    config = config_dict(name, gpus, scans_cfg, burn, args.scaling)
+    if args.scaling == "strong":
+        gpus = 1          # value = scans/s of the one ladder
     if name == "c5":
         b = cpu_baseline_c5(pg, args.cpu_threads)
         value = b["value"] / gpus * gpus      # ladder rate x N GPUs' worth of chains = the same extrapolation
         return {"impl": "reference", "metric": "pt_scans_per_s", "value": value, "unit": "scans/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * scans_cfg / b["value"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": b, "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     pt, lib, C = cpu_oracle_problem(pg, name, n_chains, burn)
     n_threads, per_scan = pick_threads(pt, lib, C, args.cpu_threads)
@@ -310,7 +322,7 @@ def reference_record(pg, name, args, budget_s):
     value = ladder * gpus
     return {"impl": "reference", "metric": "pt_scans_per_s", "value": value, "unit": "scans/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * scans_cfg / ladder, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": value, "unit": "scans/s", "cores": n_threads, "kind": "port", "host_threads": host_threads(),
                              "sample": f"{args.steps} timed steps, each a bounded sample of {sample} of the step's {scans_cfg} "
                                        f"scans of the {n_chains}-chain ladder (ms_per_step is scaled to the full step), after "
@@ -326,7 +338,8 @@ def b200_record(pg, torch, name, args, lib, comm, rank, world, local_rank, steps
     cfg = CONFIGS[name]
     gpus = max(args.gpus, 1)
     cpg = cfg["chains_per_gpu"]
-    n_chains = cpg * gpus
+    strong = args.scaling == "strong"
+    n_chains = ladder_chains(name, gpus, args.scaling)
     scans = args.scans if (args.scans and name == args.config) else cfg["scans"]
     burn = args.burn_rounds if (args.burn_rounds is not None and name == args.config) else cfg["burn"]
     pt = build_problem(pg, name, lib, n_chains, comm, local_rank, burn)
@@ -376,11 +389,11 @@ def b200_record(pg, torch, name, args, lib, comm, rank, world, local_rank, steps
     if rank == 0:
         total_scans = steps * scans
         ladder_scans_per_s = total_scans / (kernel_ms * 1e-3)
-        value = ladder_scans_per_s * gpus
-        e2e_value = total_scans / wall_s * gpus
+        value = ladder_scans_per_s * (1 if strong else gpus)
+        e2e_value = total_scans / wall_s * (1 if strong else gpus)
         peak, peak_src = read_peaks()
         launch_ms = kernel_ms / steps
-        b_scan = algorithmic_bytes_per_scan(name)
+        b_scan = algorithmic_bytes_per_scan(name) * (pt.engine.n_local / cpg)      # this GPU's chains
         data_bytes = 0.0
         if name == "c5" and batch_steps > 0:
             # SURVEY §8(d) data term P*|D|: every batched evaluation streams X (2 GiB) once per GEMM
@@ -407,8 +420,8 @@ def b200_record(pg, torch, name, args, lib, comm, rank, world, local_rank, steps
                                  "FP64 tensor pipe (DMMA): compute-bound dense contraction"}
         line = {
             "metric": "pt_scans_per_s", "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(name, gpus, scans, burn),
+            "warmup": warmup, "ms_per_step": launch_ms, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(name, gpus, scans, burn, args.scaling),
             "ladder_scans_per_s": ladder_scans_per_s,
             "log_potential_evals_per_s": {"ref_equiv": evals / (kernel_ms * 1e-3), "unique_points": pts / (kernel_ms * 1e-3),
                                           "note": "ref_equiv = log_potential/logdensity[_and_gradient] calls the reference code "
@@ -455,6 +468,9 @@ def main():
     ap.add_argument("--config", default=HEADLINE, choices=sorted(CONFIGS), help=f"headline BASELINE.json config (default {HEADLINE})")
     ap.add_argument("--also", default=None, help=f"configs carried as extra records in the same line (default '{DEFAULT_ALSO}' "
                                                  "when --config is not given, else none)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): chains per GPU fixed, the ladder grows with N; strong: the BASELINE ladder of the config "
+                         "(chains_per_gpu chains in total) is split over the N GPUs")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU baseline (0 = pick the fastest of a sweep)")
     args = ap.parse_args()
     explicit = any(a == "--config" or a.startswith("--config=") for a in sys.argv[1:])

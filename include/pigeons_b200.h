@@ -73,6 +73,10 @@ extern "C" {
 #define PGN_PRECOND_DIAGONAL 1
 #define PGN_PRECOND_MIX_DIAGONAL 2
 
+/* ---- recorder accumulation order (pgn_config.recorder_order) --------------- */
+#define PGN_RECORDERS_PER_REPLICA 0
+#define PGN_RECORDERS_PER_CHAIN 1
+
 typedef struct pgn_handle pgn_handle;
 
 /* Static configuration of one engine instance (one GPU / one rank).
@@ -103,6 +107,15 @@ typedef struct pgn_config {
   const double* log_weights;  /* GMM: [K] log mixture weights (copied)          */
   const double* data_x;       /* LOGREG: [n_data][d] row-major (copied)         */
   const double* data_y;       /* LOGREG: [n_data] labels in {0,1} (copied)      */
+  /* How the float statistics of a round are accumulated (their counts and every integer are the same either way):
+   *  PGN_RECORDERS_PER_REPLICA (0, default): as the reference does — every replica accumulates its own recorders,
+   *    keyed by chain / pair, and the round ends with reduce_recorders!: a binary-tree merge over replica indices
+   *    (src/recorders/recorders.jl:88-120, src/mpi_utils/Entangler.jl:214-277).  Needs n_chains x n_local entries
+   *    of device memory.
+   *  PGN_RECORDERS_PER_CHAIN (1): one accumulator per chain / pair, fitted in scan order; O(n_local) memory.  The
+   *    means differ from the reference's at rounding level. */
+  int32_t recorder_order;
+  int32_t reserved_;
 } pgn_config;
 
 /* Explorer parameters; mirrors the @kwdef explorer structs

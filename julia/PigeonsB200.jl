@@ -67,6 +67,9 @@ const PGN_PRECOND_IDENTITY = 0
 const PGN_PRECOND_DIAGONAL = 1
 const PGN_PRECOND_MIX_DIAGONAL = 2
 
+const PGN_RECORDERS_PER_REPLICA = 0
+const PGN_RECORDERS_PER_CHAIN = 1
+
 # --------------------------------------------------------------------------------------------------------------------
 # struct mirrors, field for field (checked against the header by tests/test_abi_layout.py)
 # --------------------------------------------------------------------------------------------------------------------
@@ -85,6 +88,8 @@ struct PgnConfig
     log_weights::Ptr{Float64}
     data_x::Ptr{Float64}
     data_y::Ptr{Float64}
+    recorder_order::Int32
+    reserved_::Int32
 end
 
 struct PgnExplorerParams
@@ -191,6 +196,7 @@ connected with `pgn_peer_attach`, so no MPI is involved.
 Base.@kwdef struct B200 <: Submission
     n_gpus::Int = 1
     devices::Vector{Int} = collect(0:(n_gpus - 1))
+    recorder_order::Int = PGN_RECORDERS_PER_REPLICA      # the reference's per-replica recorders + tree merge (recorders.jl:88-120)
 end
 
 """
@@ -358,7 +364,7 @@ function create_b200_replicas(inputs::Inputs, shared::Shared, on::B200)
     handles, firsts, counts = Ptr{Cvoid}[], Int[], Int[]
     for (rank, device) in enumerate(on.devices)
         cfg = PgnConfig(PGN_ABI_VERSION, kind, dim, N, inputs.seed, rank - 1, length(on.devices), device, n_modes, p,
-                        ptr(means), ptr(log_w), ptr(data_x), ptr(data_y))
+                        ptr(means), ptr(log_w), ptr(data_x), ptr(data_y), on.recorder_order, 0)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         GC.@preserve means log_w data_x data_y begin
             err = Ref{Cstring}(C_NULL)

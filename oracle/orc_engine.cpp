@@ -18,16 +18,16 @@
 //     instead of SplittableRandom + ziggurat (north star).
 //   * sums over coordinates use the canonical 32-leaf tree (orc_math.hpp)
 //     instead of Julia's pairwise/SIMD `sum` (unreproducible).
-//   * recorder statistics are accumulated per chain / per pair in scan order,
-//     not per replica followed by a replica-index tree merge
-//     (src/recorders/recorders.jl:88-120): identical counts and integer stats,
-//     float means differ from Pigeons at rounding level only.
+//   * (recorder_order = PGN_RECORDERS_PER_CHAIN only) recorder statistics accumulated per
+//     chain / per pair in scan order; the default follows the reference: per replica,
+//     then the replica-index tree merge of reduce_recorders! (recorders.jl:88-120).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../include/pigeons_b200.h"
@@ -73,11 +73,25 @@ struct MeanAcc {   // OnlineStatsBase.Mean with EqualWeight
   int64_t n = 0;
   double mu = 0.0;
   void fit(double x) { n += 1; mu = mu + (1.0 / (double)n) * (x - mu); }
+  // OnlineStatsBase._merge!(::Mean, ::Mean): o.n += o2.n; o.mu = smooth(o.mu, o2.mu, o2.n / o.n), smooth(a, b, g) = a + g (b - a).
+  // A statistic that was never fitted does not exist in the reference's GroupBy: merging with it is a copy.
+  void merge(const MeanAcc& o) {
+    if (o.n == 0) return;
+    if (n == 0) { *this = o; return; }
+    n += o.n;
+    mu = mu + ((double)o.n / (double)n) * (o.mu - mu);
+  }
 };
 struct LogSumAcc {  // src/recorders/LogSum.jl:1-24
   int64_t n = 0;
   double value = -INF;
   void fit(double y) { value = logaddexp_(value, y); n += 1; }
+  void merge(const LogSumAcc& o) {   // LogSum.jl:15-18
+    if (o.n == 0) return;
+    if (n == 0) { *this = o; return; }
+    value = logaddexp_(value, o.value);
+    n += o.n;
+  }
 };
 struct VarAcc {   // OnlineStatsBase.Variance with EqualWeight
   int64_t n = 0;
@@ -90,6 +104,17 @@ struct VarAcc {   // OnlineStatsBase.Variance with EqualWeight
     s2 = s2 + g * ((x - mu) * (x - mu_old) - s2);
   }
   double value() const { return n > 1 ? s2 * ((double)n / (double)(n - 1)) : 1.0; }
+  // OnlineStatsBase._merge!(::Variance, ::Variance): g = o2.n / (o.n += o2.n); delta = o2.mu - o.mu;
+  // o.s2 = smooth(o.s2, o2.s2, g) + delta^2 g (1 - g); o.mu = smooth(o.mu, o2.mu, g)
+  void merge(const VarAcc& o) {
+    if (o.n == 0) return;
+    if (n == 0) { *this = o; return; }
+    n += o.n;
+    const double g = (double)o.n / (double)n;
+    const double delta = o.mu - mu;
+    s2 = (s2 + g * (o.s2 - s2)) + ((delta * delta) * g) * (1.0 - g);
+    mu = mu + g * (o.mu - mu);
+  }
 };
 
 struct ChainStats {
@@ -99,7 +124,31 @@ struct ChainStats {
   int64_t n_steps = 0;        // explorer_n_steps (Sum)
   MeanAcc am;                 // am_factors
   MeanAcc rev;                // reversibility_rate
+  void merge(const ChainStats& o) {   // merge of the GroupBy entries of one key (Sum: integer addition)
+    swap_acc.merge(o.swap_acc); ls_fwd.merge(o.ls_fwd); ls_bwd.merge(o.ls_bwd);
+    expl_acc.merge(o.expl_acc); n_steps += o.n_steps; am.merge(o.am); rev.merge(o.rev);
+  }
 };
+
+// The recorders ONE replica carries during a round (src/recorders/recorders.jl:1-12: "each recorders object keeps track
+// of only the statistics for one replica"), restricted to the statistics of this path: the GroupBy recorders keyed by
+// chain (pair statistics under the pair's lower chain) and the target-chain online statistics.
+struct ReplicaRecorders {
+  std::unordered_map<int, ChainStats> by_chain;   // key: chain - 1
+  std::vector<VarAcc> online;                     // _transformed_online; empty until the replica visits the target chain
+};
+// merge_recorders (recorders.jl:122-131) -> Base.merge of every recorder: GroupBy merges entry by entry, inserting the
+// keys the left side lacks; OnlineStateRecorder.merge (OnlineStateRecorder.jl:44-58) copies when one side is empty.
+void merge_recorders(ReplicaRecorders& a, const ReplicaRecorders& b) {
+  for (const auto& kv : b.by_chain) {
+    auto it = a.by_chain.find(kv.first);
+    if (it == a.by_chain.end()) a.by_chain.emplace(kv.first, kv.second);
+    else it->second.merge(kv.second);
+  }
+  if (a.online.empty()) a.online = b.online;
+  else if (!b.online.empty())
+    for (size_t c = 0; c < a.online.size(); ++c) a.online[c].merge(b.online[c]);
+}
 
 // Explore-phase events are produced inside the (possibly threaded) replica
 // loop; they only touch the stats slot of the replica's own chain, and every
@@ -114,7 +163,13 @@ struct Engine {
   bool have_std = false;
   std::vector<double> beta;            // schedule, size N
   std::vector<Replica> replicas;       // sorted by chain between scans
-  std::vector<ChainStats> stats;       // per chain (index chain-1)
+  std::vector<ChainStats> stats;       // per chain (index chain-1): the reduced recorders
+  std::vector<ReplicaRecorders> rec;   // per replica (index replica_index-1), PGN_RECORDERS_PER_REPLICA
+  bool per_replica() const { return cfg.recorder_order == PGN_RECORDERS_PER_REPLICA; }
+  // the recorder entry the replica writes to: its own (keyed by its current chain), or the chain's shared one
+  ChainStats& st_of(const Replica& r) {
+    return per_replica() ? rec[r.replica_index - 1].by_chain[r.chain - 1] : stats[r.chain - 1];
+  }
   int64_t n_restarts = 0, n_round_trips = 0;
   std::vector<VarAcc> online;          // per dim, target chain
   int scan = 0;
@@ -727,7 +782,7 @@ struct Engine {
   // ------------------------------------------------------------------ explore!
   // explore!(pt, replica, explorer)  (src/pt/pigeons.jl:101-132)
   void explore(Replica& r) {
-    ChainStats& st = stats[r.chain - 1];
+    ChainStats& st = st_of(r);
     const bool is_reference = (r.chain == 1 && N() > 1);   // DEO.jl:13
     if (cfg.target_kind == PGN_TARGET_TEST_SWAPPER) return;
     if (is_reference) {
@@ -790,6 +845,7 @@ struct RoundLogs {
 void run_round(Engine& E, int64_t n_scans, pgn_round_out* out) {
   const int N = E.N(), d = E.d();
   E.stats.assign(N, ChainStats{});
+  E.rec.assign(E.per_replica() ? N : 0, ReplicaRecorders{});
   E.n_restarts = E.n_round_trips = 0;
   E.online.assign(d, VarAcc{});
   for (auto& r : E.replicas) { r.rt_state = 0; r.ref_equiv_evals = 0; }   // recorders are emptied every round (recorders.jl:113-118)
@@ -819,8 +875,14 @@ void run_round(Engine& E, int64_t n_scans, pgn_round_out* out) {
       if (E.cfg.target_kind == PGN_TARGET_ISING) E.ising_sync_x(rt);
       // online statistics are kept for vector states only (IsingState is not a
       // continuous-variable state; OnlineStateRecorder.jl:87-110 does not apply)
-      if (E.cfg.target_kind != PGN_TARGET_ISING)
-        for (int c = 0; c < d; ++c) E.online[c].fit(rt.x[c]);
+      if (E.cfg.target_kind != PGN_TARGET_ISING) {
+        std::vector<VarAcc>* on = &E.online;
+        if (E.per_replica()) {
+          on = &E.rec[rt.replica_index - 1].online;
+          if (on->empty()) on->assign(d, VarAcc{});
+        }
+        for (int c = 0; c < d; ++c) (*on)[c].fit(rt.x[c]);
+      }
       if (out->target_trace) std::memcpy(out->target_trace + (size_t)(s - 1) * d, rt.x.data(), sizeof(double) * d);
     }
     // ---- swap!  (swap.jl:6-26)
@@ -848,7 +910,7 @@ void run_round(Engine& E, int64_t n_scans, pgn_round_out* out) {
           } else {
             double e = exp_(mine.lr + other.lr);  // swap_acceptance_probability :88
             acceptance_pr = 1.0 < e ? 1.0 : e;
-            ChainStats& st = E.stats[my_chain - 1];   // record_swap_stats! :59-66
+            ChainStats& st = E.st_of(mine);           // record_swap_stats! :59-66, by the replica holding the lower chain (swap.jl:119-121)
             st.swap_acc.fit(acceptance_pr);
             st.ls_fwd.fit(mine.lr);
             st.ls_bwd.fit(other.lr);
@@ -868,6 +930,17 @@ void run_round(Engine& E, int64_t n_scans, pgn_round_out* out) {
     }
   }
   for (auto& r : E.replicas) total_ref_evals += r.ref_equiv_evals;
+
+  // ---- reduce_recorders! (recorders.jl:88-120): replicas sorted by replica_index, then the binary tree of
+  // reduce_deterministically (Entangler.jl:214-277): at the level with spacing s, entry i absorbs entry i + s for
+  // i = 1, 1 + 2s, ...; an unpaired last entry waits for the next level.
+  if (E.per_replica()) {
+    std::vector<ReplicaRecorders>& work = E.rec;
+    for (int spacing = 1; spacing < N; spacing *= 2)
+      for (int i = 0; i + spacing < N; i += 2 * spacing) merge_recorders(work[i], work[i + spacing]);
+    for (const auto& kv : work[0].by_chain) E.stats[kv.first] = kv.second;
+    if (!work[0].online.empty()) E.online = work[0].online;
+  }
 
   // ---- outputs
   for (int c = 0; c < N; ++c) {

@@ -34,6 +34,7 @@ EXPLORER_NONE, EXPLORER_TOY, EXPLORER_SLICE, EXPLORER_AUTOMALA, EXPLORER_ISING_M
 EXPLORER_SLICE_THEN_AUTOMALA = 6
 MAX_MIX = 4
 PRECOND_IDENTITY, PRECOND_DIAGONAL, PRECOND_MIX_DIAGONAL = 0, 1, 2
+RECORDERS_PER_REPLICA, RECORDERS_PER_CHAIN = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)
@@ -48,6 +49,7 @@ class pgn_config(C.Structure):
         ("seed", C.c_int64), ("rank", C.c_int32), ("world_size", C.c_int32), ("device", C.c_int32),
         ("n_modes", C.c_int32), ("p", C.c_double * 8),
         ("means", _dp), ("log_weights", _dp), ("data_x", _dp), ("data_y", _dp),
+        ("recorder_order", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -217,7 +219,7 @@ class Engine:
 
     def __init__(self, lib: EngineLib, *, target_kind: int, dim: int, n_chains: int, seed: int,
                  p=(), means=None, log_weights=None, data_x=None, data_y=None, n_modes: int = 0,
-                 rank: int = 0, world_size: int = 1, device: int = 0):
+                 rank: int = 0, world_size: int = 1, device: int = 0, recorder_order: int = RECORDERS_PER_REPLICA):
         self.lib = lib
         self.dim = int(dim)
         self.n_chains = int(n_chains)
@@ -229,6 +231,7 @@ class Engine:
         cfg.seed = seed
         cfg.rank, cfg.world_size, cfg.device = rank, world_size, device
         cfg.n_modes = n_modes
+        cfg.recorder_order = recorder_order
         for i, v in enumerate(p):
             cfg.p[i] = float(v)
         self._keep = []

@@ -58,6 +58,9 @@ void fill_params(pgn_handle* h, Params& P) {
   P.online_mean = h->online_mean.p; P.online_s2 = h->online_s2.p; P.online_n = h->online_n.p;
   P.error_flag = h->error_flag.p;
   P.timeout_ns = h->timeout_ns;
+  const bool per_replica = h->recorder_order == PGN_RECORDERS_PER_REPLICA;
+  P.rec_table = per_replica ? h->rec_table.p : nullptr;
+  P.on_table = per_replica ? h->on_table.p : nullptr;
 }
 
 void* select_scan_kernel(const pgn_handle* h) {
@@ -214,7 +217,12 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
       h->force_mem = fm != nullptr && std::string(fm) == "1";
       const char* rc = std::getenv("PGN_REGCAP");
       h->regcap = rc ? std::atoi(rc) : 0;
+      const char* to = std::getenv("PGN_TIMEOUT_S");      // hand-shake spin limit (default 20 s; the LOGREG path uses 30x)
+      if (to && std::atof(to) > 0) h->timeout_ns = (unsigned long long)(std::atof(to) * 1e9);
     }
+    if (cfg->recorder_order != PGN_RECORDERS_PER_REPLICA && cfg->recorder_order != PGN_RECORDERS_PER_CHAIN)
+      throw CudaError{PGN_ERR_INVALID, "recorder_order must be PGN_RECORDERS_PER_REPLICA (0) or PGN_RECORDERS_PER_CHAIN (1)"};
+    h->recorder_order = cfg->recorder_order;
     // the scan kernel's flag-in-data words need 16 bytes per payload double (8 header words + 2 words per double);
     // the logistic-regression and memory-resident kernels use the first 64 + 8 * pay_doubles bytes of a slot
     h->slot_bytes = (size_t)MAIL_HDR_BYTES + (size_t)h->pay_doubles * 2 * sizeof(double);
@@ -229,6 +237,16 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
     h->online_mean.alloc(h->d_pad); h->online_s2.alloc(h->d_pad); h->online_n.alloc(1);
     h->mail.alloc(h->mail_bytes);
     h->std_devs.alloc(std::max(d, 1));
+    if (h->recorder_order == PGN_RECORDERS_PER_REPLICA) {
+      // every replica's recorder entry for every local chain, and (for vector states) its target-chain online statistics
+      const size_t rec_bytes = (size_t)cfg->n_chains * (size_t)std::max(nl, 1) * sizeof(RecEntry);
+      const size_t on_bytes = (size_t)cfg->n_chains * (size_t)h->d_pad * sizeof(OnEntry);
+      if (rec_bytes + on_bytes > (size_t)48 << 30)
+        throw CudaError{PGN_ERR_INVALID, "per-replica recorders need n_chains x n_local entries (> 48 GiB here): use "
+                                         "recorder_order = PGN_RECORDERS_PER_CHAIN"};
+      h->rec_table.alloc((size_t)cfg->n_chains * std::max(nl, 1), false);
+      h->on_table.alloc((size_t)cfg->n_chains * h->d_pad, false);
+    }
     if (cfg->target_kind == PGN_TARGET_GMM) {
       // staged layout: [KMAX_MODES][d_pad] means (zero rows beyond K) + KMAX_MODES log weights (-inf beyond K)
       std::vector<double> padded((size_t)KMAX_MODES * h->d_pad + KMAX_MODES, 0.0);
@@ -425,6 +443,12 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     const bool owns_target = (h->first_chain + nl - 1 == h->cfg.n_chains);
     if (out->target_trace && owns_target) { d_trace.alloc((size_t)n_scans * std::max(d, 1), h->stream); P.target_trace = d_trace.p; }
     CUDA_CHECK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int), h->stream));
+    const bool per_replica = h->recorder_order == PGN_RECORDERS_PER_REPLICA;
+    const bool vec_online = h->cfg.target_kind != PGN_TARGET_ISING && h->cfg.target_kind != PGN_TARGET_TEST_SWAPPER && d > 0;
+    if (per_replica && n_scans > 0) {   // recorders are emptied every round (recorders.jl:113-118)
+      CUDA_CHECK(cudaMemsetAsync(h->rec_table.p, 0, h->rec_table.n * sizeof(RecEntry), h->stream));
+      if (owns_target && vec_online) CUDA_CHECK(cudaMemsetAsync(h->on_table.p, 0, h->on_table.n * sizeof(OnEntry), h->stream));
+    }
     float ms = 0.f;
     std::vector<ChainStatsDev> st(nl);
     if (is_logreg) {
@@ -540,7 +564,30 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
       }
     }
     int flag = 0;
+    int merge_launches = 0;
     h->error_flag.download(&flag, 1, h->stream);
+    if (per_replica && n_scans > 0 && flag == 0) {
+      // reduce_recorders!: the tree merge over replica indices replaces the float statistics of every chain
+      CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+      launch_merge_recorders(h->stream, h->rec_table.p, h->cfg.n_chains, nl, h->stats.p);
+      if (owns_target && vec_online)
+        launch_merge_online(h->stream, h->on_table.p, h->cfg.n_chains, d, h->d_pad, h->online_mean.p, h->online_s2.p, h->online_n.p);
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+      std::vector<ChainStatsDev> merged(nl);
+      h->stats.download(merged.data(), nl, h->stream);
+      float merge_ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&merge_ms, h->ev0, h->ev1));
+      ms += merge_ms;                         // part of the round's device time
+      merge_launches = owns_target && vec_online ? 2 : 1;
+      for (int i = 0; i < nl; ++i) {
+        ChainStatsDev& s = st[i];
+        const ChainStatsDev& m = merged[i];
+        s.swap_n = m.swap_n; s.swap_mean = m.swap_mean; s.ls_fwd = m.ls_fwd; s.ls_bwd = m.ls_bwd;
+        s.expl_acc_n = m.expl_acc_n; s.expl_acc_mean = m.expl_acc_mean;
+        s.am_n = m.am_n; s.am_mean = m.am_mean; s.rev_n = m.rev_n; s.rev_mean = m.rev_mean;
+      }
+    }
 
     if (const char* dump = std::getenv("PGN_TIMING_DUMP")) {   // diagnostics: per-chain explore / partner-wait clocks of this round
       if (FILE* f = std::fopen(dump, "a")) {
@@ -573,7 +620,7 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     out->kernel_ms = (double)ms;
     out->gemm_ms = is_logreg ? h->last_gemm_ms : 0.0;
     out->batch_steps = is_logreg ? h->last_batch_steps : 0;
-    out->n_launches = is_logreg ? h->last_launches : (n_scans > 0 ? 1 : 0);
+    out->n_launches = (is_logreg ? h->last_launches : (n_scans > 0 ? 1 : 0)) + merge_launches;
     out->active_columns = is_logreg ? h->last_active_cols : 0;
     out->gemm_columns = is_logreg ? h->last_gemm_cols : 0;
     out->online_n = 0;

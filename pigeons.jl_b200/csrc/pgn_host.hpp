@@ -137,6 +137,9 @@ struct pgn_handle {
   unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
   // ---- memory-resident scan path (any d, any number of chains; pgn_memchain.cuh)
   bool force_mem = false;
+  int recorder_order = PGN_RECORDERS_PER_REPLICA;
+  pgn::DevBuf<pgn::RecEntry> rec_table;   // per-replica recorders [n_chains][n_local] (PGN_RECORDERS_PER_REPLICA)
+  pgn::DevBuf<pgn::OnEntry> on_table;     // target-chain online statistics per replica [n_chains][d_pad]
   int regcap = 0;                // PGN_REGCAP: register cap of the d > 64 autoMALA team kernel (0: none, 128: room for teams of two)
   pgn::DevBuf<pgn::MemRec> mem_rec;
   pgn::DevBuf<double> mem_vec[10];
@@ -178,6 +181,8 @@ void launch_eval_points_mem(int target_kind, int grid, int block, cudaStream_t s
 void launch_init_toy(int grid, int block, cudaStream_t s, const Params& P);
 void launch_ising_lp(int grid, int block, cudaStream_t s, const Params& P, const double* xs, const double* betas, int n,
                      double* lp);
+void launch_merge_recorders(cudaStream_t s, RecEntry* table, int n_replicas, int n_local, ChainStatsDev* out);
+void launch_merge_online(cudaStream_t s, OnEntry* table, int n_replicas, int d, int d_pad, double* mean, double* s2, long long* n_out);
 void launch_test_math(int grid, int block, int op, const double* in, double* out, long long n, unsigned int seed_lo,
                       unsigned int seed_hi, unsigned int replica_index);
 // logistic regression (pgn_logreg_host.cu)

@@ -45,6 +45,39 @@ struct LogSumAcc {  // src/recorders/LogSum.jl:1-24
   __device__ __forceinline__ void fit(double y) { value = logaddexp_<COMPACT>(value, y); n += 1; }
 };
 
+// OnlineStatsBase._merge! for the statistics of this path (a statistic that was never fitted does not exist in the
+// reference's GroupBy: merging with it is a copy)
+__device__ __forceinline__ void merge_mean(MeanAcc& a, const MeanAcc& b) {
+  if (b.n == 0) return;
+  if (a.n == 0) { a = b; return; }
+  a.n += b.n;
+  a.mu = a.mu + ((double)b.n / (double)a.n) * (b.mu - a.mu);
+}
+__device__ __forceinline__ void merge_logsum(LogSumAcc& a, const LogSumAcc& b) {   // src/recorders/LogSum.jl:15-18
+  if (b.n == 0) return;
+  if (a.n == 0) { a = b; return; }
+  a.value = logaddexp_(a.value, b.value);
+  a.n += b.n;
+}
+
+// Per-replica recorders (PGN_RECORDERS_PER_REPLICA): what replica r has accumulated while it sat at local chain c lives
+// in rec_table[(r - 1) * n_local + c].  The warps of a chain keep the entry of the replica they currently hold in
+// registers and exchange it for the incoming replica's entry when a swap is accepted; the round ends with the
+// reference's tree merge over replica indices (merge_recorders_kernel).
+struct RecEntry {   // 96 bytes
+  MeanAcc expl_acc, am, rev, swap_acc;
+  LogSumAcc ls_fwd, ls_bwd;
+};
+struct OnEntry {    // OnlineStatsBase.Variance of one coordinate, as one replica accumulated it at the target chain
+  long long n;
+  double mu, s2;
+};
+__device__ __forceinline__ LogSumAcc load_logsum(const LogSumAcc* p) {
+  LogSumAcc v = *p;
+  if (v.n == 0) v.value = -PGN_INF;   // the table is zero-filled; an absent LogSum starts at -inf
+  return v;
+}
+
 struct ChainStatsDev {   // one per local chain, written when the round ends
   long long swap_n; double swap_mean; double ls_fwd; double ls_bwd;
   long long expl_acc_n; double expl_acc_mean; long long n_steps;
@@ -96,6 +129,9 @@ struct Params {
   int* index_process; double* swap_lr; double* swap_u; unsigned char* swap_accept; double* target_trace;
   int* error_flag;
   unsigned long long timeout_ns;
+  // per-replica recorders (null: one accumulator per chain, fitted in scan order)
+  RecEntry* rec_table;     // [n_chains replicas][n_local]
+  OnEntry* on_table;       // [n_chains replicas][d_pad], used by the shard owning chain N
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -287,6 +323,20 @@ struct VecChain {
     for (int k = 0; k < CPL; ++k)
       if (valid(k)) { P->online_mean[k * 32 + lane] = on_mu[k]; P->online_s2[k * 32 + lane] = on_s2[k]; }
     if (lane == 0) *P->online_n = on_n;
+  }
+  // per-replica recorders: the target-chain online statistics belong to the replica that produced them
+  __device__ void flush_online(OnEntry* row) const {
+#pragma unroll
+    for (int k = 0; k < CPL; ++k)
+      if (valid(k)) row[k * 32 + lane] = OnEntry{on_n, on_mu[k], on_s2[k]};
+  }
+  __device__ void load_online(const OnEntry* row) {
+    on_n = row[0].n;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const OnEntry e = valid(k) ? row[k * 32 + lane] : OnEntry{0, 0.0, 0.0};
+      on_mu[k] = e.mu; on_s2[k] = e.s2;
+    }
   }
 
   // ---- densities -----------------------------------------------------------
@@ -1139,6 +1189,8 @@ struct IsingChain {
   }
   __device__ void online_fit() {}
   __device__ void store_online() const {}
+  __device__ void flush_online(OnEntry*) const {}
+  __device__ void load_online(const OnEntry*) {}
 
   // InterpolatedLogPotential over two IsingLogPotential's (examples/ising.jl:74,77)
   __device__ __forceinline__ double lp(double b, int s) const {
@@ -1314,6 +1366,8 @@ struct TestSwapperChain {
   __device__ void write_trace(double*) const {}
   __device__ void online_fit() {}
   __device__ void store_online() const {}
+  __device__ void flush_online(OnEntry*) const {}
+  __device__ void load_online(const OnEntry*) {}
   __device__ void explore(long long, bool) {}
   __device__ double log_ratio(double) const { return 0.0; }
   __device__ __forceinline__ double draw_uniform() { return next_uniform(rng); }
@@ -1502,6 +1556,28 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
       }
       accepted = (lower ? u : u_p) < acceptance_pr;
       if (accepted) {   // adopt the partner's replica (states move, chains stay)
+        if (P.rec_table != nullptr) {
+          // per-replica recorders: what this chain's warps accumulated belongs to the outgoing replica; continue with
+          // what the incoming replica accumulated during its earlier visits of this chain (each statistic by its owner warp)
+          RecEntry* eo = P.rec_table + (size_t)(replica_index - 1) * P.n_local + wl;
+          const RecEntry* en = P.rec_table + (size_t)(ri_p - 1) * P.n_local + wl;
+          if (tw == ch.own(1)) {
+            if (lane == 0) { eo->am = ch.am; eo->swap_acc = swap_acc; }
+            ch.am = en->am; swap_acc = en->swap_acc;
+          }
+          if (tw == ch.own(2)) {
+            if (lane == 0) { eo->rev = ch.rev; eo->ls_fwd = ls_fwd; }
+            ch.rev = en->rev; ls_fwd = load_logsum(&en->ls_fwd);
+          }
+          if (tw == ch.own(3)) {
+            if (lane == 0) { eo->expl_acc = ch.expl_acc; eo->ls_bwd = ls_bwd; }
+            ch.expl_acc = en->expl_acc; ls_bwd = load_logsum(&en->ls_bwd);
+          }
+          if (is_tgt && tw == ch.own(4) && P.d > 0) {
+            ch.flush_online(P.on_table + (size_t)(replica_index - 1) * P.d_pad);
+            ch.load_online(P.on_table + (size_t)(ri_p - 1) * P.d_pad);
+          }
+        }
         replica_index = ri_p;
         rt_state = rt_p;
         ch.rng.ctr = ctr_p;
@@ -1523,6 +1599,15 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
   }
 
   if (err > 0 && lane == 0) atomicCAS(P.error_flag, 0, err);
+  if (P.rec_table != nullptr) {   // per-replica recorders: the entry of the replica each chain holds at the end of the round
+    RecEntry* eo = P.rec_table + (size_t)(replica_index - 1) * P.n_local + wl;
+    if (lane == 0) {
+      if (tw == ch.own(1)) { eo->am = ch.am; eo->swap_acc = swap_acc; }
+      if (tw == ch.own(2)) { eo->rev = ch.rev; eo->ls_fwd = ls_fwd; }
+      if (tw == ch.own(3)) { eo->expl_acc = ch.expl_acc; eo->ls_bwd = ls_bwd; }
+    }
+    if (is_tgt && tw == ch.own(4) && P.d > 0) ch.flush_online(P.on_table + (size_t)(replica_index - 1) * P.d_pad);
+  }
   // ---------------- epilogue: replica back to HBM, statistics out ----------------
   if constexpr (Chain::kTeam) {   // collect what the other warps of the team hold: their statistics and evaluation counts
     double* ex = reinterpret_cast<double*>(team_ctl + 24);

@@ -807,7 +807,31 @@ __global__ void logreg_decide_kernel(const __grid_constant__ LrParams P) {
       if (lower) { s.swap_acc.fit(acceptance_pr); s.ls_fwd.fit(s.lr); s.ls_bwd.fit(lr_p); }
       accepted = (lower ? s.u : u_p) < acceptance_pr;
       if (accepted) {
-        s.replica_index = __ldcg(&hp->replica_index);
+        const int ri_new = __ldcg(&hp->replica_index);
+        if (P.rec_table != nullptr) {   // per-replica recorders: see scan_kernel
+          RecEntry* eo = P.rec_table + (size_t)(s.replica_index - 1) * P.n_local + r;
+          const RecEntry* en = P.rec_table + (size_t)(ri_new - 1) * P.n_local + r;
+          if (lane == 0) {
+            eo->expl_acc = s.expl_acc; eo->am = s.am; eo->rev = s.rev; eo->swap_acc = s.swap_acc;
+            eo->ls_fwd = s.ls_fwd; eo->ls_bwd = s.ls_bwd;
+          }
+          s.expl_acc = en->expl_acc; s.am = en->am; s.rev = en->rev; s.swap_acc = en->swap_acc;
+          s.ls_fwd = load_logsum(&en->ls_fwd); s.ls_bwd = load_logsum(&en->ls_bwd);
+          if (chain == N) {
+            OnEntry* oo = P.on_table + (size_t)(s.replica_index - 1) * P.d_pad;
+            const OnEntry* on = P.on_table + (size_t)(ri_new - 1) * P.d_pad;
+            const long long n_old = *P.online_n;
+            __syncwarp();
+            for (int c = lane; c < P.d; c += 32) {
+              oo[c] = OnEntry{n_old, P.online_mean[c], P.online_s2[c]};
+              const OnEntry e = on[c];
+              P.online_mean[c] = e.mu; P.online_s2[c] = e.s2;
+            }
+            __syncwarp();
+            if (lane == 0) *P.online_n = on[0].n;
+          }
+        }
+        s.replica_index = ri_new;
         s.rt_state = __ldcg(&hp->rt_state);
         s.ctr = __ldcg(&hp->ctr);
         const double* pay = reinterpret_cast<const double*>(src + MAIL_HDR_BYTES);
@@ -824,6 +848,24 @@ __global__ void logreg_decide_kernel(const __grid_constant__ LrParams P) {
     if (P.swap_accept) P.swap_accept[log_at] = accepted ? 1 : 0;
     P.st[r] = s;
     if (err > 0) atomicCAS(P.error_flag, 0, err);
+  }
+}
+
+// per-replica recorders: when the round ends every chain hands the statistics it holds to its current replica's entry
+__global__ void logreg_flush_recorders_kernel(const __grid_constant__ LrParams P) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= P.n_local || P.rec_table == nullptr) return;
+  const LrChainState s = P.st[r];
+  RecEntry* eo = P.rec_table + (size_t)(s.replica_index - 1) * P.n_local + r;
+  if (lane == 0) {
+    eo->expl_acc = s.expl_acc; eo->am = s.am; eo->rev = s.rev; eo->swap_acc = s.swap_acc;
+    eo->ls_fwd = s.ls_fwd; eo->ls_bwd = s.ls_bwd;
+  }
+  if (P.first_chain + r == P.n_chains) {
+    OnEntry* oo = P.on_table + (size_t)(s.replica_index - 1) * P.d_pad;
+    const long long n = *P.online_n;
+    for (int c = lane; c < P.d; c += 32) oo[c] = OnEntry{n, P.online_mean[c], P.online_s2[c]};
   }
 }
 

@@ -122,7 +122,9 @@ void logreg_fill_params(pgn_handle* h, LrParams& P) {
   P.error_flag = h->error_flag.p;
   P.mail = h->mail.p; P.mail_left = h->mail_left; P.mail_right = h->mail_right; P.slot_bytes = h->slot_bytes;
   P.online_mean = h->online_mean.p; P.online_s2 = h->online_s2.p; P.online_n = h->online_n.p;
-  P.timeout_ns = 600ull * 1000ull * 1000ull * 1000ull;   // scans take seconds here; neighbours may lag
+  P.timeout_ns = h->timeout_ns * 30ull;   // scans take seconds here; neighbours may lag (default 600 s)
+  P.rec_table = h->recorder_order == PGN_RECORDERS_PER_REPLICA ? h->rec_table.p : nullptr;
+  P.on_table = h->recorder_order == PGN_RECORDERS_PER_REPLICA ? h->on_table.p : nullptr;
 }
 
 // run_one_round! for the logistic-regression target
@@ -188,6 +190,10 @@ void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<C
     h->last_launches += 2;
     CUDA_CHECK(cudaMemcpyAsync(&flag, h->error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
+  if (P.rec_table != nullptr && flag == 0 && n_scans > 0) {
+    logreg_flush_recorders_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
+    h->last_launches += 1;
   }
   CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
   CUDA_CHECK(cudaStreamSynchronize(h->stream));

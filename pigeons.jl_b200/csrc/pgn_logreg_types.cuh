@@ -64,6 +64,7 @@ struct LrParams {
   double* online_mean; double* online_s2; long long* online_n;
   int* index_process; double* swap_lr; double* swap_u; unsigned char* swap_accept; double* target_trace;
   unsigned long long timeout_ns;
+  RecEntry* rec_table; OnEntry* on_table;   // per-replica recorders (null: per chain), see pgn_kernels.cuh
 };
 
 }  // namespace pgn

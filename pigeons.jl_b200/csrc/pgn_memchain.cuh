@@ -618,6 +618,27 @@ __global__ void __launch_bounds__(256) scan_kernel_mem(const __grid_constant__ M
         if (lower) { r.swap_acc.fit(acceptance_pr); r.ls_fwd.fit(r.lr); r.ls_bwd.fit(lr_p); }
         accepted = (lower ? r.u : u_p) < acceptance_pr;
         if (accepted) {
+          if (P.rec_table != nullptr) {   // per-replica recorders: see scan_kernel
+            RecEntry* eo = P.rec_table + (size_t)(r.replica_index - 1) * P.n_local + cl;
+            const RecEntry* en = P.rec_table + (size_t)(ri_p - 1) * P.n_local + cl;
+            if (lane == 0) {
+              eo->expl_acc = r.expl_acc; eo->am = r.am; eo->rev = r.rev; eo->swap_acc = r.swap_acc;
+              eo->ls_fwd = r.ls_fwd; eo->ls_bwd = r.ls_bwd;
+            }
+            r.expl_acc = en->expl_acc; r.am = en->am; r.rev = en->rev; r.swap_acc = en->swap_acc;
+            r.ls_fwd = load_logsum(&en->ls_fwd); r.ls_bwd = load_logsum(&en->ls_bwd);
+            if (chain == N && P.d > 0) {   // the target-chain online statistics travel with their replica too
+              OnEntry* oo = P.on_table + (size_t)(r.replica_index - 1) * P.d_pad;
+              const OnEntry* on = P.on_table + (size_t)(ri_p - 1) * P.d_pad;
+              for (int c = lane; c < P.d; c += 32) {
+                oo[c] = OnEntry{r.on_n, P.online_mean[c], P.online_s2[c]};
+                const OnEntry e = on[c];
+                P.online_mean[c] = e.mu; P.online_s2[c] = e.s2;
+              }
+              r.on_n = on[0].n;
+              if (lane == 0) *P.online_n = r.on_n;
+            }
+          }
           r.replica_index = ri_p;
           r.rt_state = rt_p;
           r.ctr = ((unsigned long long)h5 << 32) | h4;
@@ -638,6 +659,20 @@ __global__ void __launch_bounds__(256) scan_kernel_mem(const __grid_constant__ M
     }
   }
   if (err > 0 && lane == 0) atomicCAS(P.error_flag, 0, err);
+  if (P.rec_table != nullptr && err == 0) {   // per-replica recorders: the entries of the replicas held when the round ends
+    for (int cl = w; cl < P.n_local; cl += W) {
+      const MemRec r = MP.rec[cl];
+      RecEntry* eo = P.rec_table + (size_t)(r.replica_index - 1) * P.n_local + cl;
+      if (lane == 0) {
+        eo->expl_acc = r.expl_acc; eo->am = r.am; eo->rev = r.rev; eo->swap_acc = r.swap_acc;
+        eo->ls_fwd = r.ls_fwd; eo->ls_bwd = r.ls_bwd;
+      }
+      if (P.first_chain + cl == N && P.d > 0) {
+        OnEntry* oo = P.on_table + (size_t)(r.replica_index - 1) * P.d_pad;
+        for (int c = lane; c < P.d; c += 32) oo[c] = OnEntry{r.on_n, P.online_mean[c], P.online_s2[c]};
+      }
+    }
+  }
 }
 
 // parity entry points for d > 128: one warp per point

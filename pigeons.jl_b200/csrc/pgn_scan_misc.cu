@@ -50,6 +50,69 @@ __global__ void test_math_kernel(int op, const double* in, double* out, long lon
   out[i] = r;
 }
 
+// reduce_recorders! (src/recorders/recorders.jl:88-120) for the per-replica recorder tables: the binary tree of
+// reduce_deterministically (src/mpi_utils/Entangler.jl:214-277) over the replica indices 1..N — at the level with
+// spacing s, entry i absorbs entry i + s for i = 1, 1 + 2s, ...; an unpaired last entry waits for the next level —
+// applied to the column of one local chain.  One warp per chain: the merges of a level are independent, lane l takes
+// every 32nd of them.  The result lands in the chain's ChainStatsDev.
+__global__ void merge_recorders_kernel(RecEntry* table, int n_replicas, int n_local, ChainStatsDev* out) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= n_local) return;
+  for (int spacing = 1; spacing < n_replicas; spacing *= 2) {
+    for (long long i = (long long)lane * 2 * spacing; i + spacing < n_replicas; i += 64LL * spacing) {
+      RecEntry* a = table + (size_t)i * n_local + c;
+      const RecEntry* b = table + (size_t)(i + spacing) * n_local + c;
+      if ((b->expl_acc.n | b->am.n | b->rev.n | b->swap_acc.n | b->ls_fwd.n | b->ls_bwd.n) == 0) continue;   // replica never sat here
+      RecEntry ea = *a;
+      const RecEntry eb = *b;
+      ea.ls_fwd = load_logsum(&a->ls_fwd); ea.ls_bwd = load_logsum(&a->ls_bwd);
+      merge_mean(ea.expl_acc, eb.expl_acc); merge_mean(ea.am, eb.am); merge_mean(ea.rev, eb.rev);
+      merge_mean(ea.swap_acc, eb.swap_acc);
+      merge_logsum(ea.ls_fwd, load_logsum(&b->ls_fwd)); merge_logsum(ea.ls_bwd, load_logsum(&b->ls_bwd));
+      *a = ea;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    const RecEntry e = table[c];
+    ChainStatsDev& o = out[c];
+    o.swap_n = e.swap_acc.n; o.swap_mean = e.swap_acc.mu;
+    o.ls_fwd = e.ls_fwd.n > 0 ? e.ls_fwd.value : -PGN_INF; o.ls_bwd = e.ls_bwd.n > 0 ? e.ls_bwd.value : -PGN_INF;
+    o.expl_acc_n = e.expl_acc.n; o.expl_acc_mean = e.expl_acc.mu;
+    o.am_n = e.am.n; o.am_mean = e.am.mu; o.rev_n = e.rev.n; o.rev_mean = e.rev.mu;
+  }
+}
+// The same tree for the target-chain online statistics, one thread per coordinate (OnlineStatsBase._merge!(::Variance,
+// ::Variance): g = n2 / (n += n2); delta = mu2 - mu; s2 = smooth(s2, s2', g) + delta^2 g (1 - g); mu = smooth(mu, mu2, g)).
+__global__ void merge_online_kernel(OnEntry* table, int n_replicas, int d, int d_pad, double* mean, double* s2, long long* n_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  for (int spacing = 1; spacing < n_replicas; spacing *= 2)
+    for (long long i = 0; i + spacing < n_replicas; i += 2LL * spacing) {
+      OnEntry* a = table + (size_t)i * d_pad + c;
+      const OnEntry b = table[(size_t)(i + spacing) * d_pad + c];
+      if (b.n == 0) continue;
+      OnEntry ea = *a;
+      if (ea.n == 0) { *a = b; continue; }
+      ea.n += b.n;
+      const double g = (double)b.n / (double)ea.n;
+      const double delta = b.mu - ea.mu;
+      ea.s2 = (ea.s2 + g * (b.s2 - ea.s2)) + ((delta * delta) * g) * (1.0 - g);
+      ea.mu = ea.mu + g * (b.mu - ea.mu);
+      *a = ea;
+    }
+  const OnEntry e = table[c];
+  mean[c] = e.mu; s2[c] = e.s2;
+  if (c == 0) *n_out = e.n;
+}
+void launch_merge_recorders(cudaStream_t s, RecEntry* table, int n_replicas, int n_local, ChainStatsDev* out) {
+  merge_recorders_kernel<<<(n_local + 3) / 4, 128, 0, s>>>(table, n_replicas, n_local, out);
+}
+void launch_merge_online(cudaStream_t s, OnEntry* table, int n_replicas, int d, int d_pad, double* mean, double* s2, long long* n_out) {
+  merge_online_kernel<<<(d + 127) / 128, 128, 0, s>>>(table, n_replicas, d, d_pad, mean, s2, n_out);
+}
+
 void* ising_scan_kernel() { return (void*)scan_kernel<IsingChain>; }
 void* test_swapper_scan_kernel() { return (void*)scan_kernel<TestSwapperChain>; }
 

@@ -43,6 +43,7 @@ class Inputs:
     show_report: bool = False
     checked_round: int = 0
     # engine plumbing (not in the reference)
+    recorder_order: int = _capi.RECORDERS_PER_REPLICA   # per-replica recorders + tree merge (recorders.jl:88-120); 1 = per chain
     engine_lib: Optional[_capi.EngineLib] = None
     engine_factory: Optional[Callable] = None     # (n_chains, seed, rank, world_size, device, **target_cfg) -> Engine-like
     device: int = 0
@@ -99,7 +100,7 @@ def create_pt(inputs: Inputs) -> PT:
     comm = inputs.comm
     cfg = inputs.target.engine_config()
     kw = dict(n_chains=inputs.n_chains, seed=inputs.seed, rank=comm.rank, world_size=comm.world_size,
-              device=inputs.device, **cfg)
+              device=inputs.device, recorder_order=inputs.recorder_order, **cfg)
     if inputs.engine_factory is not None:
         engine = inputs.engine_factory(**kw)
     else:

@@ -4,6 +4,11 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Several engine handles on ONE device (tests/test_gpu_shards.py) wait for each other's kernels: give every stream its own
+# hardware queue so that a spinning kernel never sits in front of the one it waits for (must be set before CUDA starts).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# a lost hand-shake should fail a test in seconds, not in the production limit of 20 s (LOGREG: 30x)
+os.environ.setdefault("PGN_TIMEOUT_S", "4")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

@@ -24,11 +24,15 @@ from oracle_adapter import load_oracle            # noqa: E402
 
 def main():
     lib = load_oracle()
+    # <name>.json: the default recorder order (per replica + tree merge, the reference's reduce_recorders!);
+    # <name>.per_chain.json: recorder_order = PGN_RECORDERS_PER_CHAIN
     for name, kw in GOLDEN_CASES.items():
-        pt = pg.pigeons(engine_lib=lib, record=[pg.index_process, pg.swap_trace], **kw())
-        with open(os.path.join(HERE, name + ".json"), "w") as f:
-            json.dump(summarise(pt), f, indent=1)
-        print("wrote", name)
+        for order, suffix in ((0, ".json"), (1, ".per_chain.json")):
+            pt = pg.pigeons(engine_lib=lib, record=[pg.index_process, pg.swap_trace], recorder_order=order, **kw())
+            with open(os.path.join(HERE, name + suffix), "w") as f:
+                json.dump(summarise(pt), f, indent=1)
+            pt.close()
+            print("wrote", name + suffix)
 
 
 if __name__ == "__main__":

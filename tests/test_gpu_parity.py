@@ -90,8 +90,30 @@ CASES = {
 
 @pytest.mark.parametrize("name", list(CASES))
 def test_multi_round_parity(name, gpu_lib, oracle_lib):
+    """Default recorder order: per-replica recorders merged by the reference's tree (recorders.jl:88-120)."""
     kw = CASES[name]
     assert_same(run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw), name)
+
+
+@pytest.mark.parametrize("name", ["c1_toy_slice", "funnel32_automala", "gmm128_automala", "logreg24_automala", "ising5",
+                                  "toy3_compose_slice_automala", "funnel8_mix_automala", "two_chains"])
+def test_multi_round_parity_per_chain_recorders(name, gpu_lib, oracle_lib):
+    """recorder_order = PGN_RECORDERS_PER_CHAIN: one accumulator per chain / pair, fitted in scan order."""
+    kw = dict(CASES[name], recorder_order=1)
+    assert_same(run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw), name + "/per_chain")
+
+
+@pytest.mark.parametrize("name", ["toy10_automala", "toy1000_automala_mem"])
+def test_recorder_orders_agree_to_rounding(name, gpu_lib):
+    """The two recorder orders describe the same statistics: after ONE round (same trajectory: adaptation has not acted yet)
+    all counts are equal and the means agree to rounding."""
+    kw = dict(target=pg.toy_mvn_target(10 if name == "toy10_automala" else 1000), explorer=pg.AutoMALA(), n_chains=6, seed=2)
+    a = run_pt(gpu_lib, n_rounds=1, **kw)["rr"]
+    b = run_pt(gpu_lib, n_rounds=1, recorder_order=1, **kw)["rr"]
+    for k in ("swap_n", "expl_acc_n", "am_n", "rev_n", "expl_n_steps"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    for k in ("swap_mean", "logsum_fwd", "logsum_bwd", "expl_acc_mean", "am_mean", "rev_mean", "online_mean", "online_var"):
+        np.testing.assert_allclose(getattr(a, k), getattr(b, k), rtol=1e-12, atol=1e-300, err_msg=k)
 
 
 def test_round_trips_known_answer(gpu_lib):

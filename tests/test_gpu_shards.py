@@ -42,8 +42,14 @@ def run_sharded(lib, world, record, checked_round=0, engine_factory=None, **kw):
     return group.run(one_rank)
 
 
-@pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("name", list(CASES))
+# The LOGREG path is a sequence of ordinary kernels per shard (controller, GEMMs, post, decide): with three shards on one
+# device the decide kernels of two shards spin while the third still has a dozen launches queued, and whether those run
+# next to the spinning ones is up to the device's queue assignment (CUDA does not promise it) — on separate GPUs the
+# question does not arise (tests/test_multigpu.py covers world 2/4/8 there).  One device: two LOGREG shards.
+PAIRS = [(n, w) for n in CASES for w in (2, 3) if not (n.startswith("logreg") and w == 3)]
+
+
+@pytest.mark.parametrize("name,world", PAIRS)
 def test_shards_on_one_gpu_match_the_oracle(name, world, gpu_lib, oracle_lib):
     kw = CASES[name]
     rec = [pg.index_process, pg.swap_trace] if name.startswith("test_swapper") else [pg.index_process, pg.swap_trace, pg.traces]
