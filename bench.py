@@ -167,11 +167,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+RECORDER_ORDER = 0
+
+
 def build_problem(pg, name, lib, n_chains, comm, device, burn_rounds, seed=1):
     """Create the PT object of config `name` and run the untimed adaptive burn-in."""
     target, explorer = make_target_and_explorer(pg, name)
     inputs = pg.Inputs(target=target, explorer=explorer, n_chains=n_chains, n_rounds=burn_rounds,
-                       seed=seed, engine_lib=lib, device=device, comm=comm)
+                       seed=seed, engine_lib=lib, device=device, comm=comm, recorder_order=RECORDER_ORDER)
     return pg.pigeons_pt(pg.create_pt(inputs))
 
 
@@ -471,6 +474,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): chains per GPU fixed, the ladder grows with N; strong: the BASELINE ladder of the config "
                          "(chains_per_gpu chains in total) is split over the N GPUs")
+    ap.add_argument("--recorder-order", type=int, default=0, choices=[0, 1],
+                    help="pgn_config.recorder_order: 0 per-replica recorders + tree merge (reference), 1 per chain")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU baseline (0 = pick the fastest of a sweep)")
     args = ap.parse_args()
     explicit = any(a == "--config" or a.startswith("--config=") for a in sys.argv[1:])
@@ -480,6 +485,8 @@ def main():
         if c not in CONFIGS:
             ap.error(f"unknown config in --also: {c}")
 
+    global RECORDER_ORDER
+    RECORDER_ORDER = args.recorder_order
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

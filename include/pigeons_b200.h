@@ -57,6 +57,8 @@ extern "C" {
 #define PGN_TARGET_ISING 4        /* examples/ising.jl:6-117                                                      */
 #define PGN_TARGET_LOGREG 5       /* analytic-gradient target pattern, test/test_custom_gradient.jl:1-33          */
 #define PGN_TARGET_TEST_SWAPPER 6 /* src/swap/pair_swapper.jl:100-149                                             */
+#define PGN_TARGET_MIXED 7        /* product of Bernoulli, Binomial and Normal coordinates: the mixed Bool / Integer /
+                                     Float state of test/test_slice_sampler.jl:56-75 (SliceSampler.jl:65-86,136-142,189) */
 
 /* ---- explorers ----------------------------------------------------------- */
 #define PGN_EXPLORER_NONE 0             /* TestSwapper: step! is a no-op (pair_swapper.jl:140-141) */
@@ -101,7 +103,12 @@ typedef struct pgn_config {
    *            p[3]=sigma_ref, p[4]=log(sigma_ref), p[5]=1/sigma_ref^2
    *  ISING   : p[0]=beta_model, p[1]=L
    *  LOGREG  : p[0]=n_data, p[3]=sigma_ref, p[4]=log(sigma_ref), p[5]=1/sigma_ref^2
-   *  TEST_SWAPPER : p[0]=constant_swap_accept_pr                               */
+   *  TEST_SWAPPER : p[0]=constant_swap_accept_pr
+   *  MIXED   : p[0]=n_bool, p[1]=n_int, p[2]=binomial n, p[3]=sigma_ref, p[4]=log(sigma_ref), p[5]=1/sigma_ref^2;
+   *            state = n_bool Bool coordinates (0.0 / 1.0), then n_int Integer coordinates, then dim - n_bool - n_int
+   *            Float coordinates; target = Bernoulli(p1) x Binomial(n, q1) x Normal(0, 1), reference = Bernoulli(p0) x
+   *            Binomial(n, q0) x Normal(0, sigma_ref); `means` holds [log p0, log(1-p0), log p1, log(1-p1), log q0,
+   *            log(1-q0), log q1, log(1-q1), p0, q0, log C(n,0..n)] (n_modes = 10 + n + 1 entries)                      */
   double p[8];
   const double* means;        /* GMM: [K][d] row-major, host pointer (copied)   */
   const double* log_weights;  /* GMM: [K] log mixture weights (copied)          */

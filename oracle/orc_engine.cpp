@@ -194,8 +194,33 @@ struct Engine {
       }
       case PGN_TARGET_ISING:
         return 0.0 * (double)r.ising_S;   // IsingLogPotential(0.0, L) (examples/ising.jl:74,77)
+      case PGN_TARGET_MIXED: return mixed_density(x, 0);
       default: return QNAN;
     }
+  }
+  // ---- mixed Bool / Integer / Float product target (the state of test/test_slice_sampler.jl:56-75): side 0 = reference
+  // Bernoulli(p0) x Binomial(n, q0) x Normal(0, s), side 1 = target Bernoulli(p1) x Binomial(n, q1) x Normal(0, 1).
+  // Distributions.logpdf of a discrete distribution at a non-integer or out-of-support point is -Inf.
+  int mixed_nb() const { return (int)cfg.p[0]; }
+  int mixed_ni() const { return (int)cfg.p[1]; }
+  int mixed_kind(int c) const { return c < mixed_nb() ? 0 : (c < mixed_nb() + mixed_ni() ? 1 : 2); }   // 0 Bool, 1 Integer, 2 Float
+  double mixed_term(int c, double v, int side) const {
+    const double* t = means.data();
+    const int n = (int)cfg.p[2];
+    switch (mixed_kind(c)) {
+      case 0: return v == 1.0 ? t[2 * side] : (v == 0.0 ? t[2 * side + 1] : -INF);
+      case 1: {
+        if (!(v >= 0.0 && v <= (double)n) || v != std::floor(v)) return -INF;
+        const int k = (int)v;
+        return (t[10 + k] + (double)k * t[4 + 2 * side]) + (double)(n - k) * t[5 + 2 * side];
+      }
+      default:
+        if (side == 1) return -(v * v + LOG2PI) * 0.5;
+        return -(v * v * cfg.p[5] + LOG2PI) * 0.5 - cfg.p[4];
+    }
+  }
+  double mixed_density(const double* x, int side) const {
+    return tree_sum(d(), [&](int c) { return mixed_term(c, x[c], side); });
   }
   // ---- logistic regression (BASELINE config 5; analytic-gradient target in the style of
   // test/test_custom_gradient.jl:1-33): target = N(0, s^2 I) prior x Bernoulli(sigmoid(X theta)).
@@ -297,6 +322,7 @@ struct Engine {
       }
       case PGN_TARGET_ISING:
         return cfg.p[0] * (double)r.ising_S;   // examples/ising.jl:74
+      case PGN_TARGET_MIXED: return mixed_density(x, 1);
       default: return QNAN;
     }
   }
@@ -475,6 +501,24 @@ struct Engine {
         ising_recompute(r);
         break;
       }
+      case PGN_TARGET_MIXED: {     // rand! of the product reference: one tick per Bool / Float coordinate, n per Binomial
+        const int n = (int)cfg.p[2];
+        const double p0 = means[8], q0 = means[9];
+        uint64_t t = r.ctr;
+        for (int c = 0; c < dd; ++c) {
+          switch (mixed_kind(c)) {
+            case 0: r.x[c] = uniform_at(r.rng, t) < p0 ? 1.0 : 0.0; t += 1; break;
+            case 1: {
+              int k = 0;
+              for (int j = 0; j < n; ++j) k += uniform_at(r.rng, t + j) < q0 ? 1 : 0;
+              r.x[c] = (double)k; t += n; break;
+            }
+            default: r.x[c] = cfg.p[3] * normal_at(r.rng, t); t += 1; break;
+          }
+        }
+        r.ctr = t;
+        break;
+      }
       default: break;              // TestSwapper: nothing (pair_swapper.jl:143)
     }
   }
@@ -500,7 +544,30 @@ struct Engine {
     }
     return cached_lp;
   }
+  // coordinate types (SliceSampler.jl dispatches on typeof(pointer[])): only the MIXED target has non-Float coordinates
+  int coord_kind(int c) const { return cfg.target_kind == PGN_TARGET_MIXED ? mixed_kind(c) : 2; }
+  // rand(rng, a:b) for integers a <= b held in doubles: a + floor(u (b - a + 1)), u the replica's next uniform
+  // (Julia's range sampler is not reproducible here; part of the documented RNG deviation)
+  static double rand_int_range(Replica& r, double a, double b) {
+    const double span = (b - a) + 1.0;
+    double k = std::floor(r.uniform() * span);
+    if (k > b - a) k = b - a;
+    return a + k;
+  }
+  // Bool coordinates: sample from the full conditional, one density evaluation (SliceSampler.jl:65-86)
+  double slice_sample_bool(Replica& r, double b, int c, double cached_lp) {
+    double& ptr = r.x[c];
+    double lp0, lp1;
+    if (ptr != 0.0) { lp1 = cached_lp; ptr = 0.0; lp0 = log_potential(b, r); }
+    else { lp0 = cached_lp; ptr = 1.0; lp1 = log_potential(b, r); }
+    const double prob_ratio = exp_(lp1 - lp0);
+    const double prob_zero = 1.0 / (1.0 + prob_ratio);
+    if (r.uniform() < prob_zero) { ptr = 0.0; return lp0; }
+    ptr = 1.0;
+    return lp1;
+  }
   double slice_sample_coord(Replica& r, ChainStats& st, double b, int c, double cached_lp) {   // :89-95
+    if (coord_kind(c) == 0) return slice_sample_bool(r, b, c, cached_lp);
     double z = cached_lp - r.exponential();
     double Lq, Rq, lp_L, lp_R;
     slice_double(r, st, b, c, z, Lq, Rq, lp_L, lp_R);
@@ -510,8 +577,16 @@ struct Engine {
                     double& potent_L, double& potent_R) {   // :97-126
     double& ptr = r.x[c];
     double old_position = ptr;
-    Lq = ptr - ep.slice_w * r.uniform();   // initialize_slice_endpoints :129-133
-    Rq = Lq + ep.slice_w;
+    if (coord_kind(c) == 1) {              // initialize_slice_endpoints for integers :136-142
+      if (ep.slice_w != std::floor(ep.slice_w))
+        throw OrcError{PGN_ERR_INVALID, "for integer variables, the width should be an integer"};
+      const double width = std::ceil(ep.slice_w);
+      Lq = ptr - rand_int_range(r, 0.0, width);
+      Rq = Lq + width;
+    } else {
+      Lq = ptr - ep.slice_w * r.uniform();   // initialize_slice_endpoints :129-133
+      Rq = Lq + ep.slice_w;
+    }
     int K = ep.slice_p;
     ptr = Lq; potent_L = log_potential(b, r);
     ptr = Rq; potent_R = log_potential(b, r);
@@ -544,7 +619,9 @@ struct Engine {
     double new_lp = 0.0;
     int n = 1;
     while (n <= ep.slice_max_iter) {
-      double new_position = Lbar + r.uniform() * (Rbar - Lbar);   // draw_new_position :188
+      const bool integer = coord_kind(c) == 1;
+      double new_position = integer ? rand_int_range(r, Lbar, Rbar)          // draw_new_position(L::Integer, R::Integer) :189
+                                    : Lbar + r.uniform() * (Rbar - Lbar);    // draw_new_position :188
       ptr = new_position;
       new_lp = log_potential(b, r);
       bool consider = z < new_lp;
@@ -555,7 +632,7 @@ struct Engine {
         return new_lp;
       }
       if (new_position < ptr) Lbar = new_position; else Rbar = new_position;
-      if (isapprox(Lbar, Rbar)) {
+      if (integer ? (Lbar == Rbar) : isapprox(Lbar, Rbar)) {   // isapprox of two Integers is ==
         ptr = old_position;
         st.n_steps += n;
         return log_potential(b, r);
@@ -1012,6 +1089,14 @@ int orc_create(const pgn_config* cfg, orc_handle** out, char** err) {
   if (cfg->target_kind == PGN_TARGET_GMM) {
     E.means.assign(cfg->means, cfg->means + (size_t)cfg->n_modes * cfg->dim);
     E.log_w.assign(cfg->log_weights, cfg->log_weights + cfg->n_modes);
+  }
+  if (cfg->target_kind == PGN_TARGET_MIXED) {
+    if (!cfg->means || cfg->n_modes != 10 + (int)cfg->p[2] + 1 || cfg->p[0] < 0 || cfg->p[1] < 0 ||
+        cfg->p[0] + cfg->p[1] > cfg->dim || cfg->p[2] < 1) {
+      delete h;
+      return fail(err, PGN_ERR_INVALID, "MIXED: parameter table / coordinate counts inconsistent");
+    }
+    E.means.assign(cfg->means, cfg->means + cfg->n_modes);
   }
   if (cfg->target_kind == PGN_TARGET_LOGREG) {
     const size_t n = (size_t)cfg->p[0];

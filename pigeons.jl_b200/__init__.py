@@ -17,7 +17,7 @@ from .pt import (PT, ChecksFailed, Inputs, Iterators, NonReversiblePT, Shared, a
                  pigeons_pt, round_trip, run_checks, run_one_round, sample_array, stepping_stone, stepping_stone_pair,
                  swap_trace, traces)
 from .recorders import ReducedRecorders                                            # noqa: F401
-from .targets import (Funnel, GaussianMixture, IsingLogPotential, LogisticRegression,  # noqa: F401
+from .targets import (Funnel, GaussianMixture, IsingLogPotential, LogisticRegression, MixedProduct,  # noqa: F401
                       ScaledPrecisionNormalPath, TestSwapper, eight_mode_mixture,
                       synthetic_logistic_regression, toy_mvn_target)
 from .tempering import (MonotoneCubic, Schedule, communication_barriers, equally_spaced_schedule,  # noqa: F401

@@ -66,9 +66,10 @@ void fill_params(pgn_handle* h, Params& P) {
 void* select_scan_kernel(const pgn_handle* h) {
   const int ex = h->ep.kind;
   switch (h->cfg.target_kind) {
-    case PGN_TARGET_TOY_MVN: return vec_scan_kernel_toy(h->cpl, ex, h->regcap);
-    case PGN_TARGET_FUNNEL: return vec_scan_kernel_funnel(h->cpl, ex, h->regcap);
-    case PGN_TARGET_GMM: return vec_scan_kernel_gmm(h->cpl, ex, h->regcap);
+    case PGN_TARGET_TOY_MVN: return vec_scan_kernel_toy(h->cpl, ex);
+    case PGN_TARGET_FUNNEL: return vec_scan_kernel_funnel(h->cpl, ex);
+    case PGN_TARGET_GMM: return vec_scan_kernel_gmm(h->cpl, ex);
+    case PGN_TARGET_MIXED: return vec_scan_kernel_mixed(h->cpl, ex);
     case PGN_TARGET_ISING: return ex == PGN_EXPLORER_ISING_METROPOLIS ? ising_scan_kernel() : nullptr;
     case PGN_TARGET_TEST_SWAPPER: return ex == PGN_EXPLORER_NONE ? test_swapper_scan_kernel() : nullptr;
     default: return nullptr;
@@ -125,6 +126,7 @@ void launch_eval_points(pgn_handle* h, const Params& P, const double* xs, const 
     case PGN_TARGET_TOY_MVN: launch_eval_points_toy(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
     case PGN_TARGET_FUNNEL: launch_eval_points_funnel(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
     case PGN_TARGET_GMM: launch_eval_points_gmm(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
+    case PGN_TARGET_MIXED: launch_eval_points_mixed(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
     default: throw CudaError{PGN_ERR_INVALID, "unsupported target"};
   }
 }
@@ -170,6 +172,12 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
       break;
     }
     case PGN_TARGET_TEST_SWAPPER: break;
+    case PGN_TARGET_MIXED:
+      if (cfg->dim < 1 || cfg->dim > 128) return fail(err, PGN_ERR_INVALID, "MIXED: 1 <= dim <= 128 (register-resident kernels only)");
+      if (!cfg->means || cfg->p[2] < 1 || cfg->n_modes != 10 + (int)cfg->p[2] + 1 || cfg->p[0] < 0 || cfg->p[1] < 0 ||
+          cfg->p[0] + cfg->p[1] > cfg->dim)
+        return fail(err, PGN_ERR_INVALID, "MIXED: parameter table / coordinate counts inconsistent");
+      break;
     case PGN_TARGET_LOGREG:
       if (cfg->dim < 1 || cfg->p[0] < 1 || !cfg->data_x || !cfg->data_y)
         return fail(err, PGN_ERR_INVALID, "LOGREG: dim, n_data, data_x, data_y required");
@@ -215,8 +223,6 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
     {
       const char* fm = std::getenv("PGN_FORCE_MEM");
       h->force_mem = fm != nullptr && std::string(fm) == "1";
-      const char* rc = std::getenv("PGN_REGCAP");
-      h->regcap = rc ? std::atoi(rc) : 0;
       const char* to = std::getenv("PGN_TIMEOUT_S");      // hand-shake spin limit (default 20 s; the LOGREG path uses 30x)
       if (to && std::atof(to) > 0) h->timeout_ns = (unsigned long long)(std::atof(to) * 1e9);
     }
@@ -258,6 +264,10 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
       h->means.upload(padded.data(), padded.size());
       h->log_w.alloc(cfg->n_modes);
       h->log_w.upload(cfg->log_weights, cfg->n_modes);
+    }
+    if (cfg->target_kind == PGN_TARGET_MIXED) {   // [log p0, log(1-p0), ..., p0, q0, log C(n, 0..n)]
+      h->means.alloc(cfg->n_modes);
+      h->means.upload(cfg->means, cfg->n_modes);
     }
     if (cfg->target_kind == PGN_TARGET_LOGREG) logreg_allocate(h, cfg);
     // default schedule: equally spaced (src/schedules/Schedule.jl:36-44)
@@ -446,7 +456,7 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     const bool per_replica = h->recorder_order == PGN_RECORDERS_PER_REPLICA;
     const bool vec_online = h->cfg.target_kind != PGN_TARGET_ISING && h->cfg.target_kind != PGN_TARGET_TEST_SWAPPER && d > 0;
     if (per_replica && n_scans > 0) {   // recorders are emptied every round (recorders.jl:113-118)
-      CUDA_CHECK(cudaMemsetAsync(h->rec_table.p, 0, h->rec_table.n * sizeof(RecEntry), h->stream));
+      launch_init_recorder_tables(h->stream, h->rec_table.p, h->rec_table.n, h->n_sms);
       if (owns_target && vec_online) CUDA_CHECK(cudaMemsetAsync(h->on_table.p, 0, h->on_table.n * sizeof(OnEntry), h->stream));
     }
     float ms = 0.f;
@@ -675,7 +685,7 @@ int pgn_log_potential(pgn_handle* h, const double* x, int32_t n_points, const do
     Params P;
     fill_params(h, P);
     switch (h->cfg.target_kind) {
-      case PGN_TARGET_TOY_MVN: case PGN_TARGET_FUNNEL: case PGN_TARGET_GMM:
+      case PGN_TARGET_TOY_MVN: case PGN_TARGET_FUNNEL: case PGN_TARGET_GMM: case PGN_TARGET_MIXED:
         launch_eval_points(h, P, dx.p, db.p, n_points, dout.p, nullptr, nullptr); break;
       case PGN_TARGET_ISING: launch_ising_lp((n_points + 3) / 4, 128, h->stream, P, dx.p, db.p, n_points, dout.p); break;
       default: return fail(err, PGN_ERR_INVALID, "unsupported target");

@@ -140,7 +140,6 @@ struct pgn_handle {
   int recorder_order = PGN_RECORDERS_PER_REPLICA;
   pgn::DevBuf<pgn::RecEntry> rec_table;   // per-replica recorders [n_chains][n_local] (PGN_RECORDERS_PER_REPLICA)
   pgn::DevBuf<pgn::OnEntry> on_table;     // target-chain online statistics per replica [n_chains][d_pad]
-  int regcap = 0;                // PGN_REGCAP: register cap of the d > 64 autoMALA team kernel (0: none, 128: room for teams of two)
   pgn::DevBuf<pgn::MemRec> mem_rec;
   pgn::DevBuf<double> mem_vec[10];
   bool mem_allocated = false;
@@ -163,9 +162,10 @@ namespace pgn {
 
 // ---- kernels compiled in the other translation units -------------------------------------------
 // scan kernels (pgn_scan_vec.cu, one object per target family; pgn_scan_misc.cu; pgn_scan_mem.cu)
-void* vec_scan_kernel_toy(int cpl, int ex, int regcap);
-void* vec_scan_kernel_funnel(int cpl, int ex, int regcap);
-void* vec_scan_kernel_gmm(int cpl, int ex, int regcap);
+void* vec_scan_kernel_toy(int cpl, int ex);
+void* vec_scan_kernel_funnel(int cpl, int ex);
+void* vec_scan_kernel_gmm(int cpl, int ex);
+void* vec_scan_kernel_mixed(int cpl, int ex);
 void* ising_scan_kernel();
 void* test_swapper_scan_kernel();
 void* mem_scan_kernel(int target_kind, int ex);
@@ -176,11 +176,14 @@ void launch_eval_points_funnel(int cpl, int grid, int block, size_t smem, cudaSt
                                const double* betas, int n, double* lp, double* ld, double* grad);
 void launch_eval_points_gmm(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
                             const double* betas, int n, double* lp, double* ld, double* grad);
+void launch_eval_points_mixed(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
+                              const double* betas, int n, double* lp, double* ld, double* grad);
 void launch_eval_points_mem(int target_kind, int grid, int block, cudaStream_t s, const MemParams& MP, const double* xs,
                             const double* betas, int n, double* lp, double* ld, double* grad);
 void launch_init_toy(int grid, int block, cudaStream_t s, const Params& P);
 void launch_ising_lp(int grid, int block, cudaStream_t s, const Params& P, const double* xs, const double* betas, int n,
                      double* lp);
+void launch_init_recorder_tables(cudaStream_t s, RecEntry* table, size_t n, int n_sms);
 void launch_merge_recorders(cudaStream_t s, RecEntry* table, int n_replicas, int n_local, ChainStatsDev* out);
 void launch_merge_online(cudaStream_t s, OnEntry* table, int n_replicas, int d, int d_pad, double* mean, double* s2, long long* n_out);
 void launch_test_math(int grid, int block, int op, const double* in, double* out, long long n, unsigned int seed_lo,

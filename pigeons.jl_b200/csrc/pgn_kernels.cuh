@@ -72,11 +72,8 @@ struct OnEntry {    // OnlineStatsBase.Variance of one coordinate, as one replic
   long long n;
   double mu, s2;
 };
-__device__ __forceinline__ LogSumAcc load_logsum(const LogSumAcc* p) {
-  LogSumAcc v = *p;
-  if (v.n == 0) v.value = -PGN_INF;   // the table is zero-filled; an absent LogSum starts at -inf
-  return v;
-}
+// The tables are filled with "absent" entries when a round starts (init_recorder_tables_kernel): every count 0, every
+// mean 0, every LogSum at -inf — an entry can be loaded into the registers as it is, no test on the load's result.
 
 struct ChainStatsDev {   // one per local chain, written when the round ends
   long long swap_n; double swap_mean; double ls_fwd; double ls_bwd;
@@ -333,8 +330,8 @@ struct VecChain {
   __device__ void load_online(const OnEntry* row) {
     on_n = row[0].n;
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-      const OnEntry e = valid(k) ? row[k * 32 + lane] : OnEntry{0, 0.0, 0.0};
+    for (int k = 0; k < CPL; ++k) {   // rows are d_pad wide and the padding stays zero: no test on the loads' results
+      const OnEntry e = row[k * 32 + lane];
       on_mu[k] = e.mu; on_s2[k] = e.s2;
     }
   }
@@ -367,6 +364,28 @@ struct VecChain {
     (void)K;
   }
 
+  // ---- mixed Bool / Integer / Float product target (PGN_TARGET_MIXED; the state of test/test_slice_sampler.jl:56-75)
+  __device__ __forceinline__ int coord_kind(int c) const {   // 0 Bool, 1 Integer, 2 Float
+    if (TK != PGN_TARGET_MIXED) return 2;
+    const int nb = (int)P->p[0], ni = (int)P->p[1];
+    return c < nb ? 0 : (c < nb + ni ? 1 : 2);
+  }
+  // log density of coordinate c at value v under side 0 (reference) or 1 (target); Distributions.logpdf of a discrete
+  // distribution at a non-integer or out-of-support point is -Inf
+  __device__ __forceinline__ double mixed_term(int c, double v, int side) const {
+    const double* t = P->means;
+    const int n = (int)P->p[2];
+    const int kind = coord_kind(c);
+    if (kind == 0) return v == 1.0 ? t[2 * side] : (v == 0.0 ? t[2 * side + 1] : -PGN_INF);
+    if (kind == 1) {
+      if (!(v >= 0.0 && v <= (double)n) || v != floor(v)) return -PGN_INF;
+      const int k = (int)v;
+      return (t[10 + k] + (double)k * t[4 + 2 * side]) + (double)(n - k) * t[5 + 2 * side];
+    }
+    if (side == 1) return -(v * v + PGN_LOG2PI) * 0.5;
+    return -(v * v * P->p[5] + PGN_LOG2PI) * 0.5 - P->p[4];
+  }
+
   // component densities at xx
   __device__ void eval(const double (&xx)[CPL], double& a0, double& a1) {
     n_points += 1;
@@ -386,6 +405,15 @@ struct VecChain {
         v[0] = v[0] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
         if (k == 0 && lane == 0) { double zy = y / sy; v[1] = v[1] + (-(zy * zy + PGN_LOG2PI) * 0.5 - lsy); }
         else { double t = xv * xv * e; v[1] = v[1] + (-(t + PGN_LOG2PI) * 0.5 - 0.5 * y); }
+      }
+      warp_sum_n<2>(v);
+      a0 = v[0]; a1 = v[1];
+    } else if (TK == PGN_TARGET_MIXED) {
+      double v[2] = {0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) if (valid(k)) {
+        v[0] = v[0] + mixed_term(k * 32 + lane, xx[k], 0);
+        v[1] = v[1] + mixed_term(k * 32 + lane, xx[k], 1);
       }
       warp_sum_n<2>(v);
       a0 = v[0]; a1 = v[1];
@@ -428,7 +456,12 @@ struct VecChain {
   // lane partial that rides along in the same butterfly (in: partial, out: sum)
   __device__ void eval_grad(const double (&xx)[CPL], double b, double& a0, double& a1, double (&g)[CPL], double& extra) {
     n_points += 1;
-    if (TK == PGN_TARGET_TOY_MVN) {
+    if (TK == PGN_TARGET_MIXED) {   // discrete coordinates: no gradient-based explorer is ever selected for this target
+      a0 = a1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) g[k] = 0.0;
+      extra = warp_sum(extra);
+    } else if (TK == PGN_TARGET_TOY_MVN) {
       double v[2] = {0.0, extra};
 #pragma unroll
       for (int k = 0; k < CPL; ++k) if (valid(k)) v[0] = v[0] + xx[k] * xx[k];
@@ -522,6 +555,25 @@ struct VecChain {
 
   // ---- sample_iid! / ToyExplorer ---------------------------------------------
   __device__ void sample_iid(double b) {
+    if (TK == PGN_TARGET_MIXED) {   // rand! of the product reference: one tick per Bool / Float coordinate, n per Binomial
+      const int nb = (int)P->p[0], ni = (int)P->p[1], n = (int)P->p[2];
+      const double p0 = P->means[8], q0 = P->means[9];
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        if (!valid(k)) continue;
+        const int c = k * 32 + lane;
+        const int kind = coord_kind(c);
+        const unsigned long long t = rng.ctr + (unsigned long long)(kind == 0 ? c : (kind == 1 ? nb + (c - nb) * n : nb + ni * n + (c - nb - ni)));
+        if (kind == 0) x[k] = uniform_at(rng, t) < p0 ? 1.0 : 0.0;
+        else if (kind == 1) {
+          int cnt = 0;
+          for (int j = 0; j < n; ++j) cnt += uniform_at(rng, t + (unsigned long long)j) < q0 ? 1 : 0;
+          x[k] = (double)cnt;
+        } else x[k] = P->p[3] * normal_at(rng, t);
+      }
+      rng.ctr += (unsigned long long)(nb + ni * n + (d - nb - ni));
+      return;
+    }
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
       if (!valid(k)) continue;
@@ -569,14 +621,40 @@ struct VecChain {
     expl_acc.fit(1.0);
     return true;
   }
+  // rand(rng, a:b) for integers a <= b held in doubles: a + floor(u (b - a + 1)), u the replica's next uniform
+  __device__ __forceinline__ double rand_int_range(double a, double b) {
+    const double span = (b - a) + 1.0;
+    double k = floor(draw_uniform() * span);
+    if (k > b - a) k = b - a;
+    return a + k;
+  }
   template <int KO>
   __device__ double slice_coord(int lo, double cached_lp) {   // :89-186
     const double w = P->slice_w;
     const double cur = __shfl_sync(PGN_FULL_MASK, x[KO], lo);
+    const int kind = coord_kind(KO * 32 + lo);
+    if (TK == PGN_TARGET_MIXED && kind == 0) {   // Bool: sample from the full conditional, one density evaluation (:65-86)
+      double lp0, lp1;
+      if (cur != 0.0) { lp1 = cached_lp; lp0 = lp_at<KO>(lo, 0.0); }
+      else { lp0 = cached_lp; lp1 = lp_at<KO>(lo, 1.0); }
+      const double prob_ratio = exp_(lp1 - lp0);
+      const double prob_zero = 1.0 / (1.0 + prob_ratio);
+      const bool zero = draw_uniform() < prob_zero;
+      if (lane == lo) x[KO] = zero ? 0.0 : 1.0;
+      return zero ? lp0 : lp1;
+    }
+    const bool integer = TK == PGN_TARGET_MIXED && kind == 1;
     const double z = cached_lp - draw_exponential();
     // slice_double :97-126
-    double L = cur - w * draw_uniform();
-    double R = L + w;
+    double L, R;
+    if (integer) {   // initialize_slice_endpoints for integers :136-142
+      if (w != floor(w)) { err = PGN_ERR_INVALID; return 0.0; }
+      L = cur - rand_int_range(0.0, ceil(w));
+      R = L + ceil(w);
+    } else {
+      L = cur - w * draw_uniform();
+      R = L + w;
+    }
     int K = P->slice_p;
     double lp_L = lp_at<KO>(lo, L);
     double lp_R = lp_at<KO>(lo, R);
@@ -591,7 +669,7 @@ struct VecChain {
     double Lbar = L, Rbar = R;
     int n = 1;
     while (n <= P->slice_max_iter) {
-      double new_position = Lbar + draw_uniform() * (Rbar - Lbar);
+      double new_position = integer ? rand_int_range(Lbar, Rbar) : Lbar + draw_uniform() * (Rbar - Lbar);   // :188-189
       double new_lp = lp_at<KO>(lo, new_position);
       bool consider = z < new_lp;
       if (consider && slice_accept<KO>(lo, cur, new_position, z, L, R, lp_L, lp_R)) {
@@ -600,7 +678,7 @@ struct VecChain {
         return new_lp;
       }
       if (new_position < cur) Lbar = new_position; else Rbar = new_position;
-      if (isapprox(Lbar, Rbar)) {
+      if (integer ? (Lbar == Rbar) : isapprox(Lbar, Rbar)) {   // isapprox of two Integers is ==
         n_steps += n;
         return lp_at<KO>(lo, cur);
       }
@@ -1374,15 +1452,6 @@ struct TestSwapperChain {
   __device__ __forceinline__ void on_replica_changed() {}
 };
 
-// A chain type with other launch bounds: the same code compiled for fewer registers per thread, so that more warps
-// (wider teams) are co-resident.  MAXT threads per block at most, MINB blocks per SM at least -> 65536 / (MAXT * MINB)
-// registers per thread.
-template <class Base, int MAXT, int MINB>
-struct CappedChain : Base {
-  static constexpr int kMaxThreads = MAXT;
-  static constexpr int kMinBlocksPerSM = MINB;
-};
-
 // ===========================================================================
 // The scan kernel
 // ===========================================================================
@@ -1567,11 +1636,11 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
           }
           if (tw == ch.own(2)) {
             if (lane == 0) { eo->rev = ch.rev; eo->ls_fwd = ls_fwd; }
-            ch.rev = en->rev; ls_fwd = load_logsum(&en->ls_fwd);
+            ch.rev = en->rev; ls_fwd = en->ls_fwd;
           }
           if (tw == ch.own(3)) {
             if (lane == 0) { eo->expl_acc = ch.expl_acc; eo->ls_bwd = ls_bwd; }
-            ch.expl_acc = en->expl_acc; ls_bwd = load_logsum(&en->ls_bwd);
+            ch.expl_acc = en->expl_acc; ls_bwd = en->ls_bwd;
           }
           if (is_tgt && tw == ch.own(4) && P.d > 0) {
             ch.flush_online(P.on_table + (size_t)(replica_index - 1) * P.d_pad);

@@ -816,7 +816,7 @@ __global__ void logreg_decide_kernel(const __grid_constant__ LrParams P) {
             eo->ls_fwd = s.ls_fwd; eo->ls_bwd = s.ls_bwd;
           }
           s.expl_acc = en->expl_acc; s.am = en->am; s.rev = en->rev; s.swap_acc = en->swap_acc;
-          s.ls_fwd = load_logsum(&en->ls_fwd); s.ls_bwd = load_logsum(&en->ls_bwd);
+          s.ls_fwd = en->ls_fwd; s.ls_bwd = en->ls_bwd;
           if (chain == N) {
             OnEntry* oo = P.on_table + (size_t)(s.replica_index - 1) * P.d_pad;
             const OnEntry* on = P.on_table + (size_t)(ri_new - 1) * P.d_pad;

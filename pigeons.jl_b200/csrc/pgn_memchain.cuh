@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(256) scan_kernel_mem(const __grid_constant__ M
               eo->ls_fwd = r.ls_fwd; eo->ls_bwd = r.ls_bwd;
             }
             r.expl_acc = en->expl_acc; r.am = en->am; r.rev = en->rev; r.swap_acc = en->swap_acc;
-            r.ls_fwd = load_logsum(&en->ls_fwd); r.ls_bwd = load_logsum(&en->ls_bwd);
+            r.ls_fwd = en->ls_fwd; r.ls_bwd = en->ls_bwd;
             if (chain == N && P.d > 0) {   // the target-chain online statistics travel with their replica too
               OnEntry* oo = P.on_table + (size_t)(r.replica_index - 1) * P.d_pad;
               const OnEntry* on = P.on_table + (size_t)(ri_p - 1) * P.d_pad;

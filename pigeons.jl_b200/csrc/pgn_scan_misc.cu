@@ -66,10 +66,9 @@ __global__ void merge_recorders_kernel(RecEntry* table, int n_replicas, int n_lo
       if ((b->expl_acc.n | b->am.n | b->rev.n | b->swap_acc.n | b->ls_fwd.n | b->ls_bwd.n) == 0) continue;   // replica never sat here
       RecEntry ea = *a;
       const RecEntry eb = *b;
-      ea.ls_fwd = load_logsum(&a->ls_fwd); ea.ls_bwd = load_logsum(&a->ls_bwd);
       merge_mean(ea.expl_acc, eb.expl_acc); merge_mean(ea.am, eb.am); merge_mean(ea.rev, eb.rev);
       merge_mean(ea.swap_acc, eb.swap_acc);
-      merge_logsum(ea.ls_fwd, load_logsum(&b->ls_fwd)); merge_logsum(ea.ls_bwd, load_logsum(&b->ls_bwd));
+      merge_logsum(ea.ls_fwd, eb.ls_fwd); merge_logsum(ea.ls_bwd, eb.ls_bwd);
       *a = ea;
     }
     __syncwarp();
@@ -106,6 +105,16 @@ __global__ void merge_online_kernel(OnEntry* table, int n_replicas, int d, int d
   mean[c] = e.mu; s2[c] = e.s2;
   if (c == 0) *n_out = e.n;
 }
+// "absent" entries for a new round (recorders are emptied every round, recorders.jl:113-118)
+__global__ void init_recorder_tables_kernel(RecEntry* table, size_t n) {
+  RecEntry e;
+  e.expl_acc = MeanAcc{0, 0.0}; e.am = e.expl_acc; e.rev = e.expl_acc; e.swap_acc = e.expl_acc;
+  e.ls_fwd = LogSumAcc{0, -PGN_INF}; e.ls_bwd = e.ls_fwd;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) table[i] = e;
+}
+void launch_init_recorder_tables(cudaStream_t s, RecEntry* table, size_t n, int n_sms) {
+  init_recorder_tables_kernel<<<n_sms * 4, 256, 0, s>>>(table, n);
+}
 void launch_merge_recorders(cudaStream_t s, RecEntry* table, int n_replicas, int n_local, ChainStatsDev* out) {
   merge_recorders_kernel<<<(n_local + 3) / 4, 128, 0, s>>>(table, n_replicas, n_local, out);
 }
@@ -127,12 +136,14 @@ void launch_test_math(int grid, int block, int op, const double* in, double* out
 }
 
 // the vector-state families: the plain and the team kernels of a family are compiled separately
-void* vec_plain_kernel_toy(int cpl, int ex);    void* vec_team_kernel_toy(int cpl, int ex, int regcap);
-void* vec_plain_kernel_funnel(int cpl, int ex); void* vec_team_kernel_funnel(int cpl, int ex, int regcap);
-void* vec_plain_kernel_gmm(int cpl, int ex);    void* vec_team_kernel_gmm(int cpl, int ex, int regcap);
+void* vec_plain_kernel_toy(int cpl, int ex);    void* vec_team_kernel_toy(int cpl, int ex);
+void* vec_plain_kernel_funnel(int cpl, int ex); void* vec_team_kernel_funnel(int cpl, int ex);
+void* vec_plain_kernel_gmm(int cpl, int ex);    void* vec_team_kernel_gmm(int cpl, int ex);
+void* vec_plain_kernel_mixed(int cpl, int ex);
 static bool is_team_explorer(int ex) { return ex == PGN_EXPLORER_AUTOMALA || ex == PGN_EXPLORER_SLICE_THEN_AUTOMALA; }
-void* vec_scan_kernel_toy(int cpl, int ex, int regcap) { return is_team_explorer(ex) ? vec_team_kernel_toy(cpl, ex, regcap) : vec_plain_kernel_toy(cpl, ex); }
-void* vec_scan_kernel_funnel(int cpl, int ex, int regcap) { return is_team_explorer(ex) ? vec_team_kernel_funnel(cpl, ex, regcap) : vec_plain_kernel_funnel(cpl, ex); }
-void* vec_scan_kernel_gmm(int cpl, int ex, int regcap) { return is_team_explorer(ex) ? vec_team_kernel_gmm(cpl, ex, regcap) : vec_plain_kernel_gmm(cpl, ex); }
+void* vec_scan_kernel_toy(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_toy(cpl, ex) : vec_plain_kernel_toy(cpl, ex); }
+void* vec_scan_kernel_funnel(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_funnel(cpl, ex) : vec_plain_kernel_funnel(cpl, ex); }
+void* vec_scan_kernel_mixed(int cpl, int ex) { return ex == PGN_EXPLORER_SLICE ? vec_plain_kernel_mixed(cpl, ex) : nullptr; }
+void* vec_scan_kernel_gmm(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_gmm(cpl, ex) : vec_plain_kernel_gmm(cpl, ex); }
 
 }  // namespace pgn

@@ -164,6 +164,47 @@ def synthetic_logistic_regression(n_data: int, dim: int, seed: int = 2) -> Logis
 
 
 @dataclass
+class MixedProduct(Target):
+    """The mixed Bool / Integer / Float state of test/test_slice_sampler.jl:56-75 as a PT target:
+    target = Bernoulli(p1)^n_bool x Binomial(n, q1)^n_int x Normal(0, 1)^n_float,
+    reference = Bernoulli(p0)^n_bool x Binomial(n, q0)^n_int x Normal(0, sigma_ref)^n_float.
+    It exists to exercise SliceSampler's Bool (full conditional, SliceSampler.jl:65-86) and Integer
+    (integer end points and draws, :136-142,:189) coordinate updates; both ends are normalised, so log(Z1/Z0) = 0."""
+    n_bool: int = 1
+    n_int: int = 1
+    n_float: int = 1
+    binomial_n: int = 10
+    p0: float = 0.3
+    p1: float = 0.5
+    q0: float = 0.35
+    q1: float = 0.5
+    sigma_ref: float = 2.0
+
+    @property
+    def dim(self):
+        return self.n_bool + self.n_int + self.n_float
+
+    def default_explorer(self):
+        from .explorers import SliceSampler
+        return SliceSampler()
+
+    def engine_config(self):
+        n = self.binomial_n
+        table = [math.log(self.p0), math.log1p(-self.p0), math.log(self.p1), math.log1p(-self.p1),
+                 math.log(self.q0), math.log1p(-self.q0), math.log(self.q1), math.log1p(-self.q1), self.p0, self.q0]
+        table += [math.lgamma(n + 1) - math.lgamma(k + 1) - math.lgamma(n - k + 1) for k in range(n + 1)]
+        p = (float(self.n_bool), float(self.n_int), float(n)) + _normal_ref_params(self.sigma_ref)
+        return dict(target_kind=_capi.TARGET_MIXED, dim=self.dim, p=p, means=np.array(table), n_modes=len(table))
+
+    def target_moments(self):
+        """mean and standard deviation of every coordinate under the target"""
+        n, q = self.binomial_n, self.q1
+        mean = [self.p1] * self.n_bool + [n * q] * self.n_int + [0.0] * self.n_float
+        std = [math.sqrt(self.p1 * (1 - self.p1))] * self.n_bool + [math.sqrt(n * q * (1 - q))] * self.n_int + [1.0] * self.n_float
+        return np.array(mean), np.array(std)
+
+
+@dataclass
 class IsingLogPotential(Target):
     """examples/ising.jl:6-117: l(state) = beta * sum_<ij> s_i s_j on an L x L
     torus; reference = same with beta = 0 (i.i.d. Bernoulli(1/2) spins)."""

@@ -27,6 +27,9 @@ GOLDEN_CASES = {
         explorer=pg.Mix(pg.AutoMALA(preconditioner=pg.IdentityPreconditioner(), base_n_refresh=1),
                         pg.AutoMALA(preconditioner=pg.MixDiagonalPreconditioner(0.0, 0.0), base_n_refresh=1),
                         pg.AutoMALA(preconditioner=pg.DiagonalPreconditioner(), base_n_refresh=1))),
+    # SliceSampler on Bool / Integer / Float coordinates (test/test_slice_sampler.jl:56-75)
+    "mixed_bool_int_float_slice_n7_r8": lambda: dict(target=pg.MixedProduct(n_bool=3, n_int=2, n_float=2), n_chains=7,
+                                                     n_rounds=8, seed=1),
     "ising5_n10_r8": lambda: dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=8, seed=1),
 }
 

@@ -83,6 +83,11 @@ CASES = {
                                                  pg.AutoMALA(preconditioner=pg.DiagonalPreconditioner(), base_n_refresh=1))),
     "toy40_mix_two_step_sizes": dict(target=pg.toy_mvn_target(40), n_chains=5, n_rounds=6, seed=3,
                                      explorer=pg.Mix(pg.AutoMALA(step_size=0.5), pg.AutoMALA(step_size=2.0, base_n_refresh=2))),
+    "mixed_bool_int_float_slice": dict(target=pg.MixedProduct(n_bool=3, n_int=2, n_float=2), n_chains=7, n_rounds=8, seed=1),
+    "mixed40_slice_2cpl": dict(target=pg.MixedProduct(n_bool=20, n_int=10, n_float=10, binomial_n=6, p1=0.8, q1=0.2),
+                               explorer=pg.SliceSampler(w=4.0, n_passes=2), n_chains=5, n_rounds=5, seed=2),
+    "mixed_int_only": dict(target=pg.MixedProduct(n_bool=0, n_int=5, n_float=0, binomial_n=30, q0=0.5, q1=0.1),
+                           n_chains=6, n_rounds=7, seed=3),
     "single_chain": dict(target=pg.toy_mvn_target(4), explorer=pg.SliceSampler(), n_chains=1, n_rounds=5, seed=1),
     "two_chains": dict(target=pg.toy_mvn_target(2), explorer=pg.AutoMALA(), n_chains=2, n_rounds=6, seed=8),
 }
@@ -476,3 +481,40 @@ def test_c5_full_shape_round(c5, gpu_lib, oracle_lib):
     assert rg.n_ref_equiv_evals == ro.n_ref_equiv_evals and rg.n_round_trips == ro.n_round_trips
     for k in sg:
         assert np.array_equal(sg[k], so[k]), f"c5 full shape: final replica {k}"
+
+
+def test_mixed_target_entry_point_and_support(gpu_lib, oracle_lib):
+    """pgn_log_potential of the Bool / Integer / Float product target, including points outside the support of the
+    discrete coordinates (a Bool that is neither 0 nor 1, a non-integer or out-of-range count): -Inf like
+    Distributions.logpdf, bit-equal to the oracle everywhere else."""
+    t = pg.MixedProduct(n_bool=2, n_int=2, n_float=1)
+    eg = pg.Engine(gpu_lib, n_chains=4, seed=1, **t.engine_config())
+    eo = pg.Engine(oracle_lib, n_chains=4, seed=1, **t.engine_config())
+    rng = np.random.default_rng(3)
+    x = np.column_stack([rng.integers(0, 2, 40), rng.integers(0, 2, 40), rng.integers(0, 11, 40), rng.integers(0, 11, 40),
+                         rng.normal(0, 2, 40)]).astype(np.float64)
+    x[0, 0] = 0.5; x[1, 2] = 2.5; x[2, 3] = -1.0; x[3, 2] = 11.0
+    beta = rng.uniform(0, 1, 40); beta[4] = 0.0; beta[5] = 1.0; beta[0] = 0.0; beta[1] = 1.0
+    lg, lo = eg.log_potential(x, beta), eo.log_potential(x, beta)
+    assert np.array_equal(lg, lo)
+    assert np.all(np.isneginf(lg[:4])) and np.all(np.isfinite(lg[4:]))
+    eg.close(); eo.close()
+
+
+def test_slice_sampler_bool_and_integer_on_the_device(gpu_lib):
+    """test/test_slice_sampler.jl:56-75 on the CUDA path: moments of [Bernoulli(0.5), Binomial(10, 0.5), Normal(0, 1)] within
+    the reference's 0.2, the discrete coordinates stay in their supports, and a non-integer width on an integer coordinate
+    is an error (test/test_slice_sampler.jl:113-121)."""
+    t = pg.MixedProduct(n_bool=1, n_int=1, n_float=1)
+    pt = pg.pigeons(target=t, n_chains=6, n_rounds=11, seed=1, record=[pg.online, pg.traces], engine_lib=gpu_lib)
+    mean, std = t.target_moments()
+    rr = pt.reduced_recorders
+    assert np.all(np.abs(rr.online_mean - mean) <= 0.2) and np.all(np.abs(np.sqrt(rr.online_var) - std) <= 0.2)
+    tr = rr.target_trace
+    assert set(np.unique(tr[:, 0])) <= {0.0, 1.0}
+    assert np.all(tr[:, 1] == np.floor(tr[:, 1])) and tr[:, 1].min() >= 0 and tr[:, 1].max() <= 10
+    assert abs(pg.stepping_stone(pt)) < 0.1
+    pt.close()
+    with pytest.raises(pg.EngineError):
+        pg.pigeons(target=pg.MixedProduct(n_bool=0, n_int=2, n_float=0), explorer=pg.SliceSampler(w=0.1, n_passes=1),
+                   n_chains=3, n_rounds=2, engine_lib=gpu_lib)

@@ -22,6 +22,7 @@ CASES = {
     "gmm_automala_n7": dict(target=pg.eight_mode_mixture(128, 8.0), explorer=pg.AutoMALA(), n_chains=7, n_rounds=4, seed=3),
     "ising_n10": dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=6, seed=4),
     "test_swapper_n8": dict(target=pg.TestSwapper(0.5), n_chains=8, n_rounds=6, seed=5),
+    "mixed_slice_n8": dict(target=pg.MixedProduct(n_bool=3, n_int=2, n_float=2), n_chains=8, n_rounds=6, seed=8),
     "logreg_automala_n7": dict(target=pg.synthetic_logistic_regression(300, 24), explorer=pg.AutoMALA(), n_chains=7,
                                n_rounds=4, seed=6),
     "toy300_automala_n6_mem": dict(target=pg.toy_mvn_target(300), explorer=pg.AutoMALA(), n_chains=6, n_rounds=4, seed=7),

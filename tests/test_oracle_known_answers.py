@@ -275,3 +275,29 @@ def test_recorders_are_per_replica_with_the_reference_tree_merge(oracle_lib):
     assert not np.array_equal(full_pc.reduced_recorders.swap_mean, rr.swap_mean), \
         "per-chain and per-replica accumulation should differ at rounding level after 7 rounds"
     full_pc.close()
+
+
+def test_slice_sampler_bool_and_integer_coordinates(oracle_lib):
+    """test/test_slice_sampler.jl:56-75 (`test_slice_sampler_vector`): a mixed Bool / Integer / Float state
+    [Bernoulli(0.5), Binomial(10, 0.5), Normal(0, 1)] sampled by SliceSampler — Bool coordinates from their full
+    conditional (SliceSampler.jl:65-86), Integer coordinates with integer slice end points and draws (:136-142, :189) —
+    has mean [0.5, 5, 0] and standard deviation [0.5, std(Binomial(10)), 1] within 0.2 (the reference's tolerance; here
+    on the target chain of a 6-chain ladder, 2^11 scans), and both ends of the path are normalised: log(Z1/Z0) = 0."""
+    t = pg.MixedProduct(n_bool=1, n_int=1, n_float=1)
+    pt = pg.pigeons(target=t, n_chains=6, n_rounds=11, seed=1, record=[pg.online, pg.traces], engine_lib=oracle_lib)
+    mean, std = t.target_moments()
+    rr = pt.reduced_recorders
+    assert np.all(np.abs(rr.online_mean - mean) <= 0.2)
+    assert np.all(np.abs(np.sqrt(rr.online_var) - std) <= 0.2)
+    tr = rr.target_trace
+    assert set(np.unique(tr[:, 0])) <= {0.0, 1.0}                       # Bool coordinate stays Bool
+    assert np.all(tr[:, 1] == np.floor(tr[:, 1])) and tr[:, 1].min() >= 0 and tr[:, 1].max() <= 10   # Integer stays in the support
+    assert abs(pg.stepping_stone(pt)) < 0.1
+    pt.close()
+
+
+def test_slice_sampler_integer_width_must_be_integer(oracle_lib):
+    """test/test_slice_sampler.jl:113-121 ("Bad width"): a non-integer slice width on an integer coordinate is an error."""
+    t = pg.MixedProduct(n_bool=0, n_int=2, n_float=0)
+    with pytest.raises(pg.EngineError):
+        pg.pigeons(target=t, explorer=pg.SliceSampler(w=0.1, n_passes=1), n_chains=3, n_rounds=2, engine_lib=oracle_lib)

@@ -36,16 +36,21 @@ def main():
 
     tmp = tempfile.mkdtemp()
     sh(["cuobjdump", "-xelf", "all", os.path.abspath(a.so)], cwd=tmp)
-    cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    syms = subprocess.run(["readelf", "-sW", cubin], capture_output=True, text=True).stdout
-    idx = None
-    for ln in syms.splitlines():
-        if " FUNC " in ln and " GLOBAL " in ln and a.kernel in ln:
-            idx = int(ln.split(":")[0])
-            name = ln.split()[-1]
+    # the library is linked from several translation units: one cubin each; find the one that defines the kernel
+    idx = cubin = name = None
+    for f in sorted(os.listdir(tmp)):
+        if not f.endswith(".cubin"):
+            continue
+        cand = os.path.join(tmp, f)
+        syms = subprocess.run(["readelf", "-sW", cand], capture_output=True, text=True).stdout
+        for ln in syms.splitlines():
+            if " FUNC " in ln and " GLOBAL " in ln and a.kernel in ln:
+                idx, cubin, name = int(ln.split(":")[0]), cand, ln.split()[-1]
+                break
+        if idx is not None:
             break
     if idx is None:
-        sys.exit("kernel not found in " + cubin)
+        sys.exit("kernel not found in the cubins of " + a.so)
     sass = subprocess.run(["nvdisasm", "-gi", "-fun", str(idx), cubin], capture_output=True, text=True).stdout
     start = sass.index(".text." + name + ":")
     insts = []          # (addr, text, [lines innermost..outermost])
