@@ -150,6 +150,7 @@ struct pgn_handle {
   pgn::DevBuf<pgn::LrChainState> lr_st;
   pgn::DevBuf<int> lr_cols;              // compacted list of the chains whose pending point is evaluated in this batch step
   pgn::DevBuf<pgn::LrControl> lr_ctl;    // device-side counters of the batched evaluation loop
+  int lr_dmma_bn = 64;           // column tile of the tensor-core GEMM (PGN_DMMA_BN)
   bool lr_use_dmma = true;       // FP64 tensor-core GEMM (same summation order as the SIMT kernel, see pgn_logreg.cuh)
   double last_gemm_ms = 0.0;     // device time spent in the two GEMMs during the last round
   long long last_batch_steps = 0;

@@ -14,7 +14,7 @@
 // The GEMMs are hand-written with a FIXED summation order (sequential fma over k for every
 // output element, split-K chunk partials added in chunk order), which is part of the arithmetic
 // spec mirrored by the CPU oracle.  Two implementations produce identical bits:
-//   dgemm_km_dmma_kernel  FP64 tensor cores (mma.sync.m8n8k4.f64 = DMMA.8x8x4), default: the
+//   dgemm_km_dmma_kernel  FP64 tensor cores (mma.sync.m8n8k4.f64 = DMMA.8x8x4), default (128 x 64 tiles, two blocks per SM): the
 //                         hardware accumulates each instruction as an fma chain in ascending k
 //                         (probed and asserted), 76 % of the measured FP64 peak;
 //   dgemm_km_kernel       SIMT DFMA, 8x8 register tiles; limited by shared-memory bandwidth
@@ -165,47 +165,55 @@ dgemm_km_kernel(const double* __restrict__ A, int lda, const double* __restrict_
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b, double c0, double c1);
 
-template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS)
+// BN = 128: 8 warps (4 x 2), one block per SM.  BN = 64 (default): 4 warps (4 x 1), TWO blocks per SM — with a single
+// block the tensor pipe idles whenever its 8 warps meet at the k-tile barrier (ncu, round 1: DMMA pipe 74 % active, 16 % of
+// the stall samples on the barrier); two independent blocks drift apart and fill each other's gaps.  The narrower tile also
+// halves the granularity of the column compaction.  The summation order per output element does not depend on the tile.
+template <int EPI, int BN>
+__global__ void __launch_bounds__(2 * BN, BN == 64 ? 2 : 1)
 dgemm_km_dmma_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, int k_total,
-                int k_chunk, double* __restrict__ C0, double* __restrict__ C1, int ldc, size_t split_stride,
-                const double* __restrict__ yvec, int n_valid_rows, const int* __restrict__ n_cols_ptr) {
+                     int k_chunk, double* __restrict__ C0, double* __restrict__ C1, int ldc, size_t split_stride,
+                     const double* __restrict__ yvec, int n_valid_rows, const int* __restrict__ n_cols_ptr) {
   // column tiles beyond the compacted list of this batch step have nothing to multiply (the count lives on the device,
   // the host launched the full grid without knowing it)
-  if ((int)blockIdx.y * GEMM_BN >= *n_cols_ptr) return;
+  if ((int)blockIdx.y * BN >= *n_cols_ptr) return;
+  constexpr int NT = 2 * BN;            // threads
+  constexpr int WN = BN / 64;           // warp columns (each warp owns 32 rows x 64 columns)
+  constexpr int LDB = BN + 4;           // padded row stride of the B tile, = 8 words mod 32 like DMMA_LD
+  constexpr int TPR = NT / GEMM_BK;     // loader threads per k-row
+  constexpr int STEP = 2 * TPR;         // doubles covered by one pass of a k-row's loader threads
   extern __shared__ double gemm_smem[];
   double (*As)[GEMM_BK][DMMA_LD] = reinterpret_cast<double (*)[GEMM_BK][DMMA_LD]>(gemm_smem);
-  double (*Bs)[GEMM_BK][DMMA_LD] = reinterpret_cast<double (*)[GEMM_BK][DMMA_LD]>(gemm_smem + 2 * GEMM_BK * DMMA_LD);
+  double (*Bs)[GEMM_BK][LDB] = reinterpret_cast<double (*)[GEMM_BK][LDB]>(gemm_smem + 2 * GEMM_BK * DMMA_LD);
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * GEMM_BN;
+  const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
   const int k_begin = blockIdx.z * k_chunk;
   const int k_end = min(k_total, k_begin + k_chunk);
-  const int lk = tid >> 4, lo = (tid & 15) * 2;
+  const int lk = tid / TPR, lo = (tid % TPR) * 2;
   const int warp = tid >> 5, lane = tid & 31;
-  const int wm = (warp >> 1) * 32;      // warp row offset inside the block tile (4 warp rows)
-  const int wn = (warp & 1) * 64;       // warp column offset (2 warp columns)
+  const int wm = (warp / WN) * 32;      // warp row offset inside the block tile (4 warp rows)
+  const int wn = (warp % WN) * 64;      // warp column offset
   const int fr = lane >> 2, fk = lane & 3;
   double acc[4][8][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-  double2 ra[4], rb[4];
+  constexpr int NA = GEMM_BM / STEP, NB = BN / STEP;
+  double2 ra[NA], rb[NB];
   auto gload = [&](int kt) {
     const double* ap = A + (size_t)(kt + lk) * lda + m0 + lo;
     const double* bp = B + (size_t)(kt + lk) * ldb + n0 + lo;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      ra[i] = *reinterpret_cast<const double2*>(ap + 32 * i);
-      rb[i] = *reinterpret_cast<const double2*>(bp + 32 * i);
-    }
+    for (int i = 0; i < NA; ++i) ra[i] = *reinterpret_cast<const double2*>(ap + STEP * i);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) rb[i] = *reinterpret_cast<const double2*>(bp + STEP * i);
   };
   auto sstore = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      *reinterpret_cast<double2*>(&As[buf][lk][lo + 32 * i]) = ra[i];
-      *reinterpret_cast<double2*>(&Bs[buf][lk][lo + 32 * i]) = rb[i];
-    }
+    for (int i = 0; i < NA; ++i) *reinterpret_cast<double2*>(&As[buf][lk][lo + STEP * i]) = ra[i];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) *reinterpret_cast<double2*>(&Bs[buf][lk][lo + STEP * i]) = rb[i];
   };
   int buf = 0;
   if (k_begin < k_end) { gload(k_begin); sstore(0); }
@@ -257,8 +265,8 @@ dgemm_km_dmma_kernel(const double* __restrict__ A, int lda, const double* __rest
 // GEMM runs 8 warps per SM, so ~150 dependent FP64 instructions per element there stall the
 // tensor pipe; measured 0.7 ms fused vs 0.2 ms as a separate pass over 128 MB.)
 __global__ void logreg_bernoulli_kernel(double* __restrict__ LL, double* __restrict__ RES, const double* __restrict__ yvec,
-                                        int ld, int n_rows_pad, int n_valid_rows, const int* __restrict__ n_cols_ptr) {
-  const int ncp = (*n_cols_ptr + GEMM_BN - 1) / GEMM_BN * GEMM_BN;   // the column tiles the GEMM filled
+                                        int ld, int n_rows_pad, int n_valid_rows, const int* __restrict__ n_cols_ptr, int col_tile) {
+  const int ncp = (*n_cols_ptr + col_tile - 1) / col_tile * col_tile;   // the column tiles the GEMM filled
   const int half = ncp / 2;
   const size_t total2 = (size_t)n_rows_pad * half;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (size_t)gridDim.x * blockDim.x) {
@@ -318,10 +326,10 @@ __global__ void logreg_finalize_grad_kernel(const double* __restrict__ Gp, int n
 
 // Thetat[c][j] = Theta[cols[j]][c] for the compacted columns j < n_cols; the rest of the last column tile is zero-filled
 __global__ void logreg_gather_transpose_kernel(const double* __restrict__ src, int cols_dim, int ld_src, const int* __restrict__ n_cols_ptr,
-                                               const int* __restrict__ cols, double* __restrict__ dst, int ld_dst) {
+                                               const int* __restrict__ cols, double* __restrict__ dst, int ld_dst, int col_tile) {
   __shared__ double tile[32][33];
   const int n_cols = *n_cols_ptr;
-  const int ncp = (n_cols + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
+  const int ncp = (n_cols + col_tile - 1) / col_tile * col_tile;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   if (r0 >= ncp) return;
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -340,7 +348,7 @@ __global__ void logreg_gather_transpose_kernel(const double* __restrict__ src, i
 // Also keeps the round's counters (batch steps that evaluated something, columns requested, columns multiplied)
 // and the per-step history the host reads once per chunk of steps.
 __global__ void logreg_compact_kernel(const LrChainState* __restrict__ st, int n_local, int* __restrict__ cols, LrControl* ctl,
-                                      int step_in_chunk) {
+                                      int step_in_chunk, int col_tile) {
   __shared__ int warp_count[32];
   __shared__ int base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
@@ -366,7 +374,7 @@ __global__ void logreg_compact_kernel(const LrChainState* __restrict__ st, int n
     if (n > 0) {
       ctl->steps += 1;
       ctl->sum_active += n;
-      ctl->sum_gemm_cols += (n + GEMM_BN - 1) / GEMM_BN * GEMM_BN;
+      ctl->sum_gemm_cols += (n + col_tile - 1) / col_tile * col_tile;
     }
   }
 }

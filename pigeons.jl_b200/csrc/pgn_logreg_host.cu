@@ -10,7 +10,8 @@ namespace pgn {
 // logistic regression: batched-GEMM engine (pgn_logreg.cuh)
 // ===========================================================================
 constexpr size_t GEMM_SMEM_BYTES = 2ull * 2 * GEMM_BK * GEMM_BM * sizeof(double);
-constexpr size_t DMMA_SMEM_BYTES = 2ull * 2 * GEMM_BK * DMMA_LD * sizeof(double);
+constexpr int DMMA_BN = 64;   // column tile of the tensor-core GEMM (two 128 x 64 blocks per SM); PGN_DMMA_BN=128: one 128 x 128 block
+constexpr size_t dmma_smem_bytes(int bn) { return 2ull * GEMM_BK * (DMMA_LD + bn + 4) * sizeof(double); }
 
 void logreg_allocate(pgn_handle* h, const pgn_config* cfg) {
   const int d = cfg->dim, dp = h->d_pad;
@@ -51,11 +52,18 @@ void logreg_allocate(pgn_handle* h, const pgn_config* cfg) {
     const char* g = std::getenv("PGN_GEMM");   // "simt" selects the DFMA kernel; default: FP64 tensor cores
     h->lr_use_dmma = !(g != nullptr && std::string(g) == "simt");
   }
-  CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMMA_SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMMA_SMEM_BYTES));
+  {
+    const char* b = std::getenv("PGN_DMMA_BN");
+    h->lr_dmma_bn = (b != nullptr && std::atoi(b) == 128) ? 128 : DMMA_BN;
+  }
+  CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_dmma_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dmma_smem_bytes(64)));
+  CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_dmma_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dmma_smem_bytes(128)));
   CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(dgemm_km_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
 }
+
+// column tile of the GEMMs of this handle: the compaction, the gather and the Bernoulli pass round n_cols up to it
+static int logreg_col_tile(const pgn_handle* h) { return h->lr_use_dmma ? h->lr_dmma_bn : GEMM_BN; }
 
 // Evaluate likelihood and its gradient at the rows cols[0..n_cols) of `theta` ([r_pad][d_pad]); results land in
 // lr_lik[cols[j]] and lr_G[cols[j]][:].  n_cols and cols live on the device (LrControl / lr_cols, written by
@@ -65,31 +73,27 @@ void logreg_eval_batch(pgn_handle* h, const double* theta, cudaEvent_t e0, cudaE
   const int dp = h->d_pad, np = h->lr_n_pad, rp = h->lr_r_pad;
   const int* ncp = &h->lr_ctl.p->n_cols;
   const int* cols = h->lr_cols.p;
+  const int bn = logreg_col_tile(h);
   {
     dim3 grid((dp + 31) / 32, (rp + 31) / 32), block(32, 8);
-    logreg_gather_transpose_kernel<<<grid, block, 0, h->stream>>>(theta, dp, dp, ncp, cols, h->lr_Thetat.p, rp);
+    logreg_gather_transpose_kernel<<<grid, block, 0, h->stream>>>(theta, dp, dp, ncp, cols, h->lr_Thetat.p, rp, bn);
   }
   if (e0) CUDA_CHECK(cudaEventRecord(e0, h->stream));
-  {
-    dim3 grid(np / GEMM_BM, rp / GEMM_BN, 1);
-    if (h->lr_use_dmma)
-      dgemm_km_dmma_kernel<0><<<grid, GEMM_THREADS, DMMA_SMEM_BYTES, h->stream>>>(
-          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, nullptr, rp, 0, nullptr, 0, ncp);
+  auto gemm = [&](const double* A, int lda, const double* B, int k_total, int k_chunk, double* C, size_t split_stride, dim3 grid) {
+    if (!h->lr_use_dmma)
+      dgemm_km_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(A, lda, B, rp, k_total, k_chunk, C, nullptr, rp, split_stride,
+                                                                             nullptr, 0, ncp);
+    else if (bn == 64)
+      dgemm_km_dmma_kernel<0, 64><<<grid, 128, dmma_smem_bytes(64), h->stream>>>(A, lda, B, rp, k_total, k_chunk, C, nullptr, rp,
+                                                                                 split_stride, nullptr, 0, ncp);
     else
-      dgemm_km_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
-          h->lr_Xt.p, np, h->lr_Thetat.p, rp, dp, dp, h->lr_LL.p, nullptr, rp, 0, nullptr, 0, ncp);
-    logreg_bernoulli_kernel<<<h->n_sms * 8, 256, 0, h->stream>>>(h->lr_LL.p, h->lr_Res.p, h->lr_y.p, rp, np, h->lr_n_data, ncp);
-  }
+      dgemm_km_dmma_kernel<0, 128><<<grid, 256, dmma_smem_bytes(128), h->stream>>>(A, lda, B, rp, k_total, k_chunk, C, nullptr, rp,
+                                                                                   split_stride, nullptr, 0, ncp);
+  };
+  gemm(h->lr_Xt.p, np, h->lr_Thetat.p, dp, dp, h->lr_LL.p, 0, dim3(np / GEMM_BM, rp / bn, 1));
+  logreg_bernoulli_kernel<<<h->n_sms * 8, 256, 0, h->stream>>>(h->lr_LL.p, h->lr_Res.p, h->lr_y.p, rp, np, h->lr_n_data, ncp, bn);
   logreg_reduce_ll_kernel<<<(rp + 7) / 8, 256, 0, h->stream>>>(h->lr_LL.p, rp, h->lr_n_data, ncp, cols, h->lr_lik.p);
-  {
-    dim3 grid(dp / GEMM_BM, rp / GEMM_BN, h->lr_splits);
-    if (h->lr_use_dmma)
-      dgemm_km_dmma_kernel<0><<<grid, GEMM_THREADS, DMMA_SMEM_BYTES, h->stream>>>(
-          h->lr_Xr.p, dp, h->lr_Res.p, rp, np, LR_CHUNK, h->lr_Gp.p, nullptr, rp, (size_t)dp * rp, nullptr, 0, ncp);
-    else
-      dgemm_km_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(
-          h->lr_Xr.p, dp, h->lr_Res.p, rp, np, LR_CHUNK, h->lr_Gp.p, nullptr, rp, (size_t)dp * rp, nullptr, 0, ncp);
-  }
+  gemm(h->lr_Xr.p, dp, h->lr_Res.p, np, LR_CHUNK, h->lr_Gp.p, (size_t)dp * rp, dim3(dp / GEMM_BM, rp / bn, h->lr_splits));
   if (e1) CUDA_CHECK(cudaEventRecord(e1, h->stream));
   {
     dim3 grid((dp + 31) / 32, (rp + 31) / 32), block(32, 8);
@@ -170,7 +174,7 @@ void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<C
     while (!scan_done && flag == 0) {
       for (int k = 0; k < LR_STEP_CHUNK; ++k) {
         logreg_controller_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
-        logreg_compact_kernel<<<1, 1024, 0, h->stream>>>(h->lr_st.p, nl, h->lr_cols.p, h->lr_ctl.p, k);
+        logreg_compact_kernel<<<1, 1024, 0, h->stream>>>(h->lr_st.p, nl, h->lr_cols.p, h->lr_ctl.p, k, logreg_col_tile(h));
         logreg_eval_batch(h, h->lr_Theta.p, ge[2 * k], ge[2 * k + 1]);
       }
       h->last_launches += (long long)LR_STEP_CHUNK * (1 + LR_EVAL_LAUNCHES);

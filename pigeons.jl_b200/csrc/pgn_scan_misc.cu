@@ -82,13 +82,14 @@ __global__ void merge_recorders_kernel(RecEntry* table, int n_replicas, int n_lo
     o.am_n = e.am.n; o.am_mean = e.am.mu; o.rev_n = e.rev.n; o.rev_mean = e.rev.mu;
   }
 }
-// The same tree for the target-chain online statistics, one thread per coordinate (OnlineStatsBase._merge!(::Variance,
+// The same tree for the target-chain online statistics, one warp per coordinate (OnlineStatsBase._merge!(::Variance,
 // ::Variance): g = n2 / (n += n2); delta = mu2 - mu; s2 = smooth(s2, s2', g) + delta^2 g (1 - g); mu = smooth(mu, mu2, g)).
 __global__ void merge_online_kernel(OnEntry* table, int n_replicas, int d, int d_pad, double* mean, double* s2, long long* n_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= d) return;
-  for (int spacing = 1; spacing < n_replicas; spacing *= 2)
-    for (long long i = 0; i + spacing < n_replicas; i += 2LL * spacing) {
+  for (int spacing = 1; spacing < n_replicas; spacing *= 2) {
+    for (long long i = (long long)lane * 2 * spacing; i + spacing < n_replicas; i += 64LL * spacing) {
       OnEntry* a = table + (size_t)i * d_pad + c;
       const OnEntry b = table[(size_t)(i + spacing) * d_pad + c];
       if (b.n == 0) continue;
@@ -101,9 +102,13 @@ __global__ void merge_online_kernel(OnEntry* table, int n_replicas, int d, int d
       ea.mu = ea.mu + g * (b.mu - ea.mu);
       *a = ea;
     }
-  const OnEntry e = table[c];
-  mean[c] = e.mu; s2[c] = e.s2;
-  if (c == 0) *n_out = e.n;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    const OnEntry e = table[c];
+    mean[c] = e.mu; s2[c] = e.s2;
+    if (c == 0) *n_out = e.n;
+  }
 }
 // "absent" entries for a new round (recorders are emptied every round, recorders.jl:113-118)
 __global__ void init_recorder_tables_kernel(RecEntry* table, size_t n) {
@@ -119,7 +124,7 @@ void launch_merge_recorders(cudaStream_t s, RecEntry* table, int n_replicas, int
   merge_recorders_kernel<<<(n_local + 3) / 4, 128, 0, s>>>(table, n_replicas, n_local, out);
 }
 void launch_merge_online(cudaStream_t s, OnEntry* table, int n_replicas, int d, int d_pad, double* mean, double* s2, long long* n_out) {
-  merge_online_kernel<<<(d + 127) / 128, 128, 0, s>>>(table, n_replicas, d, d_pad, mean, s2, n_out);
+  merge_online_kernel<<<(d + 3) / 4, 128, 0, s>>>(table, n_replicas, d, d_pad, mean, s2, n_out);
 }
 
 void* ising_scan_kernel() { return (void*)scan_kernel<IsingChain>; }

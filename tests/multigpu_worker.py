@@ -33,12 +33,17 @@ def main():
         "toy300_automala_n9_mem": dict(target=pg.toy_mvn_target(300), explorer=pg.AutoMALA(), n_chains=9, n_rounds=4, seed=7),
         "ising_n10": dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=6, seed=4),
         "test_swapper_n8": dict(target=pg.TestSwapper(0.5), n_chains=8, n_rounds=6, seed=5),
+        "mixed_slice_n9": dict(target=pg.MixedProduct(n_bool=3, n_int=2, n_float=2), n_chains=9, n_rounds=6, seed=8),
+        "funnel_automala_n24_per_chain": dict(target=pg.Funnel(32), explorer=pg.AutoMALA(), n_chains=24, n_rounds=5, seed=9,
+                                              recorder_order=1),
     }
     rec = [pg.index_process, pg.swap_trace, pg.traces]
     report = {}
     for name, kw in cases.items():
         r = [pg.index_process, pg.swap_trace] if name.startswith("test_swapper") else rec
-        pt = pg.pigeons(engine_lib=lib, comm=comm, device=local_rank, record=r, **kw)
+        # checked_round: after round 3 rank 0 re-runs rounds 1..3 on ONE device and every shard's replicas (gathered from the
+        # per-GPU pgn_get_state), the schedule and the explorer must equal the serial run (src/pt/checks.jl:36-78)
+        pt = pg.pigeons(engine_lib=lib, comm=comm, device=local_rank, record=r, checked_round=3, **kw)
         if rank == 0:
             ref = pg.pigeons(engine_lib=load_oracle(), record=r, **kw)
             a, b = pt.reduced_recorders, ref.reduced_recorders

@@ -34,18 +34,26 @@ def main():
     ap.add_argument("--outer", default=None, help="LO:HI line range of an outer function to attribute call sites to")
     a = ap.parse_args()
 
+    # The library is linked from several translation units (csrc/Makefile), several of them built from the same source
+    # with different -D flags: extract the cubin of every object file into its own directory and find the kernel.
     tmp = tempfile.mkdtemp()
-    sh(["cuobjdump", "-xelf", "all", os.path.abspath(a.so)], cwd=tmp)
-    # the library is linked from several translation units: one cubin each; find the one that defines the kernel
+    build = os.path.join(os.path.dirname(os.path.abspath(a.so)), "build")
+    objs = sorted(os.path.join(build, f) for f in os.listdir(build) if f.endswith(".o")) if os.path.isdir(build) else [os.path.abspath(a.so)]
     idx = cubin = name = None
-    for f in sorted(os.listdir(tmp)):
-        if not f.endswith(".cubin"):
-            continue
-        cand = os.path.join(tmp, f)
-        syms = subprocess.run(["readelf", "-sW", cand], capture_output=True, text=True).stdout
-        for ln in syms.splitlines():
-            if " FUNC " in ln and " GLOBAL " in ln and a.kernel in ln:
-                idx, cubin, name = int(ln.split(":")[0]), cand, ln.split()[-1]
+    for n, obj in enumerate(objs):
+        sub = os.path.join(tmp, str(n))
+        os.makedirs(sub)
+        subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=sub, capture_output=True, text=True)
+        for f in sorted(os.listdir(sub)):
+            if not f.endswith(".cubin"):
+                continue
+            cand = os.path.join(sub, f)
+            syms = subprocess.run(["readelf", "-sW", cand], capture_output=True, text=True).stdout
+            for ln in syms.splitlines():
+                if " FUNC " in ln and " GLOBAL " in ln and a.kernel in ln:
+                    idx, cubin, name = int(ln.split(":")[0]), cand, ln.split()[-1]
+                    break
+            if idx is not None:
                 break
         if idx is not None:
             break
