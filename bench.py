@@ -188,18 +188,22 @@ def one_step(pt, scans):
     return eng.run_round(scans)
 
 
+BASELINE_LADDER = {"c1": 10, "c2": 256, "c3": 1024, "c4": 4096, "c5": 2048}     # n_chains BASELINE.json names
+
+
 def ladder_chains(name, gpus, scaling):
-    cpg = CONFIGS[name]["chains_per_gpu"]
-    return cpg if scaling == "strong" else cpg * gpus
+    """weak: chains_per_gpu per GPU; strong: the ladder BASELINE.json names, split over the GPUs"""
+    return BASELINE_LADDER[name] if scaling == "strong" else CONFIGS[name]["chains_per_gpu"] * gpus
 
 
 def config_dict(name, gpus, scans, burn, scaling="weak"):
     cfg = CONFIGS[name]
     cpg = cfg["chains_per_gpu"]
     if scaling == "strong":
-        return {"workload": cfg["workload"], "name": name, "n_chains": cpg, "dim": cfg["dim"], "explorer": cfg["explorer"],
+        n = BASELINE_LADDER[name]
+        return {"workload": cfg["workload"], "name": name, "n_chains": n, "dim": cfg["dim"], "explorer": cfg["explorer"],
                 "scans_per_step": scans, "burn_in_rounds": burn, "parallelism": f"chains/{gpus}",
-                "scan_unit": f"one PT scan of the {cpg}-chain ladder, split contiguously over the N GPUs (strong scaling)",
+                "scan_unit": f"one PT scan of the {n}-chain ladder BASELINE.json names, split contiguously over the N GPUs (strong scaling)",
                 "l2": "flushed between timed steps (256 MiB write); the working set is register-resident"}
     return {"workload": cfg["workload"], "name": name, "n_chains": cpg * gpus, "dim": cfg["dim"], "explorer": cfg["explorer"],
             "scans_per_step": scans, "burn_in_rounds": burn, "parallelism": f"chains/{gpus}",

@@ -58,6 +58,7 @@ void fill_params(pgn_handle* h, Params& P) {
   P.online_mean = h->online_mean.p; P.online_s2 = h->online_s2.p; P.online_n = h->online_n.p;
   P.error_flag = h->error_flag.p;
   P.timeout_ns = h->timeout_ns;
+  P.progress = h->progress.p;
   const bool per_replica = h->recorder_order == PGN_RECORDERS_PER_REPLICA;
   P.rec_table = per_replica ? h->rec_table.p : nullptr;
   P.on_table = per_replica ? h->on_table.p : nullptr;
@@ -240,6 +241,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
     h->replica_index.alloc(nl); h->rt_state.alloc(nl); h->rng_ctr.alloc(nl);
     h->stats.alloc(nl);
     h->error_flag.alloc(1);
+    h->progress.alloc(1);
     h->online_mean.alloc(h->d_pad); h->online_s2.alloc(h->d_pad); h->online_n.alloc(1);
     h->mail.alloc(h->mail_bytes);
     h->std_devs.alloc(std::max(d, 1));
@@ -474,6 +476,11 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
       const int nl_max = (h->cfg.n_chains + std::max(h->cfg.world_size, 1) - 1) / std::max(h->cfg.world_size, 1);
       const bool vec_target = h->cfg.target_kind == PGN_TARGET_TOY_MVN || h->cfg.target_kind == PGN_TARGET_FUNNEL ||
                               h->cfg.target_kind == PGN_TARGET_GMM;
+      if (kernel && h->cfg.target_kind == PGN_TARGET_ISING && std::getenv("PGN_ISING_LITE") != nullptr &&
+          std::string(std::getenv("PGN_ISING_LITE")) == "1") {   // tests: force the table-free Ising kernel
+        kernel = ising_lite_scan_kernel();
+        wpb = 1; grid = nl; smem = 0;
+      } else
       if (kernel && !(h->force_mem && vec_target)) {
         if (is_team_kernel(h)) {
           // block = the team of W warps serving one chain.  W = the widest team (<= 8) whose blocks are all
@@ -510,6 +517,17 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, sm));
             const int g = (nl + w - 1) / w;
             if ((long long)per_sm * h->n_sms >= (nl_max + w - 1) / w) { wpb = w; grid = g; smem = sm; break; }
+          }
+          if (wpb == 0 && h->cfg.target_kind == PGN_TARGET_ISING) {
+            // more Ising chains than fit with one ratio table per chain in shared memory (~1.9 K): the table-free kernel
+            // (64 registers, no shared memory) holds up to 32 chains per SM; same mailbox layout, same results
+            kernel = ising_lite_scan_kernel();
+            for (int w = 1; w <= 2; w *= 2) {
+              int per_sm = 0;
+              CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, w * 32, 0));
+              const int g = (nl + w - 1) / w;
+              if ((long long)per_sm * h->n_sms >= (nl_max + w - 1) / w) { wpb = w; grid = g; smem = 0; break; }
+            }
           }
         }
       }

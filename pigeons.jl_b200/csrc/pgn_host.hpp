@@ -126,6 +126,7 @@ struct pgn_handle {
   pgn::DevBuf<int> replica_index, rt_state, error_flag;
   pgn::DevBuf<unsigned long long> rng_ctr;
   pgn::DevBuf<long long> online_n;
+  pgn::DevBuf<unsigned long long> progress;
   pgn::DevBuf<pgn::ChainStatsDev> stats;
   pgn::DevBuf<char> mail;
   char* mail_left = nullptr;
@@ -168,6 +169,7 @@ void* vec_scan_kernel_funnel(int cpl, int ex);
 void* vec_scan_kernel_gmm(int cpl, int ex);
 void* vec_scan_kernel_mixed(int cpl, int ex);
 void* ising_scan_kernel();
+void* ising_lite_scan_kernel();
 void* test_swapper_scan_kernel();
 void* mem_scan_kernel(int target_kind, int ex);
 // parity entry points

@@ -127,6 +127,8 @@ struct Params {
   int* error_flag;
   unsigned long long timeout_ns;
   // per-replica recorders (null: one accumulator per chain, fitted in scan order)
+  unsigned long long* progress;   // scans completed by the chains of this shard (all rounds): the hand-shake spin limit counts
+                                  // time WITHOUT progress anywhere on the shard, not time since the wait began
   RecEntry* rec_table;     // [n_chains replicas][n_local]
   OnEntry* on_table;       // [n_chains replicas][d_pad], used by the shard owning chain N
 };
@@ -1154,12 +1156,17 @@ struct VecChain {
 // ===========================================================================
 // Ising chain (examples/ising.jl): lane i holds row i of the bit-packed lattice
 // ===========================================================================
-struct IsingChain {
+// TABLE = true: the Metropolis ratios of the round are tabulated in shared memory (16.7 KB per chain: at most ~1.9 K
+// chains per GPU).  TABLE = false: the same expression is evaluated where it is needed (about twice the instructions per
+// site), no shared memory and a 64-register budget, so that up to 32 warps = 32 chains share an SM (4.7 K chains per GPU:
+// BASELINE config 4 on ONE GPU).
+template <bool TABLE>
+struct IsingChainT {
   static constexpr bool kTestSwapper = false;
   static constexpr bool kTeam = false;
   static constexpr bool kIsing = true;
-  static constexpr int kMaxThreads = 256;
-  static constexpr int kMinBlocksPerSM = 1;
+  static constexpr int kMaxThreads = TABLE ? 256 : 64;
+  static constexpr int kMinBlocksPerSM = TABLE ? 1 : 16;
   static constexpr bool kCompact = false;
   const Params* P;
   int lane, L;
@@ -1188,7 +1195,17 @@ struct IsingChain {
   int sig;             // sign of the dS that lowers lp
   int S0;              // 2 L^2
   static constexpr int TBL_PAD = 10;   // rows on either side for the wrong guesses of the speculative sweep (5 sites x +-2)
-  static __host__ __device__ int table_doubles(int L_) { return (L_ * L_ + 1 + 2 * TBL_PAD) * 2; }
+  static __host__ __device__ int table_doubles(int L_) { return TABLE ? (L_ * L_ + 1 + 2 * TBL_PAD) * 2 : 0; }
+  // exp(lp(S + dS) - lp(S)) for table index idx = 2 * row + q (row: S = S0 - 4 row; q: |dS| = 4 (q + 1)); rows outside
+  // [0, L^2] belong to refuted guesses of the speculative sweep only
+  __device__ __forceinline__ double ratio_at(int idx) const {
+    if (TABLE) return tbl[idx];
+    const int row_m = idx >> 1;
+    if (row_m < 0 || row_m > L * L) return 1.0;
+    const int s_old = S0 - 4 * row_m;
+    const int s_new = s_old + sig * 4 * ((idx & 1) + 1);
+    return exp_(lp(beta, s_new) - lp(beta, s_old));
+  }
   static __device__ void stage_shared(const Params&, double*) {}
   __device__ __forceinline__ int own(int) const { return 0; }
 
@@ -1235,6 +1252,7 @@ struct IsingChain {
     const bool decreasing = (beta > 0.0 && c < 0.0) || (beta < 0.0 && c > 0.0);   // lp decreasing in S
     sig = decreasing ? 1 : -1;
     S0 = 2 * L * L;
+    if (!TABLE) { tbl = nullptr; return; }
     for (int idx = lane; idx < table_doubles(L); idx += 32) {
       const int row_m = (idx >> 1) - TBL_PAD;
       double v = 1.0;                                    // padding rows are never used by the true trajectory
@@ -1293,7 +1311,7 @@ struct IsingChain {
       pool = uniform_at(rng, pool_base + (unsigned long long)lane);
       k = 0;
     }
-    const double accept_ratio = tbl[2 * m + q];
+    const double accept_ratio = ratio_at(2 * m + q);
     const double u = __shfl_sync(PGN_FULL_MASK, pool, k);
     const bool draws = low && accept_ratio < 1;           // rand(rng) only if accept_ratio < 1 (examples/ising.jl:110)
     const bool reject = draws && u > accept_ratio;
@@ -1366,7 +1384,7 @@ struct IsingChain {
           }
           double ratio[5];
 #pragma unroll
-          for (int t = 0; t < 5; ++t) ratio[t] = tbl[row_at[t]];
+          for (int t = 0; t < 5; ++t) ratio[t] = ratio_at(row_at[t]);
           int kk = k;
           bool ok = true;
 #pragma unroll
@@ -1411,6 +1429,8 @@ struct IsingChain {
   }
   __device__ double log_ratio(double beta_partner) const { return lp(beta_partner, S) - lp(beta, S); }
 };
+using IsingChain = IsingChainT<true>;
+using IsingChainLite = IsingChainT<false>;
 
 // ===========================================================================
 // TestSwapper (src/swap/pair_swapper.jl:100-149): no state, constant acceptance
@@ -1567,7 +1587,7 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
         }
         // ---- wait for the partner's header
         unsigned long long w = 0ull;
-        unsigned long long t0 = 0;
+        unsigned long long t0 = 0, seen = 0;
         unsigned int it = 0;
         while (true) {
           if (lane < LL_HDR_WORDS) w = ld_relaxed_sys(srcw + lane);
@@ -1579,7 +1599,8 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
             if (lane == 0) {
               if (*reinterpret_cast<volatile int*>(P.error_flag) != 0) status = 1;
               const unsigned long long now = globaltimer_ns();
-              if (t0 == 0) t0 = now;
+              const unsigned long long prog = *reinterpret_cast<volatile unsigned long long*>(P.progress);
+              if (t0 == 0 || prog != seen) { t0 = now; seen = prog; }   // some chain of the shard finished a scan: not stuck
               else if (now - t0 > P.timeout_ns) status = 2;
             }
             status = __shfl_sync(PGN_FULL_MASK, status, 0);
@@ -1664,7 +1685,10 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
         if (!got) { err = PGN_ERR_TIMEOUT; break; }
       }
     }
-    if (lane == 0 && tw == 0 && P.swap_accept) P.swap_accept[log_at] = accepted ? 1 : 0;
+    if (lane == 0 && tw == 0) {
+      if (P.swap_accept) P.swap_accept[log_at] = accepted ? 1 : 0;
+      atomicAdd(P.progress, 1ull);
+    }
   }
 
   if (err > 0 && lane == 0) atomicCAS(P.error_flag, 0, err);

@@ -128,6 +128,7 @@ void launch_merge_online(cudaStream_t s, OnEntry* table, int n_replicas, int d, 
 }
 
 void* ising_scan_kernel() { return (void*)scan_kernel<IsingChain>; }
+void* ising_lite_scan_kernel() { return (void*)scan_kernel<IsingChainLite>; }
 void* test_swapper_scan_kernel() { return (void*)scan_kernel<TestSwapperChain>; }
 
 void launch_init_toy(int grid, int block, cudaStream_t s, const Params& P) { init_toy_kernel<<<grid, block, 0, s>>>(P); }

@@ -518,3 +518,25 @@ def test_slice_sampler_bool_and_integer_on_the_device(gpu_lib):
     with pytest.raises(pg.EngineError):
         pg.pigeons(target=pg.MixedProduct(n_bool=0, n_int=2, n_float=0), explorer=pg.SliceSampler(w=0.1, n_passes=1),
                    n_chains=3, n_rounds=2, engine_lib=gpu_lib)
+
+
+@pytest.mark.parametrize("name", ["ising5", "ising32"])
+def test_ising_table_free_kernel_parity(name, gpu_lib, oracle_lib, monkeypatch):
+    """PGN_ISING_LITE=1: the Ising kernel that evaluates the Metropolis ratios where they are needed (no shared-memory
+    table, 64 registers; selected automatically for shards beyond ~1.9 K chains) gives the same bits."""
+    monkeypatch.setenv("PGN_ISING_LITE", "1")
+    kw = CASES[name]
+    assert_same(run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw), name + "/lite")
+
+
+def test_c4_full_ladder_on_one_gpu(gpu_lib, oracle_lib):
+    """BASELINE config 4 at its full shape on ONE GPU: 4096 chains of the 32 x 32 lattice (more than fit with a ratio table
+    per chain, so the table-free kernel runs), rounds 1..2, bit-exact against the oracle + the scan invariants."""
+    kw = dict(target=pg.IsingLogPotential(0.4406867935097715, 32), n_chains=4096, n_rounds=2, seed=1,
+              record=[pg.index_process, pg.swap_trace])
+    g, c = run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw)
+    assert_same(g, c, "c4_ising32_4096")
+    rr = g["rr"]
+    last = type("R", (), dict(index_process=rr.index_process[-4:], swap_accept=rr.swap_accept[-4:], swap_lr=rr.swap_lr[-4:],
+                              swap_u=rr.swap_u[-4:]))
+    check_scan_invariants(last, 4096)
