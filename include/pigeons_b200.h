@@ -67,7 +67,8 @@ extern "C" {
 #define PGN_EXPLORER_AUTOMALA 3         /* src/explorers/AutoMALA.jl:29-294                        */
 #define PGN_EXPLORER_ISING_METROPOLIS 4 /* examples/ising.jl:91-117                                */
 #define PGN_EXPLORER_MALA 5             /* src/explorers/MALA.jl:19-104 (fixed step size)          */
-#define PGN_EXPLORER_SLICE_THEN_AUTOMALA 6 /* Compose(SliceSampler(), AutoMALA()): src/explorers/Compose.jl:16-19 */
+#define PGN_EXPLORER_COMPOSE 6          /* Compose(e1, e2, ...): every explorer in turn (src/explorers/Compose.jl:16-19)   */
+#define PGN_EXPLORER_MIX 7              /* Mix(e1, e2, ...): one explorer, drawn uniformly from the replica's stream (Mix.jl:20-21) */
 #define PGN_MAX_MIX 4                   /* explorers in a Mix (src/explorers/Mix.jl:7-21)          */
 
 /* ---- preconditioners (src/explorers/Preconditioner.jl:7-77) --------------- */
@@ -149,6 +150,13 @@ typedef struct pgn_explorer_params {
      n_mix in 2..PGN_MAX_MIX: variant v uses (mix_n_refresh[v], mix_step_size[v], mix_precond_kind[v],
      mix_variant_p0[v], mix_variant_p01[v]); std_devs is shared (every variant adapts from the same
      recorders, Mix.jl:14-17). */
+  /* kind = PGN_EXPLORER_COMPOSE / PGN_EXPLORER_MIX: n_steps explorers (1..PGN_MAX_MIX) of kinds step_kind[s] in
+     {PGN_EXPLORER_TOY, PGN_EXPLORER_SLICE, PGN_EXPLORER_AUTOMALA, PGN_EXPLORER_MALA}; an autoMALA / MALA step s takes
+     its parameters from mix_n_refresh[s], mix_step_size[s], mix_precond_kind[s], mix_variant_p0[s], mix_variant_p01[s];
+     SliceSampler steps share the slice_* fields; std_devs is shared (every explorer adapts from the same recorders).
+     Vector targets on the register-resident kernels (d <= 128). */
+  int32_t n_steps;
+  int32_t step_kind[PGN_MAX_MIX];
   int32_t n_mix;
   int32_t mix_n_refresh[PGN_MAX_MIX];
   int32_t mix_precond_kind[PGN_MAX_MIX];

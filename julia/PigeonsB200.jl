@@ -61,7 +61,8 @@ const PGN_EXPLORER_SLICE = 2
 const PGN_EXPLORER_AUTOMALA = 3
 const PGN_EXPLORER_ISING_METROPOLIS = 4
 const PGN_EXPLORER_MALA = 5
-const PGN_EXPLORER_SLICE_THEN_AUTOMALA = 6
+const PGN_EXPLORER_COMPOSE = 6
+const PGN_EXPLORER_MIX = 7
 const PGN_MAX_MIX = 4
 
 const PGN_PRECOND_IDENTITY = 0
@@ -106,6 +107,8 @@ struct PgnExplorerParams
     mix_p01::Float64
     std_devs::Ptr{Float64}
     ising_n_steps::Int32
+    n_steps::Int32
+    step_kind::NTuple{4, Int32}
     n_mix::Int32
     mix_n_refresh::NTuple{4, Int32}
     mix_precond_kind::NTuple{4, Int32}
@@ -308,6 +311,8 @@ function explorer_params(explorer, dim::Int)
     nref, step, pk, p0, p01 = 0, 1.0, PGN_PRECOND_IDENTITY, 1 / 3, 2 / 3
     sd = nothing
     n_mix = 0
+    n_steps = 0
+    step_kind = zero4(Int32)
     mix_nr, mix_pk, mix_ss, mix_p0, mix_p01 = zero4(Int32), zero4(Int32), zero4(Float64), zero4(Float64), zero4(Float64)
     ising_steps = 3
     if explorer === nothing                           # TestSwapper: step! is a no-op
@@ -321,14 +326,8 @@ function explorer_params(explorer, dim::Int)
         nref, step = n_refresh(explorer, dim), explorer.step_size
         pk, p0, p01 = precond_code(explorer.preconditioner)
         sd = explorer.estimated_target_std_deviations
-    elseif explorer isa Compose && length(explorer.explorers) == 2 &&
-           explorer.explorers[1] isa SliceSampler && explorer.explorers[2] isa AutoMALA
-        kind, slice = PGN_EXPLORER_SLICE_THEN_AUTOMALA, explorer.explorers[1]
-        am = explorer.explorers[2]
-        nref, step = n_refresh(am, dim), am.step_size
-        pk, p0, p01 = precond_code(am.preconditioner)
-        sd = am.estimated_target_std_deviations
     elseif explorer isa Mix && all(e -> e isa AutoMALA, explorer.explorers) && 2 <= length(explorer.explorers) <= PGN_MAX_MIX
+        # a mixture of autoMALA kernels runs on the plain autoMALA kernel, which draws the variant itself
         kind = PGN_EXPLORER_AUTOMALA
         es = explorer.explorers
         n_mix = length(es)
@@ -342,6 +341,26 @@ function explorer_params(explorer, dim::Int)
         nref, step = n_refresh(es[1], dim), es[1].step_size
         pk, p0, p01 = codes[1]
         sd = es[1].estimated_target_std_deviations    # every variant adapts from the same recorders (Mix.jl:14-17)
+    elseif (explorer isa Compose || explorer isa Mix) && 1 <= length(explorer.explorers) <= PGN_MAX_MIX
+        # general program: every explorer in turn (Compose.jl:16-19) or one drawn uniformly (Mix.jl:20-21)
+        kind = explorer isa Compose ? PGN_EXPLORER_COMPOSE : PGN_EXPLORER_MIX
+        es = explorer.explorers
+        n_steps = length(es)
+        step_code(e) = e isa SliceSampler ? PGN_EXPLORER_SLICE : e isa AutoMALA ? PGN_EXPLORER_AUTOMALA :
+                       e isa MALA ? PGN_EXPLORER_MALA : e isa Pigeons.ToyExplorer ? PGN_EXPLORER_TOY :
+                       error("$(typeof(e)) cannot be part of a device Compose / Mix (no CPU fallback)")
+        grad(e) = e isa AutoMALA || e isa MALA
+        fills(f, T) = ntuple(i -> i <= n_steps ? T(f(es[i])) : zero(T), 4)
+        step_kind = fills(step_code, Int32)
+        mix_nr = fills(e -> grad(e) ? n_refresh(e, dim) : 0, Int32)
+        mix_pk = fills(e -> grad(e) ? precond_code(e.preconditioner)[1] : PGN_PRECOND_IDENTITY, Int32)
+        mix_ss = fills(e -> grad(e) ? e.step_size : 1.0, Float64)
+        mix_p0 = fills(e -> grad(e) ? precond_code(e.preconditioner)[2] : 1 / 3, Float64)
+        mix_p01 = fills(e -> grad(e) ? precond_code(e.preconditioner)[3] : 2 / 3, Float64)
+        for e in es
+            e isa SliceSampler && (slice = e)          # the SliceSamplers of one program share their parameters
+            grad(e) && sd === nothing && (sd = e.estimated_target_std_deviations)
+        end
     elseif hasproperty(explorer, :n_steps) && nameof(typeof(explorer)) == :IsingMetropolis     # examples/ising.jl:91-95
         kind, ising_steps = PGN_EXPLORER_ISING_METROPOLIS, explorer.n_steps
     else
@@ -350,7 +369,7 @@ function explorer_params(explorer, dim::Int)
     sd_vec = sd === nothing ? nothing : Vector{Float64}(sd)
     ep = PgnExplorerParams(kind, slice.w, slice.p, slice.n_passes, slice.max_iter, nref, step, pk, p0, p01,
                            sd_vec === nothing ? Ptr{Float64}(C_NULL) : pointer(sd_vec), ising_steps,
-                           n_mix, mix_nr, mix_pk, mix_ss, mix_p0, mix_p01)
+                           n_steps, step_kind, n_mix, mix_nr, mix_pk, mix_ss, mix_p0, mix_p01)
     return ep, sd_vec
 end
 

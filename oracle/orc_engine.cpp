@@ -771,10 +771,10 @@ struct Engine {
     }
   }
   // auto_mala! (AutoMALA.jl:106-182)
-  void auto_mala(Replica& r, ChainStats& st, bool use_mh) {
+  void auto_mala(Replica& r, ChainStats& st, bool use_mh) { auto_mala(r, st, use_mh, pick_variant(r)); }
+  void auto_mala(Replica& r, ChainStats& st, bool use_mh, const Variant& vr) {
     const int dd = d();
     const double b = beta[r.chain - 1];
-    const Variant vr = pick_variant(r);
     build_preconditioner(r, vr);
     for (int i = 0; i < vr.n_refresh; ++i) {
       r.start_state = r.x;
@@ -815,18 +815,19 @@ struct Engine {
   }
 
   // mala! (src/explorers/MALA.jl:74-97)
-  void mala(Replica& r, ChainStats& st) {
+  void mala(Replica& r, ChainStats& st) { mala(r, st, Variant{ep.n_refresh, ep.step_size, ep.precond_kind, ep.mix_p0, ep.mix_p01}); }
+  void mala(Replica& r, ChainStats& st, const Variant& vr) {
     const int dd = d();
     const double b = beta[r.chain - 1];
-    build_preconditioner(r, Variant{ep.n_refresh, ep.step_size, ep.precond_kind, ep.mix_p0, ep.mix_p01});
-    for (int i = 0; i < ep.n_refresh; ++i) {
+    build_preconditioner(r, vr);
+    for (int i = 0; i < vr.n_refresh; ++i) {
       r.start_state = r.x;
       for (int c = 0; c < dd; ++c) r.momentum[c] = normal_at(r.rng, r.ctr + c);
       r.ctr += dd;
       double init_joint_log = log_joint(logdensity(b, r), r.momentum);
       if (!std::isfinite(init_joint_log))
         throw OrcError{PGN_ERR_NOT_POSITIVE, "MALA can only be called on a configuration of positive density"};
-      leap_frog(b, r, ep.step_size);
+      leap_frog(b, r, vr.step_size);
       for (int c = 0; c < dd; ++c) r.momentum[c] = r.momentum[c] * -1.0;
       double final_joint_log = log_joint(logdensity(b, r), r.momentum);
       double e = exp_(final_joint_log - init_joint_log);
@@ -856,6 +857,18 @@ struct Engine {
         }
   }
 
+  // one explorer of a Compose / Mix program
+  void program_step(Replica& r, ChainStats& st, int s) {
+    const Variant vr{ep.mix_n_refresh[s], ep.mix_step_size[s], ep.mix_precond_kind[s], ep.mix_variant_p0[s], ep.mix_variant_p01[s]};
+    switch (ep.step_kind[s]) {
+      case PGN_EXPLORER_TOY: sample_iid(beta[r.chain - 1], r); break;
+      case PGN_EXPLORER_SLICE: slice_step(r, st); break;
+      case PGN_EXPLORER_AUTOMALA: auto_mala(r, st, scan != 1, vr); break;
+      case PGN_EXPLORER_MALA: mala(r, st, vr); break;
+      default: throw OrcError{PGN_ERR_INVALID, "unsupported explorer inside Compose / Mix"};
+    }
+  }
+
   // ------------------------------------------------------------------ explore!
   // explore!(pt, replica, explorer)  (src/pt/pigeons.jl:101-132)
   void explore(Replica& r) {
@@ -869,10 +882,15 @@ struct Engine {
         case PGN_EXPLORER_TOY: sample_iid(beta[r.chain - 1], r); break;   // ToyExplorer.jl:7-12
         case PGN_EXPLORER_SLICE: slice_step(r, st); break;
         case PGN_EXPLORER_AUTOMALA: auto_mala(r, st, scan != 1); break;   // AutoMALA.jl:87,102
-        case PGN_EXPLORER_SLICE_THEN_AUTOMALA:                            // Compose.jl:16-19
-          slice_step(r, st);
-          auto_mala(r, st, scan != 1);
+        case PGN_EXPLORER_COMPOSE:                                        // Compose.jl:16-19: every explorer in turn
+          for (int s = 0; s < ep.n_steps; ++s) program_step(r, st, s);
           break;
+        case PGN_EXPLORER_MIX: {                                          // Mix.jl:20-21: rand(rng, explorers) performs the step
+          int v = (int)(r.uniform() * (double)ep.n_steps);
+          if (v >= ep.n_steps) v = ep.n_steps - 1;
+          program_step(r, st, v);
+          break;
+        }
         case PGN_EXPLORER_MALA: mala(r, st); break;
         case PGN_EXPLORER_ISING_METROPOLIS: ising_metropolis(r); break;
         default: break;
@@ -1130,6 +1148,8 @@ int orc_set_schedule(orc_handle* h, const double* beta, int32_t n, char** err) {
 int orc_set_explorer(orc_handle* h, const pgn_explorer_params* ep, char** err) {
   Engine& E = h->E;
   if (ep->n_mix < 0 || ep->n_mix > PGN_MAX_MIX) return fail(err, PGN_ERR_INVALID, "n_mix out of range");
+  if ((ep->kind == PGN_EXPLORER_COMPOSE || ep->kind == PGN_EXPLORER_MIX) && (ep->n_steps < 1 || ep->n_steps > PGN_MAX_MIX))
+    return fail(err, PGN_ERR_INVALID, "Compose / Mix: n_steps out of range");
   E.ep = *ep;
   E.have_std = ep->std_devs != nullptr;
   if (E.have_std) E.std_devs.assign(ep->std_devs, ep->std_devs + E.cfg.dim);

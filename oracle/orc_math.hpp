@@ -5,7 +5,7 @@
 // correctly rounded on x86-64 and on sm_100a), a Philox4x32-10 counter RNG,
 // and the canonical 32-leaf summation tree.  The CUDA engine carries its own,
 // independently typed copy of these definitions
-// (pigeons.jl_b200/csrc/pgn_numerics.cuh); tests/test_numerics_gpu.py pins the
+// (pigeons.jl_b200/csrc/pgn_numerics.cuh); tests/test_gpu_parity.py::test_device_numerics_bit_identical pins the
 // two bit-for-bit against each other and tests/test_oracle_math.py pins this
 // file against libm/mpmath.
 //

@@ -32,7 +32,7 @@ ERR_NAMES = {
 TARGET_TOY_MVN, TARGET_FUNNEL, TARGET_GMM, TARGET_ISING, TARGET_LOGREG, TARGET_TEST_SWAPPER = 1, 2, 3, 4, 5, 6
 TARGET_MIXED = 7
 EXPLORER_NONE, EXPLORER_TOY, EXPLORER_SLICE, EXPLORER_AUTOMALA, EXPLORER_ISING_METROPOLIS, EXPLORER_MALA = 0, 1, 2, 3, 4, 5
-EXPLORER_SLICE_THEN_AUTOMALA = 6
+EXPLORER_COMPOSE, EXPLORER_MIX = 6, 7
 MAX_MIX = 4
 PRECOND_IDENTITY, PRECOND_DIAGONAL, PRECOND_MIX_DIAGONAL = 0, 1, 2
 RECORDERS_PER_REPLICA, RECORDERS_PER_CHAIN = 0, 1
@@ -60,6 +60,7 @@ class pgn_explorer_params(C.Structure):
         ("slice_max_iter", C.c_int32), ("n_refresh", C.c_int32), ("step_size", C.c_double),
         ("precond_kind", C.c_int32), ("mix_p0", C.c_double), ("mix_p01", C.c_double),
         ("std_devs", _dp), ("ising_n_steps", C.c_int32),
+        ("n_steps", C.c_int32), ("step_kind", C.c_int32 * MAX_MIX),
         ("n_mix", C.c_int32), ("mix_n_refresh", C.c_int32 * MAX_MIX), ("mix_precond_kind", C.c_int32 * MAX_MIX),
         ("mix_step_size", C.c_double * MAX_MIX), ("mix_variant_p0", C.c_double * MAX_MIX),
         ("mix_variant_p01", C.c_double * MAX_MIX),
@@ -265,7 +266,7 @@ class Engine:
 
     def set_explorer(self, *, kind, slice_w=10.0, slice_p=20, slice_n_passes=3, slice_max_iter=1024,
                      n_refresh=0, step_size=1.0, precond_kind=PRECOND_IDENTITY, mix_p0=1.0 / 3.0,
-                     mix_p01=1.0 / 3.0 + 1.0 / 3.0, std_devs=None, ising_n_steps=3, mix_variants=None):
+                     mix_p01=1.0 / 3.0 + 1.0 / 3.0, std_devs=None, ising_n_steps=3, mix_variants=None, steps=None):
         ep = pgn_explorer_params()
         ep.kind = kind
         ep.slice_w, ep.slice_p, ep.slice_n_passes, ep.slice_max_iter = slice_w, slice_p, slice_n_passes, slice_max_iter
@@ -283,6 +284,15 @@ class Engine:
                 raise ValueError(f"a device Mix has 2..{MAX_MIX} explorers")
             ep.n_mix = len(mix_variants)
             for v, (nr, ss, pk, q0, q01) in enumerate(mix_variants):
+                ep.mix_n_refresh[v], ep.mix_step_size[v], ep.mix_precond_kind[v] = nr, ss, pk
+                ep.mix_variant_p0[v], ep.mix_variant_p01[v] = q0, q01
+        ep.n_steps = 0
+        if steps:             # Compose / Mix program: [(kind, n_refresh, step_size, precond_kind, p0, p01), ...]
+            if not (1 <= len(steps) <= MAX_MIX):
+                raise ValueError(f"a device Compose / Mix has 1..{MAX_MIX} explorers")
+            ep.n_steps = len(steps)
+            for v, (k, nr, ss, pk, q0, q01) in enumerate(steps):
+                ep.step_kind[v] = k
                 ep.mix_n_refresh[v], ep.mix_step_size[v], ep.mix_precond_kind[v] = nr, ss, pk
                 ep.mix_variant_p0[v], ep.mix_variant_p01[v] = q0, q01
         self.lib.call("set_explorer", self._h, C.byref(ep))

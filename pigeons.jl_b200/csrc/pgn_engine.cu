@@ -43,6 +43,8 @@ void fill_params(pgn_handle* h, Params& P) {
   P.slice_max_iter = h->ep.slice_max_iter;
   P.n_refresh = h->ep.n_refresh; P.step_size = h->ep.step_size; P.precond_kind = h->ep.precond_kind;
   P.mix_p0 = h->ep.mix_p0; P.mix_p01 = h->ep.mix_p01;
+  P.n_steps = h->ep.n_steps; P.program_is_mix = h->ep.kind == PGN_EXPLORER_MIX ? 1 : 0;
+  for (int v = 0; v < PGN_MAX_MIX; ++v) P.step_kind[v] = h->ep.step_kind[v];
   P.n_mix = h->ep.n_mix;
   for (int v = 0; v < PGN_MAX_MIX; ++v) {
     P.mix_n_refresh[v] = h->ep.mix_n_refresh[v]; P.mix_precond_kind[v] = h->ep.mix_precond_kind[v];
@@ -94,7 +96,7 @@ void mem_fill_params(pgn_handle* h, const Params& P, MemParams& MP) {
 
 bool is_team_kernel(const pgn_handle* h) {   // VecChain<.., AUTOMALA>::kTeam
   const int tk = h->cfg.target_kind;
-  return (h->ep.kind == PGN_EXPLORER_AUTOMALA || h->ep.kind == PGN_EXPLORER_SLICE_THEN_AUTOMALA) && h->cpl > 0 &&
+  return (h->ep.kind == PGN_EXPLORER_AUTOMALA || h->ep.kind == PGN_EXPLORER_COMPOSE || h->ep.kind == PGN_EXPLORER_MIX) && h->cpl > 0 &&
          (tk == PGN_TARGET_TOY_MVN || tk == PGN_TARGET_FUNNEL || tk == PGN_TARGET_GMM);
 }
 // dynamic shared memory of the scan kernel: staged target constants, then (team kernels) the
@@ -331,9 +333,24 @@ int pgn_set_explorer(pgn_handle* h, const pgn_explorer_params* ep, char** err) {
   if (ep->n_mix < 0 || ep->n_mix > PGN_MAX_MIX) return fail(err, PGN_ERR_INVALID, "n_mix out of range");
   if (ep->n_mix > 1 && ep->kind != PGN_EXPLORER_AUTOMALA)
     return fail(err, PGN_ERR_INVALID, "the device mixes autoMALA kernels only (no CPU fallback for other mixtures)");
-  if ((ep->n_mix > 1 || ep->kind == PGN_EXPLORER_SLICE_THEN_AUTOMALA) &&
-      (h->cfg.target_kind == PGN_TARGET_LOGREG || h->cpl == 0 || h->force_mem))
+  const bool program = ep->kind == PGN_EXPLORER_COMPOSE || ep->kind == PGN_EXPLORER_MIX;
+  if ((ep->n_mix > 1 || program) && (h->cfg.target_kind == PGN_TARGET_LOGREG || h->cpl == 0 || h->force_mem))
     return fail(err, PGN_ERR_INVALID, "Mix / Compose explorers run on the register-resident scan kernels only (d <= 128)");
+  if (program) {
+    const int tk = h->cfg.target_kind;
+    if (tk != PGN_TARGET_TOY_MVN && tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM)
+      return fail(err, PGN_ERR_INVALID, "Mix / Compose explorers need a vector target with a gradient (toy MVN, funnel, mixture)");
+    if (ep->n_steps < 1 || ep->n_steps > PGN_MAX_MIX) return fail(err, PGN_ERR_INVALID, "Compose / Mix: n_steps out of range");
+    for (int s = 0; s < ep->n_steps; ++s) {
+      const int k = ep->step_kind[s];
+      if (k != PGN_EXPLORER_SLICE && k != PGN_EXPLORER_AUTOMALA && k != PGN_EXPLORER_MALA &&
+          !(k == PGN_EXPLORER_TOY && tk == PGN_TARGET_TOY_MVN))
+        return fail(err, PGN_ERR_INVALID, "Compose / Mix: explorers on the device are ToyExplorer (toy MVN), SliceSampler, MALA, AutoMALA "
+                                          "(no CPU fallback for others)");
+      if ((k == PGN_EXPLORER_AUTOMALA || k == PGN_EXPLORER_MALA) && !(ep->mix_step_size[s] > 0))
+        return fail(err, PGN_ERR_INVALID, "Compose / Mix: step size of a gradient-based step must be positive");
+    }
+  }
   try {
     use_device(h);
     h->ep = *ep;
@@ -495,7 +512,8 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
           for (int w = std::min(w_max, (pinned >= 1 && pinned <= 8) ? pinned : 8); w >= 1; --w) {
             // a team shares one scan's momentum draws through shared memory when they fit in 64 KB
             int max_refresh = h->ep.n_refresh;
-            for (int v = 0; v < h->ep.n_mix && v < PGN_MAX_MIX; ++v) max_refresh = std::max(max_refresh, h->ep.mix_n_refresh[v]);
+            for (int v = 0; v < std::max(h->ep.n_mix, h->ep.n_steps) && v < PGN_MAX_MIX; ++v)
+              max_refresh = std::max(max_refresh, h->ep.mix_n_refresh[v]);
             const int pool_max = (w > 1 && (size_t)max_refresh * (h->cpl * 32 + 8) * sizeof(double) <= 64 * 1024) ? max_refresh : 0;
             const bool wide_ok = w == 1 || pinned == w || (long long)nl * w <= (long long)per_smsp * 4 * h->n_sms;
             bool chosen = false;

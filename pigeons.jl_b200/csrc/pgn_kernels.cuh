@@ -16,7 +16,8 @@
 //             adopt each other's replica.
 //
 // There is NO grid-wide barrier: DEO couples a chain only to its two
-// neighbours, so warps synchronise pairwise through release/acquire flags in
+// neighbours, so warps synchronise pairwise through flag-in-data mailbox words
+// (8-byte {payload32, tag32} words, relaxed stores and loads, no fences) in
 // L2 (or, across GPUs, in the neighbour's peer-mapped mailbox over NVLink).
 // All warps are co-resident (cooperative launch), so the spin-waits cannot
 // deadlock; a spin limit turns any lost hand-shake into PGN_ERR_TIMEOUT.
@@ -107,6 +108,7 @@ struct Params {
   // explorer
   double slice_w; int slice_p, slice_n_passes, slice_max_iter;
   int n_refresh; double step_size; int precond_kind; double mix_p0, mix_p01;
+  int n_steps; int step_kind[PGN_MAX_MIX]; int program_is_mix;   // Compose / Mix program (step s: kind + mix_*[s])
   int n_mix;   // Mix of autoMALA kernels (Mix.jl:20-21): variant v = mix_*[v]
   int mix_n_refresh[PGN_MAX_MIX]; int mix_precond_kind[PGN_MAX_MIX];
   double mix_step_size[PGN_MAX_MIX], mix_variant_p0[PGN_MAX_MIX], mix_variant_p01[PGN_MAX_MIX];
@@ -186,7 +188,7 @@ struct VecChain {
   // candidate steps per round, one per warp, and replays the reference's sequential decisions on the
   // results (see automala()).  Everything else is executed redundantly by all warps of the team on
   // identical data; only team warp 0 talks to the mailboxes and writes results.
-  static constexpr bool kTeam = (EX == PGN_EXPLORER_AUTOMALA || EX == PGN_EXPLORER_SLICE_THEN_AUTOMALA);
+  static constexpr bool kTeam = (EX == PGN_EXPLORER_AUTOMALA || EX == PGN_EXPLORER_COMPOSE);
   static constexpr bool kIsing = false;
   // one coordinate per lane: teams of up to 6 warps, two teams per SM (168 registers per thread)
   static constexpr int kMaxThreads = (kTeam && CPL == 1) ? 192 : 256;
@@ -851,13 +853,16 @@ struct VecChain {
     const double* h = s + 3 * CPL * 32;
     T.a0 = h[0]; T.a1 = h[1]; T.lp1 = h[2]; T.h_after = h[3]; T.eps = h[5];
   }
-  __device__ void automala(bool use_mh, int n_refresh_eff) {
+  // step s of a Compose / Mix program (s >= 0), or the explorer's own parameters (s < 0)
+  __device__ void automala(bool use_mh, int n_refresh_eff, int s = -1) {
     double pre[CPL];
     bool pre_one = true;
     // Mix (src/explorers/Mix.jl:20-21): one tick of the replica's stream picks the autoMALA variant of this step
     double step0 = P->step_size, v_p0 = P->mix_p0, v_p01 = P->mix_p01;
     int v_precond = P->precond_kind;
-    if (n_refresh_eff > 0 && P->n_mix > 1) {
+    if (s >= 0) {
+      step0 = P->mix_step_size[s]; v_precond = P->mix_precond_kind[s]; v_p0 = P->mix_variant_p0[s]; v_p01 = P->mix_variant_p01[s];
+    } else if (n_refresh_eff > 0 && P->n_mix > 1) {
       int v = (int)(draw_uniform() * (double)P->n_mix);
       v = v >= P->n_mix ? P->n_mix - 1 : v;
       n_refresh_eff = P->mix_n_refresh[v]; step0 = P->mix_step_size[v]; v_precond = P->mix_precond_kind[v];
@@ -1080,9 +1085,12 @@ struct VecChain {
   }
 
   // mala! (src/explorers/MALA.jl:74-97): one leapfrog at the fixed step size + MH, n_refresh times
-  __device__ void mala() {
+  __device__ void mala(int s = -1) {
     double pre[CPL];
-    const bool pre_one = build_preconditioner(pre, P->precond_kind, P->mix_p0, P->mix_p01);
+    const int n_refresh = s >= 0 ? P->mix_n_refresh[s] : P->n_refresh;
+    const double step_size = s >= 0 ? P->mix_step_size[s] : P->step_size;
+    const bool pre_one = s >= 0 ? build_preconditioner(pre, P->mix_precond_kind[s], P->mix_variant_p0[s], P->mix_variant_p01[s])
+                                : build_preconditioner(pre, P->precond_kind, P->mix_p0, P->mix_p01);
     double g0[CPL];
     {
       double dummy = 0.0;
@@ -1093,7 +1101,7 @@ struct VecChain {
     }
     double lp0 = lp_ad(beta, e0, e1);
     Trial T;
-    for (int i = 0; i < P->n_refresh; ++i) {
+    for (int i = 0; i < n_refresh; ++i) {
       double p[CPL];
       double pp = 0.0;
 #pragma unroll
@@ -1104,7 +1112,7 @@ struct VecChain {
       rng.ctr += (unsigned long long)d;
       const double init_joint = lp0 - 0.5 * warp_sum(pp);
       if (!is_finite(init_joint)) { err = PGN_ERR_NOT_POSITIVE; return; }
-      run_trial(x, p, g0, pre, pre_one, P->step_size, init_joint, T);
+      run_trial(x, p, g0, pre, pre_one, step_size, init_joint, T);
       const double e = exp_(T.h_after - init_joint);   // final_joint_log at (x1, -p1) has the same partial sums
       const double prob = 1.0 < e ? 1.0 : e;
       expl_acc.fit(prob);
@@ -1120,9 +1128,28 @@ struct VecChain {
 
   // ---- explore!(pt, replica, explorer) (src/pt/pigeons.jl:101-132) --------------
   __device__ void explore(long long scan, bool is_reference) {
-    if (EX == PGN_EXPLORER_AUTOMALA || EX == PGN_EXPLORER_SLICE_THEN_AUTOMALA) {
+    if (EX == PGN_EXPLORER_COMPOSE) {
+      // Compose (Compose.jl:16-19): every explorer of the program in turn; Mix (Mix.jl:20-21): one of them, drawn with one
+      // tick of the replica's stream.  Steps that are not autoMALA run on every warp of the team, on identical data.
+      if (is_reference) { sample_iid(beta); automala(scan != 1, 0); return; }   // densities of the fresh state only
+      int first = 0, last = P->n_steps;
+      if (P->program_is_mix) {
+        int v = (int)(draw_uniform() * (double)P->n_steps);
+        v = v >= P->n_steps ? P->n_steps - 1 : v;
+        first = v; last = v + 1;
+      }
+      for (int s = first; s < last; ++s) {
+        const int kind = P->step_kind[s];
+        if (kind == PGN_EXPLORER_TOY) { sample_iid(beta); eval(x, e0, e1); }
+        else if (kind == PGN_EXPLORER_SLICE) slice_step();
+        else if (kind == PGN_EXPLORER_MALA) mala(s);
+        else automala(scan != 1, P->mix_n_refresh[s], s);   // AutoMALA.jl:87,102
+        if (err) return;
+      }
+      return;
+    }
+    if (EX == PGN_EXPLORER_AUTOMALA) {
       if (is_reference) sample_iid(beta);
-      else if (EX == PGN_EXPLORER_SLICE_THEN_AUTOMALA) { slice_step(); if (err) return; }   // Compose.jl:16-19: first, then second
       automala(scan != 1, is_reference ? 0 : P->n_refresh);   // AutoMALA.jl:87,102
       return;
     }

@@ -146,7 +146,7 @@ void* vec_plain_kernel_toy(int cpl, int ex);    void* vec_team_kernel_toy(int cp
 void* vec_plain_kernel_funnel(int cpl, int ex); void* vec_team_kernel_funnel(int cpl, int ex);
 void* vec_plain_kernel_gmm(int cpl, int ex);    void* vec_team_kernel_gmm(int cpl, int ex);
 void* vec_plain_kernel_mixed(int cpl, int ex);
-static bool is_team_explorer(int ex) { return ex == PGN_EXPLORER_AUTOMALA || ex == PGN_EXPLORER_SLICE_THEN_AUTOMALA; }
+static bool is_team_explorer(int ex) { return ex == PGN_EXPLORER_AUTOMALA || ex == PGN_EXPLORER_COMPOSE || ex == PGN_EXPLORER_MIX; }
 void* vec_scan_kernel_toy(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_toy(cpl, ex) : vec_plain_kernel_toy(cpl, ex); }
 void* vec_scan_kernel_funnel(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_funnel(cpl, ex) : vec_plain_kernel_funnel(cpl, ex); }
 void* vec_scan_kernel_mixed(int cpl, int ex) { return ex == PGN_EXPLORER_SLICE ? vec_plain_kernel_mixed(cpl, ex) : nullptr; }

@@ -2,7 +2,7 @@
 // Compiled once per (target family, part) by csrc/Makefile:
 //   -DPGN_TK=1|2|3|7 PGN_TARGET_TOY_MVN | PGN_TARGET_FUNNEL | PGN_TARGET_GMM | PGN_TARGET_MIXED (SliceSampler only)
 //   -DPGN_PART=0     ToyExplorer / SliceSampler / MALA kernels + the parity entry points
-//   -DPGN_PART=1     autoMALA team kernels (AutoMALA, Compose(SliceSampler, AutoMALA))
+//   -DPGN_PART=1     autoMALA team kernels (AutoMALA; Compose / Mix programs of ToyExplorer, SliceSampler, MALA, AutoMALA)
 // so that the heavy template instantiations build in parallel.
 #include "pgn_host.hpp"
 
@@ -43,7 +43,7 @@ template <int CPL>
 void* team_kernel_for(int ex) {
   switch (ex) {
     case PGN_EXPLORER_AUTOMALA: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_AUTOMALA>>();
-    case PGN_EXPLORER_SLICE_THEN_AUTOMALA: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_SLICE_THEN_AUTOMALA>>();
+    case PGN_EXPLORER_COMPOSE: case PGN_EXPLORER_MIX: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_COMPOSE>>();
     default: return nullptr;
   }
 }

@@ -1,7 +1,7 @@
 """Explorer configuration structs (the `explorer` informal interface,
 src/explorers/explorer.jl:7-39).  These are host-side parameter records with the
 reference's field names and defaults; the kernels that execute them live in
-csrc/pgn_scan.cu.  `adapt_explorer` restates src/explorers/AutoMALA.jl:70-79.
+csrc/pgn_kernels.cuh (VecChain / IsingChain) and csrc/pgn_logreg.cuh.  `adapt_explorer` restates src/explorers/AutoMALA.jl:70-79.
 """
 from __future__ import annotations
 
@@ -127,44 +127,80 @@ class IsingMetropolis:
         return dict(kind=_capi.EXPLORER_ISING_METROPOLIS, ising_n_steps=self.n_steps)
 
 
-@dataclass(frozen=True)
-class Compose:
-    """src/explorers/Compose.jl:5-27: `first` then `second` at every step, both feeding the same
-    recorders.  The device implements the combination the reference documents and tests,
-    `Compose(SliceSampler(), AutoMALA())` (Compose.jl:3, test/test_parallelism_invariance.jl:19,
-    test/test_DistributionLogPotential.jl:57); any other pair raises (no CPU fallback)."""
-    first: object
-    second: object
-
-    def __post_init__(self):
-        if not (isinstance(self.first, SliceSampler) and isinstance(self.second, AutoMALA)):
-            raise NotImplementedError("the device composes SliceSampler followed by AutoMALA only")
-
-    def engine_params(self, dim: int) -> dict:
-        p = dict(self.second.engine_params(dim))
-        p.update(self.first.engine_params(dim))
-        p["kind"] = _capi.EXPLORER_SLICE_THEN_AUTOMALA
-        return p
-
-    def adapt(self, round_result) -> "Compose":      # Compose.jl:10-14
-        return Compose(self.first, self.second.adapt(round_result))
+def _program_steps(explorers, dim: int):
+    """(kind, n_refresh, step_size, precond_kind, p0, p01) per explorer of a Compose / Mix, the shared SliceSampler
+    parameters and the shared std-dev estimate (every explorer adapts from the same recorders, Compose.jl:10-14, Mix.jl:14-17)."""
+    steps, slice_params, sds = [], None, None
+    for e in explorers:
+        q = e.engine_params(dim)
+        kind = q["kind"]
+        if kind == _capi.EXPLORER_SLICE:
+            sp = {k: q[k] for k in ("slice_w", "slice_p", "slice_n_passes", "slice_max_iter")}
+            if slice_params is not None and sp != slice_params:
+                raise NotImplementedError("the SliceSamplers of one Compose / Mix share their parameters on the device")
+            slice_params = sp
+            steps.append((kind, 0, 1.0, _capi.PRECOND_IDENTITY, 1.0 / 3.0, 2.0 / 3.0))
+        elif kind in (_capi.EXPLORER_AUTOMALA, _capi.EXPLORER_MALA):
+            steps.append((kind, q["n_refresh"], q["step_size"], q["precond_kind"], q["mix_p0"], q["mix_p01"]))
+            if q.get("std_devs") is not None and sds is None:
+                sds = np.asarray(q["std_devs"])
+        elif kind == _capi.EXPLORER_TOY:
+            steps.append((kind, 0, 1.0, _capi.PRECOND_IDENTITY, 1.0 / 3.0, 2.0 / 3.0))
+        else:
+            raise NotImplementedError(f"{type(e).__name__} cannot be part of a device Compose / Mix (no CPU fallback)")
+    return steps, (slice_params or {}), sds
 
 
 @dataclass(frozen=True, init=False)
-class Mix:
-    """src/explorers/Mix.jl:7-30: one of the explorers, drawn uniformly from the replica's stream,
-    performs the step.  Device support: 2..4 AutoMALA kernels (they may differ in preconditioner,
-    step size and number of refreshments — test/test_parallelism_invariance.jl:14-18)."""
+class Compose:
+    """src/explorers/Compose.jl:5-27: every explorer in turn at each step, all feeding the same recorders.
+    Device support: 1..4 explorers out of ToyExplorer (toy MVN), SliceSampler, MALA, AutoMALA, in any order
+    (`Compose(SliceSampler(), AutoMALA())` is the combination the reference documents and tests: Compose.jl:3,
+    test/test_parallelism_invariance.jl:19, test/test_DistributionLogPotential.jl:57)."""
     explorers: tuple
 
     def __init__(self, *explorers):
         if len(explorers) == 1 and isinstance(explorers[0], (tuple, list)):
             explorers = tuple(explorers[0])
-        if not (2 <= len(explorers) <= _capi.MAX_MIX) or not all(isinstance(e, AutoMALA) for e in explorers):
-            raise NotImplementedError(f"the device mixes 2..{_capi.MAX_MIX} AutoMALA explorers")
+        if not (1 <= len(explorers) <= _capi.MAX_MIX):
+            raise NotImplementedError(f"the device composes 1..{_capi.MAX_MIX} explorers")
+        object.__setattr__(self, "explorers", tuple(explorers))
+
+    @property
+    def first(self):
+        return self.explorers[0]
+
+    @property
+    def second(self):
+        return self.explorers[1]
+
+    def engine_params(self, dim: int) -> dict:
+        steps, slice_params, sds = _program_steps(self.explorers, dim)
+        return dict(kind=_capi.EXPLORER_COMPOSE, steps=steps, std_devs=sds, **slice_params)
+
+    def adapt(self, round_result) -> "Compose":      # Compose.jl:10-14
+        return Compose(*(e.adapt(round_result) if hasattr(e, "adapt") else e for e in self.explorers))
+
+
+@dataclass(frozen=True, init=False)
+class Mix:
+    """src/explorers/Mix.jl:7-30: one of the explorers, drawn uniformly from the replica's stream,
+    performs the step.  Device support: 2..4 explorers out of ToyExplorer (toy MVN), SliceSampler, MALA, AutoMALA; a
+    mixture of AutoMALA kernels only (they may differ in preconditioner, step size and number of refreshments —
+    test/test_parallelism_invariance.jl:14-18) runs on the plain autoMALA kernel, which draws the variant itself."""
+    explorers: tuple
+
+    def __init__(self, *explorers):
+        if len(explorers) == 1 and isinstance(explorers[0], (tuple, list)):
+            explorers = tuple(explorers[0])
+        if not (2 <= len(explorers) <= _capi.MAX_MIX):
+            raise NotImplementedError(f"the device mixes 2..{_capi.MAX_MIX} explorers")
         object.__setattr__(self, "explorers", tuple(explorers))
 
     def engine_params(self, dim: int) -> dict:
+        if not all(isinstance(e, AutoMALA) for e in self.explorers):
+            steps, slice_params, sds = _program_steps(self.explorers, dim)
+            return dict(kind=_capi.EXPLORER_MIX, steps=steps, std_devs=sds, **slice_params)
         p = dict(self.explorers[0].engine_params(dim))
         variants = []
         for e in self.explorers:
@@ -177,4 +213,4 @@ class Mix:
         return p
 
     def adapt(self, round_result) -> "Mix":          # Mix.jl:14-17
-        return Mix(*(e.adapt(round_result) for e in self.explorers))
+        return Mix(*(e.adapt(round_result) if hasattr(e, "adapt") else e for e in self.explorers))

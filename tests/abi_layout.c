@@ -25,6 +25,7 @@ int main(void) {
   FIELD(pgn_explorer_params, slice_n_passes); FIELD(pgn_explorer_params, slice_max_iter); FIELD(pgn_explorer_params, n_refresh);
   FIELD(pgn_explorer_params, step_size); FIELD(pgn_explorer_params, precond_kind); FIELD(pgn_explorer_params, mix_p0);
   FIELD(pgn_explorer_params, mix_p01); FIELD(pgn_explorer_params, std_devs); FIELD(pgn_explorer_params, ising_n_steps);
+  FIELD(pgn_explorer_params, n_steps); FIELD(pgn_explorer_params, step_kind);
   FIELD(pgn_explorer_params, n_mix); FIELD(pgn_explorer_params, mix_n_refresh); FIELD(pgn_explorer_params, mix_precond_kind);
   FIELD(pgn_explorer_params, mix_step_size); FIELD(pgn_explorer_params, mix_variant_p0); FIELD(pgn_explorer_params, mix_variant_p01);
   END();

@@ -27,6 +27,9 @@ GOLDEN_CASES = {
         explorer=pg.Mix(pg.AutoMALA(preconditioner=pg.IdentityPreconditioner(), base_n_refresh=1),
                         pg.AutoMALA(preconditioner=pg.MixDiagonalPreconditioner(0.0, 0.0), base_n_refresh=1),
                         pg.AutoMALA(preconditioner=pg.DiagonalPreconditioner(), base_n_refresh=1))),
+    "gmm6_mix_slice_automala_mala_n6_r6": lambda: dict(
+        target=pg.eight_mode_mixture(6, 3.0), n_chains=6, n_rounds=6, seed=6,
+        explorer=pg.Mix(pg.SliceSampler(n_passes=1), pg.AutoMALA(base_n_refresh=1), pg.MALA(step_size=0.3, base_n_refresh=2))),
     # SliceSampler on Bool / Integer / Float coordinates (test/test_slice_sampler.jl:56-75)
     "mixed_bool_int_float_slice_n7_r8": lambda: dict(target=pg.MixedProduct(n_bool=3, n_int=2, n_float=2), n_chains=7,
                                                      n_rounds=8, seed=1),

@@ -88,6 +88,19 @@ CASES = {
                                explorer=pg.SliceSampler(w=4.0, n_passes=2), n_chains=5, n_rounds=5, seed=2),
     "mixed_int_only": dict(target=pg.MixedProduct(n_bool=0, n_int=5, n_float=0, binomial_n=30, q0=0.5, q1=0.1),
                            n_chains=6, n_rounds=7, seed=3),
+    # general Compose / Mix programs (Compose.jl:16-19, Mix.jl:20-21): any order, any of ToyExplorer / SliceSampler / MALA / AutoMALA
+    "funnel8_compose_automala_then_slice": dict(target=pg.Funnel(8), explorer=pg.Compose(pg.AutoMALA(base_n_refresh=1), pg.SliceSampler(n_passes=1)),
+                                                n_chains=6, n_rounds=6, seed=4),
+    "toy5_compose_mala_slice_automala": dict(target=pg.toy_mvn_target(5), n_chains=5, n_rounds=6, seed=5,
+                                             explorer=pg.Compose(pg.MALA(step_size=0.2, base_n_refresh=1), pg.SliceSampler(n_passes=1),
+                                                                 pg.AutoMALA(base_n_refresh=1))),
+    "gmm6_mix_slice_automala_mala": dict(target=pg.eight_mode_mixture(6, 3.0), n_chains=6, n_rounds=6, seed=6,
+                                         explorer=pg.Mix(pg.SliceSampler(n_passes=1), pg.AutoMALA(base_n_refresh=1),
+                                                         pg.MALA(step_size=0.3, base_n_refresh=2))),
+    "toy3_mix_toy_slice": dict(target=pg.toy_mvn_target(3), n_chains=5, n_rounds=7, seed=7,
+                               explorer=pg.Mix(pg.ToyExplorer(), pg.SliceSampler())),
+    "toy70_compose_slice_mala_4cpl": dict(target=pg.toy_mvn_target(70), n_chains=4, n_rounds=4, seed=8,
+                                          explorer=pg.Compose(pg.SliceSampler(n_passes=1), pg.MALA(step_size=0.1, base_n_refresh=1))),
     "single_chain": dict(target=pg.toy_mvn_target(4), explorer=pg.SliceSampler(), n_chains=1, n_rounds=5, seed=1),
     "two_chains": dict(target=pg.toy_mvn_target(2), explorer=pg.AutoMALA(), n_chains=2, n_rounds=6, seed=8),
 }
@@ -213,7 +226,8 @@ def oracle_result(name, oracle_lib):
 
 @pytest.mark.parametrize("team", [1, 2, 3, 4, 5, 8])
 @pytest.mark.parametrize("name", ["funnel32_automala", "toy100_automala_4cpl", "gmm2_two_modes", "two_chains", "funnel_diag_precond",
-                                  "toy3_compose_slice_automala", "funnel8_mix_automala"])
+                                  "toy3_compose_slice_automala", "funnel8_mix_automala", "toy5_compose_mala_slice_automala",
+                                  "gmm6_mix_slice_automala_mala"])
 def test_automala_team_width_parity(name, team, gpu_lib, oracle_lib, monkeypatch):
     """PGN_TEAM=W: the autoMALA step-size search evaluated W candidate steps at a time by a team of W
     warps per chain gives the reference's sequential result bit for bit, for every team width."""

@@ -85,7 +85,11 @@ MIXED_AM = pg.Mix(pg.AutoMALA(preconditioner=pg.IdentityPreconditioner(), base_n
 
 
 @pytest.mark.parametrize("explorer", [None, pg.SliceSampler(), pg.AutoMALA(), pg.MALA(step_size=0.25),
-                                      pg.Compose(pg.SliceSampler(), pg.AutoMALA()), MIXED_AM])
+                                      pg.Compose(pg.SliceSampler(), pg.AutoMALA()), MIXED_AM,
+                                      pg.Compose(pg.AutoMALA(), pg.SliceSampler()),                       # any order
+                                      pg.Compose(pg.MALA(step_size=0.25), pg.SliceSampler(), pg.AutoMALA()),
+                                      pg.Mix(pg.SliceSampler(), pg.AutoMALA(), pg.MALA(step_size=0.25)),  # general Mix
+                                      pg.Mix(pg.ToyExplorer(), pg.SliceSampler())])
 def test_moments(explorer, oracle_lib):
     """test/test_moments.jl:1-27 and test/test_mala.jl: toy MVN d=2, mean 0 +- 0.03, var 0.1 +- 0.03."""
     kw = dict(target=pg.toy_mvn_target(2), n_chains=2, n_rounds=10 if explorer is None else 12, record=[pg.online],
