@@ -1,7 +1,7 @@
 #!/bin/bash
-# round 2, GPU call 7: recorder entries prefetched into L1 before the swap decision: parity + cost on C2 / C3.
+# round 2, GPU call 9: explorer statistics checkpointed before the hand-shake: parity + cost on C2 / C3.
 set -x
-O=gpurun_out/r2c7
+O=gpurun_out/r2c9
 mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -q -x > $O/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> $O/pytest_gpu.log; tail -4 $O/pytest_gpu.log
