@@ -1597,20 +1597,6 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
       double lr_p = 0.0, u_p = 0.0;
       unsigned long long ctr_p = 0ull;
       int ri_p = 0, rt_p = 0;
-      // ---- per-replica recorders: the explorer statistics of this scan are final now, so they are written to the current
-      // replica's entry BEFORE the hand-shake (the stores drain while the chain waits for its partner; measured on C2, same
-      // binary: the stores inside the accepted branch cost 8 % of the scan, the loads nothing).  Valid whether or not the
-      // swap is accepted: the entry is a checkpoint of what the registers hold.
-      const bool exchange = P.rec_table != nullptr;
-      if (exchange) {
-        RecEntry* eo = P.rec_table + (size_t)(replica_index - 1) * P.n_local + wl;
-        if (lane == 0) {
-          if (tw == ch.own(1)) eo->am = ch.am;
-          if (tw == ch.own(2)) eo->rev = ch.rev;
-          if (tw == ch.own(3)) eo->expl_acc = ch.expl_acc;
-        }
-        if (is_tgt && tw == ch.own(4) && P.d > 0) ch.flush_online(P.on_table + (size_t)(replica_index - 1) * P.d_pad);
-      }
       const long long t_wait0 = clock64();
       if (tw == 0) {
         {   // post: header words from lanes 0..7, then the replica
@@ -1687,25 +1673,27 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
       }
       accepted = (lower ? u : u_p) < acceptance_pr;
       if (accepted) {   // adopt the partner's replica (states move, chains stay)
-        if (exchange) {
-          // what this chain's warps accumulated belongs to the outgoing replica (its explorer statistics were checkpointed
-          // before the hand-shake; the pair statistics, fitted after it by the lower chain, follow here); continue with
-          // what the incoming replica accumulated during its earlier visits of this chain
+        if (P.rec_table != nullptr) {
+          // per-replica recorders: what this chain's warps accumulated belongs to the outgoing replica; continue with
+          // what the incoming replica accumulated during its earlier visits of this chain (each statistic by its owner warp)
           RecEntry* eo = P.rec_table + (size_t)(replica_index - 1) * P.n_local + wl;
           const RecEntry* en = P.rec_table + (size_t)(ri_p - 1) * P.n_local + wl;
           if (tw == ch.own(1)) {
-            if (lane == 0 && lower) eo->swap_acc = swap_acc;
+            if (lane == 0) { eo->am = ch.am; eo->swap_acc = swap_acc; }
             ch.am = en->am; swap_acc = en->swap_acc;
           }
           if (tw == ch.own(2)) {
-            if (lane == 0 && lower) eo->ls_fwd = ls_fwd;
+            if (lane == 0) { eo->rev = ch.rev; eo->ls_fwd = ls_fwd; }
             ch.rev = en->rev; ls_fwd = en->ls_fwd;
           }
           if (tw == ch.own(3)) {
-            if (lane == 0 && lower) eo->ls_bwd = ls_bwd;
+            if (lane == 0) { eo->expl_acc = ch.expl_acc; eo->ls_bwd = ls_bwd; }
             ch.expl_acc = en->expl_acc; ls_bwd = en->ls_bwd;
           }
-          if (is_tgt && tw == ch.own(4) && P.d > 0) ch.load_online(P.on_table + (size_t)(ri_p - 1) * P.d_pad);
+          if (is_tgt && tw == ch.own(4) && P.d > 0) {
+            ch.flush_online(P.on_table + (size_t)(replica_index - 1) * P.d_pad);
+            ch.load_online(P.on_table + (size_t)(ri_p - 1) * P.d_pad);
+          }
         }
         replica_index = ri_p;
         rt_state = rt_p;
