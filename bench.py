@@ -11,7 +11,8 @@ ladders are 8192 (C3), 2048 (C2), 4096 (C4: BASELINE's own shape) and 2048 (C5: 
 `--config cX` selects another headline, `--also ""` drops the extra records.
 
 A *step* is one `run_one_round!`-equivalent call (`pgn_run_round`) of `scans_per_step` PT scans through the C
-ABI.  `value` is device-timed (CUDA events around the kernels of the round, inputs resident in HBM); `e2e` is
+ABI (C3: 512 scans = round 9 of a run, C2 / C4: 2048 = round 11, C5: 2 steady-state scans; rounds of a few hundred
+milliseconds, so that the launch skew between the ranks of a multi-GPU run — about a millisecond — stays below 1 %).  `value` is device-timed (CUDA events around the kernels of the round, inputs resident in HBM); `e2e` is
 the same metric measured around the public call with host buffers (schedule / explorer parameters copied
 host->device and the round statistics copied device->host inside the timed region).
 
@@ -41,17 +42,17 @@ CONFIGS = {
                flops_per_point=2 * 2,
                kernel="pgn::scan_kernel<VecChain<TOY_MVN,1,SLICE>>",
                workload="C1: toy_mvn_target(2), SliceSampler, 10 chains (reference smoke test)"),
-    "c2": dict(chains_per_gpu=256, dim=32, explorer="AutoMALA", state_bytes=32 * 8, scans=1024, burn=8,
+    "c2": dict(chains_per_gpu=256, dim=32, explorer="AutoMALA", state_bytes=32 * 8, scans=2048, burn=8,
                flops_per_point=12 * 32 + 30 + 8 * 32,
                kernel="pgn::scan_kernel<VecChain<FUNNEL,1,AUTOMALA>>",
                workload="C2: Neal's funnel d=32 (test/supporting/dimensional-analysis.jl:33-47), reference N(0,9I), "
                         "AutoMALA defaults, 256 chains per GPU, chain ladder sharded contiguously"),
-    "c3": dict(chains_per_gpu=1024, dim=128, explorer="AutoMALA", state_bytes=128 * 8, scans=256, burn=8,
+    "c3": dict(chains_per_gpu=1024, dim=128, explorer="AutoMALA", state_bytes=128 * 8, scans=512, burn=8,
                flops_per_point=2 * 8 * 3 * 128 + 8 * 30 + 40 + 8 * 128,
                kernel="pgn::scan_kernel<VecChain<GMM,...,AUTOMALA>>",
                workload="C3: 8-mode Gaussian mixture d=128 (means (+-8,+-8,+-8,0,...)), reference N(0,64 I), "
                         "AutoMALA defaults, 1024 chains per GPU"),
-    "c4": dict(chains_per_gpu=512, dim=1024, explorer="IsingMetropolis", state_bytes=128, scans=1024, burn=8,
+    "c4": dict(chains_per_gpu=512, dim=1024, explorer="IsingMetropolis", state_bytes=128, scans=2048, burn=8,
                flops_per_point=0,
                kernel="pgn::scan_kernel<IsingChain>",
                workload="C4: Ising 32x32 torus (examples/ising.jl), beta = log(1+sqrt 2)/2 (critical), "
