@@ -554,3 +554,32 @@ def test_c4_full_ladder_on_one_gpu(gpu_lib, oracle_lib):
     last = type("R", (), dict(index_process=rr.index_process[-4:], swap_accept=rr.swap_accept[-4:], swap_lr=rr.swap_lr[-4:],
                               swap_u=rr.swap_u[-4:]))
     check_scan_invariants(last, 4096)
+
+
+def test_plain_c_driver_matches_the_python_binding(gpu_lib):
+    """tests/c_abi_smoke.c drives the library from plain C through include/pigeons_b200.h (dlopen, no Python, no C++):
+    toy MVN d=2, 10 chains, SliceSampler, rounds 1..6 on the default schedule.  Same calls through the ctypes binding give
+    the same numbers to the last printed digit (17 significant digits = every bit of a double)."""
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe, src = os.path.join(root, "tests", "c_abi_smoke.bin"), os.path.join(root, "tests", "c_abi_smoke.c")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+        subprocess.run(["gcc", "-std=c11", "-Wall", "-I", os.path.join(root, "include"), "-o", exe, src, "-ldl", "-lm"], check=True)
+    c = json.loads(subprocess.run([exe, pg.default_library_path()], check=True, capture_output=True, text=True).stdout)
+    assert c["rc"] == 0
+    t = pg.toy_mvn_target(2)
+    e = pg.Engine(gpu_lib, n_chains=10, seed=1, **t.engine_config())
+    e.init_replicas()
+    e.set_schedule(np.arange(10) / 9.0)
+    e.set_explorer(**pg.SliceSampler().engine_params(2))
+    for rnd in range(1, 7):
+        r = e.run_round(2 ** rnd)
+    e.close()
+    assert c["swap_mean"] == [float(v) for v in r.swap_mean[:9]]
+    assert c["online_mean"] == [float(v) for v in r.online_mean]
+    assert c["n_round_trips"] == r.n_round_trips
+    e1 = sum(float(r.logsum_fwd[i]) - np.log(float(r.swap_n[i])) for i in range(9))
+    e2 = sum(float(r.logsum_bwd[i]) - np.log(float(r.swap_n[i])) for i in range(9))
+    assert abs(c["stepping_stone"] - 0.5 * (e1 - e2)) < 1e-12
