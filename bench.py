@@ -414,9 +414,9 @@ def b200_record(pg, torch, name, args, lib, comm, rank, world, local_rank, steps
         latency_bound = name != "c5"
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": tr["dram_bytes_per_launch"] if tr else None,
-                "traffic_note": (f"DRAM bytes of one {tr['scans_in_captured_launch']}-scan launch, {tr['source']}; the replica state "
-                                 "stays on chip for the whole launch, so the traffic does not grow with the number of scans")
-                if tr else None,
+                "traffic_note": ((f"DRAM bytes of one {tr['scans_in_captured_launch']}-scan launch, {tr['source']}; the replica state "
+                                  "stays on chip for the whole launch, so the traffic does not grow with the number of scans")
+                                 if tr.get("scans_in_captured_launch") else f"DRAM bytes of one launch, {tr['source']}") if tr else None,
                 "peak_source": peak_src, "kernel": cfg["kernel"] + (" (one persistent launch per step)" if latency_bound else ""),
                 "algorithmic_bytes_per_scan": b_scan,
                 "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak if fp64_peak else None,
@@ -452,6 +452,7 @@ def b200_record(pg, torch, name, args, lib, comm, rank, world, local_rank, steps
                 "gemm": os.environ.get("PGN_GEMM", "dmma"),
                 "achieved_tflops": gemm_tflops, "peak_tflops": fp64_peak,
                 "frac": gemm_tflops / fp64_peak if fp64_peak else None,
+                "dmma_pipe_active_pct_ncu": (tr or {}).get("dmma_pipe_active_pct"),
                 "gemm_share_of_kernel_time": gemm_ms / kernel_ms, "batched_evaluations": batch_steps,
                 "columns_requested": act_cols, "columns_multiplied": gemm_cols,
                 "useful_flop_fraction": act_cols / gemm_cols if gemm_cols else None,

@@ -68,8 +68,8 @@ static int logreg_col_tile(const pgn_handle* h) { return h->lr_use_dmma ? h->lr_
 // Evaluate likelihood and its gradient at the rows cols[0..n_cols) of `theta` ([r_pad][d_pad]); results land in
 // lr_lik[cols[j]] and lr_G[cols[j]][:].  n_cols and cols live on the device (LrControl / lr_cols, written by
 // logreg_compact_kernel or by the parity entry point): the host launches the full grids, blocks of column tiles
-// beyond n_cols return at once.  [e0, e1] brackets the two GEMMs (and the Bernoulli / reduction passes between them).
-void logreg_eval_batch(pgn_handle* h, const double* theta, cudaEvent_t e0, cudaEvent_t e1) {
+// beyond n_cols return at once.  The four events bracket the two GEMM launches (not the Bernoulli / reduction passes).
+void logreg_eval_batch(pgn_handle* h, const double* theta, cudaEvent_t* ev) {   // ev: null or 4 events bracketing the two GEMMs
   const int dp = h->d_pad, np = h->lr_n_pad, rp = h->lr_r_pad;
   const int* ncp = &h->lr_ctl.p->n_cols;
   const int* cols = h->lr_cols.p;
@@ -78,7 +78,6 @@ void logreg_eval_batch(pgn_handle* h, const double* theta, cudaEvent_t e0, cudaE
     dim3 grid((dp + 31) / 32, (rp + 31) / 32), block(32, 8);
     logreg_gather_transpose_kernel<<<grid, block, 0, h->stream>>>(theta, dp, dp, ncp, cols, h->lr_Thetat.p, rp, bn);
   }
-  if (e0) CUDA_CHECK(cudaEventRecord(e0, h->stream));
   auto gemm = [&](const double* A, int lda, const double* B, int k_total, int k_chunk, double* C, size_t split_stride, dim3 grid) {
     if (!h->lr_use_dmma)
       dgemm_km_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(A, lda, B, rp, k_total, k_chunk, C, nullptr, rp, split_stride,
@@ -90,11 +89,14 @@ void logreg_eval_batch(pgn_handle* h, const double* theta, cudaEvent_t e0, cudaE
       dgemm_km_dmma_kernel<0, 128><<<grid, 256, dmma_smem_bytes(128), h->stream>>>(A, lda, B, rp, k_total, k_chunk, C, nullptr, rp,
                                                                                    split_stride, nullptr, 0, ncp);
   };
+  if (ev) CUDA_CHECK(cudaEventRecord(ev[0], h->stream));
   gemm(h->lr_Xt.p, np, h->lr_Thetat.p, dp, dp, h->lr_LL.p, 0, dim3(np / GEMM_BM, rp / bn, 1));
+  if (ev) CUDA_CHECK(cudaEventRecord(ev[1], h->stream));
   logreg_bernoulli_kernel<<<h->n_sms * 8, 256, 0, h->stream>>>(h->lr_LL.p, h->lr_Res.p, h->lr_y.p, rp, np, h->lr_n_data, ncp, bn);
   logreg_reduce_ll_kernel<<<(rp + 7) / 8, 256, 0, h->stream>>>(h->lr_LL.p, rp, h->lr_n_data, ncp, cols, h->lr_lik.p);
+  if (ev) CUDA_CHECK(cudaEventRecord(ev[2], h->stream));
   gemm(h->lr_Xr.p, dp, h->lr_Res.p, np, LR_CHUNK, h->lr_Gp.p, (size_t)dp * rp, dim3(dp / GEMM_BM, rp / bn, h->lr_splits));
-  if (e1) CUDA_CHECK(cudaEventRecord(e1, h->stream));
+  if (ev) CUDA_CHECK(cudaEventRecord(ev[3], h->stream));
   {
     dim3 grid((dp + 31) / 32, (rp + 31) / 32), block(32, 8);
     logreg_finalize_grad_kernel<<<grid, block, 0, h->stream>>>(h->lr_Gp.p, h->lr_splits, (size_t)dp * rp, rp, dp, ncp, cols,
@@ -156,7 +158,7 @@ void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<C
   // and emits the next one) -> compaction of the chains that emitted a point -> the two GEMMs over those columns only.
   // The host enqueues LR_STEP_CHUNK steps at a time and looks at the device-side counters once per chunk: steps after
   // the last chain finished its scan find n_cols = 0 and every kernel of them returns at once.
-  cudaEvent_t ge[2 * LR_STEP_CHUNK];
+  cudaEvent_t ge[4 * LR_STEP_CHUNK];
   for (auto& e : ge) CUDA_CHECK(cudaEventCreate(&e));
   h->last_gemm_ms = 0.0;
   h->last_batch_steps = 0;
@@ -175,7 +177,7 @@ void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<C
       for (int k = 0; k < LR_STEP_CHUNK; ++k) {
         logreg_controller_kernel<<<grid, wpb * 32, 0, h->stream>>>(P);
         logreg_compact_kernel<<<1, 1024, 0, h->stream>>>(h->lr_st.p, nl, h->lr_cols.p, h->lr_ctl.p, k, logreg_col_tile(h));
-        logreg_eval_batch(h, h->lr_Theta.p, ge[2 * k], ge[2 * k + 1]);
+        logreg_eval_batch(h, h->lr_Theta.p, &ge[4 * k]);
       }
       h->last_launches += (long long)LR_STEP_CHUNK * (1 + LR_EVAL_LAUNCHES);
       CUDA_CHECK(cudaMemcpyAsync(&ctl, h->lr_ctl.p, sizeof(LrControl), cudaMemcpyDeviceToHost, h->stream));
@@ -183,9 +185,10 @@ void logreg_run_round(pgn_handle* h, int64_t n_scans, LrParams& P, std::vector<C
       CUDA_CHECK(cudaStreamSynchronize(h->stream));
       for (int k = 0; k < LR_STEP_CHUNK; ++k) {
         if (ctl.hist[k] == 0) { scan_done = true; continue; }
-        float ms = 0.f;
-        CUDA_CHECK(cudaEventElapsedTime(&ms, ge[2 * k], ge[2 * k + 1]));
-        h->last_gemm_ms += ms;
+        float ms1 = 0.f, ms2 = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms1, ge[4 * k], ge[4 * k + 1]));
+        CUDA_CHECK(cudaEventElapsedTime(&ms2, ge[4 * k + 2], ge[4 * k + 3]));
+        h->last_gemm_ms += ms1 + ms2;
       }
     }
     if (flag != 0) break;
@@ -245,7 +248,7 @@ void logreg_points(pgn_handle* h, const double* x, int n_points, const double* b
       c.n_cols = m;
       CUDA_CHECK(cudaMemcpy(h->lr_ctl.p, &c, sizeof(c), cudaMemcpyHostToDevice));
     }
-    logreg_eval_batch(h, h->lr_Theta.p, nullptr, nullptr);
+    logreg_eval_batch(h, h->lr_Theta.p, nullptr);
     logreg_points_finish_kernel<<<(m + 3) / 4, 128, 0, h->stream>>>(h->lr_Theta.p, d, dp, m, db.p, h->lr_lik.p, h->lr_G.p,
                                                                    h->cfg.p[5], h->cfg.p[4], lp ? dlp.p : nullptr,
                                                                    ld ? dld.p : nullptr, dg.p);
