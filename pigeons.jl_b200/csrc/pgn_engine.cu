@@ -69,9 +69,9 @@ void fill_params(pgn_handle* h, Params& P) {
 void* select_scan_kernel(const pgn_handle* h) {
   const int ex = h->ep.kind;
   switch (h->cfg.target_kind) {
-    case PGN_TARGET_TOY_MVN: return vec_scan_kernel_toy(h->cpl, ex, h->regcap);
-    case PGN_TARGET_FUNNEL: return vec_scan_kernel_funnel(h->cpl, ex, h->regcap);
-    case PGN_TARGET_GMM: return vec_scan_kernel_gmm(h->cpl, ex, h->regcap);
+    case PGN_TARGET_TOY_MVN: return vec_scan_kernel_toy(h->cpl, ex);
+    case PGN_TARGET_FUNNEL: return vec_scan_kernel_funnel(h->cpl, ex);
+    case PGN_TARGET_GMM: return vec_scan_kernel_gmm(h->cpl, ex);
     case PGN_TARGET_MIXED: return vec_scan_kernel_mixed(h->cpl, ex);
     case PGN_TARGET_ISING: return ex == PGN_EXPLORER_ISING_METROPOLIS ? ising_scan_kernel() : nullptr;
     case PGN_TARGET_TEST_SWAPPER: return ex == PGN_EXPLORER_NONE ? test_swapper_scan_kernel() : nullptr;
@@ -226,8 +226,6 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
     {
       const char* fm = std::getenv("PGN_FORCE_MEM");
       h->force_mem = fm != nullptr && std::string(fm) == "1";
-      const char* rc = std::getenv("PGN_REGCAP");
-      h->regcap = rc ? std::atoi(rc) : 0;
       const char* to = std::getenv("PGN_TIMEOUT_S");      // hand-shake spin limit (default 20 s; the LOGREG path uses 30x)
       if (to && std::atof(to) > 0) h->timeout_ns = (unsigned long long)(std::atof(to) * 1e9);
     }

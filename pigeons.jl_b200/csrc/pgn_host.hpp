@@ -138,7 +138,6 @@ struct pgn_handle {
   unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
   // ---- memory-resident scan path (any d, any number of chains; pgn_memchain.cuh)
   bool force_mem = false;
-  int regcap = 0;                // register cap of the d > 64 mixture autoMALA kernel (0: none, 144: teams of two for 1024 chains)
   int recorder_order = PGN_RECORDERS_PER_REPLICA;
   pgn::DevBuf<pgn::RecEntry> rec_table;   // per-replica recorders [n_chains][n_local] (PGN_RECORDERS_PER_REPLICA)
   pgn::DevBuf<pgn::OnEntry> on_table;     // target-chain online statistics per replica [n_chains][d_pad]
@@ -165,9 +164,9 @@ namespace pgn {
 
 // ---- kernels compiled in the other translation units -------------------------------------------
 // scan kernels (pgn_scan_vec.cu, one object per target family; pgn_scan_misc.cu; pgn_scan_mem.cu)
-void* vec_scan_kernel_toy(int cpl, int ex, int regcap);
-void* vec_scan_kernel_funnel(int cpl, int ex, int regcap);
-void* vec_scan_kernel_gmm(int cpl, int ex, int regcap);
+void* vec_scan_kernel_toy(int cpl, int ex);
+void* vec_scan_kernel_funnel(int cpl, int ex);
+void* vec_scan_kernel_gmm(int cpl, int ex);
 void* vec_scan_kernel_mixed(int cpl, int ex);
 void* ising_scan_kernel();
 void* ising_lite_scan_kernel();

@@ -506,74 +506,50 @@ struct VecChain {
         g[k] = acc + gt * b;
       }
     } else {   // GMM
-      // Squared distances to the 8 modes in two passes of four (the reference term and the rider travel with the first):
-      // every sum keeps its own tree, so the bits are those of one pass over ten values, with 6 instead of 26 live
-      // accumulators.  A lane keeps only the log-weight term of "its" mode (lane & 7) and the running maximum; the mode
-      // weights exp(a_m - M) are evaluated one per lane and fetched by shuffle where the sums over modes need them.
       const double ivr = P->p[5], lsr = P->p[4], ivm = P->p[2], cst = P->p[1];
+      const int K = P->n_modes;
+      double v[KMAX_MODES + 2];
+#pragma unroll
+      for (int m = 0; m < KMAX_MODES + 2; ++m) v[m] = 0.0;
+      v[KMAX_MODES + 1] = extra;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) if (valid(k)) {
+        const double xv = xx[k];
+        v[KMAX_MODES] = v[KMAX_MODES] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
+#pragma unroll
+        for (int m = 0; m < KMAX_MODES; ++m) {
+          double t = xv - sm_means[m * P->d_pad + k * 32 + lane];
+          v[m] = v[m] + t * t;
+        }
+      }
+      warp_sum_n<KMAX_MODES + 2>(v);
+      a0 = v[KMAX_MODES]; extra = v[KMAX_MODES + 1];
       const double* lw = sm_means + (size_t)KMAX_MODES * P->d_pad;
-      static_assert(KMAX_MODES == 8, "two passes of four modes");
-      double mine = 0.0, M = -PGN_INF;
-      {
-        double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, extra};
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) if (valid(k)) {
-          const double xv = xx[k];
-          v[4] = v[4] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            double t = xv - sm_means[m * P->d_pad + k * 32 + lane];
-            v[m] = v[m] + t * t;
-          }
-        }
-        warp_sum_n<6>(v);
-        a0 = v[4]; extra = v[5];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const double am = lw[m] - 0.5 * v[m] * ivm - cst;
-          if (am > M) M = am;
-          mine = ((lane & 7) == m) ? am : mine;
-        }
-      }
-      {
-        double v[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) if (valid(k)) {
-          const double xv = xx[k];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            double t = xv - sm_means[(4 + m) * P->d_pad + k * 32 + lane];
-            v[m] = v[m] + t * t;
-          }
-        }
-        warp_sum_n<4>(v);
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const double am = lw[4 + m] - 0.5 * v[m] * ivm - cst;
-          if (am > M) M = am;
-          mine = ((lane & 7) == 4 + m) ? am : mine;
-        }
-      }
-      const double e = exp_(mine - M);     // lane m (and m + 8, ...) holds the weight of mode m
-      double s = 0.0;
-#pragma unroll
-      for (int m = 0; m < KMAX_MODES; ++m) s = s + __shfl_sync(PGN_FULL_MASK, e, m);
-      a1 = M + log_(s);
-      double acc[CPL];
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) acc[k] = 0.0;
+      double w[KMAX_MODES];
+      double M = -PGN_INF;
 #pragma unroll
       for (int m = 0; m < KMAX_MODES; ++m) {
-        const double wm = __shfl_sync(PGN_FULL_MASK, e, m);
-#pragma unroll
-        for (int k = 0; k < CPL; ++k)
-          if (valid(k)) acc[k] = acc[k] + wm * (sm_means[m * P->d_pad + k * 32 + lane] - xx[k]);
+        w[m] = lw[m] - 0.5 * v[m] * ivm - cst;
+        if (w[m] > M) M = w[m];
       }
+      {
+        double wexp[KMAX_MODES];
+        mode_exps(w, M, K, wexp);
+#pragma unroll
+        for (int m = 0; m < KMAX_MODES; ++m) w[m] = wexp[m];
+      }
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < KMAX_MODES; ++m) s = s + w[m];
+      a1 = M + log_(s);
 #pragma unroll
       for (int k = 0; k < CPL; ++k) {
         if (!valid(k)) { g[k] = 0.0; continue; }
         const double xv = xx[k];
-        double gt = (acc[k] / s) * ivm;
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < KMAX_MODES; ++m) acc = acc + w[m] * (sm_means[m * P->d_pad + k * 32 + lane] - xv);
+        double gt = (acc / s) * ivm;
         double gr = -xv * ivr;
         double t = gr * (1.0 - b);
         g[k] = t + gt * b;
@@ -1527,7 +1503,7 @@ struct TestSwapperChain {
 // The scan kernel
 // ===========================================================================
 template <class Chain>
-__device__ __forceinline__ void scan_body(const Params& P) {
+__global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) scan_kernel(const __grid_constant__ Params P) {
   extern __shared__ double smem[];
   Chain::stage_shared(P, smem);
   __syncthreads();
@@ -1787,17 +1763,6 @@ __device__ __forceinline__ void scan_body(const Params& P) {
     else { s.trial_cycles = s.barrier_cycles = s.decide_cycles = 0; }
     P.stats[wl] = s;
   }
-}
-
-template <class Chain>
-__global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) scan_kernel(const __grid_constant__ Params P) {
-  scan_body<Chain>(P);
-}
-// The same scan compiled for NREG registers per thread (no launch bounds: the two qualifiers exclude each other), so that
-// wider teams are co-resident: 144 registers = 14 warps per SM = teams of two for 1024 chains of d = 128 (BASELINE config 3).
-template <class Chain, int NREG>
-__global__ void __maxnreg__(NREG) scan_kernel_capped(const __grid_constant__ Params P) {
-  scan_body<Chain>(P);
 }
 
 // ===========================================================================

@@ -142,14 +142,14 @@ void launch_test_math(int grid, int block, int op, const double* in, double* out
 }
 
 // the vector-state families: the plain and the team kernels of a family are compiled separately
-void* vec_plain_kernel_toy(int cpl, int ex);    void* vec_team_kernel_toy(int cpl, int ex, int regcap);
-void* vec_plain_kernel_funnel(int cpl, int ex); void* vec_team_kernel_funnel(int cpl, int ex, int regcap);
-void* vec_plain_kernel_gmm(int cpl, int ex);    void* vec_team_kernel_gmm(int cpl, int ex, int regcap);
+void* vec_plain_kernel_toy(int cpl, int ex);    void* vec_team_kernel_toy(int cpl, int ex);
+void* vec_plain_kernel_funnel(int cpl, int ex); void* vec_team_kernel_funnel(int cpl, int ex);
+void* vec_plain_kernel_gmm(int cpl, int ex);    void* vec_team_kernel_gmm(int cpl, int ex);
 void* vec_plain_kernel_mixed(int cpl, int ex);
 static bool is_team_explorer(int ex) { return ex == PGN_EXPLORER_AUTOMALA || ex == PGN_EXPLORER_COMPOSE || ex == PGN_EXPLORER_MIX; }
-void* vec_scan_kernel_toy(int cpl, int ex, int regcap) { return is_team_explorer(ex) ? vec_team_kernel_toy(cpl, ex, regcap) : vec_plain_kernel_toy(cpl, ex); }
-void* vec_scan_kernel_funnel(int cpl, int ex, int regcap) { return is_team_explorer(ex) ? vec_team_kernel_funnel(cpl, ex, regcap) : vec_plain_kernel_funnel(cpl, ex); }
+void* vec_scan_kernel_toy(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_toy(cpl, ex) : vec_plain_kernel_toy(cpl, ex); }
+void* vec_scan_kernel_funnel(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_funnel(cpl, ex) : vec_plain_kernel_funnel(cpl, ex); }
 void* vec_scan_kernel_mixed(int cpl, int ex) { return ex == PGN_EXPLORER_SLICE ? vec_plain_kernel_mixed(cpl, ex) : nullptr; }
-void* vec_scan_kernel_gmm(int cpl, int ex, int regcap) { return is_team_explorer(ex) ? vec_team_kernel_gmm(cpl, ex, regcap) : vec_plain_kernel_gmm(cpl, ex); }
+void* vec_scan_kernel_gmm(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_gmm(cpl, ex) : vec_plain_kernel_gmm(cpl, ex); }
 
 }  // namespace pgn

@@ -40,11 +40,7 @@ void eval_points_launch(int grid, int block, size_t smem, cudaStream_t s, const 
 }
 #else
 template <int CPL>
-void* team_kernel_for(int ex, int regcap) {
-#if PGN_TK == 3
-  if (CPL == 4 && ex == PGN_EXPLORER_AUTOMALA && regcap == 144)
-    return (void*)scan_kernel_capped<VecChain<PGN_TK, 4, PGN_EXPLORER_AUTOMALA>, 144>;
-#endif
+void* team_kernel_for(int ex) {
   switch (ex) {
     case PGN_EXPLORER_AUTOMALA: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_AUTOMALA>>();
     case PGN_EXPLORER_COMPOSE: case PGN_EXPLORER_MIX: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_COMPOSE>>();
@@ -84,11 +80,11 @@ void PGN_FAMILY(launch_eval_points)(int cpl, int grid, int block, size_t smem, c
   }
 }
 #else
-void* PGN_FAMILY(vec_team_kernel)(int cpl, int ex, int regcap) {
+void* PGN_FAMILY(vec_team_kernel)(int cpl, int ex) {
   switch (cpl) {
-    case 1: return team_kernel_for<1>(ex, regcap);
-    case 2: return team_kernel_for<2>(ex, regcap);
-    case 4: return team_kernel_for<4>(ex, regcap);
+    case 1: return team_kernel_for<1>(ex);
+    case 2: return team_kernel_for<2>(ex);
+    case 4: return team_kernel_for<4>(ex);
     default: return nullptr;
   }
 }
