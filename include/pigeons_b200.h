@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PGN_ABI_VERSION 3
+#define PGN_ABI_VERSION 4
 
 /* ---- return codes ------------------------------------------------------- */
 #define PGN_OK 0
@@ -123,7 +123,13 @@ typedef struct pgn_config {
    *  PGN_RECORDERS_PER_CHAIN (1): one accumulator per chain / pair, fitted in scan order; O(n_local) memory.  The
    *    means differ from the reference's at rounding level. */
   int32_t recorder_order;
-  int32_t reserved_;
+  int32_t n_chains_variational; /* 0: one leg (NonReversiblePT).  k > 0: chains 1..k form the variational leg; with
+                                 * k < n_chains the ladder has TWO legs (StabilizedPT.jl:37-66, VariationalDEO.jl):
+                                 *   chain 1 (variational reference) .. chain k (target) | chain k+1 (target) .. chain
+                                 *   n_chains (fixed reference);  is_reference = {1, n_chains}, is_target = {k, k+1}
+                                 * (VariationalDEO.jl:19-20); pgn_set_schedule takes the concatenated parameters
+                                 * vcat(variational leg, reverse(fixed leg)) (StabilizedPT.jl:63-65).  Two legs need
+                                 * recorder_order = PGN_RECORDERS_PER_REPLICA and both target chains on one shard. */
 } pgn_config;
 
 /* Explorer parameters; mirrors the @kwdef explorer structs
@@ -198,7 +204,8 @@ typedef struct pgn_round_out {
   double* swap_lr;         /* [n_scans][n_local] SwapStat.log_ratio of the replica at each chain (NaN for self-partnered) */
   double* swap_u;          /* [n_scans][n_local] SwapStat.uniform */
   uint8_t* swap_accept;    /* [n_scans][n_local] 1 if that chain's pair swapped */
-  double* target_trace;    /* [n_scans][d] state at chain N after explore (traces recorder, recorder.jl:27-43) */
+  double* target_trace;    /* [n_scans][d] state at chain N after explore (traces recorder, recorder.jl:27-43);
+                            * two legs: [n_scans][2][d], target chains k then k+1 */
   /* work counters */
   int64_t n_density_points;   /* distinct (state) points at which the device evaluated ref+target densities */
   int64_t n_ref_equiv_evals;  /* log_potential / logdensity[_and_gradient] calls the reference code path would have made */
@@ -260,6 +267,22 @@ int pgn_log_potential(pgn_handle* h, const double* x, int32_t n_points,
 int pgn_logdensity_and_gradient(pgn_handle* h, const double* x, int32_t n_points,
                                 const double* beta, double* logdens, double* grad,
                                 char** err);
+
+/* GaussianReference (src/variational/GaussianReference.jl:4-54): a mean-field Gaussian as the reference of the
+ * variational leg (chains 1..n_chains_variational): log density sum_i -0.5 log(2 pi sd_i^2) - (x_i - mean_i)^2 / (2 sd_i^2)
+ * (:45-53), gradient -(x - mean) / sd^2 (:72-80), sample_iid! randn * sd_i + mean_i (:30-37).  mean, sd: [dim] — what
+ * update_reference! (:22-28) computed from the target-chain online statistics; mean == NULL switches back to the fixed
+ * reference (activate_variational false, :16-18).  Takes effect at the next round.  Vector targets with an
+ * InterpolatingPath on the register-resident kernels (FUNNEL, GMM; d <= 128). */
+int pgn_set_variational(pgn_handle* h, const double* mean, const double* sd, char** err);
+
+/* hamiltonian_dynamics!(target_log_potential, state, momentum, step_size, n_steps) with the identity preconditioner
+ * (src/explorers/hamiltonian_dynamics.jl:39-84): n_steps leapfrog steps of the device's own integrator (the code the
+ * autoMALA / MALA kernels run) from (x, p) at inverse temperature beta.  Parity / property entry point
+ * (test/test_auto_mala.jl:51-85: forward, flip the momentum, forward again returns to the start).
+ * Vector targets with a gradient on the register-resident kernels (d <= 128).  x, p, x_out, p_out: [n_points][d]. */
+int pgn_hamiltonian_dynamics(pgn_handle* h, const double* x, const double* p, int32_t n_points, const double* beta,
+                             double step_size, int32_t n_steps, double* x_out, double* p_out, char** err);
 
 /* Multi-GPU (one process per GPU): neighbour mailboxes are peer-mapped with
  * CUDA IPC.  Replaces the role of Entangler.transmit! (src/mpi_utils/Entangler.jl:133-184)

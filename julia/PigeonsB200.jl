@@ -39,7 +39,7 @@ export B200, B200Replicas
 # --------------------------------------------------------------------------------------------------------------------
 # constants of include/pigeons_b200.h
 # --------------------------------------------------------------------------------------------------------------------
-const PGN_ABI_VERSION = 3
+const PGN_ABI_VERSION = 4
 
 const PGN_OK = 0
 const PGN_ERROR_NAMES = Dict(
@@ -91,7 +91,7 @@ struct PgnConfig
     data_x::Ptr{Float64}
     data_y::Ptr{Float64}
     recorder_order::Int32
-    reserved_::Int32
+    n_chains_variational::Int32
 end
 
 struct PgnExplorerParams
@@ -384,7 +384,8 @@ function create_b200_replicas(inputs::Inputs, shared::Shared, on::B200)
     handles, firsts, counts = Ptr{Cvoid}[], Int[], Int[]
     for (rank, device) in enumerate(on.devices)
         cfg = PgnConfig(PGN_ABI_VERSION, kind, dim, N, inputs.seed, rank - 1, length(on.devices), device, n_modes, p,
-                        ptr(means), ptr(log_w), ptr(data_x), ptr(data_y), on.recorder_order, 0)
+                        ptr(means), ptr(log_w), ptr(data_x), ptr(data_y), on.recorder_order,
+                        Pigeons.n_chains_var(inputs))      # chains 1..n_var: the variational leg (StabilizedPT.jl:96-116)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         GC.@preserve means log_w data_x data_y begin
             err = Ref{Cstring}(C_NULL)
@@ -445,7 +446,7 @@ Caller-allocated outputs of `pgn_run_round` for one handle.  Event logs are allo
 run asked for (`index_process`, `traces`; the SwapStat log is an engine extension used by `materialise_recorders`
 when `parity_mode` replays the recorder arithmetic in the reference's order).
 """
-function allocate_round_out(n_local::Int, d::Int, n_scans::Int; index_process::Bool, traces::Bool, swap_log::Bool)
+function allocate_round_out(n_local::Int, d::Int, n_scans::Int; index_process::Bool, traces::Bool, swap_log::Bool, n_targets::Int = 1)
     z64(n) = zeros(Int64, n); zf(n) = zeros(Float64, n)
     return RoundBuffers(z64(n_local), zf(n_local), zf(n_local), zf(n_local), z64(n_local), zf(n_local), z64(n_local),
                         z64(n_local), zf(n_local), z64(n_local), zf(n_local), zf(max(d, 1)), zf(max(d, 1)),
@@ -453,7 +454,7 @@ function allocate_round_out(n_local::Int, d::Int, n_scans::Int; index_process::B
                         swap_log ? zeros(Float64, n_local, n_scans) : nothing,
                         swap_log ? zeros(Float64, n_local, n_scans) : nothing,
                         swap_log ? zeros(UInt8, n_local, n_scans) : nothing,
-                        traces ? zeros(Float64, max(d, 1), n_scans) : nothing)
+                        traces ? zeros(Float64, max(d, 1), n_targets * n_scans) : nothing)   # two legs: C [n_scans][2][d]
 end
 
 optr(a, T) = a === nothing ? Ptr{T}(C_NULL) : pointer(a)
@@ -466,14 +467,37 @@ round_out_struct(b::RoundBuffers) = PgnRoundOut(
     optr(b.index_process, Int32), optr(b.swap_lr, Float64), optr(b.swap_u, Float64), optr(b.swap_accept, UInt8),
     optr(b.target_trace, Float64), 0, 0, 0.0, 0.0, 0, 0, 0, 0)
 
+"""
+The annealing parameter of every global chain: `schedule.grids`, or for two legs the parameters of
+`vcat(variational_leg.log_potentials, reverse(fixed_leg.log_potentials))` (`StabilizedPT.jl:63-65`).
+"""
+tempering_parameters(t::Pigeons.NonReversiblePT) = Vector{Float64}(t.schedule.grids)
+tempering_parameters(t::Pigeons.StabilizedPT) =
+    vcat(Vector{Float64}(t.variational_leg.schedule.grids), reverse(Vector{Float64}(t.fixed_leg.schedule.grids)))
+
+"""
+Mean and standard deviation of the `GaussianReference` once `update_reference!` has run (`GaussianReference.jl:22-28`;
+the path of the variational leg is then `InterpolatingPath(variational, target)`, `variational.jl:36-40`), else `nothing`.
+"""
+function variational_parameters(pt)
+    v = pt.inputs.variational
+    (v isa Pigeons.GaussianReference && haskey(v.mean, :singleton_variable)) || return nothing, nothing
+    leg = pt.shared.tempering isa Pigeons.StabilizedPT ? pt.shared.tempering.variational_leg : pt.shared.tempering
+    leg.path.ref isa Pigeons.GaussianReference || return nothing, nothing            # not activated yet
+    return Vector{Float64}(v.mean[:singleton_variable]), Vector{Float64}(v.standard_deviation[:singleton_variable])
+end
+
 function Pigeons.run_one_round!(pt::PT{<:Any, B200Replicas})
     r = pt.replicas
     n_scans = n_scans_in_round(pt.shared.iterators)
-    grids = Vector{Float64}(pt.shared.tempering.schedule.grids)
+    grids = tempering_parameters(pt.shared.tempering)
+    var_mean, var_sd = variational_parameters(pt)
     ep, sd = explorer_params(pt.shared.explorer, r.dim)
     want_index = haskey(r.recorders_template, :index_process)
     want_traces = haskey(r.recorders_template, :traces)
-    bufs = [allocate_round_out(r.n_local[i], r.dim, n_scans; index_process = want_index, traces = want_traces, swap_log = false)
+    two_legs = pt.shared.tempering isa Pigeons.StabilizedPT
+    bufs = [allocate_round_out(r.n_local[i], r.dim, n_scans; index_process = want_index, traces = want_traces, swap_log = false,
+                               n_targets = two_legs ? 2 : 1)
             for i in eachindex(r.handles)]
     outs = Vector{PgnRoundOut}(undef, length(r.handles))
     timed = @timed begin
@@ -483,9 +507,14 @@ function Pigeons.run_one_round!(pt::PT{<:Any, B200Replicas})
             Threads.@spawn begin
                 h = r.handles[i]
                 err = Ref{Cstring}(C_NULL)
-                GC.@preserve grids sd bufs begin
+                GC.@preserve grids sd bufs var_mean var_sd begin
                     check(ccall((:pgn_set_schedule, libpigeons_b200[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Ref{Cstring}),
                                 h, grids, length(grids), err), err)
+                    if Pigeons.n_chains_var(pt.inputs) > 0
+                        vptr(a) = a === nothing ? Ptr{Float64}(C_NULL) : pointer(a)
+                        check(ccall((:pgn_set_variational, libpigeons_b200[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Cstring}),
+                                    h, vptr(var_mean), vptr(var_sd), err), err)
+                    end
                     check(ccall((:pgn_set_explorer, libpigeons_b200[]), Cint, (Ptr{Cvoid}, Ref{PgnExplorerParams}, Ref{Cstring}),
                                 h, ep, err), err)
                     out = Ref(round_out_struct(bufs[i]))
@@ -573,7 +602,12 @@ function materialise_recorders(pt, bufs::Vector{RoundBuffers}, outs::Vector{PgnR
         rt.n_round_trips = sum(o.n_round_trips for o in outs)
         filled[:round_trip] = rt
     end
-    last, olast = bufs[end], outs[end]                 # the handle owning chain N
+    # the handle owning the target chain(s): chain N, or with two legs chains n_var and n_var + 1 (one handle, engine rule)
+    n_var = Pigeons.n_chains_var(pt.inputs)
+    two_legs = 0 < n_var < N
+    t_chain = two_legs ? n_var : N
+    owner = findfirst(i -> r.first_chain[i] <= t_chain < r.first_chain[i] + r.n_local[i], eachindex(r.handles))
+    last, olast = bufs[owner], outs[owner]
     for key in (:_transformed_online, :online)
         haskey(template, key) || continue
         rec = OnlineStateRecorder()
@@ -596,7 +630,12 @@ function materialise_recorders(pt, bufs::Vector{RoundBuffers}, outs::Vector{PgnR
     if haskey(template, :traces)
         tr = Dict{Pair{Int, Int}, Any}()
         for s in 1:n_scans
-            tr[N => s] = last.target_trace[1:r.dim, s]
+            if two_legs                                  # both target chains record (VariationalDEO.jl:20, pigeons.jl:110-131)
+                tr[n_var => s] = last.target_trace[1:r.dim, 2 * s - 1]
+                tr[(n_var + 1) => s] = last.target_trace[1:r.dim, 2 * s]
+            else
+                tr[N => s] = last.target_trace[1:r.dim, s]
+            end
         end
         filled[:traces] = tr
     end

@@ -179,11 +179,31 @@ struct Engine {
   int d() const { return cfg.dim; }
   int L() const { return (int)cfg.p[1]; }
 
+  // ---- legs (StabilizedPT.jl:37-66, 96-116; VariationalDEO.jl:19-20): chains 1..n_var are the variational leg
+  // (reference -> target), chains n_var+1..N the fixed leg (target -> reference)
+  int n_var() const { return cfg.n_chains_variational; }
+  bool two_legs() const { return n_var() > 0 && n_var() < N(); }
+  bool is_reference(int chain) const { return (chain == 1 && N() > 1) || (two_legs() && chain == N()); }   // DEO.jl:13
+  bool is_target(int chain) const { return two_legs() ? (chain == n_var() || chain == n_var() + 1) : chain == N(); }
+  // GaussianReference (GaussianReference.jl:4-54), once activated (:16-18), replaces the reference of the variational leg
+  bool var_active = false;
+  std::vector<double> var_mean, var_sd, var_t0, var_t1, var_t2;
+  bool uses_var(int chain) const { return var_active && chain <= n_var(); }
+  // gaussian_logdensity :45-53: sum_i -0.5 log(2 pi sd_i^2) - 1/(2 sd_i^2) (x_i - mean_i)^2; the two coordinate
+  // constants are tabulated when the reference is set
+  double var_density(const double* x) const {
+    return tree_sum(d(), [&](int c) { double dx = x[c] - var_mean[c]; return var_t0[c] - var_t1[c] * (dx * dx); });
+  }
+
   // ------------------------------------------------------------------ densities
   // Component log densities.  FUNNEL: test/supporting/dimensional-analysis.jl:33-47
   // with Distributions.logpdf(Normal(0,s),x) = -(z^2+log2pi)/2 - log(s) and
   // s = exp(y/2) => z^2 = x^2 exp(-y), log s = y/2.
   double ref_density(const Replica& r) const {
+    if (uses_var(r.chain)) return var_density(r.x.data());
+    return fixed_ref_density(r);
+  }
+  double fixed_ref_density(const Replica& r) const {
     const double* x = r.x.data();
     switch (cfg.target_kind) {
       case PGN_TARGET_FUNNEL:
@@ -294,7 +314,7 @@ struct Engine {
   double tgt_density(const Replica& r) const {
     const double* x = r.x.data();
     switch (cfg.target_kind) {
-      case PGN_TARGET_LOGREG: return ref_density(r) + logreg_lik(x, nullptr);
+      case PGN_TARGET_LOGREG: return fixed_ref_density(r) + logreg_lik(x, nullptr);   // the prior is part of the posterior
       case PGN_TARGET_FUNNEL: {
         const double y = x[0];
         const double e = exp_(-y);
@@ -328,9 +348,13 @@ struct Engine {
   }
   double ref_density_grad(const Replica& r, double* g) const {
     const double* x = r.x.data();
+    if (uses_var(r.chain)) {   // GaussianReference.jl:72-80: -1/sd^2 (x - mean)
+      for (int c = 0; c < d(); ++c) g[c] = -(var_t2[c] * (x[c] - var_mean[c]));
+      return var_density(x);
+    }
     const double iv = cfg.p[5];
     for (int c = 0; c < d(); ++c) g[c] = -x[c] * iv;
-    return ref_density(r);
+    return fixed_ref_density(r);
   }
   double tgt_density_grad(const Replica& r, double* g) const {
     const double* x = r.x.data();
@@ -340,7 +364,7 @@ struct Engine {
         const double lik = logreg_lik(x, gl.data());
         const double iv = cfg.p[5];
         for (int c = 0; c < d(); ++c) g[c] = -x[c] * iv + gl[c];
-        return ref_density(r) + lik;
+        return fixed_ref_density(r) + lik;
       }
       case PGN_TARGET_FUNNEL: {
         const double y = x[0];
@@ -478,6 +502,11 @@ struct Engine {
   // sample_iid!(reference_log_potential, replica, shared)
   void sample_iid(double b, Replica& r) {
     const int dd = d();
+    if (uses_var(r.chain)) {   // GaussianReference.jl:30-37: randn * sd + mean, coordinate by coordinate
+      for (int c = 0; c < dd; ++c) r.x[c] = normal_at(r.rng, r.ctr + c) * var_sd[c] + var_mean[c];
+      r.ctr += dd;
+      return;
+    }
     switch (cfg.target_kind) {
       case PGN_TARGET_TOY_MVN: {   // toy_mvn_target.jl:15-21
         double sq = std::sqrt(toy_precision(b));
@@ -873,10 +902,10 @@ struct Engine {
   // explore!(pt, replica, explorer)  (src/pt/pigeons.jl:101-132)
   void explore(Replica& r) {
     ChainStats& st = st_of(r);
-    const bool is_reference = (r.chain == 1 && N() > 1);   // DEO.jl:13
+    const bool is_reference = this->is_reference(r.chain);
     if (cfg.target_kind == PGN_TARGET_TEST_SWAPPER) return;
     if (is_reference) {
-      sample_iid(beta[0], r);
+      sample_iid(beta[r.chain - 1], r);
     } else {
       switch (ep.kind) {
         case PGN_EXPLORER_TOY: sample_iid(beta[r.chain - 1], r); break;   // ToyExplorer.jl:7-12
@@ -922,7 +951,7 @@ struct Engine {
     r.u = r.uniform();
   }
   void record_round_trip(Replica& r) {   // RoundTripRecorder.jl:43-54
-    bool is_ref = (r.chain == 1 && N() > 1), is_tgt = (r.chain == N());
+    bool is_ref = is_reference(r.chain), is_tgt = is_target(r.chain);
     if (r.rt_state == 0 && is_ref) r.rt_state = 1;
     else if (r.rt_state == 1 && is_tgt) { r.rt_state = 2; n_restarts += 1; }
     else if (r.rt_state == 2 && is_ref) { r.rt_state = 1; n_round_trips += 1; }
@@ -964,21 +993,27 @@ void run_round(Engine& E, int64_t n_scans, pgn_round_out* out) {
       }
     }
     if (first_err.code) throw first_err;
-    // target-chain recording (pigeons.jl:110-131)
+    // target-chain recording (pigeons.jl:110-131): every replica at a target chain, into its own recorders
     {
-      Replica& rt = E.replicas[N - 1];
-      if (E.cfg.target_kind == PGN_TARGET_ISING) E.ising_sync_x(rt);
-      // online statistics are kept for vector states only (IsingState is not a
-      // continuous-variable state; OnlineStateRecorder.jl:87-110 does not apply)
-      if (E.cfg.target_kind != PGN_TARGET_ISING) {
-        std::vector<VarAcc>* on = &E.online;
-        if (E.per_replica()) {
-          on = &E.rec[rt.replica_index - 1].online;
-          if (on->empty()) on->assign(d, VarAcc{});
+      int t_idx = 0;
+      for (int chain = 1; chain <= N; ++chain) {
+        if (!E.is_target(chain)) continue;
+        Replica& rt = E.replicas[chain - 1];
+        if (E.cfg.target_kind == PGN_TARGET_ISING) E.ising_sync_x(rt);
+        // online statistics are kept for vector states only (IsingState is not a
+        // continuous-variable state; OnlineStateRecorder.jl:87-110 does not apply)
+        if (E.cfg.target_kind != PGN_TARGET_ISING) {
+          std::vector<VarAcc>* on = &E.online;
+          if (E.per_replica()) {
+            on = &E.rec[rt.replica_index - 1].online;
+            if (on->empty()) on->assign(d, VarAcc{});
+          }
+          for (int c = 0; c < d; ++c) (*on)[c].fit(rt.x[c]);
         }
-        for (int c = 0; c < d; ++c) (*on)[c].fit(rt.x[c]);
+        const int n_tgt = E.two_legs() ? 2 : 1;
+        if (out->target_trace) std::memcpy(out->target_trace + ((size_t)(s - 1) * n_tgt + t_idx) * d, rt.x.data(), sizeof(double) * d);
+        t_idx += 1;
       }
-      if (out->target_trace) std::memcpy(out->target_trace + (size_t)(s - 1) * d, rt.x.data(), sizeof(double) * d);
     }
     // ---- swap!  (swap.jl:6-26)
     for (int my_chain = 1; my_chain <= N; ++my_chain) {
@@ -1093,6 +1128,11 @@ int orc_create(const pgn_config* cfg, orc_handle** out, char** err) {
   if (cfg->abi_version != PGN_ABI_VERSION) return fail(err, PGN_ERR_INVALID, "ABI version mismatch");
   if (cfg->world_size != 1 || cfg->rank != 0) return fail(err, PGN_ERR_INVALID, "oracle is single-process");
   if (cfg->n_chains < 1) return fail(err, PGN_ERR_INVALID, "n_chains must be >= 1");
+  if (cfg->n_chains_variational < 0 || cfg->n_chains_variational > cfg->n_chains)
+    return fail(err, PGN_ERR_INVALID, "0 <= n_chains_variational <= n_chains");
+  if (cfg->n_chains_variational > 0 && cfg->n_chains_variational < cfg->n_chains &&
+      cfg->recorder_order != PGN_RECORDERS_PER_REPLICA)
+    return fail(err, PGN_ERR_INVALID, "two legs need recorder_order = PGN_RECORDERS_PER_REPLICA");
   if (cfg->target_kind == PGN_TARGET_LOGREG && (!cfg->data_x || !cfg->data_y || cfg->p[0] < 1))
     return fail(err, PGN_ERR_INVALID, "LOGREG: data_x / data_y / n_data missing");
   if (cfg->target_kind == PGN_TARGET_GMM && (cfg->n_modes < 1 || cfg->n_modes > 64))
@@ -1175,6 +1215,49 @@ int orc_init_replicas(orc_handle* h, char** err) {
   (void)err;
   return PGN_OK;
 }
+// update_reference! has run on the host (GaussianReference.jl:22-28); install its mean / standard deviation
+int orc_set_variational(orc_handle* h, const double* mean, const double* sd, char** err) {
+  Engine& E = h->E;
+  if (!mean || !sd) { E.var_active = false; return PGN_OK; }
+  const int tk = E.cfg.target_kind, d = E.d();
+  if (E.n_var() < 1) return fail(err, PGN_ERR_INVALID, "set_variational: n_chains_variational is 0");
+  if (tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM) return fail(err, PGN_ERR_INVALID, "set_variational: FUNNEL and GMM targets");
+  for (int c = 0; c < d; ++c)
+    if (!(sd[c] > 0.0) || !std::isfinite(sd[c]) || !std::isfinite(mean[c]))
+      return fail(err, PGN_ERR_INVALID, "set_variational: finite means and positive finite standard deviations");
+  E.var_mean.assign(mean, mean + d); E.var_sd.assign(sd, sd + d);
+  E.var_t0.resize(d); E.var_t1.resize(d); E.var_t2.resize(d);
+  for (int c = 0; c < d; ++c) {
+    const double s2 = sd[c] * sd[c];
+    E.var_t0[c] = -0.5 * log_(6.283185307179586 * s2);   // 2.0 * pi
+    E.var_t1[c] = 1.0 / (2.0 * s2);
+    E.var_t2[c] = 1.0 / s2;
+  }
+  E.var_active = true;
+  return PGN_OK;
+}
+
+// hamiltonian_dynamics! (hamiltonian_dynamics.jl:39-84) with the identity preconditioner: n_steps x leap_frog!
+int orc_hamiltonian_dynamics(orc_handle* h, const double* x, const double* p, int32_t n_points, const double* beta,
+                             double step_size, int32_t n_steps, double* x_out, double* p_out, char** err) {
+  Engine& E = h->E;
+  const int d = E.d(), tk = E.cfg.target_kind;
+  if (tk != PGN_TARGET_TOY_MVN && tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM && tk != PGN_TARGET_LOGREG)
+    return fail(err, PGN_ERR_INVALID, "hamiltonian_dynamics: vector targets with a gradient");
+  for (int i = 0; i < n_points; ++i) {
+    Replica r;
+    r.chain = 1; r.replica_index = 1;
+    r.x.assign(x + (size_t)i * d, x + (size_t)(i + 1) * d);
+    r.momentum.assign(p + (size_t)i * d, p + (size_t)(i + 1) * d);
+    r.precond.assign(d, 1.0); r.grad.assign(d, 0.0); r.g1.assign(d, 0.0); r.g2.assign(d, 0.0);
+    for (int s = 0; s < n_steps; ++s)
+      if (!E.leap_frog(beta[i], r, step_size)) break;
+    std::memcpy(x_out + (size_t)i * d, r.x.data(), sizeof(double) * d);
+    std::memcpy(p_out + (size_t)i * d, r.momentum.data(), sizeof(double) * d);
+  }
+  return PGN_OK;
+}
+
 int orc_get_state(orc_handle* h, pgn_replica_state* out, char** err) {
   Engine& E = h->E;
   const int N = E.N(), d = E.d();
@@ -1226,6 +1309,7 @@ int orc_log_potential(orc_handle* h, const double* x, int32_t n_points, const do
   Engine& E = h->E;
   const int d = E.d();
   Replica r;
+  r.chain = 1;   // the path of chain 1's leg: with the Gaussian reference once one is installed
   r.x.assign(d, 0.0);
   for (int i = 0; i < n_points; ++i) {
     r.x.assign(x + (size_t)i * d, x + (size_t)(i + 1) * d);
@@ -1249,6 +1333,7 @@ int orc_logdensity_and_gradient(orc_handle* h, const double* x, int32_t n_points
   if (E.cfg.target_kind == PGN_TARGET_ISING || E.cfg.target_kind == PGN_TARGET_TEST_SWAPPER)
     return fail(err, PGN_ERR_INVALID, "target has no gradient");
   Replica r;
+  r.chain = 1;
   r.g1.assign(d, 0.0); r.g2.assign(d, 0.0);
   for (int i = 0; i < n_points; ++i) {
     r.x.assign(x + (size_t)i * d, x + (size_t)(i + 1) * d);

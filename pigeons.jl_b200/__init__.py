@@ -12,7 +12,8 @@ from ._capi import Engine, EngineError, EngineLib, default_library_path         
 from .distributed import LoadBalance, SingleProcess, ThreadComm, ThreadGroup, TorchDistributed   # noqa: F401
 from .explorers import (MALA, AutoMALA, Compose, Mix, DiagonalPreconditioner, IdentityPreconditioner,  # noqa: F401
                         IsingMetropolis, MixDiagonalPreconditioner, SliceSampler, ToyExplorer)
-from .pt import (PT, ChecksFailed, Inputs, Iterators, NonReversiblePT, Shared, adapt, create_pt, global_barrier,   # noqa: F401
+from .pt import (PT, ChecksFailed, GaussianReference, Inputs, Iterators, NonReversiblePT, Shared, StabilizedPT, adapt,   # noqa: F401
+                 create_pt, create_tempering, global_barrier, global_barrier_variational, tempering_parameters,
                  index_process, n_round_trips, n_scans_in_round, n_tempered_restarts, online, pigeons, resume, write_checkpoint,
                  pigeons_pt, round_trip, run_checks, run_one_round, sample_array, stepping_stone, stepping_stone_pair,
                  swap_trace, traces)

@@ -19,7 +19,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # return codes (include/pigeons_b200.h)
 PGN_OK = 0
@@ -50,7 +50,7 @@ class pgn_config(C.Structure):
         ("seed", C.c_int64), ("rank", C.c_int32), ("world_size", C.c_int32), ("device", C.c_int32),
         ("n_modes", C.c_int32), ("p", C.c_double * 8),
         ("means", _dp), ("log_weights", _dp), ("data_x", _dp), ("data_y", _dp),
-        ("recorder_order", C.c_int32), ("reserved_", C.c_int32),
+        ("recorder_order", C.c_int32), ("n_chains_variational", C.c_int32),
     ]
 
 
@@ -96,7 +96,8 @@ DECLARED_SYMBOLS = [
     "pgn_abi_version", "pgn_create", "pgn_destroy", "pgn_free_string", "pgn_device_info", "pgn_local_range",
     "pgn_set_schedule", "pgn_set_explorer", "pgn_init_replicas", "pgn_get_state", "pgn_set_state",
     "pgn_run_round", "pgn_log_potential", "pgn_logdensity_and_gradient", "pgn_ipc_export", "pgn_ipc_attach",
-    "pgn_peer_attach", "pgn_test_math", "pgn_measure_fp64_peak", "pgn_test_dmma",
+    "pgn_peer_attach", "pgn_test_math", "pgn_measure_fp64_peak", "pgn_test_dmma", "pgn_hamiltonian_dynamics",
+    "pgn_set_variational",
 ]
 
 
@@ -221,7 +222,8 @@ class Engine:
 
     def __init__(self, lib: EngineLib, *, target_kind: int, dim: int, n_chains: int, seed: int,
                  p=(), means=None, log_weights=None, data_x=None, data_y=None, n_modes: int = 0,
-                 rank: int = 0, world_size: int = 1, device: int = 0, recorder_order: int = RECORDERS_PER_REPLICA):
+                 rank: int = 0, world_size: int = 1, device: int = 0, recorder_order: int = RECORDERS_PER_REPLICA,
+                 n_chains_variational: int = 0):
         self.lib = lib
         self.dim = int(dim)
         self.n_chains = int(n_chains)
@@ -234,6 +236,8 @@ class Engine:
         cfg.rank, cfg.world_size, cfg.device = rank, world_size, device
         cfg.n_modes = n_modes
         cfg.recorder_order = recorder_order
+        cfg.n_chains_variational = n_chains_variational
+        self.n_chains_variational = n_chains_variational
         for i, v in enumerate(p):
             cfg.p[i] = float(v)
         self._keep = []
@@ -263,6 +267,18 @@ class Engine:
     def set_schedule(self, beta):
         b = np.ascontiguousarray(beta, dtype=np.float64)
         self.lib.call("set_schedule", self._h, _ptr(b, C.c_double), C.c_int32(b.size))
+
+    def set_variational(self, mean, sd):
+        """GaussianReference of the variational leg (GaussianReference.jl:4-54); None, None switches it off."""
+        self.lib.fn("set_variational").restype = C.c_int
+        if mean is None or sd is None:
+            self.lib.call("set_variational", self._h, None, None)
+            return
+        m = np.ascontiguousarray(mean, dtype=np.float64)
+        s = np.ascontiguousarray(sd, dtype=np.float64)
+        if m.shape != (self.dim,) or s.shape != (self.dim,):
+            raise ValueError(f"set_variational: mean and sd must have shape ({self.dim},)")
+        self.lib.call("set_variational", self._h, _ptr(m, C.c_double), _ptr(s, C.c_double))
 
     def set_explorer(self, *, kind, slice_w=10.0, slice_p=20, slice_n_passes=3, slice_max_iter=1024,
                      n_refresh=0, step_size=1.0, precond_kind=PRECOND_IDENTITY, mix_p0=1.0 / 3.0,
@@ -348,7 +364,8 @@ class Engine:
             swap_lr=f64(n_scans, n) if log_swaps else None,
             swap_u=f64(n_scans, n) if log_swaps else None,
             swap_accept=np.zeros((n_scans, n), dtype=np.uint8) if log_swaps else None,
-            target_trace=f64(n_scans, d) if log_target_trace else None,
+            target_trace=(f64(n_scans, 2, d) if 0 < self.n_chains_variational < self.n_chains else f64(n_scans, d))
+            if log_target_trace else None,
             n_density_points=0, n_ref_equiv_evals=0, kernel_ms=0.0)
         out = pgn_round_out()
         out.swap_n, out.swap_mean = _ptr(res.swap_n, C.c_int64), _ptr(res.swap_mean, C.c_double)
@@ -390,6 +407,17 @@ class Engine:
         self.lib.call("logdensity_and_gradient", self._h, _ptr(x, C.c_double), C.c_int32(x.shape[0]),
                       _ptr(b, C.c_double), _ptr(ld, C.c_double), _ptr(g, C.c_double))
         return ld, g
+
+    def hamiltonian_dynamics(self, x, p, beta, step_size: float, n_steps: int):
+        """hamiltonian_dynamics! with the identity preconditioner (hamiltonian_dynamics.jl:39-84): the engine's own integrator."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.dim)
+        p = np.ascontiguousarray(p, dtype=np.float64).reshape(-1, self.dim)
+        b = np.ascontiguousarray(np.broadcast_to(beta, (x.shape[0],)), dtype=np.float64)
+        xo, po = np.empty_like(x), np.empty_like(p)
+        self.lib.fn("hamiltonian_dynamics").restype = C.c_int
+        self.lib.call("hamiltonian_dynamics", self._h, _ptr(x, C.c_double), _ptr(p, C.c_double), C.c_int32(x.shape[0]),
+                      _ptr(b, C.c_double), C.c_double(step_size), C.c_int32(n_steps), _ptr(xo, C.c_double), _ptr(po, C.c_double))
+        return xo, po
 
     # -- multi-GPU ---------------------------------------------------------------------
     def ipc_export(self) -> bytes:

@@ -64,14 +64,23 @@ void fill_params(pgn_handle* h, Params& P) {
   const bool per_replica = h->recorder_order == PGN_RECORDERS_PER_REPLICA;
   P.rec_table = per_replica ? h->rec_table.p : nullptr;
   P.on_table = per_replica ? h->on_table.p : nullptr;
+  P.n_var = h->cfg.n_chains_variational;
+  P.var_tab = h->var_active ? h->var_tab.p : nullptr;
+}
+
+// does this shard own the target chain(s)?  One leg: chain N; two legs: chains n_var and n_var + 1 (one shard, pgn_create)
+bool shard_owns_target(const pgn_handle* h) {
+  const int nv = h->cfg.n_chains_variational, N = h->cfg.n_chains;
+  const int t = (nv > 0 && nv < N) ? nv : N;
+  return t >= h->first_chain && t < h->first_chain + h->n_local;
 }
 
 void* select_scan_kernel(const pgn_handle* h) {
   const int ex = h->ep.kind;
   switch (h->cfg.target_kind) {
     case PGN_TARGET_TOY_MVN: return vec_scan_kernel_toy(h->cpl, ex);
-    case PGN_TARGET_FUNNEL: return vec_scan_kernel_funnel(h->cpl, ex);
-    case PGN_TARGET_GMM: return vec_scan_kernel_gmm(h->cpl, ex);
+    case PGN_TARGET_FUNNEL: return h->var_active ? vec_scan_kernel_funnel_var(h->cpl, ex) : vec_scan_kernel_funnel(h->cpl, ex);
+    case PGN_TARGET_GMM: return h->var_active ? vec_scan_kernel_gmm_var(h->cpl, ex) : vec_scan_kernel_gmm(h->cpl, ex);
     case PGN_TARGET_MIXED: return vec_scan_kernel_mixed(h->cpl, ex);
     case PGN_TARGET_ISING: return ex == PGN_EXPLORER_ISING_METROPOLIS ? ising_scan_kernel() : nullptr;
     case PGN_TARGET_TEST_SWAPPER: return ex == PGN_EXPLORER_NONE ? test_swapper_scan_kernel() : nullptr;
@@ -127,8 +136,14 @@ void launch_eval_points(pgn_handle* h, const Params& P, const double* xs, const 
   }
   switch (tk) {
     case PGN_TARGET_TOY_MVN: launch_eval_points_toy(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
-    case PGN_TARGET_FUNNEL: launch_eval_points_funnel(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
-    case PGN_TARGET_GMM: launch_eval_points_gmm(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
+    case PGN_TARGET_FUNNEL:
+      if (h->var_active) launch_eval_points_funnel_var(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad);
+      else launch_eval_points_funnel(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad);
+      break;
+    case PGN_TARGET_GMM:
+      if (h->var_active) launch_eval_points_gmm_var(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad);
+      else launch_eval_points_gmm(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad);
+      break;
     case PGN_TARGET_MIXED: launch_eval_points_mixed(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
     default: throw CudaError{PGN_ERR_INVALID, "unsupported target"};
   }
@@ -228,6 +243,21 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
       h->force_mem = fm != nullptr && std::string(fm) == "1";
       const char* to = std::getenv("PGN_TIMEOUT_S");      // hand-shake spin limit (default 20 s; the LOGREG path uses 30x)
       if (to && std::atof(to) > 0) h->timeout_ns = (unsigned long long)(std::atof(to) * 1e9);
+    }
+    {
+      const int nv = cfg->n_chains_variational, N = cfg->n_chains;
+      if (nv < 0 || nv > N) throw CudaError{PGN_ERR_INVALID, "0 <= n_chains_variational <= n_chains"};
+      if (nv > 0 && nv < N) {   // two legs
+        if (cfg->recorder_order != PGN_RECORDERS_PER_REPLICA)
+          throw CudaError{PGN_ERR_INVALID, "two legs need recorder_order = PGN_RECORDERS_PER_REPLICA"};
+        if (cfg->target_kind == PGN_TARGET_LOGREG || (h->cpl == 0 && cfg->target_kind != PGN_TARGET_ISING &&
+                                                     cfg->target_kind != PGN_TARGET_TEST_SWAPPER) || h->force_mem)
+          throw CudaError{PGN_ERR_INVALID, "two legs run on the register-resident scan kernels only (d <= 128)"};
+        const int last = h->first_chain + h->n_local - 1;
+        const bool has_a = nv >= h->first_chain && nv <= last, has_b = nv + 1 >= h->first_chain && nv + 1 <= last;
+        if (has_a != has_b)
+          throw CudaError{PGN_ERR_INVALID, "two legs: both target chains (n_chains_variational and the next one) must be on one shard"};
+      }
     }
     if (cfg->recorder_order != PGN_RECORDERS_PER_REPLICA && cfg->recorder_order != PGN_RECORDERS_PER_CHAIN)
       throw CudaError{PGN_ERR_INVALID, "recorder_order must be PGN_RECORDERS_PER_REPLICA (0) or PGN_RECORDERS_PER_CHAIN (1)"};
@@ -469,8 +499,9 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     if (out->swap_lr) { d_lr.alloc(nlog, h->stream); P.swap_lr = d_lr.p; }
     if (out->swap_u) { d_u.alloc(nlog, h->stream); P.swap_u = d_u.p; }
     if (out->swap_accept) { d_acc.alloc(nlog, h->stream); P.swap_accept = d_acc.p; }
-    const bool owns_target = (h->first_chain + nl - 1 == h->cfg.n_chains);
-    if (out->target_trace && owns_target) { d_trace.alloc((size_t)n_scans * std::max(d, 1), h->stream); P.target_trace = d_trace.p; }
+    const bool owns_target = shard_owns_target(h);
+    const int n_tgt = (h->cfg.n_chains_variational > 0 && h->cfg.n_chains_variational < h->cfg.n_chains) ? 2 : 1;
+    if (out->target_trace && owns_target) { d_trace.alloc((size_t)n_scans * n_tgt * std::max(d, 1), h->stream); P.target_trace = d_trace.p; }
     CUDA_CHECK(cudaMemsetAsync(h->error_flag.p, 0, sizeof(int), h->stream));
     const bool per_replica = h->recorder_order == PGN_RECORDERS_PER_REPLICA;
     const bool vec_online = h->cfg.target_kind != PGN_TARGET_ISING && h->cfg.target_kind != PGN_TARGET_TEST_SWAPPER && d > 0;
@@ -561,6 +592,9 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
         else std::memset(st.data(), 0, sizeof(ChainStatsDev) * nl);
       } else {
         // memory-resident kernel: d > 128, or more chains than fit co-resident, or PGN_FORCE_MEM=1
+        if (h->cfg.n_chains_variational > 0 && (h->cfg.n_chains_variational < h->cfg.n_chains || h->var_active))
+          throw CudaError{PGN_ERR_INVALID, "two legs / a variational reference run on the register-resident scan kernels only "
+                                           "(all chains of the shard co-resident, d <= 128)"};
         void* mk = vec_target ? select_mem_kernel(h) : nullptr;
         if (!mk) throw CudaError{PGN_ERR_INVALID, "too many chains for one GPU for this target (no memory-resident variant)"};
         mem_allocate(h);
@@ -689,7 +723,7 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
     if (out->swap_lr) d_lr.download(out->swap_lr, nlog);
     if (out->swap_u) d_u.download(out->swap_u, nlog);
     if (out->swap_accept) d_acc.download(out->swap_accept, nlog);
-    if (out->target_trace && owns_target && d > 0) d_trace.download(out->target_trace, (size_t)n_scans * d);
+    if (out->target_trace && owns_target && d > 0) d_trace.download(out->target_trace, (size_t)n_scans * n_tgt * d);
     if (flag != 0) {
       static const char* names[] = {"", "invalid explorer state (autoMALA bounds / step size)", "", "",
                                     "Got NaN log-unnormalized ratio", "non-finite log density in SliceSampler",
@@ -760,6 +794,58 @@ int pgn_logdensity_and_gradient(pgn_handle* h, const double* x, int32_t n_points
     dld.download(logdens, n_points);
     if (ldx == d) dg.download(grad, (size_t)n_points * d);
     else CUDA_CHECK(cudaMemcpy2D(grad, sizeof(double) * d, dg.p, sizeof(double) * ldx, sizeof(double) * d, n_points, cudaMemcpyDeviceToHost));
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_set_variational(pgn_handle* h, const double* mean, const double* sd, char** err) {
+  if (!h) return fail(err, PGN_ERR_INVALID, "null argument");
+  if (!mean || !sd) { h->var_active = false; return PGN_OK; }
+  const int tk = h->cfg.target_kind, d = h->cfg.dim;
+  if (h->cfg.n_chains_variational < 1) return fail(err, PGN_ERR_INVALID, "set_variational: n_chains_variational is 0");
+  if ((tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM) || h->cpl == 0 || h->force_mem)
+    return fail(err, PGN_ERR_INVALID, "set_variational: FUNNEL and GMM targets on the register-resident kernels (d <= 128)");
+  for (int c = 0; c < d; ++c)
+    if (!(sd[c] > 0.0) || !std::isfinite(sd[c]) || !std::isfinite(mean[c]))
+      return fail(err, PGN_ERR_INVALID, "set_variational: finite means and positive finite standard deviations");
+  try {
+    use_device(h);
+    if (h->var_tab.n == 0) h->var_tab.alloc((size_t)5 * h->d_pad);
+    std::vector<double> host((size_t)5 * h->d_pad, 0.0);
+    for (int c = 0; c < d; ++c) { host[c] = mean[c]; host[(size_t)h->d_pad + c] = sd[c]; }
+    for (int c = d; c < h->d_pad; ++c) host[(size_t)h->d_pad + c] = 1.0;
+    h->var_tab.upload(host.data(), host.size(), h->stream);
+    launch_var_tables(h->stream, h->var_tab.p, d, h->d_pad);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->var_active = true;
+  } catch (CudaError& e) { return fail(err, e.code, e.msg); }
+  return PGN_OK;
+}
+
+int pgn_hamiltonian_dynamics(pgn_handle* h, const double* x, const double* p, int32_t n_points, const double* beta,
+                             double step_size, int32_t n_steps, double* x_out, double* p_out, char** err) {
+  try {
+    use_device(h);
+    const int d = h->cfg.dim, tk = h->cfg.target_kind;
+    if ((tk != PGN_TARGET_TOY_MVN && tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM) || h->cpl == 0)
+      return fail(err, PGN_ERR_INVALID, "hamiltonian_dynamics: vector targets with a gradient, d <= 128");
+    if (n_points < 0 || n_steps < 0) return fail(err, PGN_ERR_INVALID, "negative count");
+    StreamBuf<double> dx, dp, db, ox, op;
+    const size_t n = (size_t)n_points * d;
+    dx.alloc(n, h->stream); dp.alloc(n, h->stream); db.alloc(n_points, h->stream); ox.alloc(n, h->stream); op.alloc(n, h->stream);
+    dx.upload(x, n); dp.upload(p, n); db.upload(beta, n_points);
+    Params P;
+    fill_params(h, P);
+    const int wpb = 4, grid = (n_points + wpb - 1) / wpb;
+    const size_t smem = scan_smem_bytes(h);
+    if (tk == PGN_TARGET_TOY_MVN) launch_leapfrog_toy(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, step_size, n_steps, n_points, ox.p, op.p);
+    else if (tk == PGN_TARGET_FUNNEL && h->var_active) launch_leapfrog_funnel_var(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, step_size, n_steps, n_points, ox.p, op.p);
+    else if (tk == PGN_TARGET_FUNNEL) launch_leapfrog_funnel(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, step_size, n_steps, n_points, ox.p, op.p);
+    else if (h->var_active) launch_leapfrog_gmm_var(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, step_size, n_steps, n_points, ox.p, op.p);
+    else launch_leapfrog_gmm(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, step_size, n_steps, n_points, ox.p, op.p);
+    CUDA_CHECK(cudaGetLastError());
+    ox.download(x_out, n); op.download(p_out, n);
   } catch (CudaError& e) { return fail(err, e.code, e.msg); }
   return PGN_OK;
 }

@@ -139,6 +139,8 @@ struct pgn_handle {
   // ---- memory-resident scan path (any d, any number of chains; pgn_memchain.cuh)
   bool force_mem = false;
   int recorder_order = PGN_RECORDERS_PER_REPLICA;
+  pgn::DevBuf<double> var_tab;          // GaussianReference tables [5][d_pad] (pgn_set_variational)
+  bool var_active = false;
   pgn::DevBuf<pgn::RecEntry> rec_table;   // per-replica recorders [n_chains][n_local] (PGN_RECORDERS_PER_REPLICA)
   pgn::DevBuf<pgn::OnEntry> on_table;     // target-chain online statistics per replica [n_chains][d_pad]
   pgn::DevBuf<pgn::MemRec> mem_rec;
@@ -168,6 +170,9 @@ void* vec_scan_kernel_toy(int cpl, int ex);
 void* vec_scan_kernel_funnel(int cpl, int ex);
 void* vec_scan_kernel_gmm(int cpl, int ex);
 void* vec_scan_kernel_mixed(int cpl, int ex);
+void* vec_scan_kernel_funnel_var(int cpl, int ex);   // ladders whose variational leg uses a GaussianReference
+void* vec_scan_kernel_gmm_var(int cpl, int ex);
+void launch_var_tables(cudaStream_t s, double* tab, int d, int d_pad);
 void* ising_scan_kernel();
 void* ising_lite_scan_kernel();
 void* test_swapper_scan_kernel();
@@ -179,6 +184,20 @@ void launch_eval_points_funnel(int cpl, int grid, int block, size_t smem, cudaSt
                                const double* betas, int n, double* lp, double* ld, double* grad);
 void launch_eval_points_gmm(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
                             const double* betas, int n, double* lp, double* ld, double* grad);
+void launch_leapfrog_toy(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
+                         const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out);
+void launch_leapfrog_funnel(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
+                            const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out);
+void launch_leapfrog_gmm(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
+                         const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out);
+void launch_eval_points_funnel_var(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
+                                   const double* betas, int n, double* lp, double* ld, double* grad);
+void launch_eval_points_gmm_var(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
+                                const double* betas, int n, double* lp, double* ld, double* grad);
+void launch_leapfrog_funnel_var(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
+                                const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out);
+void launch_leapfrog_gmm_var(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
+                             const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out);
 void launch_eval_points_mixed(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
                               const double* betas, int n, double* lp, double* ld, double* grad);
 void launch_eval_points_mem(int target_kind, int grid, int block, cudaStream_t s, const MemParams& MP, const double* xs,

@@ -132,8 +132,19 @@ struct Params {
   unsigned long long* progress;   // scans completed by the chains of this shard (all rounds): the hand-shake spin limit counts
                                   // time WITHOUT progress anywhere on the shard, not time since the wait began
   RecEntry* rec_table;     // [n_chains replicas][n_local]
-  OnEntry* on_table;       // [n_chains replicas][d_pad], used by the shard owning chain N
+  OnEntry* on_table;       // [n_chains replicas][d_pad], used by the shard owning the target chain(s)
+  // legs (pgn_config.n_chains_variational): chains 1..n_var are the variational leg; two legs when 0 < n_var < n_chains
+  int n_var;
+  const double* var_tab;   // GaussianReference, or null: [5][d_pad] mean | sd | -0.5 log(2 pi sd^2) | 1/(2 sd^2) | 1/sd^2
 };
+__device__ __forceinline__ bool two_legs(const Params& P) { return P.n_var > 0 && P.n_var < P.n_chains; }
+// is_reference / is_target of the swap graph (DEO.jl:13-14, VariationalDEO.jl:19-20)
+__device__ __forceinline__ bool chain_is_reference(const Params& P, int chain) {
+  return (chain == 1 && P.n_chains > 1) || (two_legs(P) && chain == P.n_chains);
+}
+__device__ __forceinline__ bool chain_is_target(const Params& P, int chain) {
+  return two_legs(P) ? (chain == P.n_var || chain == P.n_var + 1) : chain == P.n_chains;
+}
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -181,9 +192,12 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 // ===========================================================================
 // Vector-state chains: TOY_MVN / FUNNEL / GMM with ToyExplorer, SliceSampler, autoMALA
 // ===========================================================================
-template <int TK, int CPL, int EX>
+// VAR: the chain may sit on the variational leg and then uses the GaussianReference tables instead of the fixed
+// reference (separate instantiations, csrc/Makefile vec_*_var_*: the plain kernels carry none of this)
+template <int TK, int CPL, int EX, bool VAR = false>
 struct VecChain {
   static constexpr bool kTestSwapper = false;
+  bool var_ref;   // VAR only: this chain's reference is the Gaussian variational one
   // autoMALA runs with a TEAM of W warps per chain (block = team): the step-size search evaluates W
   // candidate steps per round, one per warp, and replays the reference's sequential decisions on the
   // results (see automala()).  Everything else is executed redundantly by all warps of the team on
@@ -251,6 +265,7 @@ struct VecChain {
   __device__ void init(const Params& Pr, const double* smem, int wl, int lane_, int replica_index) {
     P = &Pr; sm_means = smem; lane = lane_; d = Pr.d;
     beta = Pr.beta[Pr.first_chain + wl - 1];
+    var_ref = VAR && Pr.var_tab != nullptr && Pr.first_chain + wl <= Pr.n_var;
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
       x[k] = valid(k) ? Pr.x[(size_t)wl * Pr.d_pad + k * 32 + lane] : 0.0;
@@ -332,11 +347,11 @@ struct VecChain {
       if (valid(k)) row[k * 32 + lane] = OnEntry{on_n, on_mu[k], on_s2[k]};
   }
   __device__ void load_online(const OnEntry* row) {
-    on_n = row[0].n;
+    // L2 loads: between the two target chains of a two-leg ladder the row was written by ANOTHER warp (scan_kernel)
+    on_n = __ldcg(&row[0].n);
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {   // rows are d_pad wide and the padding stays zero: no test on the loads' results
-      const OnEntry e = row[k * 32 + lane];
-      on_mu[k] = e.mu; on_s2[k] = e.s2;
+      on_mu[k] = __ldcg(&row[k * 32 + lane].mu); on_s2[k] = __ldcg(&row[k * 32 + lane].s2);
     }
   }
 
@@ -390,6 +405,22 @@ struct VecChain {
     return -(v * v * P->p[5] + PGN_LOG2PI) * 0.5 - P->p[4];
   }
 
+  // reference term / gradient of coordinate slot k (valid) at xv: the fixed N(0, s^2 I) (DistributionLogPotential) or, on
+  // the variational leg, gaussian_logdensity and its gradient (GaussianReference.jl:45-53, 72-80)
+  __device__ __forceinline__ double var_t(int j, int k) const { return __ldg(P->var_tab + (size_t)j * P->d_pad + k * 32 + lane); }
+  __device__ __forceinline__ double ref_term(int k, double xv, double ivr, double lsr) const {
+    if constexpr (VAR) {
+      if (var_ref) { const double dx = xv - var_t(0, k); return var_t(2, k) - var_t(3, k) * (dx * dx); }
+    }
+    return -(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr;
+  }
+  __device__ __forceinline__ double ref_grad(int k, double xv, double ivr) const {
+    if constexpr (VAR) {
+      if (var_ref) return -(var_t(4, k) * (xv - var_t(0, k)));
+    }
+    return -xv * ivr;
+  }
+
   // component densities at xx
   __device__ void eval(const double (&xx)[CPL], double& a0, double& a1) {
     n_points += 1;
@@ -406,7 +437,7 @@ struct VecChain {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) if (valid(k)) {
         const double xv = xx[k];
-        v[0] = v[0] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
+        v[0] = v[0] + ref_term(k, xv, ivr, lsr);
         if (k == 0 && lane == 0) { double zy = y / sy; v[1] = v[1] + (-(zy * zy + PGN_LOG2PI) * 0.5 - lsy); }
         else { double t = xv * xv * e; v[1] = v[1] + (-(t + PGN_LOG2PI) * 0.5 - 0.5 * y); }
       }
@@ -430,7 +461,7 @@ struct VecChain {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) if (valid(k)) {
         const double xv = xx[k];
-        v[KMAX_MODES] = v[KMAX_MODES] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
+        v[KMAX_MODES] = v[KMAX_MODES] + ref_term(k, xv, ivr, lsr);
 #pragma unroll
         for (int m = 0; m < KMAX_MODES; ++m) {
           double t = xv - sm_means[m * P->d_pad + k * 32 + lane];
@@ -482,7 +513,7 @@ struct VecChain {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) if (valid(k)) {
         const double xv = xx[k];
-        v[0] = v[0] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
+        v[0] = v[0] + ref_term(k, xv, ivr, lsr);
         if (k == 0 && lane == 0) {
           double zy = y / sy;
           v[1] = v[1] + (-(zy * zy + PGN_LOG2PI) * 0.5 - lsy);
@@ -500,7 +531,7 @@ struct VecChain {
       for (int k = 0; k < CPL; ++k) {
         if (!valid(k)) { g[k] = 0.0; continue; }
         const double xv = xx[k];
-        double gr = -xv * ivr;
+        double gr = ref_grad(k, xv, ivr);
         double gt = (k == 0 && lane == 0) ? (-y * ivy + T) : (-xv * e);
         double acc = gr * (1.0 - b);
         g[k] = acc + gt * b;
@@ -515,7 +546,7 @@ struct VecChain {
 #pragma unroll
       for (int k = 0; k < CPL; ++k) if (valid(k)) {
         const double xv = xx[k];
-        v[KMAX_MODES] = v[KMAX_MODES] + (-(xv * xv * ivr + PGN_LOG2PI) * 0.5 - lsr);
+        v[KMAX_MODES] = v[KMAX_MODES] + ref_term(k, xv, ivr, lsr);
 #pragma unroll
         for (int m = 0; m < KMAX_MODES; ++m) {
           double t = xv - sm_means[m * P->d_pad + k * 32 + lane];
@@ -550,7 +581,7 @@ struct VecChain {
 #pragma unroll
         for (int m = 0; m < KMAX_MODES; ++m) acc = acc + w[m] * (sm_means[m * P->d_pad + k * 32 + lane] - xv);
         double gt = (acc / s) * ivm;
-        double gr = -xv * ivr;
+        double gr = ref_grad(k, xv, ivr);
         double t = gr * (1.0 - b);
         g[k] = t + gt * b;
       }
@@ -582,6 +613,7 @@ struct VecChain {
     for (int k = 0; k < CPL; ++k) {
       if (!valid(k)) continue;
       double z = normal_tick(rng.ctr + (unsigned long long)(k * 32 + lane));
+      if (VAR && var_ref) { x[k] = z * var_t(1, k) + var_t(0, k); continue; }   // GaussianReference.jl:30-37
       if (TK == PGN_TARGET_TOY_MVN) x[k] = z / sqrt(toy_precision(b));   // toy_mvn_target.jl:18-21
       else x[k] = P->p[3] * z;                                           // rand!(rng, MvNormal(0, s^2 I), x)
     }
@@ -1537,8 +1569,10 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
   LogSumAcc ls_fwd{0, -PGN_INF}, ls_bwd{0, -PGN_INF};
   long long n_restarts = 0, n_trips = 0;
   long long explore_cycles = 0, wait_cycles = 0;
-  const bool is_ref = (chain == 1 && N > 1);   // DEO.jl:13
-  const bool is_tgt = (chain == N);            // DEO.jl:14
+  const bool is_ref = chain_is_reference(P, chain);   // DEO.jl:13, VariationalDEO.jl:19
+  const bool is_tgt = chain_is_target(P, chain);      // DEO.jl:14, VariationalDEO.jl:20
+  // two legs: the two target chains are neighbours; a replica crossing between them keeps fitting the SAME online
+  // accumulators (its own recorder, pigeons.jl:110-131), so the row travels A -> table -> B under the hand-shake's order
   int err = 0;
 
   for (long long scan = 1; scan <= P.n_scans; ++scan) {
@@ -1549,7 +1583,8 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
     if (ch.err) { err = ch.err; break; }
     if (is_tgt) {   // pigeons.jl:110-131
       if (tw == ch.own(4)) ch.online_fit();
-      if (P.target_trace && tw == 0) ch.write_trace(P.target_trace + (size_t)(scan - 1) * P.d);
+      if (P.target_trace && tw == 0)   // two legs: [scan][2][d], chain n_var then chain n_var + 1
+        ch.write_trace(P.target_trace + (two_legs(P) ? (size_t)(scan - 1) * 2 + (chain == P.n_var + 1 ? 1 : 0) : (size_t)(scan - 1)) * P.d);
     }
     // ---------------- swap ----------------
     const bool even = (scan & 1LL) == 0;                                   // DEO.jl:12
@@ -1597,6 +1632,14 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
       double lr_p = 0.0, u_p = 0.0;
       unsigned long long ctr_p = 0ull;
       int ri_p = 0, rt_p = 0;
+      const bool mid = two_legs(P) && ((chain == P.n_var && partner == chain + 1) || (chain == P.n_var + 1 && partner == chain - 1));
+      if (mid && P.on_table != nullptr && P.d > 0) {
+        // the outgoing replica's online row must be in memory before the partner can see this scan's header:
+        // rows -> (team barrier) -> fence -> tagged words; the partner fences after it has seen the header
+        if (tw == ch.own(4)) ch.flush_online(P.on_table + (size_t)(replica_index - 1) * P.d_pad);
+        if constexpr (Chain::kTeam) __syncthreads(); else __syncwarp();
+        if (tw == 0) fence_acq_rel_gpu();
+      }
       const long long t_wait0 = clock64();
       if (tw == 0) {
         {   // post: header words from lanes 0..7, then the replica
@@ -1643,6 +1686,7 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
         lr_p = bits_to_double(((unsigned long long)h1 << 32) | h0);
         u_p = bits_to_double(((unsigned long long)h3 << 32) | h2);
         ctr_p = ((unsigned long long)h5 << 32) | h4;
+        if (mid) { __syncwarp(); fence_acq_rel_gpu(); }   // the partner's online row (written before its header) is visible from here on
       }
       if constexpr (Chain::kTeam) {   // team warp 0 did the hand-shake and hands the header to the team
         long long* tc = team_ctl + 8 + 8 * (int)(scan & 1LL);
@@ -1691,7 +1735,7 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
             ch.expl_acc = en->expl_acc; ls_bwd = en->ls_bwd;
           }
           if (is_tgt && tw == ch.own(4) && P.d > 0) {
-            ch.flush_online(P.on_table + (size_t)(replica_index - 1) * P.d_pad);
+            if (!mid) ch.flush_online(P.on_table + (size_t)(replica_index - 1) * P.d_pad);   // mid: done before the post
             ch.load_online(P.on_table + (size_t)(ri_p - 1) * P.d_pad);
           }
         }
@@ -1769,11 +1813,11 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
 // Parity entry points (the other small helper kernels live in pgn_scan_misc.cu)
 // ===========================================================================
 // parity entry points: one warp per point
-template <int TK, int CPL>
+template <int TK, int CPL, bool VAR = false>
 __global__ void eval_points_kernel(const __grid_constant__ Params P, const double* xs, const double* betas, int n_points, double* lp_out,
                                    double* ld_out, double* grad_out) {
   extern __shared__ double smem[];
-  typedef VecChain<TK, CPL, PGN_EXPLORER_SLICE> Chain;
+  typedef VecChain<TK, CPL, PGN_EXPLORER_SLICE, VAR> Chain;
   Chain::stage_shared(P, smem);
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -1782,6 +1826,7 @@ __global__ void eval_points_kernel(const __grid_constant__ Params P, const doubl
   Chain ch;
   ch.P = &P; ch.sm_means = smem; ch.lane = lane; ch.d = P.d; ch.beta = betas[w];
   ch.n_points = 0; ch.n_ref = 0; ch.err = 0;
+  ch.var_ref = VAR && P.var_tab != nullptr;   // the path of chain 1's leg
   double xx[CPL];
 #pragma unroll
   for (int k = 0; k < CPL; ++k) xx[k] = (k * 32 + lane < P.d) ? xs[(size_t)w * P.d + k * 32 + lane] : 0.0;
@@ -1800,6 +1845,45 @@ __global__ void eval_points_kernel(const __grid_constant__ Params P, const doubl
     for (int k = 0; k < CPL; ++k)
       if (k * 32 + lane < P.d) grad_out[(size_t)w * P.d + k * 32 + lane] = g[k];
   }
+}
+
+// hamiltonian_dynamics! with the identity preconditioner: one warp per point, n_steps x VecChain::run_trial (= leap_frog!)
+template <int TK, int CPL, bool VAR = false>
+__global__ void leapfrog_kernel(const __grid_constant__ Params P, const double* xs, const double* ps, const double* betas, double eps,
+                                int n_steps, int n_points, double* x_out, double* p_out) {
+  extern __shared__ double smem[];
+  typedef VecChain<TK, CPL, PGN_EXPLORER_MALA, VAR> Chain;
+  Chain::stage_shared(P, smem);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n_points) return;
+  Chain ch;
+  ch.P = &P; ch.sm_means = smem; ch.lane = lane; ch.d = P.d; ch.beta = betas[w];
+  ch.n_points = 0; ch.n_ref = 0; ch.err = 0;
+  ch.var_ref = VAR && P.var_tab != nullptr;
+  double x[CPL], p[CPL], g[CPL], pre[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    const bool v = k * 32 + lane < P.d;
+    x[k] = v ? xs[(size_t)w * P.d + k * 32 + lane] : 0.0;
+    p[k] = v ? ps[(size_t)w * P.d + k * 32 + lane] : 0.0;
+    pre[k] = 1.0;
+  }
+  {   // conditioned gradient at the start point (hamiltonian_dynamics.jl:45-47)
+    double a0, a1, extra = 0.0;
+    ch.eval_grad(x, ch.beta, a0, a1, g, extra);
+  }
+  typename Chain::Trial T;
+  for (int s = 0; s < n_steps; ++s) {
+    ch.run_trial(x, p, g, pre, true, eps, 0.0, T);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) { x[k] = T.x1[k]; p[k] = T.p1[k]; g[k] = T.g1c[k]; }
+    if (!is_finite(T.h_after)) break;   // :56-59, :80: the reference stops at a non-finite state
+  }
+#pragma unroll
+  for (int k = 0; k < CPL; ++k)
+    if (k * 32 + lane < P.d) { x_out[(size_t)w * P.d + k * 32 + lane] = x[k]; p_out[(size_t)w * P.d + k * 32 + lane] = p[k]; }
 }
 
 }  // namespace pgn

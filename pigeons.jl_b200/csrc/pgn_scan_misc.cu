@@ -146,10 +146,29 @@ void* vec_plain_kernel_toy(int cpl, int ex);    void* vec_team_kernel_toy(int cp
 void* vec_plain_kernel_funnel(int cpl, int ex); void* vec_team_kernel_funnel(int cpl, int ex);
 void* vec_plain_kernel_gmm(int cpl, int ex);    void* vec_team_kernel_gmm(int cpl, int ex);
 void* vec_plain_kernel_mixed(int cpl, int ex);
+void* vec_plain_kernel_funnel_var(int cpl, int ex); void* vec_team_kernel_funnel_var(int cpl, int ex);
+void* vec_plain_kernel_gmm_var(int cpl, int ex);    void* vec_team_kernel_gmm_var(int cpl, int ex);
 static bool is_team_explorer(int ex) { return ex == PGN_EXPLORER_AUTOMALA || ex == PGN_EXPLORER_COMPOSE || ex == PGN_EXPLORER_MIX; }
 void* vec_scan_kernel_toy(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_toy(cpl, ex) : vec_plain_kernel_toy(cpl, ex); }
 void* vec_scan_kernel_funnel(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_funnel(cpl, ex) : vec_plain_kernel_funnel(cpl, ex); }
 void* vec_scan_kernel_mixed(int cpl, int ex) { return ex == PGN_EXPLORER_SLICE ? vec_plain_kernel_mixed(cpl, ex) : nullptr; }
 void* vec_scan_kernel_gmm(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_gmm(cpl, ex) : vec_plain_kernel_gmm(cpl, ex); }
+void* vec_scan_kernel_funnel_var(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_funnel_var(cpl, ex) : vec_plain_kernel_funnel_var(cpl, ex); }
+void* vec_scan_kernel_gmm_var(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_gmm_var(cpl, ex) : vec_plain_kernel_gmm_var(cpl, ex); }
+
+// GaussianReference tables from (mean, sd): tab = [5][d_pad] mean | sd | -0.5 log(2 pi sd^2) | 1/(2 sd^2) | 1/sd^2
+// (gaussian_logdensity, GaussianReference.jl:45-53; 2.0 * pi is exact in binary)
+__global__ void var_tables_kernel(double* tab, int d, int d_pad) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const double sd = tab[(size_t)1 * d_pad + c];
+  const double s2 = sd * sd;
+  tab[(size_t)2 * d_pad + c] = -0.5 * log_(6.283185307179586 * s2);
+  tab[(size_t)3 * d_pad + c] = 1.0 / (2.0 * s2);
+  tab[(size_t)4 * d_pad + c] = 1.0 / s2;
+}
+void launch_var_tables(cudaStream_t s, double* tab, int d, int d_pad) {
+  var_tables_kernel<<<(d + 127) / 128, 128, 0, s>>>(tab, d, d_pad);
+}
 
 }  // namespace pgn

@@ -12,6 +12,9 @@
 #ifndef PGN_PART
 #error "compile with -DPGN_PART=0|1"
 #endif
+#ifndef PGN_VAR
+#define PGN_VAR 0   // 1: the kernels of a ladder whose variational leg uses a GaussianReference (FUNNEL, GMM)
+#endif
 
 namespace pgn {
 namespace {
@@ -24,26 +27,35 @@ template <int CPL>
 void* plain_kernel_for(int ex) {
   switch (ex) {
 #if PGN_TK == 1
-    case PGN_EXPLORER_TOY: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_TOY>>();
+    case PGN_EXPLORER_TOY: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_TOY, PGN_VAR != 0>>();
 #endif
-    case PGN_EXPLORER_SLICE: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_SLICE>>();
+    case PGN_EXPLORER_SLICE: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_SLICE, PGN_VAR != 0>>();
 #if PGN_TK != 7
-    case PGN_EXPLORER_MALA: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_MALA>>();
+    case PGN_EXPLORER_MALA: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_MALA, PGN_VAR != 0>>();
 #endif
     default: return nullptr;
   }
 }
+#if PGN_TK != 7
+template <int CPL>
+void leapfrog_launch(int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
+                     const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out) {
+  leapfrog_kernel<PGN_TK, CPL, PGN_VAR != 0><<<grid, block, smem, s>>>(P, xs, ps, betas, eps, n_steps, n, x_out, p_out);
+}
+#endif
 template <int CPL>
 void eval_points_launch(int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* betas,
                         int n, double* lp, double* ld, double* grad) {
-  eval_points_kernel<PGN_TK, CPL><<<grid, block, smem, s>>>(P, xs, betas, n, lp, ld, grad);
+  eval_points_kernel<PGN_TK, CPL, PGN_VAR != 0><<<grid, block, smem, s>>>(P, xs, betas, n, lp, ld, grad);
 }
 #else
 template <int CPL>
 void* team_kernel_for(int ex) {
   switch (ex) {
-    case PGN_EXPLORER_AUTOMALA: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_AUTOMALA>>();
+    case PGN_EXPLORER_AUTOMALA: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_AUTOMALA, PGN_VAR != 0>>();
+#if !PGN_VAR   // Compose / Mix programs are not built for the variational leg
     case PGN_EXPLORER_COMPOSE: case PGN_EXPLORER_MIX: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_COMPOSE>>();
+#endif
     default: return nullptr;
   }
 }
@@ -53,6 +65,10 @@ void* team_kernel_for(int ex) {
 
 #if PGN_TK == 1
 #define PGN_FAMILY(name) name##_toy
+#elif PGN_TK == 2 && PGN_VAR
+#define PGN_FAMILY(name) name##_funnel_var
+#elif PGN_TK == 3 && PGN_VAR
+#define PGN_FAMILY(name) name##_gmm_var
 #elif PGN_TK == 2
 #define PGN_FAMILY(name) name##_funnel
 #elif PGN_TK == 3
@@ -79,6 +95,17 @@ void PGN_FAMILY(launch_eval_points)(int cpl, int grid, int block, size_t smem, c
     default: throw CudaError{PGN_ERR_INVALID, "unsupported dimension"};
   }
 }
+#if PGN_TK != 7
+void PGN_FAMILY(launch_leapfrog)(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
+                                 const double* ps, const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out) {
+  switch (cpl) {
+    case 1: leapfrog_launch<1>(grid, block, smem, s, P, xs, ps, betas, eps, n_steps, n, x_out, p_out); break;
+    case 2: leapfrog_launch<2>(grid, block, smem, s, P, xs, ps, betas, eps, n_steps, n, x_out, p_out); break;
+    case 4: leapfrog_launch<4>(grid, block, smem, s, P, xs, ps, betas, eps, n_steps, n, x_out, p_out); break;
+    default: throw CudaError{PGN_ERR_INVALID, "unsupported dimension"};
+  }
+}
+#endif
 #else
 void* PGN_FAMILY(vec_team_kernel)(int cpl, int ex) {
   switch (cpl) {

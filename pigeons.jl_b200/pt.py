@@ -9,6 +9,7 @@ looping over scans on the host it makes ONE C-ABI call per round
 """
 from __future__ import annotations
 
+import copy
 import math
 from dataclasses import dataclass, field, replace
 from typing import Callable, List, Optional, Sequence
@@ -37,6 +38,8 @@ class Inputs:
     seed: int = 1
     n_rounds: int = 10
     n_chains: int = 10
+    n_chains_variational: int = 0      # Inputs.jl:21-32: chains of the variational leg (two legs when n_chains > 0 as well)
+    variational: object = None         # Inputs.jl:42-44: GaussianReference(...) or None
     explorer: object = None
     record: Sequence[str] = ()
     multithreaded: bool = False        # accepted for API compatibility; the device runs all replicas concurrently
@@ -54,6 +57,14 @@ class Inputs:
             self.explorer = self.target.default_explorer()     # target.jl:24, explorer.jl:49-54
         if self.comm is None:
             self.comm = SingleProcess()
+        if self.variational is not None:     # the run owns (and mutates) its reference: never the caller's object
+            self.variational = copy.deepcopy(self.variational)
+        if self.n_chains_variational > 0 and self.recorder_order != _capi.RECORDERS_PER_REPLICA and self.n_chains > 0:
+            raise ValueError("two legs need recorder_order = RECORDERS_PER_REPLICA")
+
+    @property
+    def n_chains_total(self) -> int:       # Inputs.jl:128
+        return self.n_chains + self.n_chains_variational
 
 
 @dataclass
@@ -75,10 +86,63 @@ class NonReversiblePT:
 
 
 @dataclass
+class GaussianReference:
+    """src/variational/GaussianReference.jl:4-28: mean-field Gaussian reference of the variational leg, re-fitted
+    after every round >= first_tuning_round from the target chains' online mean / variance."""
+    first_tuning_round: int = 6
+    mean: Optional[np.ndarray] = None
+    standard_deviation: Optional[np.ndarray] = None
+
+    def activate(self, it: "Iterators") -> bool:          # :16-18
+        return it.round >= self.first_tuning_round
+
+    def update_reference(self, rr) -> None:               # :22-28
+        self.mean = np.asarray(rr.online_mean, dtype=np.float64).copy()
+        self.standard_deviation = np.sqrt(np.asarray(rr.online_var, dtype=np.float64))
+
+
+@dataclass
+class StabilizedPT:
+    """src/tempering/StabilizedPT.jl:8-66: a fixed and a variational leg sharing the target.  Global chains
+    1..n_var are the variational leg (reference -> target), n_var+1..N the fixed leg reversed (target -> reference)
+    (:96-116); the swap graph is the ordinary even/odd graph over all N chains (VariationalDEO.jl, OddEven.jl:16-48)."""
+    fixed_leg: NonReversiblePT
+    variational_leg: NonReversiblePT
+
+    @property
+    def n_var(self) -> int:
+        return self.variational_leg.schedule.n_chains
+
+    @property
+    def n_fixed(self) -> int:
+        return self.fixed_leg.schedule.n_chains
+
+    @property
+    def communication_barriers(self):                     # global_barrier(::StabilizedPT): the fixed leg's (:131)
+        return self.fixed_leg.communication_barriers
+
+
+def tempering_parameters(tempering) -> np.ndarray:
+    """The annealing parameter of every global chain: `schedule.grids`, or for two legs
+    vcat(variational leg, reverse(fixed leg)) (concatenate_log_potentials, StabilizedPT.jl:63-65)."""
+    if isinstance(tempering, StabilizedPT):
+        return np.concatenate([tempering.variational_leg.schedule.grids, tempering.fixed_leg.schedule.grids[::-1]])
+    return tempering.schedule.grids
+
+
+def create_tempering(inputs: "Inputs"):
+    """tempering.jl:65-71."""
+    if inputs.n_chains == 0 or inputs.n_chains_variational == 0:
+        return NonReversiblePT(equally_spaced_schedule(inputs.n_chains_total))
+    return StabilizedPT(NonReversiblePT(equally_spaced_schedule(inputs.n_chains)),
+                        NonReversiblePT(equally_spaced_schedule(inputs.n_chains_variational)))
+
+
+@dataclass
 class Shared:
     """src/pt/Shared.jl:12-41."""
     iterators: Iterators
-    tempering: NonReversiblePT
+    tempering: object       # NonReversiblePT or StabilizedPT
     explorer: object
 
 
@@ -99,18 +163,20 @@ def create_pt(inputs: Inputs) -> PT:
     """PT(inputs) (PT.jl:46-51): Shared + create_replicas (replicas.jl:65-99)."""
     comm = inputs.comm
     cfg = inputs.target.engine_config()
-    kw = dict(n_chains=inputs.n_chains, seed=inputs.seed, rank=comm.rank, world_size=comm.world_size,
+    n_total = inputs.n_chains_total
+    kw = dict(n_chains=n_total, seed=inputs.seed, rank=comm.rank, world_size=comm.world_size,
               device=inputs.device, recorder_order=inputs.recorder_order, **cfg)
+    if inputs.n_chains_variational > 0:     # only then: engine factories of single-leg callers need not know the keyword
+        kw["n_chains_variational"] = inputs.n_chains_variational
     if inputs.engine_factory is not None:
         engine = inputs.engine_factory(**kw)
     else:
         engine = _capi.Engine(inputs.engine_lib or _capi.EngineLib(), **kw)
-    lb = LoadBalance(comm.rank + 1, comm.world_size, inputs.n_chains)
+    lb = LoadBalance(comm.rank + 1, comm.world_size, n_total)
     assert engine.first_chain == lb.my_first_global_idx() and engine.n_local == lb.my_load(), \
         "engine shard geometry disagrees with LoadBalance"
     comm.connect_neighbours(engine)
-    tempering = NonReversiblePT(equally_spaced_schedule(inputs.n_chains))
-    shared = Shared(Iterators(), tempering, inputs.explorer)
+    shared = Shared(Iterators(), create_tempering(inputs), inputs.explorer)
     engine.init_replicas()
     return PT(inputs, shared, engine)
 
@@ -121,7 +187,13 @@ def run_one_round(pt: PT) -> ReducedRecorders:
     it = pt.shared.iterators
     eng = pt.engine
     dim = pt.inputs.target.dim
-    eng.set_schedule(pt.shared.tempering.schedule.grids)
+    eng.set_schedule(tempering_parameters(pt.shared.tempering))
+    var = pt.inputs.variational
+    if pt.inputs.n_chains_variational > 0:      # the path of the variational leg (update_path_variational, variational.jl:36-40)
+        if var is not None and var.mean is not None:
+            eng.set_variational(var.mean, var.standard_deviation)
+        else:
+            eng.set_variational(None, None)
     if pt.shared.explorer is None:
         eng.set_explorer(kind=_capi.EXPLORER_NONE)
     else:
@@ -131,20 +203,36 @@ def run_one_round(pt: PT) -> ReducedRecorders:
                         log_index_process=index_process in rec,
                         log_swaps=swap_trace in rec,
                         log_target_trace=traces in rec)
-    merged = merge_round_results(pt.inputs.comm, res, pt.inputs.n_chains, dim)
+    merged = merge_round_results(pt.inputs.comm, res, pt.inputs.n_chains_total, dim,
+                                 pt.inputs.n_chains_variational if pt.inputs.n_chains > 0 else 0)
     return merged
 
 
 def adapt(pt: PT, rr: ReducedRecorders) -> PT:
     """adapt (pigeons.jl:152-162): adapt_tempering (NonReversiblePT.jl:52-66) then adapt_explorer."""
     temp = pt.shared.tempering
-    n = temp.schedule.n_chains
-    if n > 1:     # adaptation.jl:103-112: a pair that never recorded counts as acceptance 0.5
-        rej = rejections(rr.swap_n, rr.swap_mean, n)
-        new_temp = NonReversiblePT(optimal_schedule(rej, temp.schedule),
-                                   communication_barriers(rej, temp.schedule.grids))
+    var = pt.inputs.variational
+
+    def adapt_leg(leg: NonReversiblePT, pair_idx, variational) -> NonReversiblePT:
+        """adapt_tempering(::NonReversiblePT, ..., chain_indices) (NonReversiblePT.jl:52-66); pair_idx: 0-based index of
+        the lower chain of every pair of the leg, from its reference to the chain before its target."""
+        if leg.schedule.n_chains == 1:
+            return leg
+        if variational is not None and variational.activate(pt.shared.iterators):     # update_path_if_needed, variational.jl:28-34
+            variational.update_reference(rr)
+        acc = np.where(np.asarray(rr.swap_n)[pair_idx] > 0, np.asarray(rr.swap_mean)[pair_idx], 0.5)   # adaptation.jl:103-112
+        rej = 1.0 - acc
+        return NonReversiblePT(optimal_schedule(rej, leg.schedule), communication_barriers(rej, leg.schedule.grids))
+
+    if isinstance(temp, StabilizedPT):      # StabilizedPT.jl:51-61
+        n_var, n = temp.n_var, temp.n_var + temp.n_fixed
+        new_var = adapt_leg(temp.variational_leg, np.arange(0, n_var - 1), var)
+        new_fixed = adapt_leg(temp.fixed_leg, np.arange(n - 2, n_var - 1, -1), None)    # pairs (N-1,N), ..., (n_var+1,n_var+2)
+        new_temp = StabilizedPT(new_fixed, new_var)
     else:
-        new_temp = temp
+        n = temp.schedule.n_chains
+        leg_var = var if pt.inputs.n_chains_variational > 0 else None
+        new_temp = adapt_leg(temp, np.arange(0, n - 1), leg_var)
     explorer = pt.shared.explorer
     if isinstance(explorer, (AutoMALA, MALA, Compose, Mix)):
         explorer = explorer.adapt(rr)
@@ -174,11 +262,13 @@ def run_checks(pt: PT) -> None:
     if comm.rank == 0:
         try:
             # the serial re-run uses the same engine library / factory as the run it checks
-            serial = replace(inputs, comm=SingleProcess(), n_rounds=inputs.checked_round, checked_round=0, show_report=False)
+            fresh_var = None if inputs.variational is None else replace(inputs.variational, mean=None, standard_deviation=None)
+            serial = replace(inputs, comm=SingleProcess(), n_rounds=inputs.checked_round, checked_round=0, show_report=False,
+                             variational=fresh_var)
             ref = pigeons_pt(create_pt(serial))
             rs = ref.engine.get_state()
             bad = [k for k in whole if not np.array_equal(whole[k].reshape(rs[k].shape), rs[k])]
-            if not np.array_equal(pt.shared.tempering.schedule.grids, ref.shared.tempering.schedule.grids):
+            if not np.array_equal(tempering_parameters(pt.shared.tempering), tempering_parameters(ref.shared.tempering)):
                 bad.append("schedule")
             if pt.shared.explorer != ref.shared.explorer:
                 bad.append("explorer")
@@ -225,9 +315,10 @@ def write_checkpoint(pt: PT) -> dict:
     continue the run bit for bit — `Shared` (round counter, schedule, adapted explorer) and the `Replica`s
     (state, chain <-> replica index, RNG position, round-trip state; `pgn_get_state`).  A plain dict of numpy
     arrays / dataclasses, not the reference's `.jls` wire format."""
-    return dict(round=pt.shared.iterators.round, grids=pt.shared.tempering.schedule.grids.copy(),
+    return dict(round=pt.shared.iterators.round, grids=tempering_parameters(pt.shared.tempering).copy(),
+                tempering=copy.deepcopy(pt.shared.tempering), variational=copy.deepcopy(pt.inputs.variational),
                 communication_barriers=pt.shared.tempering.communication_barriers, explorer=pt.shared.explorer,
-                replicas=pt.engine.get_state(), n_chains=pt.inputs.n_chains, seed=pt.inputs.seed,
+                replicas=pt.engine.get_state(), n_chains=pt.inputs.n_chains_total, seed=pt.inputs.seed,
                 world_size=pt.inputs.comm.world_size, rank=pt.inputs.comm.rank, first_chain=pt.engine.first_chain,
                 n_local=pt.engine.n_local, dim=pt.inputs.target.dim, target_config=_target_fingerprint(pt.inputs.target))
 
@@ -237,7 +328,7 @@ def resume(checkpoint: dict, inputs: Inputs) -> PT:
     checkpoint and run rounds `checkpoint round + 1 .. inputs.n_rounds`.  `inputs` supplies what a
     checkpoint does not serialise in the reference either (the target and the engine handle are rebuilt,
     `ext/PigeonsBridgeStanExt/interface.jl:27-48`)."""
-    if inputs.n_chains != checkpoint["n_chains"] or inputs.seed != checkpoint["seed"]:
+    if inputs.n_chains_total != checkpoint["n_chains"] or inputs.seed != checkpoint["seed"]:
         raise ValueError("the checkpoint was written by a run with a different n_chains / seed")
     if checkpoint.get("target_config") is not None and checkpoint["target_config"] != _target_fingerprint(inputs.target):
         raise ValueError("the checkpoint was written for a different target")
@@ -251,9 +342,14 @@ def resume(checkpoint: dict, inputs: Inputs) -> PT:
     st = checkpoint["replicas"]
     pt.engine.set_state(x=st["x"] if st["x"].size else None, replica_index=st["replica_index"],
                         rng_counter=st["rng_counter"], round_trip_state=st["round_trip_state"])
-    sched = Schedule(np.asarray(checkpoint["grids"], dtype=np.float64).copy())
-    pt.shared = Shared(Iterators(round=checkpoint["round"]), NonReversiblePT(sched, checkpoint["communication_barriers"]),
-                       checkpoint["explorer"])
+    if checkpoint.get("tempering") is not None:
+        tempering = copy.deepcopy(checkpoint["tempering"])
+    else:
+        sched = Schedule(np.asarray(checkpoint["grids"], dtype=np.float64).copy())
+        tempering = NonReversiblePT(sched, checkpoint["communication_barriers"])
+    if checkpoint.get("variational") is not None:
+        pt.inputs.variational = copy.deepcopy(checkpoint["variational"])
+    pt.shared = Shared(Iterators(round=checkpoint["round"]), tempering, checkpoint["explorer"])
     return pigeons_pt(pt)
 
 
@@ -268,7 +364,10 @@ def stepping_stone_pair(pt: PT):
     rr = pt.reduced_recorders
     e1 = 0.0
     e2 = 0.0
-    for i in range(pt.inputs.n_chains - 1):
+    temp = pt.shared.tempering
+    # two legs: only the pairs inside the variational leg (stepping_stone_keys, stepping_stone.jl:50-66)
+    n_pairs = temp.n_var - 1 if isinstance(temp, StabilizedPT) else pt.inputs.n_chains_total - 1
+    for i in range(n_pairs):
         if rr.swap_n[i] > 0:
             e1 += rr.logsum_fwd[i] - math.log(rr.swap_n[i])
             e2 += rr.logsum_bwd[i] - math.log(rr.swap_n[i])
@@ -290,6 +389,14 @@ def global_barrier(pt: PT) -> float:        # NonReversiblePT.jl:74
     if cb is None:      # a single chain (or no round run yet): the reference leaves the tempering untouched
         return float("nan")
     return cb.globalbarrier
+
+
+def global_barrier_variational(pt: PT) -> float:      # StabilizedPT.jl:133
+    temp = pt.shared.tempering
+    if not isinstance(temp, StabilizedPT):
+        raise TypeError("global_barrier_variational needs two legs")
+    cb = temp.variational_leg.communication_barriers
+    return float("nan") if cb is None else cb.globalbarrier
 
 
 def n_round_trips(pt: PT) -> int:           # RoundTripRecorder.jl:23

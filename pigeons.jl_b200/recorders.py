@@ -38,7 +38,7 @@ class ReducedRecorders:
     swap_lr: Optional[np.ndarray]
     swap_u: Optional[np.ndarray]
     swap_accept: Optional[np.ndarray]
-    target_trace: Optional[np.ndarray]    # [n_scans, d]
+    target_trace: Optional[np.ndarray]    # [n_scans, d]; two legs: [n_scans, 2, d] (chains n_var, n_var + 1)
     n_density_points: int
     n_ref_equiv_evals: int
     kernel_ms: float
@@ -54,8 +54,10 @@ _PER_CHAIN = ["swap_n", "swap_mean", "logsum_fwd", "logsum_bwd", "expl_acc_n", "
 _PER_SCAN_CHAIN = ["index_process", "swap_lr", "swap_u", "swap_accept"]
 
 
-def merge_round_results(comm, res, n_chains: int, dim: int) -> ReducedRecorders:
-    """Concatenate the shards' arrays in chain order (rank order == chain order)."""
+def merge_round_results(comm, res, n_chains: int, dim: int, n_chains_variational: int = 0) -> ReducedRecorders:
+    """Concatenate the shards' arrays in chain order (rank order == chain order).  The target-chain recorders come from
+    the shard owning the target chain(s): chain N, or with two legs chains n_var and n_var + 1 (one shard, engine rule)."""
+    two_legs = 0 < n_chains_variational < n_chains
     if comm.world_size == 1:
         g = {k: getattr(res, k) for k in _PER_CHAIN + _PER_SCAN_CHAIN}
         restarts, trips = res.n_tempered_restarts, res.n_round_trips
@@ -79,13 +81,14 @@ def merge_round_results(comm, res, n_chains: int, dim: int) -> ReducedRecorders:
         restarts, trips, pts, evals = (int(v) for v in tot)
         times = np.stack(comm.all_gather_array(np.array([res.kernel_ms, res.wall_s])))
         kms, wall = float(times[:, 0].max()), float(times[:, 1].max())
-        last = comm.world_size - 1          # the shard owning chain N
+        from .distributed import LoadBalance
+        last = LoadBalance(1, comm.world_size, n_chains).find_process(n_chains_variational if two_legs else n_chains) - 1
         online_n = int(comm.all_gather_array(np.array([res.online_n], dtype=np.int64))[last][0])
         online_mean = comm.all_gather_array(res.online_mean)[last]
         online_var = comm.all_gather_array(res.online_var)[last]
         trace = None
         if res.target_trace is not None:
-            trace = comm.all_gather_array(res.target_trace)[last].reshape(res.n_scans, dim)
+            trace = comm.all_gather_array(res.target_trace)[last].reshape((res.n_scans, 2, dim) if two_legs else (res.n_scans, dim))
     for k in _PER_CHAIN:
         assert g[k].shape[0] == n_chains, (k, g[k].shape, n_chains)
     return ReducedRecorders(

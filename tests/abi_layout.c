@@ -18,7 +18,7 @@ int main(void) {
   FIELD(pgn_config, abi_version); FIELD(pgn_config, target_kind); FIELD(pgn_config, dim); FIELD(pgn_config, n_chains);
   FIELD(pgn_config, seed); FIELD(pgn_config, rank); FIELD(pgn_config, world_size); FIELD(pgn_config, device);
   FIELD(pgn_config, n_modes); FIELD(pgn_config, p); FIELD(pgn_config, means); FIELD(pgn_config, log_weights);
-  FIELD(pgn_config, data_x); FIELD(pgn_config, data_y); FIELD(pgn_config, recorder_order); FIELD(pgn_config, reserved_);
+  FIELD(pgn_config, data_x); FIELD(pgn_config, data_y); FIELD(pgn_config, recorder_order); FIELD(pgn_config, n_chains_variational);
   END();
   BEGIN(pgn_explorer_params);
   FIELD(pgn_explorer_params, kind); FIELD(pgn_explorer_params, slice_w); FIELD(pgn_explorer_params, slice_p);

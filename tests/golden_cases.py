@@ -33,6 +33,12 @@ GOLDEN_CASES = {
     # SliceSampler on Bool / Integer / Float coordinates (test/test_slice_sampler.jl:56-75)
     "mixed_bool_int_float_slice_n7_r8": lambda: dict(target=pg.MixedProduct(n_bool=3, n_int=2, n_float=2), n_chains=7,
                                                      n_rounds=8, seed=1),
+    # two legs + GaussianReference (StabilizedPT.jl, GaussianReference.jl)
+    "two_legs_gmm6_automala_gaussian_r7": lambda: dict(target=pg.eight_mode_mixture(6, 3.0), explorer=pg.AutoMALA(), n_chains=5,
+                                                       n_chains_variational=5, variational=pg.GaussianReference(first_tuning_round=2),
+                                                       n_rounds=7, seed=4),
+    "two_legs_funnel8_slice_gaussian_r7": lambda: dict(target=pg.Funnel(8), explorer=pg.SliceSampler(), n_chains=5, n_chains_variational=4,
+                                                       variational=pg.GaussianReference(first_tuning_round=3), n_rounds=7, seed=3),
     "ising5_n10_r8": lambda: dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=8, seed=1),
 }
 
@@ -53,7 +59,7 @@ def summarise(pt):
         "swap_lr_sha256": hashlib.sha256(np.ascontiguousarray(rr.swap_lr, dtype=np.float64).tobytes()).hexdigest(),
         "swap_mean": _hex(rr.swap_mean),
         "logsum_fwd": _hex(rr.logsum_fwd),
-        "schedule": _hex(pt.shared.tempering.schedule.grids),
+        "schedule": _hex(pg.tempering_parameters(pt.shared.tempering)),
         "stepping_stone": float(pg.stepping_stone(pt)).hex(),
         "n_round_trips": int(rr.n_round_trips),
         "n_ref_equiv_evals": int(rr.n_ref_equiv_evals),

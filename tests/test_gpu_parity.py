@@ -20,7 +20,7 @@ def run_pt(lib, **kw):
     pt = pg.pigeons(engine_lib=lib, **kw)
     rr = pt.reduced_recorders
     state = pt.engine.get_state()
-    out = dict(rr=rr, schedule=pt.shared.tempering.schedule.grids.copy(), logz=pg.stepping_stone(pt), state=state,
+    out = dict(rr=rr, schedule=pg.tempering_parameters(pt.shared.tempering).copy(), logz=pg.stepping_stone(pt), state=state,
                explorer=pt.shared.explorer, log=pt.round_log)
     pt.close()
     return out
@@ -101,6 +101,27 @@ CASES = {
                                explorer=pg.Mix(pg.ToyExplorer(), pg.SliceSampler())),
     "toy70_compose_slice_mala_4cpl": dict(target=pg.toy_mvn_target(70), n_chains=4, n_rounds=4, seed=8,
                                           explorer=pg.Compose(pg.SliceSampler(n_passes=1), pg.MALA(step_size=0.1, base_n_refresh=1))),
+    # two legs (StabilizedPT.jl, VariationalDEO.jl) and the Gaussian variational reference (GaussianReference.jl)
+    "two_legs_test_swapper": dict(target=pg.TestSwapper(0.5), n_chains=5, n_chains_variational=5, n_rounds=9, seed=1,
+                                  record=[pg.index_process, pg.swap_trace]),
+    "two_legs_toy_slice_no_variational": dict(target=pg.toy_mvn_target(3), explorer=pg.SliceSampler(), n_chains=4, n_chains_variational=5,
+                                              n_rounds=7, seed=2),
+    "two_legs_funnel8_slice_gaussian": dict(target=pg.Funnel(8), explorer=pg.SliceSampler(), n_chains=5, n_chains_variational=4,
+                                            variational=pg.GaussianReference(first_tuning_round=3), n_rounds=7, seed=3),
+    "two_legs_gmm6_automala_gaussian": dict(target=pg.eight_mode_mixture(6, 3.0), explorer=pg.AutoMALA(), n_chains=5,
+                                            n_chains_variational=5, variational=pg.GaussianReference(first_tuning_round=2),
+                                            n_rounds=7, seed=4),
+    "two_legs_gmm128_automala_gaussian_4cpl": dict(target=pg.eight_mode_mixture(128, 8.0), explorer=pg.AutoMALA(), n_chains=4,
+                                                   n_chains_variational=4, variational=pg.GaussianReference(first_tuning_round=2),
+                                                   n_rounds=5, seed=5),
+    "two_legs_funnel40_mala_gaussian_2cpl": dict(target=pg.Funnel(40), explorer=pg.MALA(step_size=0.1), n_chains=4, n_chains_variational=4,
+                                                 variational=pg.GaussianReference(first_tuning_round=3), n_rounds=6, seed=6),
+    "one_leg_variational_gmm1": dict(target=pg.GaussianMixture(means=[[1.0]], reference_sigma=1.0), explorer=pg.SliceSampler(),
+                                     n_chains=0, n_chains_variational=6, variational=pg.GaussianReference(first_tuning_round=2),
+                                     n_rounds=8, seed=7),
+    "two_legs_ising5": dict(target=pg.IsingLogPotential(0.8, 5), n_chains=5, n_chains_variational=4, n_rounds=7, seed=8),
+    "two_legs_never_activated": dict(target=pg.Funnel(8), explorer=pg.AutoMALA(), n_chains=4, n_chains_variational=4,
+                                     variational=pg.GaussianReference(first_tuning_round=99), n_rounds=6, seed=9),
     "single_chain": dict(target=pg.toy_mvn_target(4), explorer=pg.SliceSampler(), n_chains=1, n_rounds=5, seed=1),
     "two_chains": dict(target=pg.toy_mvn_target(2), explorer=pg.AutoMALA(), n_chains=2, n_rounds=6, seed=8),
 }
@@ -393,6 +414,86 @@ def test_leapfrog_involution_on_the_device(target, gpu_lib):
     e.close()
 
 
+@pytest.mark.parametrize("target", [pg.toy_mvn_target(10), pg.Funnel(8), pg.eight_mode_mixture(6, 3.0),
+                                    pg.toy_mvn_target(100), pg.eight_mode_mixture(128, 8.0)])
+def test_device_integrator_is_an_involution_and_matches_the_oracle(target, gpu_lib, oracle_lib):
+    """test/test_auto_mala.jl:51-85 on the DEVICE's own leapfrog (VecChain::run_trial, the code autoMALA and MALA run):
+    forward n steps, flip the momentum, forward n steps, flip -> back at the start; and every intermediate result is the
+    oracle's `hamiltonian_dynamics!` bit for bit."""
+    rng = np.random.default_rng(11)
+    d = target.dim
+    n_pts = 9
+    x0 = rng.standard_normal((n_pts, d)) * 0.7
+    p0 = rng.standard_normal((n_pts, d))
+    betas = np.linspace(0.0, 1.0, n_pts)
+    dev = pg.Engine(gpu_lib, n_chains=2, seed=1, **target.engine_config())
+    orc = pg.Engine(oracle_lib, n_chains=2, seed=1, **target.engine_config())
+    eps, n = 0.02, 40
+    x1, p1 = dev.hamiltonian_dynamics(x0, p0, betas, eps, n)
+    ox1, op1 = orc.hamiltonian_dynamics(x0, p0, betas, eps, n)
+    assert np.array_equal(x1, ox1) and np.array_equal(p1, op1)
+    assert np.abs(x1 - x0).max() > 1e-3                       # it moved
+    x2, p2 = dev.hamiltonian_dynamics(x1, -p1, betas, eps, n)
+    ox2, op2 = orc.hamiltonian_dynamics(ox1, -op1, betas, eps, n)
+    assert np.array_equal(x2, ox2) and np.array_equal(p2, op2)
+    assert np.abs(x2 - x0).max() < 1e-9 and np.abs(-p2 - p0).max() < 1e-9
+    # zero steps is the identity; one step equals the leapfrog written out in numpy on the gradient entry point
+    xz, pz = dev.hamiltonian_dynamics(x0, p0, betas, eps, 0)
+    assert np.array_equal(xz, x0) and np.array_equal(pz, p0)
+    _, g0 = dev.logdensity_and_gradient(x0, betas)
+    ph = p0 + (eps / 2) * g0
+    xs = x0 + eps * ph
+    _, g1 = dev.logdensity_and_gradient(xs, betas)
+    xd, pd = dev.hamiltonian_dynamics(x0, p0, betas, eps, 1)
+    assert np.array_equal(xd, xs) and np.array_equal(pd, ph + (eps / 2) * g1)
+    dev.close(); orc.close()
+
+
+def test_variational_entry_points_match_the_oracle(gpu_lib, oracle_lib):
+    """With a GaussianReference installed the parity entry points evaluate the variational leg's path: log potential,
+    logdensity + gradient and the integrator, device vs oracle bit for bit; and the reference's own 'Manual diff check'
+    (test/test_variational.jl:71-84): the hand-written gradient equals the derivative of gaussian_logdensity."""
+    rng = np.random.default_rng(5)
+    for target in (pg.Funnel(8), pg.eight_mode_mixture(70, 4.0)):
+        d = target.dim
+        mean, sd = rng.standard_normal(d), rng.uniform(0.3, 2.0, d)
+        x = rng.standard_normal((7, d))
+        betas = np.array([0.0, 0.1, 0.37, 0.5, 0.9, 1.0, 0.0])
+        res = []
+        for lib in (gpu_lib, oracle_lib):
+            e = pg.Engine(lib, n_chains=4, n_chains_variational=2, seed=1, **target.engine_config())
+            e.set_variational(mean, sd)
+            lp = e.log_potential(x, betas)
+            ld, g = e.logdensity_and_gradient(x, betas)
+            hd = e.hamiltonian_dynamics(x, rng.standard_normal((7, d)) * 0 + 0.5, betas, 0.01, 10)
+            e.set_variational(None, None)
+            lp_fixed = e.log_potential(x, betas)
+            e.close()
+            res.append((lp, ld, g, hd[0], hd[1], lp_fixed))
+        for a, b in zip(*res):
+            assert np.array_equal(a, b)
+        lp, ld, g = res[0][0], res[0][1], res[0][2]
+        ref0 = np.sum(-0.5 * np.log(2.0 * np.pi * sd ** 2) - (x[0] - mean) ** 2 / (2.0 * sd ** 2))      # beta = 0: the reference alone
+        np.testing.assert_allclose(lp[0], ref0, rtol=1e-12)
+        np.testing.assert_allclose(g[0], -(x[0] - mean) / sd ** 2, rtol=1e-12)
+        assert not np.array_equal(res[0][0][:5], res[0][5][:5]) and res[0][0][5] == res[0][5][5]         # beta = 1: the target alone
+
+
+def test_two_legs_refuse_what_they_cannot_run(gpu_lib):
+    with pytest.raises(pg.EngineError):      # per-chain recorder order
+        pg.Engine(gpu_lib, n_chains=6, n_chains_variational=3, seed=1, recorder_order=1, **pg.Funnel(4).engine_config())
+    with pytest.raises(pg.EngineError):      # the two target chains on different shards
+        pg.Engine(gpu_lib, n_chains=6, n_chains_variational=3, seed=1, rank=0, world_size=2, **pg.Funnel(4).engine_config())
+    e = pg.Engine(gpu_lib, n_chains=6, n_chains_variational=3, seed=1, **pg.toy_mvn_target(4).engine_config())
+    with pytest.raises(pg.EngineError):      # a Gaussian reference needs an InterpolatingPath (FUNNEL, GMM)
+        e.set_variational(np.zeros(4), np.ones(4))
+    e.close()
+    e = pg.Engine(gpu_lib, n_chains=6, n_chains_variational=3, seed=1, **pg.Funnel(4).engine_config())
+    with pytest.raises(pg.EngineError):
+        e.set_variational(np.zeros(4), np.array([1.0, 0.0, 1.0, 1.0]))
+    e.close()
+
+
 RESUME_CASES = {
     "toy_slice": dict(target=pg.toy_mvn_target(3), explorer=pg.SliceSampler(), n_chains=5, seed=2),
     "funnel_automala_team": dict(target=pg.Funnel(32), explorer=pg.AutoMALA(), n_chains=12, seed=3),
@@ -401,6 +502,8 @@ RESUME_CASES = {
     "logreg": dict(target=pg.synthetic_logistic_regression(300, 24), explorer=pg.AutoMALA(), n_chains=5, seed=5),
     "toy300_mem": dict(target=pg.toy_mvn_target(300), explorer=pg.MALA(step_size=0.1), n_chains=4, seed=6),
     "test_swapper": dict(target=pg.TestSwapper(0.7), n_chains=6, seed=7),
+    "two_legs_gaussian": dict(target=pg.eight_mode_mixture(6, 3.0), explorer=pg.AutoMALA(), n_chains=4, n_chains_variational=4,
+                              variational=pg.GaussianReference(first_tuning_round=2), seed=8),
 }
 
 
@@ -421,7 +524,7 @@ def test_device_resume_is_bit_identical(name, gpu_lib, oracle_lib):
         for k in ("index_process", "swap_lr", "swap_u", "swap_accept", "swap_mean", "logsum_fwd", "logsum_bwd", "expl_n_steps",
                   "expl_acc_mean", "am_mean", "rev_mean"):
             assert np.array_equal(getattr(a, k), getattr(b, k)), f"{name}/{label}: {k}"
-        assert np.array_equal(straight.shared.tempering.schedule.grids, other.shared.tempering.schedule.grids)
+        assert np.array_equal(pg.tempering_parameters(straight.shared.tempering), pg.tempering_parameters(other.shared.tempering))
         assert straight.shared.explorer == other.shared.explorer
         sa, sb = straight.engine.get_state(), other.engine.get_state()
         for k in sa:

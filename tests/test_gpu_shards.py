@@ -25,6 +25,9 @@ CASES = {
     "mixed_slice_n8": dict(target=pg.MixedProduct(n_bool=3, n_int=2, n_float=2), n_chains=8, n_rounds=6, seed=8),
     "logreg_automala_n7": dict(target=pg.synthetic_logistic_regression(300, 24), explorer=pg.AutoMALA(), n_chains=7,
                                n_rounds=4, seed=6),
+    # two legs: 11 chains, targets 5 and 6 — on one shard for world 2 (1-6 | 7-11) and world 3 (1-4 | 5-8 | 9-11)
+    "two_legs_gmm_gaussian_n11": dict(target=pg.eight_mode_mixture(6, 3.0), explorer=pg.AutoMALA(), n_chains=6, n_chains_variational=5,
+                                      variational=pg.GaussianReference(first_tuning_round=2), n_rounds=5, seed=9),
     "toy300_automala_n6_mem": dict(target=pg.toy_mvn_target(300), explorer=pg.AutoMALA(), n_chains=6, n_rounds=4, seed=7),
 }
 
@@ -35,7 +38,7 @@ def run_sharded(lib, world, record, checked_round=0, engine_factory=None, **kw):
     def one_rank(comm):
         pt = pg.pigeons(engine_lib=lib, comm=comm, record=record, checked_round=checked_round,
                         engine_factory=engine_factory, **kw)
-        out = dict(rr=pt.reduced_recorders, schedule=pt.shared.tempering.schedule.grids.copy(), logz=pg.stepping_stone(pt),
+        out = dict(rr=pt.reduced_recorders, schedule=pg.tempering_parameters(pt.shared.tempering).copy(), logz=pg.stepping_stone(pt),
                    state=pt.engine.get_state(), first=pt.engine.first_chain)
         comm.barrier()          # nobody destroys a mailbox a neighbour's kernel may still read
         pt.close()
@@ -65,7 +68,7 @@ def test_shards_on_one_gpu_match_the_oracle(name, world, gpu_lib, oracle_lib):
             assert np.array_equal(a.target_trace, b.target_trace)
         assert a.n_round_trips == b.n_round_trips and a.n_tempered_restarts == b.n_tempered_restarts
         assert a.n_ref_equiv_evals == b.n_ref_equiv_evals
-        assert np.array_equal(sh["schedule"], ref.shared.tempering.schedule.grids)
+        assert np.array_equal(sh["schedule"], pg.tempering_parameters(ref.shared.tempering))
         assert sh["logz"] == pg.stepping_stone(ref) or (np.isnan(sh["logz"]) and np.isnan(pg.stepping_stone(ref)))
     whole = {k: np.concatenate([sh["state"][k] for sh in shards], axis=0) for k in shards[0]["state"]}
     rs = ref.engine.get_state()

@@ -93,7 +93,7 @@ def test_capi_library_loads_and_exports_every_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), name
     lib.pgn_abi_version.restype = C.c_int
-    assert lib.pgn_abi_version() == pg._capi.ABI_VERSION == 3
+    assert lib.pgn_abi_version() == pg._capi.ABI_VERSION == 4
 
 
 def test_product_fails_loudly_without_gpu():

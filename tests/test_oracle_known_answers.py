@@ -216,6 +216,13 @@ def test_leapfrog_involution(target, oracle_lib):
         dx, dp, moved = leapfrog_involution_error(e, target, beta)
         assert moved > 1e-3                       # the trajectory went somewhere
         assert dx < 1e-9 and dp < 1e-9            # and came back (isapprox in the reference)
+    # the engine's OWN integrator (Engine::leap_frog, what auto_mala / mala call): same property
+    rng = np.random.default_rng(3)
+    x0, p0 = rng.normal(0, 0.3, (5, target.dim)), rng.normal(0, 1.0, (5, target.dim))
+    betas = np.linspace(0, 1, 5)
+    x1, p1 = e.hamiltonian_dynamics(x0, p0, betas, 0.01, 40)
+    x2, p2 = e.hamiltonian_dynamics(x1, -p1, betas, 0.01, 40)
+    assert np.abs(x1 - x0).max() > 1e-3 and np.abs(x2 - x0).max() < 1e-9 and np.abs(-p2 - p0).max() < 1e-9
     e.close()
 
 
@@ -305,3 +312,85 @@ def test_slice_sampler_integer_width_must_be_integer(oracle_lib):
     t = pg.MixedProduct(n_bool=0, n_int=2, n_float=0)
     with pytest.raises(pg.EngineError):
         pg.pigeons(target=t, explorer=pg.SliceSampler(w=0.1, n_passes=1), n_chains=3, n_rounds=2, engine_lib=oracle_lib)
+
+
+# ---- two legs and the variational reference (test/test_variational.jl, test/test_two_legs.jl) -----------------------
+def test_two_references_double_the_restarts(oracle_lib):
+    """test/test_variational.jl:49-63: TestSwapper(0.5), 5 chains, 15 rounds; with a second (variational) leg of 5 chains
+    the number of tempered restarts doubles (|2 - ratio| <= 0.05)."""
+    kw = dict(target=pg.TestSwapper(0.5), record=[pg.round_trip], n_chains=5, n_rounds=15, seed=1, engine_lib=oracle_lib)
+    r1 = pg.n_tempered_restarts(pg.pigeons(**kw))
+    r2 = pg.n_tempered_restarts(pg.pigeons(n_chains_variational=5, **kw))
+    assert abs(2.0 - r2 / r1) <= 0.05
+
+
+def test_two_reference_barriers(oracle_lib):
+    """test/test_variational.jl:86-133 ('Two reference restarts'): target exp(-(x-1)^2/2), reference N(0,1), SliceSampler,
+    5 + 5 chains, 13 rounds.  (i) with GaussianReference the variational leg's global barrier is ~0; (ii) without it both legs
+    agree; (iii) the fixed leg agrees with single-leg PT.  All within the reference's 0.05."""
+    t = pg.GaussianMixture(means=[[1.0]], reference_sigma=1.0)       # N(1, 1), normalised: log(Z1/Z0) = 0
+    kw = dict(target=t, explorer=pg.SliceSampler(), n_chains=5, seed=1, n_rounds=13, record=[pg.online], engine_lib=oracle_lib)
+    pt = pg.pigeons(n_chains_variational=5, variational=pg.GaussianReference(), **kw)
+    assert abs(pg.global_barrier_variational(pt) - 0.0) <= 0.05
+    assert isinstance(pt.shared.tempering, pg.StabilizedPT)
+    v = pt.inputs.variational
+    assert abs(v.mean[0] - 1.0) < 0.05 and abs(v.standard_deviation[0] - 1.0) < 0.05      # the fitted reference IS the target
+    assert abs(pg.stepping_stone(pt)) < 0.01                                              # variational leg only, both normalised
+    pt = pg.pigeons(n_chains_variational=5, **kw)
+    gcb_fixed, gcb_var = pg.global_barrier(pt), pg.global_barrier_variational(pt)
+    assert abs(gcb_fixed - gcb_var) <= 0.05
+    pt = pg.pigeons(**kw)
+    assert abs(gcb_fixed - pg.global_barrier(pt)) <= 0.05
+
+
+def test_single_leg_variational(oracle_lib):
+    """test/test_variational.jl:20-31: n_chains = 0, n_chains_variational = 10: one leg whose reference becomes the
+    GaussianReference at first_tuning_round; before that it is the fixed reference."""
+    t = pg.eight_mode_mixture(3, 2.0)
+    kw = dict(target=t, explorer=pg.AutoMALA(), n_chains=0, n_chains_variational=10, seed=1, engine_lib=oracle_lib)
+    pt = pg.pigeons(variational=pg.GaussianReference(), n_rounds=5, **kw)
+    assert isinstance(pt.shared.tempering, pg.NonReversiblePT) and pt.inputs.variational.mean is None     # rounds 1-5: not yet
+    pt = pg.pigeons(variational=pg.GaussianReference(first_tuning_round=3), n_rounds=9, **kw)
+    assert pt.inputs.variational.mean is not None and pt.shared.tempering.schedule.n_chains == 10
+    plain = pg.pigeons(target=t, explorer=pg.AutoMALA(), n_chains=10, n_rounds=9, seed=1, engine_lib=oracle_lib)
+    assert pg.global_barrier(pt) < pg.global_barrier(plain)          # a fitted reference is closer to the target
+
+
+def test_two_legs_structure(oracle_lib):
+    """test/test_two_legs.jl ('Issue #290') and OddEven.jl:16-48 on the event log: references {1, N} and targets
+    {n_var, n_var + 1} are disjoint; the pair between the two targets always swaps (both hold the target: ratio 0);
+    the never-activated variational leg behaves like a second fixed leg (global barriers agree, rtol 0.1 in the reference)."""
+    n_fixed, n_var, n_rounds = 8, 7, 10
+    pt = pg.pigeons(target=pg.Funnel(2), explorer=pg.SliceSampler(), n_chains=n_fixed, n_chains_variational=n_var,
+                    variational=pg.GaussianReference(first_tuning_round=n_rounds + 1), n_rounds=n_rounds, seed=1,
+                    record=[pg.index_process, pg.swap_trace, pg.traces], engine_lib=oracle_lib)
+    rr = pt.reduced_recorders
+    n = n_fixed + n_var
+    betas = pg.tempering_parameters(pt.shared.tempering)
+    assert betas.shape == (n,) and betas[0] == 0.0 and betas[n_var - 1] == 1.0 and betas[n_var] == 1.0 and betas[-1] == 0.0
+    assert np.all(np.diff(betas[:n_var]) > 0) and np.all(np.diff(betas[n_var:]) < 0)
+    mid = rr.swap_accept[:, n_var - 1]                     # lower chain of the pair (n_var, n_var + 1)
+    active = np.array([(s + 1) % 2 == (0 if n_var % 2 == 0 else 1) for s in range(rr.n_scans)])      # OddEven.jl:23-31
+    assert np.all(mid[active] == 1) and np.all(rr.swap_lr[active, n_var - 1] == 0.0)
+    assert rr.target_trace.shape == (rr.n_scans, 2, 2)
+    one_leg = pg.pigeons(target=pg.Funnel(2), explorer=pg.SliceSampler(), n_chains=n_fixed, n_rounds=n_rounds, seed=1,
+                         engine_lib=oracle_lib)
+    g1, g21, g22 = pg.global_barrier(one_leg), pg.global_barrier(pt), pg.global_barrier_variational(pt)
+    assert abs(g21 - g1) < 0.1 * g1 + 0.05 and abs(g22 - g1) < 0.1 * g1 + 0.05
+
+
+def test_gaussian_reference_gradient_manual_diff_check(oracle_lib):
+    """test/test_variational.jl:71-84: the hand-written gradient of the GaussianReference against finite differences."""
+    rng = np.random.default_rng(1)
+    t = pg.Funnel(2)
+    e = pg.Engine(oracle_lib, n_chains=3, n_chains_variational=2, seed=1, **t.engine_config())
+    mean, sd, x = rng.random(2), rng.random(2) + 0.1, rng.random((1, 2))
+    e.set_variational(mean, sd)
+    ld, g = e.logdensity_and_gradient(x, np.array([0.0]))             # beta = 0: the reference alone
+    f = lambda y: float(np.sum(-0.5 * np.log(2.0 * np.pi * sd ** 2) - (y - mean) ** 2 / (2.0 * sd ** 2)))     # noqa: E731
+    assert abs(ld[0] - f(x[0])) < 1e-12
+    h = 1e-6
+    for i in range(2):
+        dx = np.zeros(2); dx[i] = h
+        assert abs(g[0, i] - (f(x[0] + dx) - f(x[0] - dx)) / (2 * h)) < 1e-6
+    e.close()
