@@ -129,7 +129,8 @@ typedef struct pgn_config {
                                  *   n_chains (fixed reference);  is_reference = {1, n_chains}, is_target = {k, k+1}
                                  * (VariationalDEO.jl:19-20); pgn_set_schedule takes the concatenated parameters
                                  * vcat(variational leg, reverse(fixed leg)) (StabilizedPT.jl:63-65).  Two legs need
-                                 * recorder_order = PGN_RECORDERS_PER_REPLICA and both target chains on one shard. */
+                                 * recorder_order = PGN_RECORDERS_PER_REPLICA; with several shards chain k+1 joins
+                                 * chain k's shard when the balanced split would separate them (pgn_local_range). */
 } pgn_config;
 
 /* Explorer parameters; mirrors the @kwdef explorer structs

@@ -9,7 +9,7 @@ Only the scan path (explore! + DEO swap!) runs on the device; everything in
 this package is host-side glue around the C ABI in include/pigeons_b200.h.
 """
 from ._capi import Engine, EngineError, EngineLib, default_library_path          # noqa: F401
-from .distributed import LoadBalance, SingleProcess, ThreadComm, ThreadGroup, TorchDistributed   # noqa: F401
+from .distributed import LoadBalance, SingleProcess, ThreadComm, ThreadGroup, TorchDistributed, shard_layout   # noqa: F401
 from .explorers import (MALA, AutoMALA, Compose, Mix, DiagonalPreconditioner, IdentityPreconditioner,  # noqa: F401
                         IsingMetropolis, MixDiagonalPreconditioner, SliceSampler, ToyExplorer)
 from .pt import (PT, ChecksFailed, GaussianReference, Inputs, Iterators, NonReversiblePT, Shared, StabilizedPT, adapt,   # noqa: F401

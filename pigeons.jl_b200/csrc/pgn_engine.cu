@@ -20,11 +20,29 @@ int fail(char** err, int code, const std::string& msg) {
 }
 
 // LoadBalance (src/mpi_utils/LoadBalance.jl:70-73,119-128), 0-based rank
-void shard_range(int n_chains, int world, int rank, int& first_chain, int& n_local) {
+void balanced_range(int n_chains, int world, int rank, int& first_chain, int& n_local) {
   const int basic = n_chains / world, extras = n_chains % world;
   n_local = basic + (rank < extras ? 1 : 0);
   const int with_extra = std::min(rank, extras);
   first_chain = 1 + (rank - with_extra) * basic + with_extra * (basic + 1);
+}
+// Two legs (0 < n_var < n_chains): the two target chains n_var and n_var + 1 stay on one shard — when a boundary of the
+// balanced split falls between them, chain n_var + 1 moves to the lower shard (same rule in distributed.py:shard_layout).
+// Returns false when that would empty the upper shard.
+bool shard_range(int n_chains, int world, int rank, int n_var, int& first_chain, int& n_local) {
+  balanced_range(n_chains, world, rank, first_chain, n_local);
+  if (!(n_var > 0 && n_var < n_chains) || world < 2) return true;
+  for (int r = 0; r + 1 < world; ++r) {
+    int f, n;
+    balanced_range(n_chains, world, r, f, n);
+    if (f + n - 1 != n_var) continue;
+    int f2, n2;
+    balanced_range(n_chains, world, r + 1, f2, n2);
+    if (n2 < 2) return false;
+    if (rank == r) n_local += 1;
+    if (rank == r + 1) { first_chain += 1; n_local -= 1; }
+  }
+  return true;
 }
 
 void fill_params(pgn_handle* h, Params& P) {
@@ -220,7 +238,8 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
     CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
     if (!prop.cooperativeLaunch) throw CudaError{PGN_ERR_NO_DEVICE, "device lacks cooperative launch"};
     h->n_sms = prop.multiProcessorCount;
-    shard_range(cfg->n_chains, cfg->world_size, cfg->rank, h->first_chain, h->n_local);
+    if (!shard_range(cfg->n_chains, cfg->world_size, cfg->rank, cfg->n_chains_variational, h->first_chain, h->n_local))
+      throw CudaError{PGN_ERR_INVALID, "two legs: too few chains per shard to keep both target chains on one shard"};
     const int d = cfg->dim;
     if (cfg->target_kind == PGN_TARGET_ISING) { h->cpl = 1; h->d_pad = 64; h->pay_doubles = 32; }
     else if (cfg->target_kind == PGN_TARGET_TEST_SWAPPER) { h->cpl = 1; h->d_pad = 1; h->pay_doubles = 0; }
@@ -253,10 +272,6 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
         if (cfg->target_kind == PGN_TARGET_LOGREG || (h->cpl == 0 && cfg->target_kind != PGN_TARGET_ISING &&
                                                      cfg->target_kind != PGN_TARGET_TEST_SWAPPER) || h->force_mem)
           throw CudaError{PGN_ERR_INVALID, "two legs run on the register-resident scan kernels only (d <= 128)"};
-        const int last = h->first_chain + h->n_local - 1;
-        const bool has_a = nv >= h->first_chain && nv <= last, has_b = nv + 1 >= h->first_chain && nv + 1 <= last;
-        if (has_a != has_b)
-          throw CudaError{PGN_ERR_INVALID, "two legs: both target chains (n_chains_variational and the next one) must be on one shard"};
       }
     }
     if (cfg->recorder_order != PGN_RECORDERS_PER_REPLICA && cfg->recorder_order != PGN_RECORDERS_PER_CHAIN)
@@ -521,7 +536,8 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
       int wpb = 0, grid = 0;
       // every rank must pick the same kernel family (the register-resident kernels and the memory-resident one lay
       // their mailbox slots out differently), so co-residency is judged on the largest shard of the ladder
-      const int nl_max = (h->cfg.n_chains + std::max(h->cfg.world_size, 1) - 1) / std::max(h->cfg.world_size, 1);
+      const int nl_max = (h->cfg.n_chains + std::max(h->cfg.world_size, 1) - 1) / std::max(h->cfg.world_size, 1) +
+                         ((h->cfg.n_chains_variational > 0 && h->cfg.n_chains_variational < h->cfg.n_chains) ? 1 : 0);   // shard_range
       const bool vec_target = h->cfg.target_kind == PGN_TARGET_TOY_MVN || h->cfg.target_kind == PGN_TARGET_FUNNEL ||
                               h->cfg.target_kind == PGN_TARGET_GMM;
       if (kernel && h->cfg.target_kind == PGN_TARGET_ISING && std::getenv("PGN_ISING_LITE") != nullptr &&

@@ -53,6 +53,27 @@ class LoadBalance:
         return 1 + self.n_extras() + (global_idx - first_block - 1) // basic
 
 
+def shard_layout(n_chains: int, world_size: int, n_chains_variational: int = 0):
+    """[(first_chain, n_local)] per rank as the engine lays a ladder out (`pgn_local_range`): LoadBalance's balanced
+    blocks, except that a two-leg ladder keeps its two target chains (n_var, n_var + 1) on one shard — when a block
+    boundary falls between them, chain n_var + 1 moves to the lower shard."""
+    blocks = []
+    for r in range(1, world_size + 1):
+        lb = LoadBalance(r, world_size, n_chains)
+        blocks.append([lb.my_first_global_idx(), lb.my_load()])
+    nv = n_chains_variational
+    if 0 < nv < n_chains:
+        for r in range(world_size - 1):
+            if blocks[r][0] + blocks[r][1] - 1 == nv:
+                if blocks[r + 1][1] < 2:
+                    raise ValueError("two legs: too few chains per shard to keep both target chains on one shard")
+                blocks[r][1] += 1
+                blocks[r + 1][0] += 1
+                blocks[r + 1][1] -= 1
+                break
+    return [tuple(b) for b in blocks]
+
+
 class Communicator:
     """Minimal collective surface the host driver needs."""
     rank: int = 0

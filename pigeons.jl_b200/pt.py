@@ -17,7 +17,7 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 
 from . import _capi
-from .distributed import Communicator, LoadBalance, SingleProcess
+from .distributed import Communicator, SingleProcess, shard_layout
 from .explorers import MALA, AutoMALA, Compose, Mix
 from .recorders import ReducedRecorders, merge_round_results
 from .tempering import (CommunicationBarriers, Schedule, communication_barriers, equally_spaced_schedule,
@@ -172,9 +172,8 @@ def create_pt(inputs: Inputs) -> PT:
         engine = inputs.engine_factory(**kw)
     else:
         engine = _capi.Engine(inputs.engine_lib or _capi.EngineLib(), **kw)
-    lb = LoadBalance(comm.rank + 1, comm.world_size, n_total)
-    assert engine.first_chain == lb.my_first_global_idx() and engine.n_local == lb.my_load(), \
-        "engine shard geometry disagrees with LoadBalance"
+    layout = shard_layout(n_total, comm.world_size, inputs.n_chains_variational if inputs.n_chains > 0 else 0)
+    assert (engine.first_chain, engine.n_local) == layout[comm.rank], "engine shard geometry disagrees with LoadBalance"
     comm.connect_neighbours(engine)
     shared = Shared(Iterators(), create_tempering(inputs), inputs.explorer)
     engine.init_replicas()

@@ -81,8 +81,10 @@ def merge_round_results(comm, res, n_chains: int, dim: int, n_chains_variational
         restarts, trips, pts, evals = (int(v) for v in tot)
         times = np.stack(comm.all_gather_array(np.array([res.kernel_ms, res.wall_s])))
         kms, wall = float(times[:, 0].max()), float(times[:, 1].max())
-        from .distributed import LoadBalance
-        last = LoadBalance(1, comm.world_size, n_chains).find_process(n_chains_variational if two_legs else n_chains) - 1
+        from .distributed import shard_layout
+        t_chain = n_chains_variational if two_legs else n_chains
+        last = next(r for r, (f, n) in enumerate(shard_layout(n_chains, comm.world_size, n_chains_variational if two_legs else 0))
+                    if f <= t_chain < f + n)
         online_n = int(comm.all_gather_array(np.array([res.online_n], dtype=np.int64))[last][0])
         online_mean = comm.all_gather_array(res.online_mean)[last]
         online_var = comm.all_gather_array(res.online_var)[last]

@@ -106,12 +106,12 @@ def main():
             same = all(np.array_equal(getattr(a, k), getattr(b, k)) for k in
                        ("index_process", "swap_lr", "swap_u", "swap_accept", "swap_n", "swap_mean", "logsum_fwd",
                         "logsum_bwd", "expl_n_steps", "am_mean", "online_mean", "online_var", "target_trace"))
-            same = same and np.array_equal(pt.shared.tempering.schedule.grids, ref.shared.tempering.schedule.grids)
+            same = same and np.array_equal(pg.tempering_parameters(pt.shared.tempering), pg.tempering_parameters(ref.shared.tempering))
             same = same and pg.stepping_stone(pt) == pg.stepping_stone(ref)
             same = same and a.n_round_trips == b.n_round_trips and a.n_ref_equiv_evals == b.n_ref_equiv_evals
             report[name] = bool(same)
     # all ranks hold the same adapted schedule (adaptation ran on identical merged statistics)
-    sched = comm.all_gather_array(pt.shared.tempering.schedule.grids)
+    sched = comm.all_gather_array(pg.tempering_parameters(pt.shared.tempering))
     report_sched = all(np.array_equal(sched[0], s) for s in sched)
     if rank == 0:
         report["schedules_identical_on_all_ranks"] = bool(report_sched)

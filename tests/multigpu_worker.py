@@ -34,6 +34,9 @@ def main():
         "ising_n10": dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=6, seed=4),
         "test_swapper_n8": dict(target=pg.TestSwapper(0.5), n_chains=8, n_rounds=6, seed=5),
         "mixed_slice_n9": dict(target=pg.MixedProduct(n_bool=3, n_int=2, n_float=2), n_chains=9, n_rounds=6, seed=8),
+        # two legs of 8 chains: the balanced split separates the target chains 8 | 9 at every world size, chain 9 joins chain 8's GPU
+        "two_legs_gmm_gaussian_n16": dict(target=pg.eight_mode_mixture(6, 3.0), explorer=pg.AutoMALA(), n_chains=8, n_chains_variational=8,
+                                          variational=pg.GaussianReference(first_tuning_round=2), n_rounds=5, seed=11),
         "funnel_automala_n24_per_chain": dict(target=pg.Funnel(32), explorer=pg.AutoMALA(), n_chains=24, n_rounds=5, seed=9,
                                               recorder_order=1),
     }
@@ -52,7 +55,7 @@ def main():
             if a.target_trace is not None:
                 keys.append("target_trace")
             bad = [k for k in keys if not np.array_equal(getattr(a, k), getattr(b, k))]
-            if not np.array_equal(pt.shared.tempering.schedule.grids, ref.shared.tempering.schedule.grids):
+            if not np.array_equal(pg.tempering_parameters(pt.shared.tempering), pg.tempering_parameters(ref.shared.tempering)):
                 bad.append("schedule")
             if a.n_round_trips != b.n_round_trips or a.n_ref_equiv_evals != b.n_ref_equiv_evals:
                 bad.append("counters")

@@ -482,8 +482,15 @@ def test_variational_entry_points_match_the_oracle(gpu_lib, oracle_lib):
 def test_two_legs_refuse_what_they_cannot_run(gpu_lib):
     with pytest.raises(pg.EngineError):      # per-chain recorder order
         pg.Engine(gpu_lib, n_chains=6, n_chains_variational=3, seed=1, recorder_order=1, **pg.Funnel(4).engine_config())
-    with pytest.raises(pg.EngineError):      # the two target chains on different shards
-        pg.Engine(gpu_lib, n_chains=6, n_chains_variational=3, seed=1, rank=0, world_size=2, **pg.Funnel(4).engine_config())
+    # several shards: the balanced split 1-3 | 4-6 would separate the targets 3 and 4: chain 4 joins the lower shard
+    e = pg.Engine(gpu_lib, n_chains=6, n_chains_variational=3, seed=1, rank=0, world_size=2, **pg.Funnel(4).engine_config())
+    assert (e.first_chain, e.n_local) == (1, 4) == pg.shard_layout(6, 2, 3)[0]
+    e.close()
+    e = pg.Engine(gpu_lib, n_chains=6, n_chains_variational=3, seed=1, rank=1, world_size=2, **pg.Funnel(4).engine_config())
+    assert (e.first_chain, e.n_local) == (5, 2) == pg.shard_layout(6, 2, 3)[1]
+    e.close()
+    with pytest.raises(pg.EngineError):      # ... which must not empty the upper shard
+        pg.Engine(gpu_lib, n_chains=4, n_chains_variational=1, seed=1, rank=0, world_size=4, **pg.Funnel(4).engine_config())
     e = pg.Engine(gpu_lib, n_chains=6, n_chains_variational=3, seed=1, **pg.toy_mvn_target(4).engine_config())
     with pytest.raises(pg.EngineError):      # a Gaussian reference needs an InterpolatingPath (FUNNEL, GMM)
         e.set_variational(np.zeros(4), np.ones(4))

@@ -28,6 +28,9 @@ CASES = {
     # two legs: 11 chains, targets 5 and 6 — on one shard for world 2 (1-6 | 7-11) and world 3 (1-4 | 5-8 | 9-11)
     "two_legs_gmm_gaussian_n11": dict(target=pg.eight_mode_mixture(6, 3.0), explorer=pg.AutoMALA(), n_chains=6, n_chains_variational=5,
                                       variational=pg.GaussianReference(first_tuning_round=2), n_rounds=5, seed=9),
+    # equal legs on two shards: the balanced boundary 5 | 6 falls between the targets, chain 6 joins the lower shard (1-6 | 7-10)
+    "two_legs_funnel_slice_n10": dict(target=pg.Funnel(8), explorer=pg.SliceSampler(), n_chains=5, n_chains_variational=5,
+                                      variational=pg.GaussianReference(first_tuning_round=3), n_rounds=5, seed=10),
     "toy300_automala_n6_mem": dict(target=pg.toy_mvn_target(300), explorer=pg.AutoMALA(), n_chains=6, n_rounds=4, seed=7),
 }
 

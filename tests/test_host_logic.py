@@ -251,3 +251,24 @@ def test_adaptation_without_swap_statistics():
     pt = adapt(pt, rr)
     assert pg.global_barrier(pt) == pytest.approx(0.5 * 4)
     pt.close()
+
+
+def test_shard_layout_keeps_both_target_chains_together():
+    """Engine rule for two legs (pgn_local_range): balanced LoadBalance blocks, except that chain n_var + 1 joins chain
+    n_var's shard when a block boundary would separate the two target chains."""
+    for n in range(2, 40):
+        for world in range(1, min(n, 9) + 1):
+            plain = pg.shard_layout(n, world)
+            assert plain == [(pg.LoadBalance(r, world, n).my_first_global_idx(), pg.LoadBalance(r, world, n).my_load())
+                             for r in range(1, world + 1)]
+            for nv in range(1, n):
+                try:
+                    lay = pg.shard_layout(n, world, nv)
+                except ValueError:
+                    assert any(f + c - 1 == nv and plain[r + 1][1] < 2 for r, (f, c) in enumerate(plain[:-1]))
+                    continue
+                assert lay[0][0] == 1 and sum(c for _, c in lay) == n and all(c >= 1 for _, c in lay)
+                assert all(lay[r][0] + lay[r][1] == lay[r + 1][0] for r in range(world - 1))          # contiguous, ordered
+                owner = [r for r, (f, c) in enumerate(lay) if f <= nv < f + c]
+                assert len(owner) == 1 and lay[owner[0]][0] <= nv + 1 < lay[owner[0]][0] + lay[owner[0]][1]
+                assert sum(a != b for a, b in zip(lay, plain)) in (0, 2)
