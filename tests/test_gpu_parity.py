@@ -122,6 +122,9 @@ CASES = {
     "two_legs_ising5": dict(target=pg.IsingLogPotential(0.8, 5), n_chains=5, n_chains_variational=4, n_rounds=7, seed=8),
     "two_legs_never_activated": dict(target=pg.Funnel(8), explorer=pg.AutoMALA(), n_chains=4, n_chains_variational=4,
                                      variational=pg.GaussianReference(first_tuning_round=99), n_rounds=6, seed=9),
+    "two_legs_gmm128_automala_gaussian_n96": dict(target=pg.eight_mode_mixture(128, 8.0), explorer=pg.AutoMALA(), n_chains=48,
+                                                  n_chains_variational=48, variational=pg.GaussianReference(first_tuning_round=3),
+                                                  n_rounds=6, seed=12),
     "single_chain": dict(target=pg.toy_mvn_target(4), explorer=pg.SliceSampler(), n_chains=1, n_rounds=5, seed=1),
     "two_chains": dict(target=pg.toy_mvn_target(2), explorer=pg.AutoMALA(), n_chains=2, n_rounds=6, seed=8),
 }
@@ -477,6 +480,35 @@ def test_variational_entry_points_match_the_oracle(gpu_lib, oracle_lib):
         np.testing.assert_allclose(lp[0], ref0, rtol=1e-12)
         np.testing.assert_allclose(g[0], -(x[0] - mean) / sd ** 2, rtol=1e-12)
         assert not np.array_equal(res[0][0][:5], res[0][5][:5]) and res[0][0][5] == res[0][5][5]         # beta = 1: the target alone
+
+
+def test_two_legs_at_c3_width(gpu_lib):
+    """BASELINE config 3's ladder as TWO legs of 512 chains (GMM d = 128, autoMALA, GaussianReference from round 3): too large
+    for the oracle, so size-independent properties — every scan's index process is a permutation, both partners log the same
+    decision, the pair between the two target chains always swaps with log ratio 0, references and targets are visited
+    (tempered restarts > 0), the fitted reference is finite, and a second run is bit-identical."""
+    kw = dict(target=pg.eight_mode_mixture(128, 8.0), explorer=pg.AutoMALA(), n_chains=512, n_chains_variational=512,
+              variational=pg.GaussianReference(first_tuning_round=3), n_rounds=6, seed=1,
+              record=[pg.index_process, pg.swap_trace, pg.round_trip], engine_lib=gpu_lib)
+    pt = pg.pigeons(**kw)
+    rr, n, nv = pt.reduced_recorders, 1024, 512
+    ip = rr.index_process
+    assert ip.shape == (64, n) and np.array_equal(np.sort(ip, axis=1), np.broadcast_to(np.arange(1, n + 1), ip.shape))
+    for s in range(ip.shape[0]):
+        even = (s + 1) % 2 == 0
+        c = np.arange(1, n + 1)
+        partner = np.clip(c + np.where((c % 2 == 0) == even, 1, -1), 1, n)
+        assert np.array_equal(rr.swap_accept[s], rr.swap_accept[s][partner - 1])
+        if partner[nv - 1] == nv + 1:
+            assert rr.swap_accept[s, nv - 1] == 1 and rr.swap_lr[s, nv - 1] == 0.0 and rr.swap_lr[s, nv] == 0.0
+    v = pt.inputs.variational
+    assert v.mean is not None and np.all(np.isfinite(v.mean)) and np.all(v.standard_deviation > 0)
+    assert isinstance(pt.shared.tempering, pg.StabilizedPT) and pg.global_barrier_variational(pt) > 0
+    again = pg.pigeons(**kw)
+    assert np.array_equal(again.reduced_recorders.index_process, ip)
+    assert np.array_equal(again.reduced_recorders.online_mean, rr.online_mean)
+    assert np.array_equal(pg.tempering_parameters(again.shared.tempering), pg.tempering_parameters(pt.shared.tempering))
+    pt.close(); again.close()
 
 
 def test_two_legs_refuse_what_they_cannot_run(gpu_lib):
