@@ -59,6 +59,11 @@ extern "C" {
 #define PGN_TARGET_TEST_SWAPPER 6 /* src/swap/pair_swapper.jl:100-149                                             */
 #define PGN_TARGET_MIXED 7        /* product of Bernoulli, Binomial and Normal coordinates: the mixed Bool / Integer /
                                      Float state of test/test_slice_sampler.jl:56-75 (SliceSampler.jl:65-86,136-142,189) */
+#define PGN_TARGET_UNID 8         /* the unidentifiable product of test/test_DistributionLogPotential.jl:7-21 (and of
+                                     toy_turing_unid_target, ext/PigeonsDynamicPPLExt/toy_examples.jl:17-19): dim 2,
+                                     l(p1, p2) = s log(p1 p2) + (n - s) log1p(-p1 p2) on [0,1]^2, -Inf outside;
+                                     reference Uniform(0,1)^2; p[0] = n_trials n, p[1] = n_successes s; initial state
+                                     (0.5, 0.5); SliceSampler only (no analytic gradient is built) */
 
 /* ---- explorers ----------------------------------------------------------- */
 #define PGN_EXPLORER_NONE 0             /* TestSwapper: step! is a no-op (pair_swapper.jl:140-141) */

@@ -54,6 +54,7 @@ const PGN_TARGET_ISING = 4
 const PGN_TARGET_LOGREG = 5
 const PGN_TARGET_TEST_SWAPPER = 6
 const PGN_TARGET_MIXED = 7
+const PGN_TARGET_UNID = 8
 
 const PGN_EXPLORER_NONE = 0
 const PGN_EXPLORER_TOY = 1

@@ -215,6 +215,8 @@ struct Engine {
       case PGN_TARGET_ISING:
         return 0.0 * (double)r.ising_S;   // IsingLogPotential(0.0, L) (examples/ising.jl:74,77)
       case PGN_TARGET_MIXED: return mixed_density(x, 0);
+      case PGN_TARGET_UNID:   // logpdf(product_distribution([Uniform(), Uniform()]), x): 0 inside the unit square, -Inf outside
+        return ((x[0] >= 0.0 && x[0] <= 1.0) ? 0.0 : -INF) + ((x[1] >= 0.0 && x[1] <= 1.0) ? 0.0 : -INF);
       default: return QNAN;
     }
   }
@@ -343,6 +345,11 @@ struct Engine {
       case PGN_TARGET_ISING:
         return cfg.p[0] * (double)r.ising_S;   // examples/ising.jl:74
       case PGN_TARGET_MIXED: return mixed_density(x, 1);
+      case PGN_TARGET_UNID: {   // unid_log_potential, test/test_DistributionLogPotential.jl:8-13
+        if (!((x[0] >= 0.0 && x[0] <= 1.0) && (x[1] >= 0.0 && x[1] <= 1.0))) return -INF;
+        const double pr = x[0] * x[1];
+        return cfg.p[1] * log_(pr) + (cfg.p[0] - cfg.p[1]) * log1p_(-pr);
+      }
       default: return QNAN;
     }
   }
@@ -496,6 +503,9 @@ struct Engine {
         r.rows.assign(L(), 0u);
         ising_recompute(r);
         break;
+      case PGN_TARGET_UNID:        // test/test_DistributionLogPotential.jl:14
+        r.x.assign(dd, 0.5);
+        break;
       default: break;              // zeros (dimensional-analysis.jl:24)
     }
   }
@@ -530,6 +540,10 @@ struct Engine {
         ising_recompute(r);
         break;
       }
+      case PGN_TARGET_UNID:        // rand!(rng, product_distribution([Uniform(), Uniform()]), x)
+        for (int c = 0; c < dd; ++c) r.x[c] = uniform_at(r.rng, r.ctr + c);
+        r.ctr += dd;
+        break;
       case PGN_TARGET_MIXED: {     // rand! of the product reference: one tick per Bool / Float coordinate, n per Binomial
         const int n = (int)cfg.p[2];
         const double p0 = means[8], q0 = means[9];
@@ -1148,6 +1162,10 @@ int orc_create(const pgn_config* cfg, orc_handle** out, char** err) {
     E.means.assign(cfg->means, cfg->means + (size_t)cfg->n_modes * cfg->dim);
     E.log_w.assign(cfg->log_weights, cfg->log_weights + cfg->n_modes);
   }
+  if (cfg->target_kind == PGN_TARGET_UNID && (cfg->dim != 2 || !(cfg->p[0] >= cfg->p[1]) || cfg->p[1] < 0)) {
+    delete h;
+    return fail(err, PGN_ERR_INVALID, "UNID: dim == 2 and 0 <= n_successes <= n_trials");
+  }
   if (cfg->target_kind == PGN_TARGET_MIXED) {
     if (!cfg->means || cfg->n_modes != 10 + (int)cfg->p[2] + 1 || cfg->p[0] < 0 || cfg->p[1] < 0 ||
         cfg->p[0] + cfg->p[1] > cfg->dim || cfg->p[2] < 1) {
@@ -1190,6 +1208,8 @@ int orc_set_explorer(orc_handle* h, const pgn_explorer_params* ep, char** err) {
   if (ep->n_mix < 0 || ep->n_mix > PGN_MAX_MIX) return fail(err, PGN_ERR_INVALID, "n_mix out of range");
   if ((ep->kind == PGN_EXPLORER_COMPOSE || ep->kind == PGN_EXPLORER_MIX) && (ep->n_steps < 1 || ep->n_steps > PGN_MAX_MIX))
     return fail(err, PGN_ERR_INVALID, "Compose / Mix: n_steps out of range");
+  if (E.cfg.target_kind == PGN_TARGET_UNID && ep->kind != PGN_EXPLORER_SLICE)
+    return fail(err, PGN_ERR_INVALID, "UNID: SliceSampler only");
   E.ep = *ep;
   E.have_std = ep->std_devs != nullptr;
   if (E.have_std) E.std_devs.assign(ep->std_devs, ep->std_devs + E.cfg.dim);
@@ -1330,7 +1350,7 @@ int orc_logdensity_and_gradient(orc_handle* h, const double* x, int32_t n_points
                                 double* logdens, double* grad, char** err) {
   Engine& E = h->E;
   const int d = E.d();
-  if (E.cfg.target_kind == PGN_TARGET_ISING || E.cfg.target_kind == PGN_TARGET_TEST_SWAPPER)
+  if (E.cfg.target_kind == PGN_TARGET_ISING || E.cfg.target_kind == PGN_TARGET_TEST_SWAPPER || E.cfg.target_kind == PGN_TARGET_UNID)
     return fail(err, PGN_ERR_INVALID, "target has no gradient");
   Replica r;
   r.chain = 1;
@@ -1354,6 +1374,7 @@ int orc_test_math(int32_t device, int32_t op, const double* in, double* out, int
       case 4: out[i] = uniform_at(g, (uint64_t)in[i]); break;
       case 5: out[i] = exponential_at(g, (uint64_t)in[i]); break;
       case 6: out[i] = logaddexp_(in[2 * i], in[2 * i + 1]); break;
+      case 7: out[i] = log1p_(in[i]); break;
       default: out[i] = QNAN;
     }
   }

@@ -19,7 +19,7 @@ from .pt import (PT, ChecksFailed, GaussianReference, Inputs, Iterators, NonReve
                  swap_trace, traces)
 from .recorders import ReducedRecorders                                            # noqa: F401
 from .targets import (Funnel, GaussianMixture, IsingLogPotential, LogisticRegression, MixedProduct,  # noqa: F401
-                      ScaledPrecisionNormalPath, TestSwapper, eight_mode_mixture,
+                      ScaledPrecisionNormalPath, TestSwapper, UnidentifiableProduct, eight_mode_mixture,
                       synthetic_logistic_regression, toy_mvn_target)
 from .tempering import (MonotoneCubic, Schedule, communication_barriers, equally_spaced_schedule,  # noqa: F401
                         optimal_schedule, rejections)

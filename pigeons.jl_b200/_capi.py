@@ -31,6 +31,7 @@ ERR_NAMES = {
 
 TARGET_TOY_MVN, TARGET_FUNNEL, TARGET_GMM, TARGET_ISING, TARGET_LOGREG, TARGET_TEST_SWAPPER = 1, 2, 3, 4, 5, 6
 TARGET_MIXED = 7
+TARGET_UNID = 8
 EXPLORER_NONE, EXPLORER_TOY, EXPLORER_SLICE, EXPLORER_AUTOMALA, EXPLORER_ISING_METROPOLIS, EXPLORER_MALA = 0, 1, 2, 3, 4, 5
 EXPLORER_COMPOSE, EXPLORER_MIX = 6, 7
 MAX_MIX = 4

@@ -100,6 +100,7 @@ void* select_scan_kernel(const pgn_handle* h) {
     case PGN_TARGET_FUNNEL: return h->var_active ? vec_scan_kernel_funnel_var(h->cpl, ex) : vec_scan_kernel_funnel(h->cpl, ex);
     case PGN_TARGET_GMM: return h->var_active ? vec_scan_kernel_gmm_var(h->cpl, ex) : vec_scan_kernel_gmm(h->cpl, ex);
     case PGN_TARGET_MIXED: return vec_scan_kernel_mixed(h->cpl, ex);
+    case PGN_TARGET_UNID: return vec_scan_kernel_unid(h->cpl, ex);
     case PGN_TARGET_ISING: return ex == PGN_EXPLORER_ISING_METROPOLIS ? ising_scan_kernel() : nullptr;
     case PGN_TARGET_TEST_SWAPPER: return ex == PGN_EXPLORER_NONE ? test_swapper_scan_kernel() : nullptr;
     default: return nullptr;
@@ -163,6 +164,7 @@ void launch_eval_points(pgn_handle* h, const Params& P, const double* xs, const 
       else launch_eval_points_gmm(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad);
       break;
     case PGN_TARGET_MIXED: launch_eval_points_mixed(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
+    case PGN_TARGET_UNID: launch_eval_points_unid(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
     default: throw CudaError{PGN_ERR_INVALID, "unsupported target"};
   }
 }
@@ -208,6 +210,10 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
       break;
     }
     case PGN_TARGET_TEST_SWAPPER: break;
+    case PGN_TARGET_UNID:
+      if (cfg->dim != 2 || !(cfg->p[0] >= cfg->p[1]) || cfg->p[1] < 0)
+        return fail(err, PGN_ERR_INVALID, "UNID: dim == 2 and 0 <= n_successes <= n_trials");
+      break;
     case PGN_TARGET_MIXED:
       if (cfg->dim < 1 || cfg->dim > 128) return fail(err, PGN_ERR_INVALID, "MIXED: 1 <= dim <= 128 (register-resident kernels only)");
       if (!cfg->means || cfg->p[2] < 1 || cfg->n_modes != 10 + (int)cfg->p[2] + 1 || cfg->p[0] < 0 || cfg->p[1] < 0 ||
@@ -378,6 +384,8 @@ int pgn_set_explorer(pgn_handle* h, const pgn_explorer_params* ep, char** err) {
   if (ep->n_mix < 0 || ep->n_mix > PGN_MAX_MIX) return fail(err, PGN_ERR_INVALID, "n_mix out of range");
   if (ep->n_mix > 1 && ep->kind != PGN_EXPLORER_AUTOMALA)
     return fail(err, PGN_ERR_INVALID, "the device mixes autoMALA kernels only (no CPU fallback for other mixtures)");
+  if (h->cfg.target_kind == PGN_TARGET_UNID && ep->kind != PGN_EXPLORER_SLICE)
+    return fail(err, PGN_ERR_INVALID, "UNID: SliceSampler only");
   const bool program = ep->kind == PGN_EXPLORER_COMPOSE || ep->kind == PGN_EXPLORER_MIX;
   if ((ep->n_mix > 1 || program) && (h->cfg.target_kind == PGN_TARGET_LOGREG || h->cpl == 0 || h->force_mem))
     return fail(err, PGN_ERR_INVALID, "Mix / Compose explorers run on the register-resident scan kernels only (d <= 128)");
@@ -417,6 +425,11 @@ int pgn_init_replicas(pgn_handle* h, char** err) {
     h->rt_state.upload(rt.data(), nl, h->stream);
     h->rng_ctr.upload(ctr.data(), nl, h->stream);
     CUDA_CHECK(cudaMemsetAsync(h->x.p, 0, std::max<size_t>(1, (size_t)nl * h->d_pad) * sizeof(double), h->stream));
+    if (h->cfg.target_kind == PGN_TARGET_UNID) {   // initialization = [0.5, 0.5] (test/test_DistributionLogPotential.jl:14)
+      std::vector<double> x0((size_t)nl * h->d_pad, 0.0);
+      for (int i = 0; i < nl; ++i) x0[(size_t)i * h->d_pad] = x0[(size_t)i * h->d_pad + 1] = 0.5;
+      h->x.upload(x0.data(), x0.size(), h->stream);
+    }
     if (h->cfg.target_kind == PGN_TARGET_TOY_MVN) {
       Params P;
       fill_params(h, P);
@@ -771,7 +784,7 @@ int pgn_log_potential(pgn_handle* h, const double* x, int32_t n_points, const do
     Params P;
     fill_params(h, P);
     switch (h->cfg.target_kind) {
-      case PGN_TARGET_TOY_MVN: case PGN_TARGET_FUNNEL: case PGN_TARGET_GMM: case PGN_TARGET_MIXED:
+      case PGN_TARGET_TOY_MVN: case PGN_TARGET_FUNNEL: case PGN_TARGET_GMM: case PGN_TARGET_MIXED: case PGN_TARGET_UNID:
         launch_eval_points(h, P, dx.p, db.p, n_points, dout.p, nullptr, nullptr); break;
       case PGN_TARGET_ISING: launch_ising_lp((n_points + 3) / 4, 128, h->stream, P, dx.p, db.p, n_points, dout.p); break;
       default: return fail(err, PGN_ERR_INVALID, "unsupported target");

@@ -443,6 +443,14 @@ struct VecChain {
       }
       warp_sum_n<2>(v);
       a0 = v[0]; a1 = v[1];
+    } else if (TK == PGN_TARGET_UNID) {   // unid_log_potential on the unit square, Uniform(0,1)^2 reference (warp-uniform)
+      const double x0 = __shfl_sync(PGN_FULL_MASK, xx[0], 0), x1 = __shfl_sync(PGN_FULL_MASK, xx[0], 1);
+      const bool in0 = x0 >= 0.0 && x0 <= 1.0, in1 = x1 >= 0.0 && x1 <= 1.0;
+      a0 = (in0 ? 0.0 : -PGN_INF) + (in1 ? 0.0 : -PGN_INF);
+      if (in0 && in1) {
+        const double pr = x0 * x1;
+        a1 = P->p[1] * log_(pr) + (P->p[0] - P->p[1]) * log1p_<false>(-pr);
+      } else a1 = -PGN_INF;
     } else if (TK == PGN_TARGET_MIXED) {
       double v[2] = {0.0, 0.0};
 #pragma unroll
@@ -491,7 +499,7 @@ struct VecChain {
   // lane partial that rides along in the same butterfly (in: partial, out: sum)
   __device__ void eval_grad(const double (&xx)[CPL], double b, double& a0, double& a1, double (&g)[CPL], double& extra) {
     n_points += 1;
-    if (TK == PGN_TARGET_MIXED) {   // discrete coordinates: no gradient-based explorer is ever selected for this target
+    if (TK == PGN_TARGET_MIXED || TK == PGN_TARGET_UNID) {   // no gradient-based explorer is ever selected for these targets
       a0 = a1 = 0.0;
 #pragma unroll
       for (int k = 0; k < CPL; ++k) g[k] = 0.0;
@@ -607,6 +615,13 @@ struct VecChain {
         } else x[k] = P->p[3] * normal_at(rng, t);
       }
       rng.ctr += (unsigned long long)(nb + ni * n + (d - nb - ni));
+      return;
+    }
+    if (TK == PGN_TARGET_UNID) {   // rand!(rng, product_distribution([Uniform(), Uniform()]), x)
+#pragma unroll
+      for (int k = 0; k < CPL; ++k)
+        if (valid(k)) x[k] = uniform_at(rng, rng.ctr + (unsigned long long)(k * 32 + lane));
+      rng.ctr += (unsigned long long)d;
       return;
     }
 #pragma unroll

@@ -45,6 +45,7 @@ __global__ void test_math_kernel(int op, const double* in, double* out, long lon
     case 4: r = uniform_at(g, (unsigned long long)in[i]); break;
     case 5: r = exponential_at(g, (unsigned long long)in[i]); break;
     case 6: r = logaddexp_(in[2 * i], in[2 * i + 1]); break;
+    case 7: r = log1p_<false>(in[i]); break;
     default: r = PGN_NAN;
   }
   out[i] = r;
@@ -146,12 +147,14 @@ void* vec_plain_kernel_toy(int cpl, int ex);    void* vec_team_kernel_toy(int cp
 void* vec_plain_kernel_funnel(int cpl, int ex); void* vec_team_kernel_funnel(int cpl, int ex);
 void* vec_plain_kernel_gmm(int cpl, int ex);    void* vec_team_kernel_gmm(int cpl, int ex);
 void* vec_plain_kernel_mixed(int cpl, int ex);
+void* vec_plain_kernel_unid(int cpl, int ex);
 void* vec_plain_kernel_funnel_var(int cpl, int ex); void* vec_team_kernel_funnel_var(int cpl, int ex);
 void* vec_plain_kernel_gmm_var(int cpl, int ex);    void* vec_team_kernel_gmm_var(int cpl, int ex);
 static bool is_team_explorer(int ex) { return ex == PGN_EXPLORER_AUTOMALA || ex == PGN_EXPLORER_COMPOSE || ex == PGN_EXPLORER_MIX; }
 void* vec_scan_kernel_toy(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_toy(cpl, ex) : vec_plain_kernel_toy(cpl, ex); }
 void* vec_scan_kernel_funnel(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_funnel(cpl, ex) : vec_plain_kernel_funnel(cpl, ex); }
 void* vec_scan_kernel_mixed(int cpl, int ex) { return ex == PGN_EXPLORER_SLICE ? vec_plain_kernel_mixed(cpl, ex) : nullptr; }
+void* vec_scan_kernel_unid(int cpl, int ex) { return ex == PGN_EXPLORER_SLICE ? vec_plain_kernel_unid(cpl, ex) : nullptr; }
 void* vec_scan_kernel_gmm(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_gmm(cpl, ex) : vec_plain_kernel_gmm(cpl, ex); }
 void* vec_scan_kernel_funnel_var(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_funnel_var(cpl, ex) : vec_plain_kernel_funnel_var(cpl, ex); }
 void* vec_scan_kernel_gmm_var(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_gmm_var(cpl, ex) : vec_plain_kernel_gmm_var(cpl, ex); }

@@ -1,13 +1,13 @@
 // pgn_scan_vec.cu — the register-resident scan kernels of one vector-state target family.
 // Compiled once per (target family, part) by csrc/Makefile:
-//   -DPGN_TK=1|2|3|7 PGN_TARGET_TOY_MVN | PGN_TARGET_FUNNEL | PGN_TARGET_GMM | PGN_TARGET_MIXED (SliceSampler only)
+//   -DPGN_TK=1|2|3|7|8 PGN_TARGET_TOY_MVN | PGN_TARGET_FUNNEL | PGN_TARGET_GMM | PGN_TARGET_MIXED, PGN_TARGET_UNID (SliceSampler only)
 //   -DPGN_PART=0     ToyExplorer / SliceSampler / MALA kernels + the parity entry points
 //   -DPGN_PART=1     autoMALA team kernels (AutoMALA; Compose / Mix programs of ToyExplorer, SliceSampler, MALA, AutoMALA)
 // so that the heavy template instantiations build in parallel.
 #include "pgn_host.hpp"
 
 #ifndef PGN_TK
-#error "compile with -DPGN_TK=1|2|3|7"
+#error "compile with -DPGN_TK=1|2|3|7|8"
 #endif
 #ifndef PGN_PART
 #error "compile with -DPGN_PART=0|1"
@@ -30,13 +30,13 @@ void* plain_kernel_for(int ex) {
     case PGN_EXPLORER_TOY: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_TOY, PGN_VAR != 0>>();
 #endif
     case PGN_EXPLORER_SLICE: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_SLICE, PGN_VAR != 0>>();
-#if PGN_TK != 7
+#if PGN_TK < 7
     case PGN_EXPLORER_MALA: return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_MALA, PGN_VAR != 0>>();
 #endif
     default: return nullptr;
   }
 }
-#if PGN_TK != 7
+#if PGN_TK < 7
 template <int CPL>
 void leapfrog_launch(int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
                      const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out) {
@@ -73,6 +73,8 @@ void* team_kernel_for(int ex) {
 #define PGN_FAMILY(name) name##_funnel
 #elif PGN_TK == 3
 #define PGN_FAMILY(name) name##_gmm
+#elif PGN_TK == 8
+#define PGN_FAMILY(name) name##_unid
 #else
 #define PGN_FAMILY(name) name##_mixed
 #endif
@@ -95,7 +97,7 @@ void PGN_FAMILY(launch_eval_points)(int cpl, int grid, int block, size_t smem, c
     default: throw CudaError{PGN_ERR_INVALID, "unsupported dimension"};
   }
 }
-#if PGN_TK != 7
+#if PGN_TK < 7
 void PGN_FAMILY(launch_leapfrog)(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
                                  const double* ps, const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out) {
   switch (cpl) {

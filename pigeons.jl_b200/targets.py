@@ -205,6 +205,40 @@ class MixedProduct(Target):
 
 
 @dataclass
+class UnidentifiableProduct(Target):
+    """The unidentifiable two-parameter model the reference's own tests use (test/test_DistributionLogPotential.jl:7-21
+    in the constrained parametrisation; toy_turing_unid_target, ext/PigeonsDynamicPPLExt/toy_examples.jl:17-19):
+    n_successes ~ Binomial(n_trials, p1 p2), p1, p2 ~ Uniform(0, 1); l(p1, p2) = s log(p1 p2) + (n - s) log1p(-p1 p2) on the
+    unit square, -Inf outside; the reference is the Uniform(0,1)^2 prior.  SliceSampler only."""
+    n_trials: int = 100
+    n_successes: Optional[int] = None
+
+    def __post_init__(self):
+        if self.n_successes is None:
+            self.n_successes = math.ceil(self.n_trials / 2)
+
+    @property
+    def dim(self):
+        return 2
+
+    def default_explorer(self):
+        from .explorers import SliceSampler
+        return SliceSampler()
+
+    def engine_config(self):
+        return dict(target_kind=_capi.TARGET_UNID, dim=2, p=(float(self.n_trials), float(self.n_successes)))
+
+    def analytic_lognormalization(self) -> float:
+        """log of int_0^1 int_0^1 (p1 p2)^s (1 - p1 p2)^(n - s) dp1 dp2 = log( sum_{k >= s+1}^{n+1} 1/k * B(s+1, n-s+1) ... ) — by
+        substitution u = p1 p2 (density -log u on (0,1)): Z = int_0^1 u^s (1-u)^(n-s) (-log u) du, evaluated by quadrature."""
+        from scipy import integrate, special
+        s, n = self.n_successes, self.n_trials
+        logb = special.betaln(s + 1, n - s + 1)
+        # E_{u ~ Beta(s+1, n-s+1)}[-log u] = digamma(n + 2) - digamma(s + 1)
+        return float(logb + math.log(special.digamma(n + 2) - special.digamma(s + 1)))
+
+
+@dataclass
 class IsingLogPotential(Target):
     """examples/ising.jl:6-117: l(state) = beta * sum_<ij> s_i s_j on an L x L
     torus; reference = same with beta = 0 (i.i.d. Bernoulli(1/2) spins)."""

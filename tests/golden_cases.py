@@ -39,6 +39,8 @@ GOLDEN_CASES = {
                                                        n_rounds=7, seed=4),
     "two_legs_funnel8_slice_gaussian_r7": lambda: dict(target=pg.Funnel(8), explorer=pg.SliceSampler(), n_chains=5, n_chains_variational=4,
                                                        variational=pg.GaussianReference(first_tuning_round=3), n_rounds=7, seed=3),
+    # test/test_DistributionLogPotential.jl:7-21 (global barrier 1.39 +- 0.1 in the reference)
+    "unid_dlp_multivariate_n4_r10": lambda: dict(target=pg.UnidentifiableProduct(100, 50), n_chains=4, n_rounds=10, seed=1),
     "ising5_n10_r8": lambda: dict(target=pg.IsingLogPotential(1.0, 5), n_chains=10, n_rounds=8, seed=1),
 }
 

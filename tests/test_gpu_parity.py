@@ -119,6 +119,15 @@ CASES = {
     "one_leg_variational_gmm1": dict(target=pg.GaussianMixture(means=[[1.0]], reference_sigma=1.0), explorer=pg.SliceSampler(),
                                      n_chains=0, n_chains_variational=6, variational=pg.GaussianReference(first_tuning_round=2),
                                      n_rounds=8, seed=7),
+    # test/test_DistributionLogPotential.jl:23-31: N(3,1) against a fixed reference N(-3,1) (never re-fitted)
+    "dlp_univariate_fixed_gaussian_reference": dict(
+        target=pg.GaussianMixture(means=[[3.0]], reference_sigma=1.0), explorer=pg.SliceSampler(), n_chains=0, n_chains_variational=8,
+        variational=pg.GaussianReference(first_tuning_round=10 ** 9, mean=np.array([-3.0]), standard_deviation=np.array([1.0])),
+        n_rounds=8, seed=1),
+    # the reference's own test targets: test/test_DistributionLogPotential.jl:7-21 and test/test_two_legs.jl
+    "unid_dlp_multivariate": dict(target=pg.UnidentifiableProduct(100, 50), n_chains=4, n_rounds=10, seed=1),
+    "unid_two_legs_100000": dict(target=pg.UnidentifiableProduct(100000), n_chains=8, n_chains_variational=7,
+                                 variational=pg.GaussianReference(first_tuning_round=99), n_rounds=9, seed=1),
     "two_legs_ising5": dict(target=pg.IsingLogPotential(0.8, 5), n_chains=5, n_chains_variational=4, n_rounds=7, seed=8),
     "two_legs_never_activated": dict(target=pg.Funnel(8), explorer=pg.AutoMALA(), n_chains=4, n_chains_variational=4,
                                      variational=pg.GaussianReference(first_tuning_round=99), n_rounds=6, seed=9),
@@ -211,6 +220,7 @@ def test_device_numerics_bit_identical(gpu_lib, oracle_lib):
         4: np.arange(0, 40000, dtype=np.float64),
         5: np.arange(0, 40000, dtype=np.float64),
         6: rng.normal(0, 30, 40000),
+        7: np.concatenate([-rng.uniform(0, 1, 20000), rng.uniform(0, 5, 10000), rng.normal(0, 1e-9, 10000), [0.0, -1.0, -0.5, 1e-300, -1e-17]]),
     }
     for op, v in xs.items():
         a = gpu_lib.test_math(op, v, seed=12345678901, replica_index=17)

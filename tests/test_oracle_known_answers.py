@@ -111,6 +111,50 @@ def test_global_barrier_two_normals_surrogate(oracle_lib):
     assert 1.0 < pg.global_barrier(pt) < 4.0
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_global_barrier_dlp_univariate(seed, oracle_lib):
+    """test/test_DistributionLogPotential.jl:23-31 ('DLP: Univariate'), the reference's own number: target N(3, 1),
+    reference N(-3, 1), 8 chains, default 10 rounds -> global barrier 3.15 +- 0.1.  The path is built from the one-component
+    mixture N(3, 1) and a FIXED Gaussian reference N(-3, 1) installed on a single variational leg (never re-fitted)."""
+    var = pg.GaussianReference(first_tuning_round=10 ** 9, mean=np.array([-3.0]), standard_deviation=np.array([1.0]))
+    pt = pg.pigeons(target=pg.GaussianMixture(means=[[3.0]], reference_sigma=1.0), explorer=pg.SliceSampler(), n_chains=0,
+                    n_chains_variational=8, variational=var, n_rounds=10, seed=seed, engine_lib=oracle_lib)
+    assert abs(pg.global_barrier(pt) - 3.15) < 0.1
+    assert abs(pg.stepping_stone(pt)) < 0.15          # both ends normalised
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_global_barrier_dlp_multivariate(seed, oracle_lib):
+    """test/test_DistributionLogPotential.jl:7-21 ('DLP: Multivariate'), the reference's own number: the unidentifiable
+    product l(p1, p2) = 50 log(p1 p2) + 50 log1p(-p1 p2) against the Uniform(0,1)^2 reference, 4 chains, default explorer
+    (SliceSampler) and rounds -> global barrier 1.39 +- 0.1.  Also: the stepping stone against the closed form
+    log Z = log B(s+1, n-s+1) + log(psi(n+2) - psi(s+1))."""
+    t = pg.UnidentifiableProduct(100, 50)
+    pt = pg.pigeons(target=t, n_chains=4, seed=seed, engine_lib=oracle_lib)
+    assert abs(pg.global_barrier(pt) - 1.39) < 0.1
+    assert abs(pg.stepping_stone(pt) - t.analytic_lognormalization()) < 0.3
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_two_legs_schedule_adaptation(seed, oracle_lib):
+    """test/test_two_legs.jl:1-28, the reference's own numbers: toy_turing_unid_target() (n_trials = 100000) in the constrained
+    parametrisation, 8 + 7 chains with a never-activated GaussianReference, 10 rounds: the global barrier of the single-leg run
+    and of BOTH legs of the two-leg run are 3.5 within rtol 0.1."""
+    t = pg.UnidentifiableProduct(100000)
+    n_rounds = 10
+    two = pg.pigeons(target=t, n_chains=8, n_chains_variational=7, variational=pg.GaussianReference(first_tuning_round=n_rounds + 1),
+                     n_rounds=n_rounds, seed=seed, engine_lib=oracle_lib)
+    one = pg.pigeons(target=t, n_chains=8, n_chains_variational=0, variational=pg.GaussianReference(first_tuning_round=n_rounds + 1),
+                     n_rounds=n_rounds, seed=seed, engine_lib=oracle_lib)
+    truth = 3.5
+    for approx in (pg.global_barrier(one), pg.global_barrier(two), pg.global_barrier_variational(two)):
+        assert abs(approx - truth) <= 0.1 * truth, approx
+    # 'Issue #290': targets and references are different chains, one of each per leg
+    n, nv = 15, 7
+    refs, tgts = {1, n}, {nv, nv + 1}
+    assert not (refs & tgts) and min(tgts) <= nv < max(tgts) and min(refs) <= nv < max(refs)
+
+
 def test_funnel_normalisation(oracle_lib):
     """Both ends of the funnel path are normalised densities: log(Z1/Z0) = 0."""
     pt = pg.pigeons(target=pg.Funnel(8), explorer=pg.AutoMALA(), n_chains=10, n_rounds=11, engine_lib=oracle_lib)

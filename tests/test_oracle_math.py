@@ -61,6 +61,16 @@ def test_logaddexp(oracle_lib):
     assert oracle_lib.test_math(6, np.array([2.0, -np.inf]))[0] == 2.0
 
 
+def test_log1p(oracle_lib):
+    """log1p_ (Kahan: log(w) t / (w - 1), w = 1 + t) on (-1, inf): the unidentifiable target evaluates log1p(-p1 p2)."""
+    rng = np.random.default_rng(6)
+    t = np.concatenate([-rng.uniform(0, 1, 4000), rng.uniform(0, 5, 2000), rng.normal(0, 1e-9, 2000)])
+    got = oracle_lib.test_math(7, t)
+    np.testing.assert_allclose(got, np.log1p(t), rtol=5e-16, atol=0)
+    edge = oracle_lib.test_math(7, np.array([0.0, -1.0, 1e-300, -1e-17]))
+    assert edge[0] == 0.0 and edge[1] == -np.inf and edge[2] == 1e-300 and edge[3] == -1e-17
+
+
 def test_philox_known_answers(oracle_lib):
     """Random123 kat_vectors for philox4x32-10."""
     f = oracle_lib.lib.orc_philox
