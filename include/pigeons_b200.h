@@ -279,7 +279,7 @@ int pgn_logdensity_and_gradient(pgn_handle* h, const double* x, int32_t n_points
  * (:45-53), gradient -(x - mean) / sd^2 (:72-80), sample_iid! randn * sd_i + mean_i (:30-37).  mean, sd: [dim] — what
  * update_reference! (:22-28) computed from the target-chain online statistics; mean == NULL switches back to the fixed
  * reference (activate_variational false, :16-18).  Takes effect at the next round.  Vector targets with an
- * InterpolatingPath on the register-resident kernels (FUNNEL, GMM; d <= 128). */
+ * InterpolatingPath on the register-resident kernels (FUNNEL, GMM, UNID; d <= 128). */
 int pgn_set_variational(pgn_handle* h, const double* mean, const double* sd, char** err);
 
 /* hamiltonian_dynamics!(target_log_potential, state, momentum, step_size, n_steps) with the identity preconditioner

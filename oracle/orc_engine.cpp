@@ -1241,7 +1241,8 @@ int orc_set_variational(orc_handle* h, const double* mean, const double* sd, cha
   if (!mean || !sd) { E.var_active = false; return PGN_OK; }
   const int tk = E.cfg.target_kind, d = E.d();
   if (E.n_var() < 1) return fail(err, PGN_ERR_INVALID, "set_variational: n_chains_variational is 0");
-  if (tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM) return fail(err, PGN_ERR_INVALID, "set_variational: FUNNEL and GMM targets");
+  if (tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM && tk != PGN_TARGET_UNID)
+    return fail(err, PGN_ERR_INVALID, "set_variational: FUNNEL, GMM and UNID targets");
   for (int c = 0; c < d; ++c)
     if (!(sd[c] > 0.0) || !std::isfinite(sd[c]) || !std::isfinite(mean[c]))
       return fail(err, PGN_ERR_INVALID, "set_variational: finite means and positive finite standard deviations");

@@ -100,7 +100,7 @@ void* select_scan_kernel(const pgn_handle* h) {
     case PGN_TARGET_FUNNEL: return h->var_active ? vec_scan_kernel_funnel_var(h->cpl, ex) : vec_scan_kernel_funnel(h->cpl, ex);
     case PGN_TARGET_GMM: return h->var_active ? vec_scan_kernel_gmm_var(h->cpl, ex) : vec_scan_kernel_gmm(h->cpl, ex);
     case PGN_TARGET_MIXED: return vec_scan_kernel_mixed(h->cpl, ex);
-    case PGN_TARGET_UNID: return vec_scan_kernel_unid(h->cpl, ex);
+    case PGN_TARGET_UNID: return h->var_active ? vec_scan_kernel_unid_var(h->cpl, ex) : vec_scan_kernel_unid(h->cpl, ex);
     case PGN_TARGET_ISING: return ex == PGN_EXPLORER_ISING_METROPOLIS ? ising_scan_kernel() : nullptr;
     case PGN_TARGET_TEST_SWAPPER: return ex == PGN_EXPLORER_NONE ? test_swapper_scan_kernel() : nullptr;
     default: return nullptr;
@@ -164,7 +164,10 @@ void launch_eval_points(pgn_handle* h, const Params& P, const double* xs, const 
       else launch_eval_points_gmm(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad);
       break;
     case PGN_TARGET_MIXED: launch_eval_points_mixed(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
-    case PGN_TARGET_UNID: launch_eval_points_unid(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad); break;
+    case PGN_TARGET_UNID:
+      if (h->var_active) launch_eval_points_unid_var(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad);
+      else launch_eval_points_unid(h->cpl, grid, wpb * 32, smem, h->stream, P, xs, betas, n, lp, ld, grad);
+      break;
     default: throw CudaError{PGN_ERR_INVALID, "unsupported target"};
   }
 }
@@ -832,8 +835,8 @@ int pgn_set_variational(pgn_handle* h, const double* mean, const double* sd, cha
   if (!mean || !sd) { h->var_active = false; return PGN_OK; }
   const int tk = h->cfg.target_kind, d = h->cfg.dim;
   if (h->cfg.n_chains_variational < 1) return fail(err, PGN_ERR_INVALID, "set_variational: n_chains_variational is 0");
-  if ((tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM) || h->cpl == 0 || h->force_mem)
-    return fail(err, PGN_ERR_INVALID, "set_variational: FUNNEL and GMM targets on the register-resident kernels (d <= 128)");
+  if ((tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM && tk != PGN_TARGET_UNID) || h->cpl == 0 || h->force_mem)
+    return fail(err, PGN_ERR_INVALID, "set_variational: FUNNEL, GMM and UNID targets on the register-resident kernels (d <= 128)");
   for (int c = 0; c < d; ++c)
     if (!(sd[c] > 0.0) || !std::isfinite(sd[c]) || !std::isfinite(mean[c]))
       return fail(err, PGN_ERR_INVALID, "set_variational: finite means and positive finite standard deviations");

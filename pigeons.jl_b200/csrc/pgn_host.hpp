@@ -171,6 +171,7 @@ void* vec_scan_kernel_funnel(int cpl, int ex);
 void* vec_scan_kernel_gmm(int cpl, int ex);
 void* vec_scan_kernel_mixed(int cpl, int ex);
 void* vec_scan_kernel_unid(int cpl, int ex);
+void* vec_scan_kernel_unid_var(int cpl, int ex);
 void* vec_scan_kernel_funnel_var(int cpl, int ex);   // ladders whose variational leg uses a GaussianReference
 void* vec_scan_kernel_gmm_var(int cpl, int ex);
 void launch_var_tables(cudaStream_t s, double* tab, int d, int d_pad);
@@ -199,6 +200,8 @@ void launch_leapfrog_funnel_var(int cpl, int grid, int block, size_t smem, cudaS
                                 const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out);
 void launch_leapfrog_gmm_var(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
                              const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out);
+void launch_eval_points_unid_var(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
+                                 const double* betas, int n, double* lp, double* ld, double* grad);
 void launch_eval_points_unid(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
                              const double* betas, int n, double* lp, double* ld, double* grad);
 void launch_eval_points_mixed(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,

@@ -447,6 +447,14 @@ struct VecChain {
       const double x0 = __shfl_sync(PGN_FULL_MASK, xx[0], 0), x1 = __shfl_sync(PGN_FULL_MASK, xx[0], 1);
       const bool in0 = x0 >= 0.0 && x0 <= 1.0, in1 = x1 >= 0.0 && x1 <= 1.0;
       a0 = (in0 ? 0.0 : -PGN_INF) + (in1 ? 0.0 : -PGN_INF);
+      if constexpr (VAR) {   // variational leg: the Gaussian reference instead of the uniform prior
+        if (var_ref) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) if (valid(k)) acc = acc + ref_term(k, xx[k], 0.0, 0.0);
+          a0 = warp_sum(acc);
+        }
+      }
       if (in0 && in1) {
         const double pr = x0 * x1;
         a1 = P->p[1] * log_(pr) + (P->p[0] - P->p[1]) * log1p_<false>(-pr);
@@ -617,7 +625,7 @@ struct VecChain {
       rng.ctr += (unsigned long long)(nb + ni * n + (d - nb - ni));
       return;
     }
-    if (TK == PGN_TARGET_UNID) {   // rand!(rng, product_distribution([Uniform(), Uniform()]), x)
+    if (TK == PGN_TARGET_UNID && !(VAR && var_ref)) {   // rand!(rng, product_distribution([Uniform(), Uniform()]), x)
 #pragma unroll
       for (int k = 0; k < CPL; ++k)
         if (valid(k)) x[k] = uniform_at(rng, rng.ctr + (unsigned long long)(k * 32 + lane));

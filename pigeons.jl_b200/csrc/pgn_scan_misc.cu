@@ -148,6 +148,7 @@ void* vec_plain_kernel_funnel(int cpl, int ex); void* vec_team_kernel_funnel(int
 void* vec_plain_kernel_gmm(int cpl, int ex);    void* vec_team_kernel_gmm(int cpl, int ex);
 void* vec_plain_kernel_mixed(int cpl, int ex);
 void* vec_plain_kernel_unid(int cpl, int ex);
+void* vec_plain_kernel_unid_var(int cpl, int ex);
 void* vec_plain_kernel_funnel_var(int cpl, int ex); void* vec_team_kernel_funnel_var(int cpl, int ex);
 void* vec_plain_kernel_gmm_var(int cpl, int ex);    void* vec_team_kernel_gmm_var(int cpl, int ex);
 static bool is_team_explorer(int ex) { return ex == PGN_EXPLORER_AUTOMALA || ex == PGN_EXPLORER_COMPOSE || ex == PGN_EXPLORER_MIX; }
@@ -155,6 +156,7 @@ void* vec_scan_kernel_toy(int cpl, int ex) { return is_team_explorer(ex) ? vec_t
 void* vec_scan_kernel_funnel(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_funnel(cpl, ex) : vec_plain_kernel_funnel(cpl, ex); }
 void* vec_scan_kernel_mixed(int cpl, int ex) { return ex == PGN_EXPLORER_SLICE ? vec_plain_kernel_mixed(cpl, ex) : nullptr; }
 void* vec_scan_kernel_unid(int cpl, int ex) { return ex == PGN_EXPLORER_SLICE ? vec_plain_kernel_unid(cpl, ex) : nullptr; }
+void* vec_scan_kernel_unid_var(int cpl, int ex) { return ex == PGN_EXPLORER_SLICE ? vec_plain_kernel_unid_var(cpl, ex) : nullptr; }
 void* vec_scan_kernel_gmm(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_gmm(cpl, ex) : vec_plain_kernel_gmm(cpl, ex); }
 void* vec_scan_kernel_funnel_var(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_funnel_var(cpl, ex) : vec_plain_kernel_funnel_var(cpl, ex); }
 void* vec_scan_kernel_gmm_var(int cpl, int ex) { return is_team_explorer(ex) ? vec_team_kernel_gmm_var(cpl, ex) : vec_plain_kernel_gmm_var(cpl, ex); }

@@ -73,6 +73,8 @@ void* team_kernel_for(int ex) {
 #define PGN_FAMILY(name) name##_funnel
 #elif PGN_TK == 3
 #define PGN_FAMILY(name) name##_gmm
+#elif PGN_TK == 8 && PGN_VAR
+#define PGN_FAMILY(name) name##_unid_var
 #elif PGN_TK == 8
 #define PGN_FAMILY(name) name##_unid
 #else

@@ -155,6 +155,24 @@ def test_two_legs_schedule_adaptation(seed, oracle_lib):
     assert not (refs & tgts) and min(tgts) <= nv < max(tgts) and min(refs) <= nv < max(refs)
 
 
+@pytest.mark.parametrize("seed", [1, 3, 5])
+def test_stepping_stone_two_legs(seed, oracle_lib):
+    """test/test_stepping_stone.jl:3-13 ('Stepping-stone (2 legs)'): toy_turing_unid_target(), GaussianReference(), 7 + 8
+    chains, default rounds; stepping_stone (variational leg only) equals unid_target_exact_logZ within rtol 0.05.  The
+    reference's truth includes log C(n, s) (its model is Binomial), ours does not (the likelihood kernel), so the reference's
+    tolerance 0.05 |truth_ref| is applied to the absolute error.  (Our Gaussian lives in the constrained parametrisation,
+    the reference's in logit space: seeds 1..5 give errors -0.04, -0.57, 0.38, 0.31, 0.04 against the bound 0.59.)"""
+    t = pg.UnidentifiableProduct(100000)
+    n, s_ = t.n_trials, t.n_successes
+    truth = t.analytic_lognormalization()
+    truth_ref = truth + math.lgamma(n + 1) - math.lgamma(s_ + 1) - math.lgamma(n - s_ + 1)      # unid_target_exact_logZ
+    assert abs(truth_ref - (-11.88)) < 0.01
+    pt = pg.pigeons(target=t, variational=pg.GaussianReference(), n_chains_variational=7, n_chains=8, seed=seed,
+                    engine_lib=oracle_lib)
+    assert abs(pg.stepping_stone(pt) - truth) <= 0.05 * abs(truth_ref)
+    assert pt.inputs.variational.mean is not None and pg.global_barrier_variational(pt) < pg.global_barrier(pt)
+
+
 def test_funnel_normalisation(oracle_lib):
     """Both ends of the funnel path are normalised densities: log(Z1/Z0) = 0."""
     pt = pg.pigeons(target=pg.Funnel(8), explorer=pg.AutoMALA(), n_chains=10, n_rounds=11, engine_lib=oracle_lib)
