@@ -301,6 +301,9 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out, char** err) {
     h->online_mean.alloc(h->d_pad); h->online_s2.alloc(h->d_pad); h->online_n.alloc(1);
     h->mail.alloc(h->mail_bytes);
     h->std_devs.alloc(std::max(d, 1));
+    // GaussianReference tables: allocated here, not in pgn_set_variational — a device allocation between rounds could wait
+    // for another handle's running scan kernel on the same device, which in turn waits for this handle
+    if (cfg->n_chains_variational > 0) h->var_tab.alloc((size_t)5 * h->d_pad);
     if (h->recorder_order == PGN_RECORDERS_PER_REPLICA) {
       // every replica's recorder entry for every local chain, and (for vector states) its target-chain online statistics
       const size_t rec_bytes = (size_t)cfg->n_chains * (size_t)std::max(nl, 1) * sizeof(RecEntry);
@@ -842,7 +845,6 @@ int pgn_set_variational(pgn_handle* h, const double* mean, const double* sd, cha
       return fail(err, PGN_ERR_INVALID, "set_variational: finite means and positive finite standard deviations");
   try {
     use_device(h);
-    if (h->var_tab.n == 0) h->var_tab.alloc((size_t)5 * h->d_pad);
     std::vector<double> host((size_t)5 * h->d_pad, 0.0);
     for (int c = 0; c < d; ++c) { host[c] = mean[c]; host[(size_t)h->d_pad + c] = sd[c]; }
     for (int c = d; c < h->d_pad; ++c) host[(size_t)h->d_pad + c] = 1.0;

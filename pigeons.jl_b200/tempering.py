@@ -122,7 +122,8 @@ def optimal_schedule_generator(intensity, old_schedule, nudged: bool = False) ->
     old = np.asarray(old_schedule, dtype=np.float64)
     assert old.size == intensity.size + 1 and np.all(intensity >= 0), f"Bad intensities: {intensity}"
     x = np.concatenate([[0.0], np.cumsum(intensity)])
-    x = x / x[-1]
+    with np.errstate(invalid="ignore", divide="ignore"):      # all-zero intensities: 0/0 = NaN, caught by the uniqueness test as in the reference
+        x = x / x[-1]
     if np.unique(x).size != x.size:
         assert not nudged
         return optimal_schedule_generator(intensity + 1e-6, old, True)

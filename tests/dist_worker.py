@@ -27,8 +27,12 @@ class ShardedOracleView:
 
     def __init__(self, lib, rank, world_size, n_chains, **kw):
         self.full = pg.Engine(lib, n_chains=n_chains, rank=0, world_size=1, **kw)
-        self.lb = pg.LoadBalance(rank + 1, world_size, n_chains)
-        self.first_chain, self.n_local = self.lb.my_first_global_idx(), self.lb.my_load()
+        nv = kw.get("n_chains_variational", 0)
+        self.two_legs = 0 < nv < n_chains
+        # the engine's layout rule (pgn_local_range): balanced blocks, two target chains kept on one shard
+        self.layout = pg.shard_layout(n_chains, world_size, nv if self.two_legs else 0)
+        self.first_chain, self.n_local = self.layout[rank]
+        self.target_chain = nv if self.two_legs else n_chains
         self.dim = self.full.dim
         self.rank, self.world_size, self.n_chains = rank, world_size, n_chains
         self.attached = {}
@@ -57,7 +61,7 @@ class ShardedOracleView:
             a = getattr(res, k)
             if a is not None:
                 setattr(res, k, np.ascontiguousarray(a[:, lo:hi]))
-        owner_of_target = self.rank == self.world_size - 1
+        owner_of_target = self.first_chain <= self.target_chain < self.first_chain + self.n_local
         if self.rank != 0:   # global counters are reported once (by the first shard)
             res.n_tempered_restarts = res.n_round_trips = 0
             res.n_density_points = res.n_ref_equiv_evals = 0
@@ -79,6 +83,10 @@ def main():
     cases = {
         "toy_slice": dict(target=pg.toy_mvn_target(2), explorer=pg.SliceSampler(), n_chains=11, n_rounds=6, seed=1),
         "funnel_automala": dict(target=pg.Funnel(8), explorer=pg.AutoMALA(), n_chains=6, n_rounds=5, seed=2),
+        # two legs of equal length: the balanced split separates the target chains, the layout rule re-unites them
+        "two_legs_gmm_gaussian": dict(target=pg.eight_mode_mixture(6, 3.0), explorer=pg.AutoMALA(), n_chains=4, n_chains_variational=4,
+                                      variational=pg.GaussianReference(first_tuning_round=2), n_rounds=5, seed=3),
+        "two_legs_unid_slice": dict(target=pg.UnidentifiableProduct(100, 50), n_chains=4, n_chains_variational=3, n_rounds=5, seed=4),
     }
     report = {}
     for name, kw in cases.items():

@@ -26,4 +26,5 @@ def test_host_driver_is_invariant_to_world_size(world, tmp_path, oracle_lib):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     report = json.loads(out.read_text())
-    assert report == {"toy_slice": True, "funnel_automala": True, "schedules_identical_on_all_ranks": True}, report
+    assert report == {"toy_slice": True, "funnel_automala": True, "two_legs_gmm_gaussian": True, "two_legs_unid_slice": True,
+                      "schedules_identical_on_all_ranks": True}, report

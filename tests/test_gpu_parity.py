@@ -130,6 +130,8 @@ CASES = {
                                  variational=pg.GaussianReference(first_tuning_round=99), n_rounds=9, seed=1),
     "unid_two_legs_gaussian": dict(target=pg.UnidentifiableProduct(100000), n_chains=8, n_chains_variational=7,
                                    variational=pg.GaussianReference(first_tuning_round=4), n_rounds=9, seed=2),
+    "two_legs_toy_mala_test_mala_jl": dict(target=pg.toy_mvn_target(2), n_chains=2, explorer=pg.MALA(), n_chains_variational=4,
+                                           n_rounds=9, seed=1),
     "two_legs_ising5": dict(target=pg.IsingLogPotential(0.8, 5), n_chains=5, n_chains_variational=4, n_rounds=7, seed=8),
     "two_legs_never_activated": dict(target=pg.Funnel(8), explorer=pg.AutoMALA(), n_chains=4, n_chains_variational=4,
                                      variational=pg.GaussianReference(first_tuning_round=99), n_rounds=6, seed=9),

@@ -102,6 +102,16 @@ def test_moments(explorer, oracle_lib):
     assert np.all(np.abs(rr.online_var - 0.1) < 0.03)
 
 
+def test_mala_two_legs_moments(oracle_lib):
+    """test/test_mala.jl:6-25 verbatim: toy_mvn_target(2), n_chains = 2, MALA(), n_chains_variational = 4 (no variational
+    family: a second fixed leg), online recorder, 10 rounds: mean 0 +- 0.03, variance 0.1 +- 0.03 (both target chains record)."""
+    pt = pg.pigeons(target=pg.toy_mvn_target(2), n_chains=2, explorer=pg.MALA(), n_chains_variational=4, record=[pg.online],
+                    n_rounds=10, engine_lib=oracle_lib)
+    rr = pt.reduced_recorders
+    assert rr.online_n == 2 * 2 ** 10
+    assert np.all(np.abs(rr.online_mean) < 0.03) and np.all(np.abs(rr.online_var - 0.1) < 0.03)
+
+
 def test_global_barrier_two_normals_surrogate(oracle_lib):
     """test/test_DistributionLogPotential.jl:23-31 shape: well separated modes give a
     large barrier; here the mixture N(-8,I)/N(8,I) in d=2 vs N(0,64 I): log Z = 0 exactly."""
