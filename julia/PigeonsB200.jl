@@ -265,6 +265,8 @@ struct DeviceFunnel;   dim::Int; sigma_y::Float64; sigma_ref::Float64; end
 struct DeviceIsing;    beta::Float64; L::Int; end
 struct DeviceMixture;  means::Matrix{Float64}; log_weights::Vector{Float64}; sigma::Float64; sigma_ref::Float64; end   # means: K x d
 struct DeviceLogistic; x::Matrix{Float64}; y::Vector{Float64}; prior_sigma::Float64; end                               # x: n x d
+# the unidentifiable product of test/test_DistributionLogPotential.jl:7-21 (reference: Uniform(0,1)^2, SliceSampler only)
+struct DeviceUnid;     n_trials::Int; n_successes::Int; end
 
 device_target(t::DeviceFunnel, reference) =
     (PGN_TARGET_FUNNEL, t.dim, pad8(t.sigma_y, log(t.sigma_y), 1.0 / t.sigma_y^2, normal_ref_params(t.sigma_ref)...), 0,
@@ -284,6 +286,9 @@ function device_target(t::DeviceLogistic, reference)
     x_rowmajor = collect(transpose(t.x))              # [n][d] row-major
     (PGN_TARGET_LOGREG, d, pad8(n, 0.0, 0.0, normal_ref_params(t.prior_sigma)...), 0, nothing, nothing, vec(x_rowmajor), copy(t.y))
 end
+
+device_target(t::DeviceUnid, reference) =
+    (PGN_TARGET_UNID, 2, pad8(t.n_trials, t.n_successes), 0, nothing, nothing, nothing, nothing)
 
 device_target(t, reference) =
     error("no device implementation for a target of type $(typeof(t)): the B200 engine supports a closed family of " *
