@@ -102,6 +102,17 @@ def test_moments(explorer, oracle_lib):
     assert np.all(np.abs(rr.online_var - 0.1) < 0.03)
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_mass_matrix_adaptation(seed, oracle_lib):
+    """test/test_auto_mala.jl:37-42 ('Mass-matrix') on the toy target: one chain, AutoMALA, 10 rounds — the adapted
+    `estimated_target_std_deviations` are the target's (1/sqrt(10) here; the reference checks 1/sqrt(500) within 0.01, i.e.
+    within 22 % — 10 % is asserted) and the mean MH acceptance is above 0.5."""
+    pt = pg.pigeons(target=pg.toy_mvn_target(2), explorer=pg.AutoMALA(), n_chains=1, n_rounds=10, seed=seed, engine_lib=oracle_lib)
+    sd = np.asarray(pt.shared.explorer.estimated_target_std_deviations)
+    assert np.all(np.abs(sd - 1.0 / math.sqrt(10.0)) < 0.1 / math.sqrt(10.0))
+    assert pt.reduced_recorders.expl_acc_mean[0] > 0.5
+
+
 def test_mala_two_legs_moments(oracle_lib):
     """test/test_mala.jl:6-25 verbatim: toy_mvn_target(2), n_chains = 2, MALA(), n_chains_variational = 4 (no variational
     family: a second fixed leg), online recorder, 10 rounds: mean 0 +- 0.03, variance 0.1 +- 0.03 (both target chains record)."""
