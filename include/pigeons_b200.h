@@ -282,13 +282,16 @@ int pgn_logdensity_and_gradient(pgn_handle* h, const double* x, int32_t n_points
  * InterpolatingPath on the register-resident kernels (FUNNEL, GMM, UNID; d <= 128). */
 int pgn_set_variational(pgn_handle* h, const double* mean, const double* sd, char** err);
 
-/* hamiltonian_dynamics!(target_log_potential, state, momentum, step_size, n_steps) with the identity preconditioner
- * (src/explorers/hamiltonian_dynamics.jl:39-84): n_steps leapfrog steps of the device's own integrator (the code the
- * autoMALA / MALA kernels run) from (x, p) at inverse temperature beta.  Parity / property entry point
- * (test/test_auto_mala.jl:51-85: forward, flip the momentum, forward again returns to the start).
- * Vector targets with a gradient on the register-resident kernels (d <= 128).  x, p, x_out, p_out: [n_points][d]. */
+/* hamiltonian_dynamics!(target_log_potential, diag_precond, state, momentum, step_size, n_steps)
+ * (src/explorers/hamiltonian_dynamics.jl:39-84) as n_steps applications of leap_frog! (:86-93) — the device's own integrator,
+ * the code the autoMALA / MALA kernels run (the reference's n-step form merges the inner half-steps, :73-76: the same map up to
+ * rounding) — from (x, p) at inverse temperature beta.  diag_precond: [d], or NULL for the identity.  step_size may be
+ * negative.  Parity / property entry point (test/test_auto_mala.jl:51-85: forward, then flip the momentum or the step, returns
+ * to the start).  Vector targets with a gradient on the register-resident kernels (d <= 128).
+ * x, p, x_out, p_out: [n_points][d]. */
 int pgn_hamiltonian_dynamics(pgn_handle* h, const double* x, const double* p, int32_t n_points, const double* beta,
-                             double step_size, int32_t n_steps, double* x_out, double* p_out, char** err);
+                             const double* diag_precond, double step_size, int32_t n_steps, double* x_out, double* p_out,
+                             char** err);
 
 /* Multi-GPU (one process per GPU): neighbour mailboxes are peer-mapped with
  * CUDA IPC.  Replaces the role of Entangler.transmit! (src/mpi_utils/Entangler.jl:133-184)

@@ -1260,7 +1260,8 @@ int orc_set_variational(orc_handle* h, const double* mean, const double* sd, cha
 
 // hamiltonian_dynamics! (hamiltonian_dynamics.jl:39-84) with the identity preconditioner: n_steps x leap_frog!
 int orc_hamiltonian_dynamics(orc_handle* h, const double* x, const double* p, int32_t n_points, const double* beta,
-                             double step_size, int32_t n_steps, double* x_out, double* p_out, char** err) {
+                             const double* diag_precond, double step_size, int32_t n_steps, double* x_out, double* p_out,
+                             char** err) {
   Engine& E = h->E;
   const int d = E.d(), tk = E.cfg.target_kind;
   if (tk != PGN_TARGET_TOY_MVN && tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM && tk != PGN_TARGET_LOGREG)
@@ -1271,6 +1272,7 @@ int orc_hamiltonian_dynamics(orc_handle* h, const double* x, const double* p, in
     r.x.assign(x + (size_t)i * d, x + (size_t)(i + 1) * d);
     r.momentum.assign(p + (size_t)i * d, p + (size_t)(i + 1) * d);
     r.precond.assign(d, 1.0); r.grad.assign(d, 0.0); r.g1.assign(d, 0.0); r.g2.assign(d, 0.0);
+    if (diag_precond) r.precond.assign(diag_precond, diag_precond + d);
     for (int s = 0; s < n_steps; ++s)
       if (!E.leap_frog(beta[i], r, step_size)) break;
     std::memcpy(x_out + (size_t)i * d, r.x.data(), sizeof(double) * d);

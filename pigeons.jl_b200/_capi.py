@@ -409,15 +409,18 @@ class Engine:
                       _ptr(b, C.c_double), _ptr(ld, C.c_double), _ptr(g, C.c_double))
         return ld, g
 
-    def hamiltonian_dynamics(self, x, p, beta, step_size: float, n_steps: int):
-        """hamiltonian_dynamics! with the identity preconditioner (hamiltonian_dynamics.jl:39-84): the engine's own integrator."""
+    def hamiltonian_dynamics(self, x, p, beta, step_size: float, n_steps: int, diag_precond=None):
+        """n_steps x leap_frog! (hamiltonian_dynamics.jl:39-93) by the engine's own integrator; diag_precond None = identity."""
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.dim)
         p = np.ascontiguousarray(p, dtype=np.float64).reshape(-1, self.dim)
         b = np.ascontiguousarray(np.broadcast_to(beta, (x.shape[0],)), dtype=np.float64)
         xo, po = np.empty_like(x), np.empty_like(p)
         self.lib.fn("hamiltonian_dynamics").restype = C.c_int
+        pre = None if diag_precond is None else np.ascontiguousarray(diag_precond, dtype=np.float64)
+        if pre is not None and pre.shape != (self.dim,):
+            raise ValueError(f"diag_precond must have shape ({self.dim},)")
         self.lib.call("hamiltonian_dynamics", self._h, _ptr(x, C.c_double), _ptr(p, C.c_double), C.c_int32(x.shape[0]),
-                      _ptr(b, C.c_double), C.c_double(step_size), C.c_int32(n_steps), _ptr(xo, C.c_double), _ptr(po, C.c_double))
+                      _ptr(b, C.c_double), _ptr(pre, C.c_double), C.c_double(step_size), C.c_int32(n_steps), _ptr(xo, C.c_double), _ptr(po, C.c_double))
         return xo, po
 
     # -- multi-GPU ---------------------------------------------------------------------

@@ -858,26 +858,32 @@ int pgn_set_variational(pgn_handle* h, const double* mean, const double* sd, cha
 }
 
 int pgn_hamiltonian_dynamics(pgn_handle* h, const double* x, const double* p, int32_t n_points, const double* beta,
-                             double step_size, int32_t n_steps, double* x_out, double* p_out, char** err) {
+                             const double* diag_precond, double step_size, int32_t n_steps, double* x_out, double* p_out,
+                             char** err) {
   try {
     use_device(h);
     const int d = h->cfg.dim, tk = h->cfg.target_kind;
     if ((tk != PGN_TARGET_TOY_MVN && tk != PGN_TARGET_FUNNEL && tk != PGN_TARGET_GMM) || h->cpl == 0)
       return fail(err, PGN_ERR_INVALID, "hamiltonian_dynamics: vector targets with a gradient, d <= 128");
     if (n_points < 0 || n_steps < 0) return fail(err, PGN_ERR_INVALID, "negative count");
-    StreamBuf<double> dx, dp, db, ox, op;
+    StreamBuf<double> dx, dp, db, ox, op, dpre;
     const size_t n = (size_t)n_points * d;
+    if (diag_precond) {
+      for (int c = 0; c < d; ++c)
+        if (!(diag_precond[c] != 0.0) || !std::isfinite(diag_precond[c])) return fail(err, PGN_ERR_INVALID, "diag_precond: finite and non-zero");
+      dpre.alloc(d, h->stream); dpre.upload(diag_precond, d);
+    }
     dx.alloc(n, h->stream); dp.alloc(n, h->stream); db.alloc(n_points, h->stream); ox.alloc(n, h->stream); op.alloc(n, h->stream);
     dx.upload(x, n); dp.upload(p, n); db.upload(beta, n_points);
     Params P;
     fill_params(h, P);
     const int wpb = 4, grid = (n_points + wpb - 1) / wpb;
     const size_t smem = scan_smem_bytes(h);
-    if (tk == PGN_TARGET_TOY_MVN) launch_leapfrog_toy(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, step_size, n_steps, n_points, ox.p, op.p);
-    else if (tk == PGN_TARGET_FUNNEL && h->var_active) launch_leapfrog_funnel_var(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, step_size, n_steps, n_points, ox.p, op.p);
-    else if (tk == PGN_TARGET_FUNNEL) launch_leapfrog_funnel(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, step_size, n_steps, n_points, ox.p, op.p);
-    else if (h->var_active) launch_leapfrog_gmm_var(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, step_size, n_steps, n_points, ox.p, op.p);
-    else launch_leapfrog_gmm(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, step_size, n_steps, n_points, ox.p, op.p);
+    if (tk == PGN_TARGET_TOY_MVN) launch_leapfrog_toy(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, dpre.p, step_size, n_steps, n_points, ox.p, op.p);
+    else if (tk == PGN_TARGET_FUNNEL && h->var_active) launch_leapfrog_funnel_var(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, dpre.p, step_size, n_steps, n_points, ox.p, op.p);
+    else if (tk == PGN_TARGET_FUNNEL) launch_leapfrog_funnel(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, dpre.p, step_size, n_steps, n_points, ox.p, op.p);
+    else if (h->var_active) launch_leapfrog_gmm_var(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, dpre.p, step_size, n_steps, n_points, ox.p, op.p);
+    else launch_leapfrog_gmm(h->cpl, grid, wpb * 32, smem, h->stream, P, dx.p, dp.p, db.p, dpre.p, step_size, n_steps, n_points, ox.p, op.p);
     CUDA_CHECK(cudaGetLastError());
     ox.download(x_out, n); op.download(p_out, n);
   } catch (CudaError& e) { return fail(err, e.code, e.msg); }

@@ -187,19 +187,19 @@ void launch_eval_points_funnel(int cpl, int grid, int block, size_t smem, cudaSt
 void launch_eval_points_gmm(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
                             const double* betas, int n, double* lp, double* ld, double* grad);
 void launch_leapfrog_toy(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
-                         const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out);
+                         const double* betas, const double* precond, double eps, int n_steps, int n, double* x_out, double* p_out);
 void launch_leapfrog_funnel(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
-                            const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out);
+                            const double* betas, const double* precond, double eps, int n_steps, int n, double* x_out, double* p_out);
 void launch_leapfrog_gmm(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
-                         const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out);
+                         const double* betas, const double* precond, double eps, int n_steps, int n, double* x_out, double* p_out);
 void launch_eval_points_funnel_var(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
                                    const double* betas, int n, double* lp, double* ld, double* grad);
 void launch_eval_points_gmm_var(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
                                 const double* betas, int n, double* lp, double* ld, double* grad);
 void launch_leapfrog_funnel_var(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
-                                const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out);
+                                const double* betas, const double* precond, double eps, int n_steps, int n, double* x_out, double* p_out);
 void launch_leapfrog_gmm_var(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
-                             const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out);
+                             const double* betas, const double* precond, double eps, int n_steps, int n, double* x_out, double* p_out);
 void launch_eval_points_unid_var(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
                                  const double* betas, int n, double* lp, double* ld, double* grad);
 void launch_eval_points_unid(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,

@@ -1872,8 +1872,8 @@ __global__ void eval_points_kernel(const __grid_constant__ Params P, const doubl
 
 // hamiltonian_dynamics! with the identity preconditioner: one warp per point, n_steps x VecChain::run_trial (= leap_frog!)
 template <int TK, int CPL, bool VAR = false>
-__global__ void leapfrog_kernel(const __grid_constant__ Params P, const double* xs, const double* ps, const double* betas, double eps,
-                                int n_steps, int n_points, double* x_out, double* p_out) {
+__global__ void leapfrog_kernel(const __grid_constant__ Params P, const double* xs, const double* ps, const double* betas,
+                                const double* precond, double eps, int n_steps, int n_points, double* x_out, double* p_out) {
   extern __shared__ double smem[];
   typedef VecChain<TK, CPL, PGN_EXPLORER_MALA, VAR> Chain;
   Chain::stage_shared(P, smem);
@@ -1891,15 +1891,18 @@ __global__ void leapfrog_kernel(const __grid_constant__ Params P, const double* 
     const bool v = k * 32 + lane < P.d;
     x[k] = v ? xs[(size_t)w * P.d + k * 32 + lane] : 0.0;
     p[k] = v ? ps[(size_t)w * P.d + k * 32 + lane] : 0.0;
-    pre[k] = 1.0;
+    pre[k] = (v && precond != nullptr) ? precond[k * 32 + lane] : 1.0;
   }
-  {   // conditioned gradient at the start point (hamiltonian_dynamics.jl:45-47)
+  const bool pre_one = precond == nullptr;
+  {   // conditioned gradient at the start point (hamiltonian_dynamics.jl:31-35, 45-47)
     double a0, a1, extra = 0.0;
     ch.eval_grad(x, ch.beta, a0, a1, g, extra);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) g[k] = pre_one ? g[k] : g[k] / pre[k];
   }
   typename Chain::Trial T;
   for (int s = 0; s < n_steps; ++s) {
-    ch.run_trial(x, p, g, pre, true, eps, 0.0, T);
+    ch.run_trial(x, p, g, pre, pre_one, eps, 0.0, T);
 #pragma unroll
     for (int k = 0; k < CPL; ++k) { x[k] = T.x1[k]; p[k] = T.p1[k]; g[k] = T.g1c[k]; }
     if (!is_finite(T.h_after)) break;   // :56-59, :80: the reference stops at a non-finite state

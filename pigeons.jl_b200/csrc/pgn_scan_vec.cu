@@ -39,8 +39,8 @@ void* plain_kernel_for(int ex) {
 #if PGN_TK < 7
 template <int CPL>
 void leapfrog_launch(int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs, const double* ps,
-                     const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out) {
-  leapfrog_kernel<PGN_TK, CPL, PGN_VAR != 0><<<grid, block, smem, s>>>(P, xs, ps, betas, eps, n_steps, n, x_out, p_out);
+                     const double* betas, const double* precond, double eps, int n_steps, int n, double* x_out, double* p_out) {
+  leapfrog_kernel<PGN_TK, CPL, PGN_VAR != 0><<<grid, block, smem, s>>>(P, xs, ps, betas, precond, eps, n_steps, n, x_out, p_out);
 }
 #endif
 template <int CPL>
@@ -101,11 +101,11 @@ void PGN_FAMILY(launch_eval_points)(int cpl, int grid, int block, size_t smem, c
 }
 #if PGN_TK < 7
 void PGN_FAMILY(launch_leapfrog)(int cpl, int grid, int block, size_t smem, cudaStream_t s, const Params& P, const double* xs,
-                                 const double* ps, const double* betas, double eps, int n_steps, int n, double* x_out, double* p_out) {
+                                 const double* ps, const double* betas, const double* precond, double eps, int n_steps, int n, double* x_out, double* p_out) {
   switch (cpl) {
-    case 1: leapfrog_launch<1>(grid, block, smem, s, P, xs, ps, betas, eps, n_steps, n, x_out, p_out); break;
-    case 2: leapfrog_launch<2>(grid, block, smem, s, P, xs, ps, betas, eps, n_steps, n, x_out, p_out); break;
-    case 4: leapfrog_launch<4>(grid, block, smem, s, P, xs, ps, betas, eps, n_steps, n, x_out, p_out); break;
+    case 1: leapfrog_launch<1>(grid, block, smem, s, P, xs, ps, betas, precond, eps, n_steps, n, x_out, p_out); break;
+    case 2: leapfrog_launch<2>(grid, block, smem, s, P, xs, ps, betas, precond, eps, n_steps, n, x_out, p_out); break;
+    case 4: leapfrog_launch<4>(grid, block, smem, s, P, xs, ps, betas, precond, eps, n_steps, n, x_out, p_out); break;
     default: throw CudaError{PGN_ERR_INVALID, "unsupported dimension"};
   }
 }

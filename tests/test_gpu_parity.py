@@ -454,6 +454,15 @@ def test_device_integrator_is_an_involution_and_matches_the_oracle(target, gpu_l
     ox2, op2 = orc.hamiltonian_dynamics(ox1, -op1, betas, eps, n)
     assert np.array_equal(x2, ox2) and np.array_equal(p2, op2)
     assert np.abs(x2 - x0).max() < 1e-9 and np.abs(-p2 - p0).max() < 1e-9
+    # the reference's own variant (test/test_auto_mala.jl:51-85): a non-trivial diagonal preconditioner, and the "flip step"
+    # form (forward with +eps, back with -eps) next to the "flip momentum" form above
+    cond = rng.uniform(0.5, 2.5, d)
+    xc, pc = dev.hamiltonian_dynamics(x0, p0, betas, 0.1 * eps * 5, n, diag_precond=cond)
+    oxc, opc = orc.hamiltonian_dynamics(x0, p0, betas, 0.1 * eps * 5, n, diag_precond=cond)
+    assert np.array_equal(xc, oxc) and np.array_equal(pc, opc)
+    assert np.abs(xc - x0).max() > 1e-3 and not np.array_equal(xc, x1)
+    xb, pb = dev.hamiltonian_dynamics(xc, pc, betas, -0.1 * eps * 5, n, diag_precond=cond)
+    assert np.abs(xb - x0).max() < 1e-9 and np.abs(pb - p0).max() < 1e-9
     # zero steps is the identity; one step equals the leapfrog written out in numpy on the gradient entry point
     xz, pz = dev.hamiltonian_dynamics(x0, p0, betas, eps, 0)
     assert np.array_equal(xz, x0) and np.array_equal(pz, p0)

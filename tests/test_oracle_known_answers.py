@@ -306,6 +306,11 @@ def test_leapfrog_involution(target, oracle_lib):
     x1, p1 = e.hamiltonian_dynamics(x0, p0, betas, 0.01, 40)
     x2, p2 = e.hamiltonian_dynamics(x1, -p1, betas, 0.01, 40)
     assert np.abs(x1 - x0).max() > 1e-3 and np.abs(x2 - x0).max() < 1e-9 and np.abs(-p2 - p0).max() < 1e-9
+    # 'Flip step' with a diagonal preconditioner (test/test_auto_mala.jl:52-70: some_cond = [2.3, 0.8], +-0.1, 40 leaps)
+    cond = np.resize(np.array([2.3, 0.8]), target.dim)
+    x3, p3 = e.hamiltonian_dynamics(x0, p0, betas, 0.01, 40, diag_precond=cond)
+    x4, p4 = e.hamiltonian_dynamics(x3, p3, betas, -0.01, 40, diag_precond=cond)
+    assert np.abs(x3 - x0).max() > 1e-3 and np.abs(x4 - x0).max() < 1e-9 and np.abs(p4 - p0).max() < 1e-9
     e.close()
 
 
