@@ -93,6 +93,8 @@ bool shard_owns_target(const pgn_handle* h) {
   return t >= h->first_chain && t < h->first_chain + h->n_local;
 }
 
+constexpr bool kMixedTeamsDefault = true;    // "mixed teams" launch of single-warp autoMALA ladders (pgn_run_round); PGN_MIXED_TEAMS overrides
+
 void* select_scan_kernel(const pgn_handle* h) {
   const int ex = h->ep.kind;
   switch (h->cfg.target_kind) {
@@ -615,6 +617,65 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
           }
         }
       }
+      // ---- mixed teams: a single-warp-per-chain autoMALA launch usually leaves warp slots free (C3: 1024 chains at 255
+      // registers, 1184 slots).  Blocks of two warps then serve EITHER one chain as a team of two OR two chains with one warp
+      // each, and the teams go to the chains that did most work in the previous round (explorer_n_steps: independent of the
+      // team width).  The ladder runs at the local pace of its slowest region, so that is where a second warp pays.
+      // Same kernels per chain as the uniform launch (every team width gives the same bits), same mailbox layout.
+      StreamBuf<int> d_block_map;
+      h->last_mixed_teams = 0;
+      {
+        const char* mx = std::getenv("PGN_MIXED_TEAMS");        // "1" / "0"; unset: kMixedTeamsDefault
+        // a pinned team width (PGN_TEAM) is honoured as it is unless mixed teams are asked for explicitly
+        const bool want = mx != nullptr ? std::string(mx) == "1" : (kMixedTeamsDefault && std::getenv("PGN_TEAM") == nullptr);
+        const char* mcap = std::getenv("PGN_MIXED_MAX_TEAMS");   // tests: cap the number of teams (mixes team and pair blocks on small ladders)
+        void* mk = nullptr;
+        if (want && wpb == 1 && is_team_kernel(h) && h->ep.kind == PGN_EXPLORER_AUTOMALA && !h->var_active && nl >= 4) {
+          switch (h->cfg.target_kind) {
+            case PGN_TARGET_TOY_MVN: mk = vec_mixed_team_kernel_toy(h->cpl); break;
+            case PGN_TARGET_FUNNEL: mk = vec_mixed_team_kernel_funnel(h->cpl); break;
+            case PGN_TARGET_GMM: mk = vec_mixed_team_kernel_gmm(h->cpl); break;
+            default: break;
+          }
+        }
+        if (mk) {
+          // shared memory of a block: the staged target constants + two single-warp team regions
+          const size_t sm_mixed = scan_smem_bytes(h) + (size_t)2 * ((24 + h->cpl * 32) + 3 * (3 * h->cpl * 32 + 8)) * sizeof(double);
+          if (sm_mixed > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_mixed));
+          int per_sm = 0;
+          CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mk, 64, sm_mixed));
+          const long long blocks_max = (long long)per_sm * h->n_sms;
+          // K teams need K + ceil((nl - K) / 2) blocks
+          int K = (int)std::min<long long>(nl, 2 * blocks_max - nl);
+          if (mcap && std::atoi(mcap) >= 0) K = std::min(K, std::atoi(mcap));
+          while (K > 0 && K + (nl - K + 1) / 2 > blocks_max) --K;
+          if (K >= 1 && K + (nl - K + 1) / 2 <= blocks_max) {
+            std::vector<int> order(nl);
+            for (int i = 0; i < nl; ++i) order[i] = i;
+            if ((int)h->last_explore.size() == nl)
+              std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->last_explore[a] > h->last_explore[b]; });
+            else
+              std::reverse(order.begin(), order.end());   // no history yet: the top of the shard
+            std::vector<char> team(nl, 0);
+            for (int i = 0; i < K; ++i) team[order[i]] = 1;
+            std::vector<int> map;
+            for (int c = 0; c < nl; ++c) if (team[c]) { map.push_back(c); map.push_back(-2); }
+            int pending = -1;
+            for (int c = 0; c < nl; ++c) {
+              if (team[c]) continue;
+              if (pending < 0) pending = c;
+              else { map.push_back(pending); map.push_back(c); pending = -1; }
+            }
+            if (pending >= 0) { map.push_back(pending); map.push_back(-1); }
+            d_block_map.alloc(map.size(), h->stream);
+            d_block_map.upload(map.data(), map.size());
+            P.block_map = d_block_map.p;
+            P.pool_refresh = 0;
+            kernel = mk; wpb = 2; grid = (int)(map.size() / 2); smem = sm_mixed;
+            h->last_mixed_teams = K;
+          }
+        }
+      }
       if (wpb != 0) {
         void* args[] = {(void*)&P};
         CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
@@ -625,6 +686,10 @@ int pgn_run_round(pgn_handle* h, int64_t n_scans, pgn_round_out* out, char** err
         CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         if (n_scans > 0) h->stats.download(st.data(), nl, h->stream);
         else std::memset(st.data(), 0, sizeof(ChainStatsDev) * nl);
+        if (n_scans > 0 && is_team_kernel(h)) {   // work per chain of this round (leapfrog steps of the reference's sequential walk)
+          h->last_explore.resize(nl);
+          for (int i = 0; i < nl; ++i) h->last_explore[i] = st[i].n_steps;
+        }
       } else {
         // memory-resident kernel: d > 128, or more chains than fit co-resident, or PGN_FORCE_MEM=1
         if (h->cfg.n_chains_variational > 0 && (h->cfg.n_chains_variational < h->cfg.n_chains || h->var_active))

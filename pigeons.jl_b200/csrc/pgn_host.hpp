@@ -139,6 +139,8 @@ struct pgn_handle {
   // ---- memory-resident scan path (any d, any number of chains; pgn_memchain.cuh)
   bool force_mem = false;
   int recorder_order = PGN_RECORDERS_PER_REPLICA;
+  std::vector<long long> last_explore;  // explore cycles per local chain in the previous round (mixed teams: who is slowest)
+  int last_mixed_teams = 0;             // chains that ran as a team of two in the last round (diagnostics)
   pgn::DevBuf<double> var_tab;          // GaussianReference tables [5][d_pad] (pgn_set_variational)
   bool var_active = false;
   pgn::DevBuf<pgn::RecEntry> rec_table;   // per-replica recorders [n_chains][n_local] (PGN_RECORDERS_PER_REPLICA)
@@ -170,6 +172,10 @@ void* vec_scan_kernel_toy(int cpl, int ex);
 void* vec_scan_kernel_funnel(int cpl, int ex);
 void* vec_scan_kernel_gmm(int cpl, int ex);
 void* vec_scan_kernel_mixed(int cpl, int ex);
+// "mixed teams" variants of the autoMALA kernels (blocks of two warps: a team of two, or two single-warp chains)
+void* vec_mixed_team_kernel_toy(int cpl);
+void* vec_mixed_team_kernel_funnel(int cpl);
+void* vec_mixed_team_kernel_gmm(int cpl);
 void* vec_scan_kernel_unid(int cpl, int ex);
 void* vec_scan_kernel_unid_var(int cpl, int ex);
 void* vec_scan_kernel_funnel_var(int cpl, int ex);   // ladders whose variational leg uses a GaussianReference

@@ -135,6 +135,9 @@ struct Params {
   OnEntry* on_table;       // [n_chains replicas][d_pad], used by the shard owning the target chain(s)
   // legs (pgn_config.n_chains_variational): chains 1..n_var are the variational leg; two legs when 0 < n_var < n_chains
   int n_var;
+  // mixed teams (VecChain<..., MIXED>): per block of two warps, [2 b] = local chain of warp 0, [2 b + 1] = local chain of warp 1,
+  // -1 (no chain) or -2 (warp 1 is the second warp of warp 0's team)
+  const int* block_map;
   const double* var_tab;   // GaussianReference, or null: [5][d_pad] mean | sd | -0.5 log(2 pi sd^2) | 1/(2 sd^2) | 1/sd^2
 };
 __device__ __forceinline__ bool two_legs(const Params& P) { return P.n_var > 0 && P.n_var < P.n_chains; }
@@ -194,9 +197,21 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 // ===========================================================================
 // VAR: the chain may sit on the variational leg and then uses the GaussianReference tables instead of the fixed
 // reference (separate instantiations, csrc/Makefile vec_*_var_*: the plain kernels carry none of this)
-template <int TK, int CPL, int EX, bool VAR = false>
+// MIXED: blocks of two warps that are EITHER one chain's team of two OR two independent single-warp chains (Params::block_map):
+// the warp slots the register file leaves free go to the slowest chains (pgn_engine.cu, "mixed teams")
+template <int TK, int CPL, int EX, bool VAR = false, bool MIXED = false>
 struct VecChain {
   static constexpr bool kTestSwapper = false;
+  static constexpr bool kMixed = MIXED;
+  // barrier over the warps of THIS chain's team: the whole block, or (mixed blocks) a named barrier over the team's 32 W threads
+  __device__ __forceinline__ void team_barrier() const {
+    if constexpr (MIXED) {
+      if (W > 1) asm volatile("bar.sync 1, %0;" ::"r"(W * 32) : "memory");
+      else __syncwarp();
+    } else {
+      __syncthreads();
+    }
+  }
   bool var_ref;   // VAR only: this chain's reference is the Gaussian variational one
   // autoMALA runs with a TEAM of W warps per chain (block = team): the step-size search evaluates W
   // candidate steps per round, one per warp, and replays the reference's sequential decisions on the
@@ -956,7 +971,7 @@ struct VecChain {
         if (lane < 3) { rp[CPL * 32 + lane] = uu; rp[CPL * 32 + 4 + lane] = lu; }
         if (lane == 3) rp[CPL * 32 + 3] = spp;
       }
-      __syncthreads();
+      team_barrier();
     }
     Trial T;
 #pragma unroll 1
@@ -1037,7 +1052,7 @@ struct VecChain {
           const int buf = gen;
           gen = gen == 2 ? 0 : gen + 1;
           publish(buf, T, diff);
-          __syncthreads();
+          team_barrier();
           const long long tc2 = clock64();
           t_barrier += tc2 - tc1;
           // Replay of the reference's sequential walk over the published candidates: lane l holds candidate l of
@@ -1247,6 +1262,7 @@ struct IsingChainT {
   static constexpr bool kTestSwapper = false;
   static constexpr bool kTeam = false;
   static constexpr bool kIsing = true;
+  static constexpr bool kMixed = false;
   static constexpr int kMaxThreads = TABLE ? 256 : 64;
   static constexpr int kMinBlocksPerSM = TABLE ? 1 : 16;
   static constexpr bool kCompact = false;
@@ -1521,6 +1537,7 @@ struct TestSwapperChain {
   static constexpr bool kTestSwapper = true;
   static constexpr bool kTeam = false;
   static constexpr bool kIsing = false;
+  static constexpr bool kMixed = false;
   static constexpr int kMaxThreads = 256;
   static constexpr int kMinBlocksPerSM = 1;
   static constexpr bool kCompact = false;
@@ -1564,8 +1581,17 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
   __syncthreads();
   const int lane = threadIdx.x & 31;
   // team kernels (autoMALA): block = the W warps serving one chain; otherwise one warp per chain
-  const int tw = Chain::kTeam ? (int)(threadIdx.x >> 5) : 0;
-  const int wl = Chain::kTeam ? (int)blockIdx.x : (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  int tw = Chain::kTeam ? (int)(threadIdx.x >> 5) : 0;
+  int wl = Chain::kTeam ? (int)blockIdx.x : (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  int tW = Chain::kTeam ? (int)(blockDim.x >> 5) : 1;
+  int team_slot = 0;   // mixed blocks: which of the block's two team regions in shared memory
+  if constexpr (Chain::kMixed) {
+    const int warp = (int)(threadIdx.x >> 5);
+    const int c0 = P.block_map[2 * blockIdx.x], c1 = P.block_map[2 * blockIdx.x + 1];
+    if (c1 == -2) { wl = c0; tw = warp; tW = 2; }                        // one chain, a team of two
+    else { wl = warp == 0 ? c0 : c1; tw = 0; tW = 1; team_slot = warp; }   // two chains, one warp each
+    if (wl < 0) return;
+  }
   if (wl >= P.n_local) return;
   // team control words: [2] evaluation counter, [3] payload status, [8..23] partner header (two alternating
   // sets of 8), [24..] the adopted state for the other warps of the team
@@ -1579,14 +1605,15 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
   ch.init(P, smem, wl, lane, replica_index);
   if constexpr (Chain::kIsing) ch.build_table(smem);
   if constexpr (Chain::kTeam) {
-    double* team_base = smem + Chain::target_smem_doubles(P.d_pad);
+    // mixed blocks reserve two single-warp regions; a team of two uses both (CTL + 6 slots <= 2 (CTL + 3 slots))
+    double* team_base = smem + Chain::target_smem_doubles(P.d_pad) +
+                        (size_t)team_slot * (Chain::TEAM_CTL_DOUBLES + 3 * Chain::SLOT_DOUBLES);
     team_ctl = reinterpret_cast<long long*>(team_base);
-    const int tW = (int)(blockDim.x >> 5);
     double* slots = team_base + Chain::TEAM_CTL_DOUBLES;
     // the momentum pool follows the trial slots when the launch reserved room for it (P.pool_refresh > 0)
     ch.set_team(tw, tW, slots, P.pool_refresh > 0 ? slots + (size_t)3 * tW * Chain::SLOT_DOUBLES : nullptr);
-    if (threadIdx.x == 0) team_ctl[2] = 0;
-    __syncthreads();
+    if (tw == 0 && lane == 0) team_ctl[2] = 0;
+    ch.team_barrier();
   }
   MeanAcc swap_acc{0, 0.0};
   LogSumAcc ls_fwd{0, -PGN_INF}, ls_bwd{0, -PGN_INF};
@@ -1660,7 +1687,7 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
         // the outgoing replica's online row must be in memory before the partner can see this scan's header:
         // rows -> (team barrier) -> fence -> tagged words; the partner fences after it has seen the header
         if (tw == ch.own(4)) ch.flush_online(P.on_table + (size_t)(replica_index - 1) * P.d_pad);
-        if constexpr (Chain::kTeam) __syncthreads(); else __syncwarp();
+        if constexpr (Chain::kTeam) ch.team_barrier(); else __syncwarp();
         if (tw == 0) fence_acq_rel_gpu();
       }
       const long long t_wait0 = clock64();
@@ -1713,11 +1740,11 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
       }
       if constexpr (Chain::kTeam) {   // team warp 0 did the hand-shake and hands the header to the team
         long long* tc = team_ctl + 8 + 8 * (int)(scan & 1LL);
-        if (threadIdx.x == 0) {
+        if (tw == 0 && lane == 0) {
           tc[0] = status; tc[1] = (long long)double_to_bits(lr_p); tc[2] = (long long)double_to_bits(u_p);
           tc[3] = (long long)ctr_p; tc[4] = ri_p; tc[5] = rt_p;
         }
-        __syncthreads();
+        ch.team_barrier();
         status = (int)tc[0];
         lr_p = bits_to_double((unsigned long long)tc[1]); u_p = bits_to_double((unsigned long long)tc[2]);
         ctr_p = (unsigned long long)tc[3]; ri_p = (int)tc[4]; rt_p = (int)tc[5];
@@ -1772,7 +1799,7 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
         if constexpr (Chain::kTeam) {
           double* sx = reinterpret_cast<double*>(team_ctl + 24);
           if (tw == 0) { ch.share_state(sx); if (lane == 0) team_ctl[3] = got ? 1 : 0; }
-          __syncthreads();
+          ch.team_barrier();
           if (tw != 0) ch.load_state(sx);
           got = team_ctl[3] != 0;
         }
@@ -1806,7 +1833,7 @@ __global__ void __launch_bounds__(Chain::kMaxThreads, Chain::kMinBlocksPerSM) sc
       if (tw == ch.own(2)) { exl[4] = ch.rev.n; ex[5] = ch.rev.mu; exl[6] = ls_fwd.n; ex[7] = ls_fwd.value; }
       if (tw == ch.own(3)) { exl[8] = ch.expl_acc.n; ex[9] = ch.expl_acc.mu; exl[10] = ls_bwd.n; ex[11] = ls_bwd.value; }
     }
-    __syncthreads();
+    ch.team_barrier();
     if (tw != 0) return;
     ch.n_points += team_ctl[2];
     ch.am.n = exl[0]; ch.am.mu = ex[1]; swap_acc.n = exl[2]; swap_acc.mu = ex[3];

@@ -49,6 +49,11 @@ void eval_points_launch(int grid, int block, size_t smem, cudaStream_t s, const 
   eval_points_kernel<PGN_TK, CPL, PGN_VAR != 0><<<grid, block, smem, s>>>(P, xs, betas, n, lp, ld, grad);
 }
 #else
+#if !PGN_VAR && PGN_TK <= 3
+// mixed blocks (two warps: one chain's team of two, or two single-warp chains): autoMALA on the gradient targets
+template <int CPL>
+void* mixed_team_kernel_for() { return scan_kernel_ptr<VecChain<PGN_TK, CPL, PGN_EXPLORER_AUTOMALA, false, true>>(); }
+#endif
 template <int CPL>
 void* team_kernel_for(int ex) {
   switch (ex) {
@@ -111,6 +116,16 @@ void PGN_FAMILY(launch_leapfrog)(int cpl, int grid, int block, size_t smem, cuda
 }
 #endif
 #else
+#if !PGN_VAR && PGN_TK <= 3
+void* PGN_FAMILY(vec_mixed_team_kernel)(int cpl) {
+  switch (cpl) {
+    case 1: return mixed_team_kernel_for<1>();
+    case 2: return mixed_team_kernel_for<2>();
+    case 4: return mixed_team_kernel_for<4>();
+    default: return nullptr;
+  }
+}
+#endif
 void* PGN_FAMILY(vec_team_kernel)(int cpl, int ex) {
   switch (cpl) {
     case 1: return team_kernel_for<1>(ex);

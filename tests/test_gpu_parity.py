@@ -505,6 +505,29 @@ def test_variational_entry_points_match_the_oracle(gpu_lib, oracle_lib):
         assert not np.array_equal(res[0][0][:5], res[0][5][:5]) and res[0][0][5] == res[0][5][5]         # beta = 1: the target alone
 
 
+@pytest.mark.parametrize("name,cap", [("toy100_automala_4cpl", 2), ("funnel32_automala", 7), ("gmm128_automala", 5),
+                                      ("toy40_mix_two_step_sizes", 1), ("gmm2_two_modes", 9), ("funnel_diag_precond", 0)])
+def test_mixed_teams_parity(name, cap, gpu_lib, oracle_lib, monkeypatch):
+    """"Mixed teams": blocks of two warps serve either one chain as a team of two or two chains with one warp each, the
+    teams going to the chains that did most work in the previous round.  Forced here on small ladders (PGN_TEAM=1 selects the
+    single-warp launch the mixed one replaces; PGN_MIXED_MAX_TEAMS caps the teams so that team blocks, pair blocks and a
+    half-empty block all occur): bit-identical to the oracle, like every other team width."""
+    monkeypatch.setenv("PGN_TEAM", "1")
+    monkeypatch.setenv("PGN_MIXED_TEAMS", "1")
+    monkeypatch.setenv("PGN_MIXED_MAX_TEAMS", str(cap))
+    kw = CASES[name]
+    assert_same(run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw), name + "/mixed")
+
+
+def test_mixed_teams_at_c3_width_match_the_oracle(gpu_lib, oracle_lib, monkeypatch):
+    """BASELINE config 3 at its full width (1024 chains, GMM d = 128, autoMALA): the single-warp launch leaves 160 warp slots
+    free; with mixed teams they go to the 160 chains that worked most.  4 rounds against the oracle, bit for bit."""
+    monkeypatch.setenv("PGN_MIXED_TEAMS", "1")
+    kw = dict(target=pg.eight_mode_mixture(128, 8.0), explorer=pg.AutoMALA(), n_chains=1024, n_rounds=4, seed=3,
+              record=[pg.index_process, pg.swap_trace])
+    assert_same(run_pt(gpu_lib, **kw), run_pt(oracle_lib, **kw), "c3_width/mixed")
+
+
 def test_two_legs_at_c3_width(gpu_lib):
     """BASELINE config 3's ladder as TWO legs of 512 chains (GMM d = 128, autoMALA, GaussianReference from round 3): too large
     for the oracle, so size-independent properties — every scan's index process is a permutation, both partners log the same
