@@ -49,7 +49,8 @@ CONFIGS = {
                         "AutoMALA defaults, 256 chains per GPU, chain ladder sharded contiguously"),
     "c3": dict(chains_per_gpu=1024, dim=128, explorer="AutoMALA", state_bytes=128 * 8, scans=512, burn=8,
                flops_per_point=2 * 8 * 3 * 128 + 8 * 30 + 40 + 8 * 128,
-               kernel="pgn::scan_kernel<VecChain<GMM,...,AUTOMALA>>",
+               kernel="pgn::scan_kernel<VecChain<GMM,4,AUTOMALA,MIXED>> (blocks of two warps: the free warp slots serve the chains "
+                      "that worked most as teams of two, DESIGN.md 'Mixed teams'; uniform one-warp launch with PGN_MIXED_TEAMS=0)",
                workload="C3: 8-mode Gaussian mixture d=128 (means (+-8,+-8,+-8,0,...)), reference N(0,64 I), "
                         "AutoMALA defaults, 1024 chains per GPU"),
     "c4": dict(chains_per_gpu=512, dim=1024, explorer="IsingMetropolis", state_bytes=128, scans=2048, burn=8,
